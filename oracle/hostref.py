@@ -1,0 +1,232 @@
+"""numpy restatements of the reference's inline (``__main__``-body) hot-path blocks.
+
+CPU ORACLE -- test infrastructure only.  Each function cites the reference lines it follows
+(paths relative to the fuxi-planner repo).  These blocks are not callable in the reference
+(they live inside ``if __name__ == '__main__':`` loops), hence the restatement.
+"""
+import math
+
+import numpy as np
+
+
+# --------------------------------------------------------------------------- a12
+def decode_occupancy_grid(data, width, height):
+    """scripts/global_planner_st.py:15-20 (= global_planner_ccst.py:17-24).
+
+    nav_msgs/OccupancyGrid row-major int8 (index = y*width + x) -> array[x][y]; 100 -> 1, -1 -> 0;
+    other values (1..99) survive and count as occupied for the inflation (``> 0``)."""
+    m = np.array(data).reshape(height, width).T
+    m = m.copy()
+    m[np.where(m == 100)] = 1
+    m[np.where(m == -1)] = 0
+    return m
+
+
+def encode_occupancy_grid(mapu):
+    """scripts/global_planner_st.py:102-115 (publish_map): 1 -> 100, then data = mapu.T.flatten()."""
+    m = np.array(mapu).copy()
+    m[np.where(m == 1)] = 100
+    return m.T.reshape(-1).astype(np.int8)
+
+
+# --------------------------------------------------------------------------- a13
+def assemble_grid(mapu, map_o, map_reso, start_xy, goal_xy, ifa, variant="st"):
+    """scripts/global_planner_st.py:226-250,266-267 / global_planner_ccst.py:411-436,452-453.
+
+    Returns (padded float64 grid, map_start, map_goal, new map_o, map_d).  ``astype(int)`` truncates
+    toward zero (not floor), as in the reference."""
+    mapu = np.asarray(mapu)
+    map_c, map_r = mapu.shape
+    map_o = np.array(map_o, dtype=float)
+    map_goal = ((np.array(goal_xy[0:2], dtype=float) - map_o) / map_reso).astype(int)
+    map_start = ((np.array(start_xy[0:2], dtype=float) - map_o) / map_reso).astype(int)
+    map_o2 = np.array([-2 * ifa, -2 * ifa])
+    if map_goal[0] < 0 or map_start[0] < 0:
+        map_o2[0] = min(map_goal[0], map_start[0]) + map_o2[0]
+    if map_goal[1] < 0 or map_start[1] < 0:
+        map_o2[1] = min(map_goal[1], map_start[1]) + map_o2[1]
+    map_d = abs(map_o2)
+    new_o = list(map_o2 * map_reso + map_o)
+    map_c = max(map_c, map_goal[0], map_start[0]) + map_d[0]
+    map_r = max(map_r, map_goal[1], map_start[1]) + map_d[1]
+    mapu0 = np.zeros([map_c + 4 * ifa, map_r + 4 * ifa])
+    mapu0[map_d[0]:len(mapu) + map_d[0], map_d[1]:len(mapu[0]) + map_d[1]] = mapu
+    if variant == "st":
+        map_start = map_start + map_d - 1
+        map_goal = map_goal + map_d - 1
+    else:
+        map_start = map_start + map_d
+        map_goal = map_goal + map_d
+    return mapu0, map_start, map_goal, new_o, map_d
+
+
+# --------------------------------------------------------------------------- a10 / a11
+def inflate_st(mapu, ifa):
+    """scripts/global_planner_st.py:256-262: 9-point stencil {-ifa, 0, +ifa}^2 (dense 3x3 for ifa=1)."""
+    mapu = np.array(mapu, dtype=np.float64)
+    occ = np.where(mapu > 0)
+    for i in range(-ifa, ifa + 1, ifa):
+        for j in range(-ifa, ifa + 1, ifa):
+            mapu[(occ[0] + i, occ[1] + j)] = 1
+    return mapu
+
+
+def inflate_ccst(mapu, ifa):
+    """scripts/global_planner_ccst.py:442-448: dense (2*ifa+1)^2 square dilation."""
+    mapu = np.array(mapu, dtype=np.float64)
+    occ = np.where(mapu > 0)
+    for i in range(-ifa, ifa + 1, 1):
+        for j in range(-ifa, ifa + 1, 1):
+            mapu[(occ[0] + i, occ[1] + j)] = 1
+    return mapu
+
+
+# --------------------------------------------------------------------------- a14
+def relocate_goal(mapu, map_goal):
+    """scripts/global_planner_st.py:268-275 (= ccst:454-458).  Returns (goal, end_occu)."""
+    map_goal = np.array(map_goal).copy()
+    if mapu[map_goal[0], map_goal[1]] == 1:
+        try:
+            free = np.where(mapu[map_goal[0], :] == 0)
+            map_goal[1] = free[0][np.argmin(abs(free - map_goal[1]))]
+        except Exception:
+            free = np.where(mapu[:, map_goal[1]] == 0)
+            map_goal[0] = free[0][np.argmin(abs(free - map_goal[0]))]
+        return map_goal, 1
+    return map_goal, 0
+
+
+def path_to_world(path, map_reso, map_o, variant="st"):
+    """scripts/global_planner_st.py:292-298 (offset [1,1]) / global_planner_ccst.py:487-495 (offset [1,0])."""
+    off = np.array([1, 1]) if variant == "st" else np.array([1, 0])
+    path2 = np.array(path) + off
+    path3 = path2 * map_reso + map_o
+    return np.c_[path3, np.zeros([len(path3), 1])]
+
+
+def map_line_col(p2, p1, mapu):
+    """scripts/global_planner_ccst.py:258-283: True = no occupied cell on the sampled line (one sample per
+    integer x strictly between the endpoints, y = rint(slope * x) + int(p1.y)); False = collision."""
+    blc = np.where(mapu == 1)
+    if len(blc[0]) > 0:
+        p1 = np.array(p1)
+        p2 = np.array(p2)
+        p0 = np.array([min(p1[0], p2[0]), min(p1[1], p2[1])]).astype(float)
+        p1 = p1 - p0
+        p2 = p2 - p0
+        if p2[0] < p1[0]:
+            p1, p2 = p2.copy(), p1.copy()
+        xs = np.arange(p1[0] + 1, p2[0], 1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ys = np.rint((p2[1] - p1[1]) / (p2[0] - p1[0]) * xs).astype(int) + int(p1[1])
+        occ = set(zip(blc[0].tolist(), blc[1].tolist()))
+        for x, y in zip(xs.astype(int).tolist(), ys.tolist()):
+            if (x, y) in occ:
+                return False
+    return True
+
+
+# --------------------------------------------------------------------------- a15 / a16
+def body_to_earth_frame(ii, jj, kk):
+    """scripts/utils.py:21-28: R = Rz(kk) * Ry(jj) * Rx(ii)."""
+    ci, cj, ck = math.cos(ii), math.cos(jj), math.cos(kk)
+    si, sj, sk = math.sin(ii), math.sin(jj), math.sin(kk)
+    return np.array([[ck * cj, ck * sj * si - sk * ci, ck * sj * ci + sk * si],
+                     [sk * cj, sk * sj * si + ck * ci, sk * sj * ci - ck * si],
+                     [-sj, cj * si, cj * ci]])
+
+
+def transform_cloud(plc, rpy, pos, dt=0.0, ang_vel=(0.0, 0.0, 0.0), line_vel=(0.0, 0.0, 0.0)):
+    """scripts/plc_point2_st.py:244-251: camera -> body axis swap (+0.12 m lever arm), attitude and
+    position extrapolated by dt, then earth frame.  float64 like the reference."""
+    plc = np.asarray(plc, dtype=np.float64)
+    plc_c = np.zeros([len(plc), 3])
+    plc_c[:, 0] = plc[:, 2] + 0.12
+    plc_c[:, 1] = -plc[:, 0]
+    plc_c[:, 2] = -plc[:, 1]
+    r, p, y = np.array(rpy, dtype=float) + dt * np.array(ang_vel, dtype=float)
+    b2e = body_to_earth_frame(r, p, y)
+    local_pos1 = dt * np.array(line_vel, dtype=float) + np.array(pos, dtype=float)
+    return np.matmul(b2e, plc_c.T).T + np.tile(local_pos1, (len(plc), 1))
+
+
+def cloud_affine(rpy, pos, dt=0.0, ang_vel=(0.0, 0.0, 0.0), line_vel=(0.0, 0.0, 0.0)):
+    """The same transform folded into one 3x4 [R*S | R*l + t] matrix acting on camera-frame (x,y,z):
+    S is the axis swap (x_b=z_c, y_b=-x_c, z_b=-y_c), l = (0.12,0,0).  This is what fx_project takes."""
+    r, p, y = np.array(rpy, dtype=float) + dt * np.array(ang_vel, dtype=float)
+    R = body_to_earth_frame(r, p, y)
+    S = np.array([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])
+    t = dt * np.array(line_vel, dtype=float) + np.array(pos, dtype=float)
+    A = np.zeros((3, 4))
+    A[:, :3] = R @ S
+    A[:, 3] = R @ np.array([0.12, 0.0, 0.0]) + t
+    return A
+
+
+def height_filter(plc_c, zmin=0.3):
+    """scripts/plc_point2_st.py:255-256."""
+    plc_c = np.asarray(plc_c)
+    return plc_c[plc_c[:, 2] > zmin]
+
+
+# --------------------------------------------------------------------------- a17 / a18
+def distance_filter(plc, dis):
+    """scripts/plc_point2_st.py:139-148: keep |p| < dis, sort by (d, z, y, x) (np.lexsort: last key primary)."""
+    plc = np.asarray(plc, dtype=np.float64)
+    d_point = np.linalg.norm(plc, axis=1)
+    filtered = np.c_[plc, d_point]
+    filtered = filtered[d_point < dis]
+    if len(filtered) > 0:
+        filtered = filtered[np.lexsort(filtered.T)]
+    return filtered[:, 0:3]
+
+
+def pack_pointcloud2(points):
+    """scripts/plc_point2_st.py:112-138: float32 x,y,z at offsets 0/4/8, point_step 12, little endian.
+    (The reference's ``.tostring()`` is ``.tobytes()`` on numpy >= 2.)"""
+    pts = np.asarray(points, np.float32)
+    return {"height": 1, "width": len(pts), "point_step": 12, "row_step": 12 * pts.shape[0],
+            "is_bigendian": False, "is_dense": int(np.isfinite(pts).all()),
+            "data": pts.astype("<f4").tobytes()}
+
+
+# --------------------------------------------------------------------------- a20 (NEW semantics, parity unpinned)
+def project(points, affine, zmin, zmax, ox, oy, reso, W, H):
+    """3D -> 2D projection as DEFINED by this framework (the reference delegates it to octomap_server /
+    ccmapping, un-vendored: launch/map_st.launch:3, launch/map_ccst.launch:2).
+
+    All arithmetic in float32, one rounding per operation, fixed order, no FMA:
+        e_k = ((a_k0*x + a_k1*y) + a_k2*z) + a_k3
+        fx  = floor((e_x - ox) / reso),  fy = floor((e_y - oy) / reso)
+        occupied[fx, fy] = 1  iff  zmin < e_z <= zmax  and  0 <= fx < W  and  0 <= fy < H
+    """
+    f = np.float32
+    p = np.asarray(points, dtype=f)
+    A = np.asarray(affine, dtype=f).reshape(3, 4)
+    x, y, z = p[:, 0], p[:, 1], p[:, 2]
+    e = []
+    for k in range(3):
+        e.append(((A[k, 0] * x + A[k, 1] * y) + A[k, 2] * z) + A[k, 3])
+    with np.errstate(invalid="ignore", over="ignore", divide="ignore"):
+        fx = np.floor((e[0] - f(ox)) / f(reso))
+        fy = np.floor((e[1] - f(oy)) / f(reso))
+        ok = (e[2] > f(zmin)) & (e[2] <= f(zmax)) & (fx >= 0) & (fx < W) & (fy >= 0) & (fy < H)
+    grid = np.zeros((W, H), dtype=np.uint8)
+    grid[fx[ok].astype(np.int64), fy[ok].astype(np.int64)] = 1
+    return grid
+
+
+# --------------------------------------------------------------------------- Appendix B (PNG fixtures)
+def png_to_grid(img_l):
+    """Inverse of the save block scripts/global_planner_st.py:365-374: 'L' image array -> m[x][y], 1 = occupied."""
+    a = np.asarray(img_l)
+    return (a[::-1].T == 0).astype(np.uint8)
+
+
+def grid_to_png_array(mapu):
+    """scripts/global_planner_st.py:368-372: 0 -> 255 (free), non-zero -> 0, then .T[::-1]."""
+    mapu = np.asarray(mapu)
+    ms = mapu.copy()
+    ms[mapu != 0] = 0
+    ms[mapu == 0] = 255
+    return np.uint8(ms.T[::-1])

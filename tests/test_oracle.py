@@ -1,0 +1,187 @@
+"""Pins the CPU oracle (oracle/) against golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py).  CPU only."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import unpack_grid, large_grid
+
+
+def _check(oracle, m, rec, check_path=True):
+    path, cost, _ = oracle.jps(m, rec["start"], rec["goal"], rec["h"])
+    if rec["cost"] is None:
+        assert path == 0
+        return
+    assert path != 0
+    assert cost == float(rec["cost"]), (rec, cost)          # bit-exact float64, both metrics
+    if check_path and "path" in rec:
+        assert [list(p) for p in path] == rec["path"]       # identical jump points, identical order
+
+
+def test_appendix_a_shas(maps):
+    # SURVEY Appendix A fixture identity
+    sha = lambda m: hashlib.sha256(np.ascontiguousarray(m.astype(np.uint8)).tobytes()).hexdigest()[:12]
+    assert len(maps) == 35
+    assert sha(maps["-16.40-4.80_out.png"]) == "8109bc9f892c"
+    assert maps["-16.40-4.80_out.png"].shape == (148, 52) and int(maps["-16.40-4.80_out.png"].sum()) == 675
+    assert sha(maps["4.601.00_out.png"]) == "0cff56b9a866"
+
+
+def test_jps_restatement_on_all_maps(oracle, golden, maps):
+    n = 0
+    for name, recs in golden["maps"].items():
+        for rec in recs:
+            _check(oracle, maps[name], rec)
+            n += 1
+    assert n == 35 * 21 * 2
+
+
+def test_cfg1_known_answers(oracle, golden, maps):
+    m = maps["-16.40-4.80_out.png"]
+    _, c1, _ = oracle.jps(m, (0, 0), (147, 51), 1)
+    _, c2, _ = oracle.jps(m, (0, 0), (147, 51), 2)
+    assert c1 == 1674.0 and c2 == 168.12489168102775
+    for rec in golden["cfg1"]:
+        _check(oracle, m, rec)
+
+
+def test_edge_cases(oracle, golden):
+    for rec in golden["edge"]:
+        _check(oracle, np.array(rec["grid"]), rec)
+    byname = {(r["name"], r["h"]): r for r in golden["edge"]}
+    assert byname[("start_eq_goal", 1)]["cost"] == "0.0" or float(byname[("start_eq_goal", 1)]["cost"]) == 0
+    assert byname[("goal_on_obstacle", 1)]["cost"] is None
+    assert float(byname[("start_on_obstacle", 1)]["cost"]) == 28.0
+    assert byname[("diagonal_squeeze", 1)]["cost"] is None
+    assert float(byname[("single_corner_cut", 1)]["cost"]) == 14.0
+    assert float(byname[("value_100_is_free", 1)]["cost"]) == 40.0
+
+
+def test_random_small(oracle, golden):
+    for g in golden["random_small"]:
+        m = unpack_grid(g)
+        for rec in g["queries"]:
+            _check(oracle, m, rec)
+
+
+def test_large(oracle, golden):
+    for g in golden["large"]:
+        m = large_grid(g)
+        for rec in g["queries"]:
+            _check(oracle, m, rec)
+
+
+def test_dijkstra_equals_jps_metric1(oracle, golden, maps):
+    """Graph equivalence: JPS cost == shortest path on the 'not blocked' graph."""
+    for name, recs in golden["maps"].items():
+        m = maps[name]
+        for rec in recs:
+            if rec["h"] != 1:
+                continue
+            c, _ = oracle.sssp_cost(m, rec["start"], rec["goal"], 1)
+            if rec["cost"] is None:
+                assert c == -1
+            else:
+                assert float(c) == float(rec["cost"])
+    for g in golden["random_small"]:
+        m = unpack_grid(g)
+        for rec in g["queries"]:
+            if rec["h"] != 1:
+                continue
+            c, _ = oracle.sssp_cost(m, rec["start"], rec["goal"], 1)
+            assert (c == -1) if rec["cost"] is None else float(c) == float(rec["cost"])
+
+
+def _true_len(oracle, m, rec):
+    """Euclidean length of the path that is optimal in the 2^16 fixed-point metric."""
+    c, _ = oracle.sssp_cost(m, rec["start"], rec["goal"], 2)
+    return c
+
+
+def test_fixed_point_metric2_within_tolerance(oracle, golden, maps):
+    """The 2^16 fixed-point Euclidean metric used on the GPU reproduces jps1's float cost to << 1e-5."""
+    from oracle.capi import FX_WS
+    worst = 0.0
+    for g in golden["large"]:
+        m = large_grid(g)
+        for rec in g["queries"]:
+            if rec["h"] != 2 or rec["cost"] is None:
+                continue
+            c = _true_len(oracle, m, rec) / FX_WS
+            ref = float(rec["cost"])
+            worst = max(worst, abs(c - ref) / ref)
+    assert worst < 5e-6, worst
+
+
+def test_field_full_vs_goal_directed(oracle, maps):
+    m = maps["-16.20-11.40_out.png"]
+    f = oracle.sssp_field(m, (0, 0), 1)
+    free = np.argwhere(m == 0)
+    for g in free[::97]:
+        c, _ = oracle.sssp_cost(m, (0, 0), g, 1)
+        assert c == f[g[0], g[1]]
+    assert (f[m == 1] == -1).all()
+
+
+def test_inflate_matches_reference_formulation(oracle):
+    rng = np.random.default_rng(5)
+    for ifa in (1, 2, 3):
+        core = (rng.random((50, 37)) < 0.1) * rng.integers(1, 101, (50, 37))
+        m = np.zeros((50 + 6 * ifa, 37 + 6 * ifa))
+        m[2 * ifa:2 * ifa + 50, 2 * ifa:2 * ifa + 37] = core          # padding as st:230-250 guarantees
+        st = oracle.hostref.inflate_st(m, ifa)
+        cc = oracle.hostref.inflate_ccst(m, ifa)
+        assert set(np.unique(st)) <= {0.0, 1.0}
+        assert np.array_equal(oracle.inflate(m, ifa, ifa), st.astype(np.uint8))
+        assert np.array_equal(oracle.inflate(m, ifa, 1), cc.astype(np.uint8))
+
+
+def test_edt_vs_scipy(oracle):
+    from scipy.ndimage import distance_transform_edt
+    rng = np.random.default_rng(6)
+    for shape, fill in (((64, 48), 0.05), ((33, 129), 0.3), ((200, 7), 0.01), ((1, 50), 0.1)):
+        m = (rng.random(shape) < fill).astype(np.uint8)
+        if m.sum() == 0:
+            m[0, 0] = 1
+        ref = np.rint(distance_transform_edt(m == 0) ** 2).astype(np.int64)
+        assert np.array_equal(oracle.edt(m).astype(np.int64), ref)
+    assert (oracle.edt(np.zeros((5, 5), np.uint8)) == np.iinfo(np.int32).max).all()
+
+
+def test_hostref_vs_reference_functions(oracle, hostfn_golden):
+    h = hostfn_golden
+    for a, R in zip(h["rpy"], h["R"]):
+        assert np.array_equal(oracle.hostref.body_to_earth_frame(*a), R)
+    assert np.array_equal(oracle.hostref.distance_filter(h["df_in"], 4), h["df_out"])
+    g = h["los_grid"]
+    for a, want in zip(h["los_segs"], h["los_out"]):
+        if want < 0:
+            continue
+        got = oracle.hostref.map_line_col(np.array(a[0:2], dtype=float), np.array(a[2:4], dtype=float), g)
+        assert int(bool(got)) == want, a
+
+
+def test_transform_affine_equivalence(oracle):
+    rng = np.random.default_rng(3)
+    pts = rng.uniform(-5, 5, (100, 3))
+    rpy, pos = (0.1, -0.2, 1.0), (3.0, -2.0, 1.5)
+    e = oracle.hostref.transform_cloud(pts, rpy, pos, dt=0.02, ang_vel=(0.1, 0.0, -0.3), line_vel=(1.0, 0.5, 0.0))
+    A = oracle.hostref.cloud_affine(rpy, pos, dt=0.02, ang_vel=(0.1, 0.0, -0.3), line_vel=(1.0, 0.5, 0.0))
+    e2 = pts @ A[:, :3].T + A[:, 3]
+    assert np.allclose(e, e2, atol=1e-12)
+
+
+@pytest.mark.reference
+def test_live_reference_agrees_with_golden(golden, maps):
+    """Build container only: re-run the unmodified reference and diff against the committed fixture."""
+    from oracle import refload
+    if not refload.available():
+        pytest.skip("reference tree absent")
+    for name in ("-16.40-4.80_out.png", "4.601.00_out.png"):
+        for rec in golden["maps"][name][:6]:
+            path, cost, _ = refload.method(maps[name].astype(np.float64), tuple(rec["start"]), tuple(rec["goal"]), rec["h"])
+            if rec["cost"] is None:
+                assert path == 0
+            else:
+                assert cost == float(rec["cost"]) and [list(map(int, p)) for p in path] == rec["path"]
