@@ -1,0 +1,13 @@
+"""fuxi_planner_b200 -- B200-native (sm_100a) implementation of FUXI's global-planning hot path:
+point cloud -> 2D occupancy grid -> obstacle inflation -> batched shortest paths on the 8-connected grid.
+
+Everything compute runs in hand-written CUDA behind the C ABI in include/fuxi_b200.h
+(libfuxi_b200.so, built in-tree by fuxi_planner_b200/build.py).  There is no CPU fallback.
+"""
+from ._lib import Context, FuxiError, default_context, load, SO_PATH  # noqa: F401
+from .api import (PlanResult, edt, field, field_relax, field_status, inflate, map_host, plan_batch, plan_host,  # noqa: F401
+                  project, search_stats)
+from . import jps1  # noqa: F401
+
+__all__ = ["Context", "FuxiError", "default_context", "load", "SO_PATH", "PlanResult", "edt", "field", "field_relax",
+           "field_status", "inflate", "map_host", "plan_batch", "plan_host", "project", "search_stats", "jps1"]

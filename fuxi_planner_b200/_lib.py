@@ -1,0 +1,103 @@
+"""ctypes binding of libfuxi_b200.so (include/fuxi_b200.h).  No CPU fallback: if the shared library
+or a CUDA device is missing every entry point raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libfuxi_b200.so")
+
+FX_OK = 0
+FX_COST_UNREACHABLE = -1
+FX_COST_START_OOB = -2
+FX_COST_OVERFLOW = -3
+FX_EUCLID_WS = 65536
+FX_EUCLID_WD = 92682
+
+# every symbol include/fuxi_b200.h declares (tests/test_boundary.py checks the .so exports all of them)
+SYMBOLS = ["fx_create", "fx_destroy", "fx_last_error", "fx_version", "fx_launch_count", "fx_set_search_tuning",
+           "fx_project", "fx_inflate", "fx_edt", "fx_search_batch", "fx_field", "fx_field_relax", "fx_field_status",
+           "fx_search_stats", "fx_plan_host", "fx_map_host"]
+
+_lib = None
+
+
+class FuxiError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the library (does not touch the GPU)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise FuxiError("libfuxi_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "or `python fuxi_planner_b200/build.py`. There is no CPU fallback." % SO_PATH)
+    lib = C.CDLL(SO_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    lib.fx_create.argtypes = [i32, C.POINTER(vp)]
+    lib.fx_destroy.argtypes = [vp]
+    lib.fx_last_error.argtypes = [vp]
+    lib.fx_last_error.restype = C.c_char_p
+    lib.fx_version.argtypes = []
+    lib.fx_launch_count.argtypes = [vp]
+    lib.fx_launch_count.restype = i64
+    lib.fx_set_search_tuning.argtypes = [vp, i32, i32]
+    lib.fx_project.argtypes = [vp, vp, i64, i32, C.POINTER(f32), f32, f32, f32, f32, f32, i32, i32, vp, i32, vp]
+    lib.fx_inflate.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.fx_edt.argtypes = [vp, vp, vp, i32, i32, vp]
+    lib.fx_search_batch.argtypes = [vp, vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp, i32, vp]
+    lib.fx_field.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
+    lib.fx_field_relax.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
+    lib.fx_field_status.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    lib.fx_search_stats.argtypes = [vp, C.POINTER(i64)]
+    lib.fx_plan_host.argtypes = [vp, vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp, i32]
+    lib.fx_map_host.argtypes = [vp, vp, i64, i32, C.POINTER(f32), f32, f32, f32, f32, f32, i32, i32, i32, i32, vp]
+    for s in SYMBOLS:
+        if s not in ("fx_last_error", "fx_launch_count"):
+            getattr(lib, s).restype = i32
+    _lib = lib
+    return lib
+
+
+class Context:
+    """One fx_context bound to one CUDA device."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.fx_create(int(device), C.byref(h))
+        if rc != FX_OK:
+            raise FuxiError("fx_create(%d) failed (%d): %s" % (device, rc, self.lib.fx_last_error(None).decode()))
+        self.handle = h
+        self.device = int(device)
+
+    def check(self, rc, what):
+        if rc != FX_OK:
+            raise FuxiError("%s failed (%d): %s" % (what, rc, self.lib.fx_last_error(self.handle).decode()))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.fx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(self.lib.fx_launch_count(self.handle))
+
+
+_default = {}
+
+
+def default_context(device=0):
+    ctx = _default.get(device)
+    if ctx is None or ctx.handle is None:
+        ctx = Context(device)
+        _default[device] = ctx
+    return ctx

@@ -1,0 +1,205 @@
+"""Python surface over the C ABI.  torch is used only for device buffers and streams.
+
+Grid convention everywhere: uint8 ``[W][H]`` C-contiguous, ``grid[x, y]`` == the reference's
+``matrix[x][y]`` (scripts/global_planner_st.py:16-18); for the search 1 is an obstacle, anything
+else is free (scripts/jps1.py:20-29).
+"""
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FuxiError, default_context
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _ctx(ctx, tensor=None):
+    if ctx is not None:
+        return ctx
+    dev = tensor.device.index if tensor is not None and tensor.is_cuda else torch.cuda.current_device()
+    return default_context(dev if dev is not None else 0)
+
+
+def _u8_grid(grid):
+    if not (isinstance(grid, torch.Tensor) and grid.is_cuda):
+        raise FuxiError("grid must be a CUDA tensor (use plan_host / map_host for host buffers)")
+    if grid.dim() != 2:
+        raise FuxiError("grid must be 2-D [W][H]")
+    if grid.dtype != torch.uint8:
+        raise FuxiError("grid must be uint8")
+    return grid.contiguous()
+
+
+def project(points, affine=None, zmin=0.3, zmax=math.inf, origin=(0.0, 0.0), reso=0.2, shape=None, out=None,
+            clear=True, ctx=None):
+    """Point cloud -> occupancy grid (fx_project).  ``points``: float32 CUDA tensor [N,3] or [N,4];
+    ``affine``: 3x4 (camera->earth incl. axis swap, see cloud.cloud_affine) or None for identity."""
+    if not (isinstance(points, torch.Tensor) and points.is_cuda and points.dtype == torch.float32 and points.dim() == 2
+            and points.shape[1] in (3, 4)):
+        raise FuxiError("points must be a float32 CUDA tensor of shape [N,3] or [N,4]")
+    points = points.contiguous()
+    ctx = _ctx(ctx, points)
+    if out is None:
+        if shape is None:
+            raise FuxiError("shape=(W,H) or out= is required")
+        out = torch.empty((int(shape[0]), int(shape[1])), dtype=torch.uint8, device=points.device)
+    W, H = out.shape
+    A = np.eye(3, 4, dtype=np.float32) if affine is None else np.ascontiguousarray(np.asarray(affine, dtype=np.float32).reshape(3, 4))
+    rc = ctx.lib.fx_project(ctx.handle, _ptr(points), points.shape[0], points.shape[1],
+                            A.ctypes.data_as(C.POINTER(C.c_float)), float(zmin), float(zmax), float(origin[0]),
+                            float(origin[1]), float(reso), W, H, _ptr(out), 1 if clear else 0, _stream())
+    ctx.check(rc, "fx_project")
+    return out
+
+
+def inflate(grid, radius, variant="ccst", out=None, ctx=None):
+    """Obstacle inflation (fx_inflate).  variant "ccst": dense (2r+1)^2 square (global_planner_ccst.py:442-448);
+    "st": 9-point stencil {-r,0,+r}^2 (global_planner_st.py:256-262; identical to dense for r == 1)."""
+    grid = _u8_grid(grid)
+    ctx = _ctx(ctx, grid)
+    if out is None:
+        out = torch.empty_like(grid)
+    step = 1 if variant == "ccst" else max(int(radius), 1)
+    W, H = grid.shape
+    ctx.check(ctx.lib.fx_inflate(ctx.handle, _ptr(grid), _ptr(out), W, H, int(radius), step, _stream()), "fx_inflate")
+    return out
+
+
+def edt(grid, out=None, ctx=None):
+    """Exact squared Euclidean distance (cells^2) to the nearest cell > 0 (fx_edt)."""
+    grid = _u8_grid(grid)
+    ctx = _ctx(ctx, grid)
+    if out is None:
+        out = torch.empty(grid.shape, dtype=torch.int32, device=grid.device)
+    W, H = grid.shape
+    ctx.check(ctx.lib.fx_edt(ctx.handle, _ptr(grid), _ptr(out), W, H, _stream()), "fx_edt")
+    return out
+
+
+@dataclass
+class PlanResult:
+    cost_i: torch.Tensor    # int32 [Q]   metric 1: 10/14 cost; metric 2: 2^-16 fixed point; <0: FX_COST_*
+    cost_f: torch.Tensor    # float64 [Q] metric 2: straight + diagonal*sqrt(2); metric 1: float(cost_i)
+    path_xy: torch.Tensor   # int32 [Q, max_path, 2] turning points (start .. goal) or None
+    path_len: torch.Tensor  # int32 [Q]   number of turning points (<0: FX_COST_*)
+
+    def path(self, q):
+        """Query q as the reference returns it: list of (x, y) tuples, or the int 0 when there is no path."""
+        n = int(self.path_len[q])
+        if n <= 0:
+            return 0
+        if n > self.path_xy.shape[1]:
+            raise FuxiError("path of query %d has %d turning points > max_path=%d" % (q, n, self.path_xy.shape[1]))
+        return [tuple(int(v) for v in p) for p in self.path_xy[q, :n].tolist()]
+
+
+def plan_batch(grid, starts, goals, metric=2, max_path=512, ctx=None):
+    """Q shortest-path queries in one launch (fx_search_batch).  starts/goals: int32 CUDA tensors [Q,2]."""
+    grid = _u8_grid(grid)
+    ctx = _ctx(ctx, grid)
+    starts = starts.to(device=grid.device, dtype=torch.int32).contiguous()
+    goals = goals.to(device=grid.device, dtype=torch.int32).contiguous()
+    if starts.shape != goals.shape or starts.dim() != 2 or starts.shape[1] != 2:
+        raise FuxiError("starts/goals must both be [Q,2]")
+    Q = starts.shape[0]
+    W, H = grid.shape
+    cost_i = torch.empty(Q, dtype=torch.int32, device=grid.device)
+    cost_f = torch.empty(Q, dtype=torch.float64, device=grid.device)
+    path_len = torch.empty(Q, dtype=torch.int32, device=grid.device)
+    path_xy = torch.empty((Q, max_path, 2), dtype=torch.int32, device=grid.device) if max_path > 0 else None
+    rc = ctx.lib.fx_search_batch(ctx.handle, _ptr(grid), W, H, _ptr(starts), _ptr(goals), Q, int(metric), _ptr(cost_i),
+                                 _ptr(cost_f), _ptr(path_xy), _ptr(path_len), int(max_path), _stream())
+    ctx.check(rc, "fx_search_batch")
+    return PlanResult(cost_i, cost_f, path_xy, path_len)
+
+
+def search_stats(ctx=None):
+    """(settled cells, wavefront levels, passes, band-only answers) of the last batch (synchronises)."""
+    ctx = _ctx(ctx)
+    a = (C.c_int64 * 4)()
+    ctx.check(ctx.lib.fx_search_stats(ctx.handle, a), "fx_search_stats")
+    return tuple(int(v) for v in a)
+
+
+def field(grid, source, metric=1, out=None, ctx=None, check=True):
+    """Cost-from-source field, int32 [W][H], -1 = unreachable (fx_field)."""
+    grid = _u8_grid(grid)
+    ctx = _ctx(ctx, grid)
+    if out is None:
+        out = torch.empty(grid.shape, dtype=torch.int32, device=grid.device)
+    W, H = grid.shape
+    ctx.check(ctx.lib.fx_field(ctx.handle, _ptr(grid), W, H, int(source[0]), int(source[1]), int(metric), _ptr(out),
+                               _stream()), "fx_field")
+    if check:
+        ctx.check(ctx.lib.fx_field_status(ctx.handle, None, None), "fx_field")
+    return out
+
+
+def field_relax(grid, fld, metric=1, changed=None, ctx=None, check=True):
+    """Relax an int32 field holding seeds to its fixpoint in place (fx_field_relax); returns the `changed` tensor."""
+    grid = _u8_grid(grid)
+    ctx = _ctx(ctx, grid)
+    if not (fld.is_cuda and fld.dtype == torch.int32 and fld.is_contiguous() and fld.shape == grid.shape):
+        raise FuxiError("field must be a contiguous int32 CUDA tensor of the grid's shape")
+    if changed is None:
+        changed = torch.zeros(1, dtype=torch.int32, device=grid.device)
+    W, H = grid.shape
+    ctx.check(ctx.lib.fx_field_relax(ctx.handle, _ptr(grid), W, H, int(metric), _ptr(fld), _ptr(changed), _stream()),
+              "fx_field_relax")
+    if check:
+        ctx.check(ctx.lib.fx_field_status(ctx.handle, None, None), "fx_field_relax")
+    return changed
+
+
+def field_status(ctx=None):
+    ctx = _ctx(ctx)
+    lv, st = C.c_int64(0), C.c_int64(0)
+    ctx.check(ctx.lib.fx_field_status(ctx.handle, C.byref(lv), C.byref(st)), "fx_field_status")
+    return lv.value, st.value
+
+
+# ---------------------------------------------------------------------------------- host-buffer calls
+def plan_host(grid, starts, goals, metric=2, max_path=512, ctx=None, device=0):
+    """numpy in / numpy out through fx_plan_host (H2D + search + D2H inside the call).
+    Returns (cost_i int32[Q], cost_f float64[Q], path_xy int32[Q,max_path,2] or None, path_len int32[Q])."""
+    ctx = ctx or default_context(device)
+    g = np.ascontiguousarray(grid, dtype=np.uint8)
+    s = np.ascontiguousarray(starts, dtype=np.int32).reshape(-1, 2)
+    t = np.ascontiguousarray(goals, dtype=np.int32).reshape(-1, 2)
+    Q = len(s)
+    W, H = g.shape
+    cost_i = np.empty(Q, dtype=np.int32)
+    cost_f = np.empty(Q, dtype=np.float64)
+    path_len = np.empty(Q, dtype=np.int32)
+    path_xy = np.empty((Q, max_path, 2), dtype=np.int32) if max_path > 0 else None
+    vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    rc = ctx.lib.fx_plan_host(ctx.handle, vp(g), W, H, vp(s), vp(t), Q, int(metric), vp(cost_i), vp(cost_f), vp(path_xy),
+                              vp(path_len), int(max_path))
+    ctx.check(rc, "fx_plan_host")
+    return cost_i, cost_f, path_xy, path_len
+
+
+def map_host(points, affine=None, zmin=0.3, zmax=math.inf, origin=(0.0, 0.0), reso=0.2, shape=(1024, 1024), radius=0,
+             variant="ccst", ctx=None, device=0):
+    """numpy cloud [N,3|4] float32 -> inflated uint8 grid [W][H] through fx_map_host."""
+    ctx = ctx or default_context(device)
+    p = np.ascontiguousarray(points, dtype=np.float32)
+    A = np.eye(3, 4, dtype=np.float32) if affine is None else np.ascontiguousarray(np.asarray(affine, dtype=np.float32).reshape(3, 4))
+    W, H = int(shape[0]), int(shape[1])
+    out = np.empty((W, H), dtype=np.uint8)
+    step = 1 if variant == "ccst" else max(int(radius), 1)
+    rc = ctx.lib.fx_map_host(ctx.handle, p.ctypes.data_as(C.c_void_p), p.shape[0], p.shape[1],
+                             A.ctypes.data_as(C.POINTER(C.c_float)), float(zmin), float(zmax), float(origin[0]),
+                             float(origin[1]), float(reso), W, H, int(radius), step, out.ctypes.data_as(C.c_void_p))
+    ctx.check(rc, "fx_map_host")
+    return out

@@ -1,0 +1,202 @@
+// api.cu -- context lifetime, error reporting and the host-buffer entry points of libfuxi_b200.so.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+static char g_create_err[512] = "";
+
+int fx_set_err(fx_context *ctx, int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx ? ctx->err : g_create_err, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" int fx_version(void) { return 1; }
+
+extern "C" const char *fx_last_error(fx_context *ctx) { return ctx ? ctx->err : g_create_err; }
+
+extern "C" int64_t fx_launch_count(fx_context *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int fx_create(int device, fx_context **out)
+{
+    if (!out) return FX_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fx_set_err(nullptr, FX_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fx_set_err(nullptr, FX_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    fx_context *ctx = (fx_context *)calloc(1, sizeof(fx_context));
+    if (!ctx) return FX_ERR_NOMEM;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        fx_set_err(nullptr, FX_ERR_CUDA, "cudaSetDevice/GetDeviceProperties: %s", cudaGetErrorString(e));
+        free(ctx);
+        return FX_ERR_CUDA;
+    }
+    if (prop.major < 10) {
+        fx_set_err(nullptr, FX_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        free(ctx);
+        return FX_ERR_UNSUPPORTED;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->l2_bytes = (size_t)prop.l2CacheSize;
+    e = cudaMalloc(&ctx->counters, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ctx->counters, 0, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->fstate, 32 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(ctx->fstate, 0, 32 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->edt_flag, sizeof(int));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        fx_set_err(nullptr, FX_ERR_CUDA, "context allocation: %s", cudaGetErrorString(e));
+        fx_destroy(ctx);
+        return FX_ERR_CUDA;
+    }
+    *out = ctx;
+    return FX_OK;
+}
+
+extern "C" int fx_destroy(fx_context *ctx)
+{
+    if (!ctx) return FX_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    void *dev[] = {ctx->fields, ctx->dirty, ctx->queues, ctx->tmp_path, ctx->moves, ctx->counters, ctx->fq, ctx->fstate,
+                   ctx->seeds, ctx->seeds_sorted, ctx->seed_hist, ctx->edt_g, ctx->edt_s, ctx->edt_t, ctx->edt_flag,
+                   ctx->d_grid, ctx->d_grid2, ctx->d_q, ctx->d_out_i, ctx->d_out_f, ctx->d_path, ctx->d_pts};
+    for (size_t i = 0; i < sizeof(dev) / sizeof(dev[0]); i++)
+        if (dev[i]) cudaFree(dev[i]);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    free(ctx);
+    return FX_OK;
+}
+
+extern "C" int fx_set_search_tuning(fx_context *ctx, int slots, int band0)
+{
+    if (!ctx || slots < 0 || band0 < 0) return FX_ERR_ARG;
+    if (slots != ctx->cfg_slots) {  // force re-allocation of the per-slot scratch
+        cudaSetDevice(ctx->device);
+        cudaDeviceSynchronize();
+        if (ctx->fields) cudaFree(ctx->fields);
+        if (ctx->dirty) cudaFree(ctx->dirty);
+        if (ctx->queues) cudaFree(ctx->queues);
+        if (ctx->tmp_path) cudaFree(ctx->tmp_path);
+        ctx->fields = nullptr; ctx->dirty = nullptr; ctx->queues = nullptr; ctx->tmp_path = nullptr;
+        ctx->sW = ctx->sH = 0;
+    }
+    ctx->cfg_slots = slots;
+    ctx->cfg_band0 = band0;
+    return FX_OK;
+}
+
+template <typename T>
+static int grow(fx_context *ctx, T **p, size_t *cap, size_t want_bytes)
+{
+    if (*cap >= want_bytes && *p) return FX_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    FX_CUDA(ctx, cudaMalloc((void **)p, want_bytes));
+    *cap = want_bytes;
+    return FX_OK;
+}
+static int grow_pinned(fx_context *ctx, size_t want)
+{
+    if (ctx->h_pin_cap >= want && ctx->h_pin) return FX_OK;
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    ctx->h_pin = nullptr; ctx->h_pin_cap = 0;
+    FX_CUDA(ctx, cudaMallocHost(&ctx->h_pin, want));
+    ctx->h_pin_cap = want;
+    return FX_OK;
+}
+
+// Host-buffer planning call: H2D (grid + queries) -> search -> D2H (costs, path lengths, paths).
+// Replaces the whole of `jps1.method(...)` for Q queries (scripts/jps1.py:183-230) from the caller's view.
+extern "C" int fx_plan_host(fx_context *ctx, const uint8_t *h_grid, int W, int H, const int32_t *h_starts_xy,
+                            const int32_t *h_goals_xy, int Q, int metric, int32_t *h_cost_i, double *h_cost_f,
+                            int32_t *h_path_xy, int32_t *h_path_len, int max_path)
+{
+    if (!ctx) return FX_ERR_ARG;
+    if (!h_grid || W <= 0 || H <= 0 || Q < 0 || (Q > 0 && (!h_starts_xy || !h_goals_xy || !h_cost_i)) || max_path < 0)
+        return fx_set_err(ctx, FX_ERR_ARG, "fx_plan_host: bad argument");
+    if (Q == 0) return FX_OK;
+    FX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->own_stream;
+    const size_t cells = (size_t)W * H;
+    const bool want_path = h_path_xy && max_path > 0;
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_grid, &ctx->d_grid_cap, cells))) return rc;
+    if ((rc = grow(ctx, &ctx->d_q, &ctx->d_q_cap, (size_t)Q * 4 * sizeof(int32_t)))) return rc;
+    // d_out_i and d_out_f share one capacity counter (both sized by Q)
+    if (ctx->d_out_cap < (size_t)Q) {
+        if (ctx->d_out_i) cudaFree(ctx->d_out_i);
+        if (ctx->d_out_f) cudaFree(ctx->d_out_f);
+        ctx->d_out_i = nullptr; ctx->d_out_f = nullptr; ctx->d_out_cap = 0;
+        FX_CUDA(ctx, cudaMalloc(&ctx->d_out_i, (size_t)Q * 2 * sizeof(int32_t)));
+        FX_CUDA(ctx, cudaMalloc(&ctx->d_out_f, (size_t)Q * sizeof(double)));
+        ctx->d_out_cap = (size_t)Q;
+    }
+    const size_t path_bytes = want_path ? (size_t)Q * max_path * 2 * sizeof(int32_t) : 0;
+    if (want_path && (rc = grow(ctx, &ctx->d_path, &ctx->d_path_cap, path_bytes))) return rc;
+    // pinned staging: [grid | starts | goals | cost_i | path_len | cost_f | paths]
+    const size_t qb = (size_t)Q * 2 * sizeof(int32_t);
+    size_t off_grid = 0, off_s = (cells + 15) / 16 * 16, off_g = off_s + qb, off_ci = off_g + qb,
+           off_pl = off_ci + (size_t)Q * 4, off_cf = (off_pl + (size_t)Q * 4 + 7) / 8 * 8, off_p = off_cf + (size_t)Q * 8;
+    if ((rc = grow_pinned(ctx, off_p + path_bytes))) return rc;
+    char *pin = (char *)ctx->h_pin;
+    memcpy(pin + off_grid, h_grid, cells);
+    memcpy(pin + off_s, h_starts_xy, qb);
+    memcpy(pin + off_g, h_goals_xy, qb);
+    FX_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid, pin + off_grid, cells, cudaMemcpyHostToDevice, st));
+    FX_CUDA(ctx, cudaMemcpyAsync(ctx->d_q, pin + off_s, 2 * qb, cudaMemcpyHostToDevice, st));
+    int32_t *d_s = ctx->d_q, *d_g = ctx->d_q + (size_t)Q * 2;
+    int32_t *d_ci = ctx->d_out_i, *d_pl = ctx->d_out_i + Q;
+    rc = fx_search_batch(ctx, ctx->d_grid, W, H, d_s, d_g, Q, metric, d_ci, ctx->d_out_f, want_path ? ctx->d_path : nullptr,
+                         d_pl, want_path ? max_path : 0, (void *)st);
+    if (rc) return rc;
+    FX_CUDA(ctx, cudaMemcpyAsync(pin + off_ci, d_ci, (size_t)Q * 8, cudaMemcpyDeviceToHost, st));  // cost_i + path_len
+    FX_CUDA(ctx, cudaMemcpyAsync(pin + off_cf, ctx->d_out_f, (size_t)Q * 8, cudaMemcpyDeviceToHost, st));
+    if (want_path) FX_CUDA(ctx, cudaMemcpyAsync(pin + off_p, ctx->d_path, path_bytes, cudaMemcpyDeviceToHost, st));
+    FX_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(h_cost_i, pin + off_ci, (size_t)Q * 4);
+    if (h_path_len) memcpy(h_path_len, pin + off_pl, (size_t)Q * 4);
+    if (h_cost_f) memcpy(h_cost_f, pin + off_cf, (size_t)Q * 8);
+    if (want_path) memcpy(h_path_xy, pin + off_p, path_bytes);
+    return FX_OK;
+}
+
+// Host-buffer map call: cloud -> occupancy grid -> inflated grid.
+extern "C" int fx_map_host(fx_context *ctx, const float *h_pts, int64_t n, int stride_floats, const float *h_affine3x4,
+                           float zmin, float zmax, float ox, float oy, float reso, int W, int H, int radius, int step,
+                           uint8_t *h_grid_out)
+{
+    if (!ctx) return FX_ERR_ARG;
+    if (n < 0 || (n > 0 && !h_pts) || !h_grid_out || W <= 0 || H <= 0 || (stride_floats != 3 && stride_floats != 4))
+        return fx_set_err(ctx, FX_ERR_ARG, "fx_map_host: bad argument");
+    FX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->own_stream;
+    const size_t cells = (size_t)W * H, pbytes = (size_t)n * stride_floats * sizeof(float);
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_grid, &ctx->d_grid_cap, cells))) return rc;
+    if ((rc = grow(ctx, &ctx->d_grid2, &ctx->d_grid2_cap, cells))) return rc;
+    if ((rc = grow(ctx, &ctx->d_pts, &ctx->d_pts_cap, pbytes + 16))) return rc;
+    FX_CUDA(ctx, cudaMemcpyAsync(ctx->d_pts, h_pts, pbytes, cudaMemcpyHostToDevice, st));
+    rc = fx_project(ctx, ctx->d_pts, n, stride_floats, h_affine3x4, zmin, zmax, ox, oy, reso, W, H, ctx->d_grid, 1, (void *)st);
+    if (rc) return rc;
+    const uint8_t *result = ctx->d_grid;
+    if (radius > 0) {
+        rc = fx_inflate(ctx, ctx->d_grid, ctx->d_grid2, W, H, radius, step, (void *)st);
+        if (rc) return rc;
+        result = ctx->d_grid2;
+    }
+    FX_CUDA(ctx, cudaMemcpyAsync(h_grid_out, result, cells, cudaMemcpyDeviceToHost, st));
+    FX_CUDA(ctx, cudaStreamSynchronize(st));
+    return FX_OK;
+}

@@ -1,0 +1,84 @@
+// common.cuh -- shared declarations for libfuxi_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/fuxi_b200.h"
+
+#define FX_INF 0xFFFFFFFFu
+#define FX_SEARCH_THREADS 256
+#define FX_DIRTY_SHIFT 5 /* one dirty flag per 32 field cells (one 128 B line) */
+
+struct fx_context {
+    int device;
+    int sm_count;
+    size_t l2_bytes;
+    char err[512];
+    int64_t launches;
+
+    // tuning
+    int cfg_slots;
+    int cfg_band0;
+
+    // search scratch (sized for sW x sH, reallocated when the grid shape grows)
+    int sW, sH, slots, qcap, path_cap;
+    size_t cells, dirty_n;
+    uint32_t *fields;   // [slots][cells]   cost-from-start, FX_INF = unreached
+    uint8_t *dirty;     // [slots][dirty_n] one flag per 32 cells
+    uint32_t *queues;   // [slots][4][qcap] rotating Dial buckets of packed (x<<16|y)
+    int32_t *tmp_path;  // [slots][path_cap][2] goal->start turning points before reversal
+    uint8_t *moves;     // [cells] legal-move mask per cell
+    size_t moves_cap;
+    unsigned long long *counters;  // [8]: 0 work counter, 1 settled, 2 levels, 3 passes, 4 band-only, 5 flags
+    // full-field (cooperative) scratch
+    uint32_t *fq;       // [4][fqcap]
+    size_t fqcap;
+    unsigned int *fstate;  // small device state block for the cooperative kernel
+    uint2 *seeds;       // (cost, packed xy) seed list for fx_field_relax
+    uint2 *seeds_sorted;
+    unsigned int *seed_hist;
+    size_t seed_cap, seed_hist_cap;
+    // EDT scratch
+    uint16_t *edt_g;
+    uint16_t *edt_s, *edt_t;
+    size_t edt_cap, edt_st_cap;
+    int *edt_flag;
+    // host-buffer entry points: device buffers + pinned staging
+    uint8_t *d_grid, *d_grid2;  size_t d_grid_cap, d_grid2_cap;
+    int32_t *d_q;               size_t d_q_cap;      // starts, goals
+    int32_t *d_out_i;           size_t d_out_cap;    // cost_i + path_len
+    double *d_out_f;
+    int32_t *d_path;            size_t d_path_cap;
+    float *d_pts;               size_t d_pts_cap;
+    void *h_pin;                size_t h_pin_cap;
+    cudaStream_t own_stream;
+};
+
+int fx_set_err(fx_context *ctx, int code, const char *fmt, ...);
+#define FX_CUDA(ctx, call)                                                                        \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return fx_set_err(ctx, e__ == cudaErrorMemoryAllocation ? FX_ERR_NOMEM : FX_ERR_CUDA, \
+                              "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define FX_LAUNCH_CHECK(ctx)                 \
+    do {                                     \
+        (ctx)->launches++;                   \
+        FX_CUDA(ctx, cudaGetLastError());    \
+    } while (0)
+
+// direction d in 0..7: 0:(-1,0) 1:(+1,0) 2:(0,-1) 3:(0,+1) 4:(-1,-1) 5:(-1,+1) 6:(+1,-1) 7:(+1,+1)
+// (d < 4 straight, d >= 4 diagonal; the opposite of d is d^1 for straight, 11-d for diagonal)
+// packed 2-bit tables of (delta + 1), d0 in the low bits
+__host__ __device__ constexpr int fx_dx(int d) { return (int)((0xA058u >> (2 * d)) & 3u) - 1; }
+__host__ __device__ constexpr int fx_dy(int d) { return (int)((0x8885u >> (2 * d)) & 3u) - 1; }
+static_assert(fx_dx(0) == -1 && fx_dy(0) == 0 && fx_dx(1) == 1 && fx_dy(1) == 0, "dir table");
+static_assert(fx_dx(2) == 0 && fx_dy(2) == -1 && fx_dx(3) == 0 && fx_dy(3) == 1, "dir table");
+static_assert(fx_dx(4) == -1 && fx_dy(4) == -1 && fx_dx(5) == -1 && fx_dy(5) == 1, "dir table");
+static_assert(fx_dx(6) == 1 && fx_dy(6) == -1 && fx_dx(7) == 1 && fx_dy(7) == 1, "dir table");
+
+int fx_search_reserve(fx_context *ctx, int W, int H, int max_path);
+int fx_build_moves(fx_context *ctx, const uint8_t *grid, int W, int H, cudaStream_t st);

@@ -1,0 +1,234 @@
+// edt.cu -- exact squared Euclidean distance transform of the occupancy grid (sm_100a).
+//
+// Not in the reference (its inflation is the square dilation in inflate.cu); added by the north star
+// as the exact-clearance counterpart.  Oracle: scipy.ndimage.distance_transform_edt.
+// Separable: pass 1 along y (the contiguous axis) gives g(x,y) = distance to the nearest occupied
+// cell in the same row (uint16, 0xFFFF = none); pass 2 along x takes min over x' of (x-x')^2 + g(x',y)^2.
+//   pass 1: one warp per row; the row is squeezed to a bit mask in shared memory (H/8 bytes), nearest
+//           set bits come from clz/ffs on the mask words plus a word-level prefix.
+//   pass 2a (windowed, fully parallel): only rows with |x-x'| < g(x,y) can win, so each cell scans a
+//           window that closes as soon as d^2 >= best.  Cells that have not closed within EDT_WIN rows
+//           raise a flag ...
+//   pass 2b (Meijster lower envelope, one thread per column, coalesced across columns) ... which makes
+//           this kernel redo the whole grid exactly.  It returns immediately when the flag is clear.
+#include "common.cuh"
+
+#define EDT_WIN 48
+#define EDT_NONE 0xFFFFu
+
+// ---- pass 1 -------------------------------------------------------------------------------------
+// one warp per row; smem per warp: (H+31)/32 mask words + 2 * that for the prefix arrays
+__global__ void __launch_bounds__(256) k_edt_rows(const uint8_t *__restrict__ occ, uint16_t *__restrict__ g, int W, int H)
+{
+    extern __shared__ unsigned sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int nwords = (H + 31) / 32;
+    unsigned *mask = sm + (size_t)warp * 3 * nwords;
+    int *leftp = reinterpret_cast<int *>(mask + nwords);   // nearest occupied y strictly before word w (or -1)
+    int *rightp = leftp + nwords;                          // nearest occupied y strictly after word w (or -1)
+    const bool vec = (H % 16 == 0) && (((uintptr_t)occ & 15u) == 0);
+    for (int x = blockIdx.x * nwarps + warp; x < W; x += gridDim.x * nwarps) {
+        const uint8_t *row = occ + (size_t)x * H;
+        // build the bit mask
+        if (vec) {
+            const int nchunks = H / 16;  // 16 cells per lane-load
+            for (int c0 = 0; c0 < nchunks; c0 += 32) {
+                const int c = c0 + lane;
+                unsigned b = 0;
+                if (c < nchunks) {
+                    uint4 v = __ldcs(reinterpret_cast<const uint4 *>(row) + c);
+                    unsigned w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        unsigned nz = __vcmpne4(w4[i], 0u) & 0x01010101u;
+                        b |= (((nz * 0x01020408u) >> 24) & 0xFu) << (4 * i);
+                    }
+                }
+                // two 16-bit chunks -> one 32-bit word
+                unsigned hi = __shfl_down_sync(0xFFFFFFFFu, b, 1);
+                if (!(lane & 1) && c < nchunks) mask[c >> 1] = b | (hi << 16);
+            }
+        } else {
+            for (int w = lane; w < nwords; w += 32) {
+                unsigned m = 0;
+                for (int j = 0; j < 32; j++) {
+                    int y = w * 32 + j;
+                    if (y < H && row[y]) m |= 1u << j;
+                }
+                mask[w] = m;
+            }
+        }
+        __syncwarp();
+        // word-level prefix: last occupied y before word w / first occupied y after word w
+        int carry = -1;
+        for (int w0 = 0; w0 < nwords; w0 += 32) {
+            const int w = w0 + lane;
+            unsigned m = w < nwords ? mask[w] : 0u;
+            int mine = m ? (w * 32 + 31 - __clz(m)) : -1;  // highest set bit position
+            int incl = mine;
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl = max(incl, t); }
+            int excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+            if (lane == 0) excl = -1;
+            excl = max(excl, carry);
+            if (w < nwords) leftp[w] = excl;
+            carry = max(carry, __shfl_sync(0xFFFFFFFFu, incl, 31));
+        }
+        carry = 0x7FFFFFFF;
+        for (int w0 = ((nwords - 1) / 32) * 32; w0 >= 0; w0 -= 32) {
+            const int w = w0 + lane;
+            unsigned m = w < nwords ? mask[w] : 0u;
+            int mine = m ? (w * 32 + __ffs(m) - 1) : 0x7FFFFFFF;  // lowest set bit position
+            int incl = mine;
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_down_sync(0xFFFFFFFFu, incl, o); if (lane + o < 32) incl = min(incl, t); }
+            int excl = __shfl_down_sync(0xFFFFFFFFu, incl, 1);
+            if (lane == 31) excl = 0x7FFFFFFF;
+            excl = min(excl, carry);
+            if (w < nwords) rightp[w] = excl == 0x7FFFFFFF ? -1 : excl;
+            carry = min(carry, __shfl_sync(0xFFFFFFFFu, incl, 0));
+        }
+        __syncwarp();
+        // distances: each lane owns 16 consecutive cells (32-byte store)
+        uint16_t *grow = g + (size_t)x * H;
+        for (int c0 = 0; c0 * 16 < H; c0 += 32) {
+            const int c = c0 + lane, ybase = c * 16;
+            if (ybase >= H) continue;
+            const int w = ybase >> 5, sh = ybase & 31;
+            const unsigned m = mask[w];
+            const int lp = leftp[w], rp = rightp[w];
+            unsigned short d16[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int bit = sh + j, y = ybase + j;
+                const unsigned below = m & (0xFFFFFFFFu >> (31 - bit));   // bits <= bit
+                const unsigned above = m >> bit;                          // bits >= bit (shifted)
+                int dl = below ? bit - (31 - __clz(below)) : (lp >= 0 ? y - lp : 0x7FFFFFFF);
+                int dr = above ? __ffs(above) - 1 : (rp >= 0 ? rp - y : 0x7FFFFFFF);
+                int dd = min(dl, dr);
+                d16[j] = (unsigned short)(dd > 0xFFFE ? EDT_NONE : dd);
+            }
+            if (ybase + 16 <= H && vec) {
+                uint4 lo, hi;
+                lo.x = d16[0] | (d16[1] << 16); lo.y = d16[2] | (d16[3] << 16); lo.z = d16[4] | (d16[5] << 16); lo.w = d16[6] | (d16[7] << 16);
+                hi.x = d16[8] | (d16[9] << 16); hi.y = d16[10] | (d16[11] << 16); hi.z = d16[12] | (d16[13] << 16); hi.w = d16[14] | (d16[15] << 16);
+                uint4 *dst = reinterpret_cast<uint4 *>(grow + ybase);
+                dst[0] = lo; dst[1] = hi;
+            } else {
+                for (int j = 0; j < 16 && ybase + j < H; j++) grow[ybase + j] = d16[j];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- pass 2a: windowed ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_edt_cols_window(const uint16_t *__restrict__ g, int32_t *__restrict__ out,
+                                                         int W, int H, int *__restrict__ flag)
+{
+    const size_t total = (size_t)W * H;
+    bool open = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i / H);
+        const unsigned g0 = g[i];
+        long long best = g0 == EDT_NONE ? (long long)1 << 40 : (long long)g0 * g0;
+        int d = 1;
+        for (; d <= EDT_WIN; d++) {
+            if ((long long)d * d >= best) break;
+            if (x - d < 0 && x + d >= W) break;  // nothing left on either side
+            if (x - d >= 0) {
+                unsigned gv = __ldg(g + i - (size_t)d * H);
+                if (gv != EDT_NONE) best = min(best, (long long)d * d + (long long)gv * gv);
+            }
+            if (x + d < W) {
+                unsigned gv = __ldg(g + i + (size_t)d * H);
+                if (gv != EDT_NONE) best = min(best, (long long)d * d + (long long)gv * gv);
+            }
+        }
+        if (d > EDT_WIN && (long long)d * d < best && !(x - d < 0 && x + d >= W)) open = true;
+        out[i] = best > 0x7FFFFFFFLL ? 0x7FFFFFFF : (int32_t)best;
+    }
+    if (open) *flag = 1;
+}
+
+// ---- pass 2b: Meijster et al. lower envelope, one thread per column ------------------------------
+__device__ __forceinline__ long long edt_f(int x, int i, long long gi2) { return (long long)(x - i) * (x - i) + gi2; }
+__global__ void __launch_bounds__(128) k_edt_cols_exact(const uint16_t *__restrict__ g, int32_t *__restrict__ out, int W, int H,
+                                                        uint16_t *__restrict__ S, uint16_t *__restrict__ T,
+                                                        const int *__restrict__ flag)
+{
+    if (*flag == 0) return;
+    const long long BIG = (long long)1 << 40;
+    for (int y = blockIdx.x * blockDim.x + threadIdx.x; y < H; y += gridDim.x * blockDim.x) {
+        auto G2 = [&](int i) -> long long { unsigned v = g[(size_t)i * H + y]; return v == EDT_NONE ? BIG : (long long)v * v; };
+        int q = 0;
+        int s_top = 0, t_top = 0;
+        long long gs_top = G2(0);
+        S[y] = 0; T[y] = 0;
+        for (int u = 1; u < W; u++) {
+            const long long gu = G2(u);
+            while (q >= 0 && edt_f(t_top, s_top, gs_top) > edt_f(t_top, u, gu)) {
+                q--;
+                if (q >= 0) { s_top = S[(size_t)q * H + y]; t_top = T[(size_t)q * H + y]; gs_top = G2(s_top); }
+            }
+            if (q < 0) {
+                q = 0; s_top = u; t_top = 0; gs_top = gu;
+                S[y] = (uint16_t)u; T[y] = 0;
+            } else {
+                // Sep(i,u) = (u^2 - i^2 + g(u)^2 - g(i)^2) div (2(u-i)), floor division (numerator may be negative)
+                long long num = (long long)u * u - (long long)s_top * s_top + gu - gs_top;
+                long long den = 2LL * (u - s_top);
+                long long sep = num >= 0 ? num / den : -((-num + den - 1) / den);
+                long long w = 1 + sep;
+                if (w < W) {
+                    if (w < 0) w = 0;
+                    q++; s_top = u; t_top = (int)w; gs_top = gu;
+                    S[(size_t)q * H + y] = (uint16_t)u; T[(size_t)q * H + y] = (uint16_t)w;
+                }
+            }
+        }
+        for (int u = W - 1; u >= 0; u--) {
+            long long v = edt_f(u, s_top, gs_top);
+            out[(size_t)u * H + y] = v > 0x7FFFFFFFLL ? 0x7FFFFFFF : (int32_t)v;
+            if (u == t_top && q > 0) {
+                q--;
+                s_top = S[(size_t)q * H + y]; t_top = T[(size_t)q * H + y]; gs_top = G2(s_top);
+            }
+        }
+    }
+}
+
+extern "C" int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W, int H, void *stream)
+{
+    if (!ctx) return FX_ERR_ARG;
+    if (!occ || !dist2 || W <= 0 || H <= 0) return fx_set_err(ctx, FX_ERR_ARG, "fx_edt: bad argument");
+    if (W > 65534 || H > 65534) return fx_set_err(ctx, FX_ERR_UNSUPPORTED, "fx_edt: W,H must be <= 65534");
+    cudaStream_t st = (cudaStream_t)stream;
+    FX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t cells = (size_t)W * H;
+    if (ctx->edt_cap < cells) {
+        if (ctx->edt_g) cudaFree(ctx->edt_g);
+        if (ctx->edt_s) cudaFree(ctx->edt_s);
+        if (ctx->edt_t) cudaFree(ctx->edt_t);
+        ctx->edt_g = ctx->edt_s = ctx->edt_t = nullptr; ctx->edt_cap = 0;
+        FX_CUDA(ctx, cudaMalloc(&ctx->edt_g, cells * 2 + 64));
+        FX_CUDA(ctx, cudaMalloc(&ctx->edt_s, cells * 2));
+        FX_CUDA(ctx, cudaMalloc(&ctx->edt_t, cells * 2));
+        ctx->edt_cap = cells;
+    }
+    FX_CUDA(ctx, cudaMemsetAsync(ctx->edt_flag, 0, sizeof(int), st));
+    const int nwords = (H + 31) / 32;
+    // warps per CTA limited by shared memory (3 arrays of nwords per warp)
+    int warps = 8;
+    size_t smem = (size_t)warps * 3 * nwords * 4;
+    while (smem > 48 * 1024 && warps > 1) { warps >>= 1; smem = (size_t)warps * 3 * nwords * 4; }
+    int blocks = (W + warps - 1) / warps;
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    k_edt_rows<<<blocks, warps * 32, smem, st>>>(occ, ctx->edt_g, W, H);
+    FX_LAUNCH_CHECK(ctx);
+    int b2 = (int)((cells + 255) / 256);
+    if (b2 > ctx->sm_count * 16) b2 = ctx->sm_count * 16;
+    k_edt_cols_window<<<b2, 256, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_flag);
+    FX_LAUNCH_CHECK(ctx);
+    k_edt_cols_exact<<<(H + 127) / 128, 128, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_s, ctx->edt_t, ctx->edt_flag);
+    FX_LAUNCH_CHECK(ctx);
+    return FX_OK;
+}

@@ -1,0 +1,124 @@
+// inflate.cu -- obstacle inflation (binary dilation) on the uint8 [W][H] grid (sm_100a).
+//
+// Replaces scripts/global_planner_st.py:256-262 (9-point stencil {-r,0,+r}^2, step == r) and
+// scripts/global_planner_ccst.py:442-448 (dense (2r+1)^2 square, step == 1).  Both stencils are
+// product sets S x S, so the dilation is separable: OR over y offsets, then OR over x offsets.
+//
+// Fast path (H % 16 == 0, 16-byte aligned pointers, r <= 16): one CTA owns a tile of TX rows x 512
+// cells.  Each warp streams whole 512-byte row segments with one 16-byte load per lane, squeezes the
+// 16 cells to 16 bits ("> 0" test), does the y pass on a 48-bit window built from the neighbouring
+// lanes' bits (shuffles; the two halo chunks come from one extra load on lanes 0 and 31), and parks
+// the row's bits in shared memory.  After one barrier the x pass ORs 2r/step+1 rows of bits, expands
+// back to bytes and writes 16 bytes per lane.  HBM traffic is ~ (1 + 2r/TX) B read + 1 B written per cell.
+#include "common.cuh"
+
+#define INF_TY 512     /* cells per tile row (32 lanes x 16 B) */
+#define INF_MAXR 16
+#define INF_MAXTX 64
+
+__device__ __forceinline__ unsigned bytes_to_bits16(uint4 v)
+{
+    // byte > 0 -> bit; 4 bytes -> 4 bits via a carry-free multiply
+    unsigned r = 0;
+    unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        unsigned nz = __vcmpne4(w[i], 0u) & 0x01010101u;
+        r |= (((nz * 0x01020408u) >> 24) & 0xFu) << (4 * i);
+    }
+    return r;
+}
+__device__ __forceinline__ uint4 bits16_to_bytes(unsigned b)
+{
+    uint4 v;
+    v.x = ((b & 0xFu) * 0x00204081u) & 0x01010101u;
+    v.y = (((b >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+    v.z = (((b >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
+    v.w = (((b >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_inflate_tiled(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
+                                                       int W, int H, int r, int step, int TX)
+{
+    __shared__ unsigned short rowbits[INF_MAXTX + 2 * INF_MAXR][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int x0 = blockIdx.y * TX, y0 = blockIdx.x * INF_TY;
+    const int rows = TX + 2 * r;
+    const int yl = y0 + 16 * lane;
+    // pass 1: y dilation, one row per warp iteration
+    for (int rr = warp; rr < rows; rr += nwarps) {
+        const int x = x0 - r + rr;
+        unsigned b = 0, extra = 0;
+        if (x >= 0 && x < W) {
+            const uint8_t *row = in + (size_t)x * H;
+            if (yl < H) b = bytes_to_bits16(__ldg(reinterpret_cast<const uint4 *>(row + yl)));
+            const int ye = lane == 0 ? y0 - 16 : y0 + INF_TY;
+            if ((lane == 0 || lane == 31) && ye >= 0 && ye < H)
+                extra = bytes_to_bits16(__ldg(reinterpret_cast<const uint4 *>(row + ye)));
+        }
+        unsigned prev = __shfl_up_sync(0xFFFFFFFFu, b, 1), next = __shfl_down_sync(0xFFFFFFFFu, b, 1);
+        if (lane == 0) prev = extra;
+        if (lane == 31) next = extra;
+        const unsigned long long win = (unsigned long long)prev | ((unsigned long long)b << 16) | ((unsigned long long)next << 32);
+        unsigned acc = 0;
+        for (int s = -r; s <= r; s += step) acc |= (unsigned)(win >> (16 + s));
+        rowbits[rr][lane] = (unsigned short)(acc & 0xFFFFu);
+    }
+    __syncthreads();
+    // pass 2: x dilation + expand + store
+    for (int ox = warp; ox < TX; ox += nwarps) {
+        const int x = x0 + ox;
+        if (x >= W) break;
+        unsigned acc = 0;
+        for (int s = -r; s <= r; s += step) acc |= rowbits[ox + r + s][lane];
+        if (yl < H) __stcs(reinterpret_cast<uint4 *>(out + (size_t)x * H + yl), bits16_to_bytes(acc));
+    }
+}
+
+// any shape / alignment / radius: one thread per output cell, reads the stencil directly
+__global__ void __launch_bounds__(256) k_inflate_generic(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
+                                                         int W, int H, int r, int step)
+{
+    const size_t total = (size_t)W * H;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i / H), y = (int)(i - (size_t)x * H);
+        unsigned hit = 0;
+        for (int a = -r; a <= r && !hit; a += step) {
+            const int xx = x + a;
+            if (xx < 0 || xx >= W) continue;
+            for (int b = -r; b <= r; b += step) {
+                const int yy = y + b;
+                if (yy < 0 || yy >= H) continue;
+                if (__ldg(in + (size_t)xx * H + yy)) { hit = 1; break; }
+            }
+        }
+        out[i] = (uint8_t)hit;
+    }
+}
+
+extern "C" int fx_inflate(fx_context *ctx, const uint8_t *in, uint8_t *out, int W, int H, int radius, int step, void *stream)
+{
+    if (!ctx) return FX_ERR_ARG;
+    if (!in || !out || in == out || W <= 0 || H <= 0 || radius < 0 || step < 0)
+        return fx_set_err(ctx, FX_ERR_ARG, "fx_inflate: bad argument");
+    if (step == 0 || radius == 0) step = 1;
+    if (radius % step != 0) return fx_set_err(ctx, FX_ERR_ARG, "fx_inflate: step must divide radius");
+    cudaStream_t st = (cudaStream_t)stream;
+    FX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool fast = (H % 16 == 0) && (((uintptr_t)in | (uintptr_t)out) & 15u) == 0 && radius <= INF_MAXR;
+    if (fast) {
+        // small grids: shorter tiles so that the grid still covers the SMs
+        long long tiles64 = (long long)((W + 63) / 64) * ((H + INF_TY - 1) / INF_TY);
+        int TX = tiles64 >= 2LL * ctx->sm_count ? 64 : 16;
+        dim3 g((H + INF_TY - 1) / INF_TY, (W + TX - 1) / TX);
+        k_inflate_tiled<<<g, 256, 0, st>>>(in, out, W, H, radius, step, TX);
+    } else {
+        size_t total = (size_t)W * H;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+        k_inflate_generic<<<blocks, 256, 0, st>>>(in, out, W, H, radius, step);
+    }
+    FX_LAUNCH_CHECK(ctx);
+    return FX_OK;
+}

@@ -1,0 +1,529 @@
+// search.cu -- batched shortest-path queries on the 8-connected occupancy grid (sm_100a).
+//
+// Replaces scripts/jps1.py:183-230 (method) and everything below it for Q queries per launch.
+// Graph: edges are exactly `not blocked(c, d)` of scripts/jps1.py:14-31, precomputed once per
+// grid into an 8-bit legal-move mask per cell (k_build_moves).
+//
+// Algorithm (one persistent CTA per concurrent query, queries fetched from an atomic counter):
+//   level-synchronous wavefront = Dial / delta-stepping with bucket width == the straight weight.
+//   Every edge weighs >= one bucket, so when bucket k is popped all of its cells are final (no
+//   intra-bucket re-relaxation), a straight move lands in bucket k+1 and a diagonal in k+1 or k+2:
+//   four rotating bucket queues suffice and one __syncthreads() per level orders everything.
+//   Frontier compaction: warp-ballot + popc prefix, one shared-memory atomicAdd per warp and bucket.
+//   Pruning: a cell is relaxed only if g + octile(cell, goal) <= U (A*-style ellipse); a pass that
+//   reaches the goal with cost <= U is exact, because every path of cost <= U lies inside the ellipse.
+//   U comes from a first pass restricted to a narrow band around the start-goal line (any path it
+//   finds is a valid upper bound); if that cost already equals the octile lower bound it is final.
+//   The cost field lives in a per-slot scratch array in HBM (L2-resident working set); only the
+//   128-byte lines a query touched are reset afterwards (dirty flags).
+//   Path: warp-parallel descent from the goal along cost-consistent predecessors, 32 cells of a
+//   straight run per round trip, emitting turning points.
+#include "common.cuh"
+
+#define FLAG_OVERFLOW 1u
+
+template <int METRIC> struct Wt;
+template <> struct Wt<1> { static constexpr uint32_t WS = 10, WD = 14; };
+template <> struct Wt<2> { static constexpr uint32_t WS = FX_EUCLID_WS, WD = FX_EUCLID_WD; };
+
+struct SearchParams {
+    const uint8_t *grid;
+    const uint8_t *moves;
+    int W, H;
+    const int32_t *starts, *goals;
+    int Q;
+    int32_t *cost_i;
+    double *cost_f;
+    int32_t *path_xy;
+    int32_t *path_len;
+    int max_path;
+    uint32_t *fields;
+    uint8_t *dirty;
+    uint32_t *queues;
+    int32_t *tmp_path;
+    size_t cells, dirty_n;
+    int qcap, path_cap;
+    unsigned long long *counters;
+    int band0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// legal-move mask: bit d of moves[c] == not blocked(c, dir d)   (scripts/jps1.py:14-31)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_build_moves(const uint8_t *__restrict__ grid, int W, int H,
+                                                     uint8_t *__restrict__ moves)
+{
+    size_t total = (size_t)W * H;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int x = (int)(i / H), y = (int)(i - (size_t)x * H);
+        // 3x3 neighbourhood: 1 = obstacle (== 1) or outside the array
+        unsigned nb = 0;  // bit (dx+1)*3 + (dy+1)
+#pragma unroll
+        for (int a = -1; a <= 1; a++)
+#pragma unroll
+            for (int b = -1; b <= 1; b++) {
+                int xx = x + a, yy = y + b;
+                bool blk = xx < 0 || xx >= W || yy < 0 || yy >= H;
+                if (!blk) blk = __ldg(grid + (size_t)xx * H + yy) == 1;
+                nb |= (blk ? 1u : 0u) << ((a + 1) * 3 + (b + 1));
+            }
+        auto B = [&](int a, int b) { return (nb >> ((a + 1) * 3 + (b + 1))) & 1u; };
+        unsigned m = 0;
+#pragma unroll
+        for (int d = 0; d < 8; d++) {
+            int a = fx_dx(d), b = fx_dy(d);
+            bool ok = !B(a, b);
+            if (d >= 4) ok = ok && !(B(a, 0) && B(0, b));
+            m |= (ok ? 1u : 0u) << d;
+        }
+        moves[i] = (uint8_t)m;
+    }
+}
+
+int fx_build_moves(fx_context *ctx, const uint8_t *grid, int W, int H, cudaStream_t st)
+{
+    size_t total = (size_t)W * H;
+    if (ctx->moves_cap < total) {
+        if (ctx->moves) cudaFree(ctx->moves);
+        ctx->moves = nullptr; ctx->moves_cap = 0;
+        FX_CUDA(ctx, cudaMalloc(&ctx->moves, total));
+        ctx->moves_cap = total;
+    }
+    int blocks = (int)((total + 255) / 256);
+    int maxb = ctx->sm_count * 16;
+    if (blocks > maxb) blocks = maxb;
+    k_build_moves<<<blocks, 256, 0, st>>>(grid, W, H, ctx->moves);
+    FX_LAUNCH_CHECK(ctx);
+    return FX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-CTA shared state
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) CtaState {
+    unsigned tail[4];
+    unsigned goal;   // best known cost of the goal cell (FX_INF = not reached)
+    unsigned U;      // prune bound on g + h
+    unsigned flags;
+    int q;
+    unsigned long long settled, levels;
+};
+
+__device__ __forceinline__ uint32_t octile(int ax, int ay, uint32_t ws, uint32_t wdiff)
+{
+    // ax, ay >= 0.  ws*max + (wd-ws)*min; fits 32 bits for W,H <= 32767 (checked on the host side)
+    int mx = max(ax, ay), mn = min(ax, ay);
+    return ws * (uint32_t)mx + wdiff * (uint32_t)mn;
+}
+
+// One search pass.  Returns (to every thread) the goal cost or FX_INF.  bandL < 0 disables the band.
+template <int METRIC>
+__device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__restrict__ field,
+                             uint8_t *__restrict__ dirty, uint32_t *__restrict__ queue,
+                             int sx, int sy, int gx, int gy, uint32_t U0, float bandL)
+{
+    constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
+    const int H = P.H, W = P.W;
+    const int tid = threadIdx.x, lane = tid & 31, nthreads = blockDim.x;
+    const unsigned qcap = (unsigned)P.qcap;
+    const size_t sidx = (size_t)sx * H + sy, gidx = (size_t)gx * H + gy;
+    const float qdx = (float)(gx - sx), qdy = (float)(gy - sy);
+    const uint8_t *__restrict__ moves = P.moves;
+    (void)W;
+
+    if (tid == 0) {
+        S.tail[0] = 1; S.tail[1] = 0; S.tail[2] = 0; S.tail[3] = 0;
+        S.goal = FX_INF; S.U = U0;
+        __stcg(queue, ((uint32_t)sx << 16) | (uint32_t)sy);
+        __stcg(field + sidx, 0u);
+        dirty[sidx >> FX_DIRTY_SHIFT] = 1;
+    }
+    __syncthreads();
+
+    unsigned my_settled = 0;
+    unsigned k = 0;
+    uint32_t result = FX_INF;
+    for (;;) {
+        const unsigned n = S.tail[k & 3], n1 = S.tail[(k + 1) & 3];
+        const unsigned goalc = S.goal;
+        if (goalc != FX_INF && goalc / WS <= k) { result = goalc; break; }
+        if ((n == 0 && n1 == 0) || (S.flags & FLAG_OVERFLOW)) break;
+        if (n > qcap || n1 > qcap) { if (tid == 0) S.flags |= FLAG_OVERFLOW; break; }
+        if (tid == 0) S.tail[(k + 3) & 3] = 0;  // bucket k-1 is done; levels k+1.. will refill this slot
+        const uint32_t U = S.U;
+        const uint32_t *__restrict__ qk = queue + (size_t)(k & 3) * qcap;
+        uint32_t *__restrict__ q1 = queue + (size_t)((k + 1) & 3) * qcap;
+        uint32_t *__restrict__ q2 = queue + (size_t)((k + 2) & 3) * qcap;
+        const unsigned total = n * 8u;
+        for (unsigned i0 = (unsigned)(tid - lane); i0 < total; i0 += (unsigned)nthreads) {
+            const unsigned i = i0 + lane;
+            bool act = i < total;
+            const int d = (int)(i & 7u);
+            uint32_t xy = act ? __ldcg(qk + (i >> 3)) : 0u;
+            const int x = (int)(xy >> 16), y = (int)(xy & 0xFFFFu);
+            const size_t idx = (size_t)x * H + y;
+            const uint32_t g = act ? __ldcg(field + idx) : FX_INF;
+            act = act && g != FX_INF && (g / WS) == k;  // stale entry: the cell moved to an earlier bucket
+            if (act && d == 0) my_settled++;
+            const unsigned m = act ? (unsigned)__ldg(moves + idx) : 0u;
+            act = act && ((m >> d) & 1u);
+            const int ddx = fx_dx(d), ddy = fx_dy(d);
+            const int nx = x + ddx, ny = y + ddy;
+            const uint32_t ng = g + (d < 4 ? WS : WD);
+            if (act) {
+                const uint32_t h = octile(abs(nx - gx), abs(ny - gy), WS, WD - WS);
+                act = ((uint64_t)ng + h) <= (uint64_t)U;
+                if (bandL >= 0.f) {
+                    float lat = (float)(nx - sx) * qdy - (float)(ny - sy) * qdx;
+                    act = act && fabsf(lat) <= bandL;
+                }
+            }
+            const size_t nidx = (size_t)((long long)idx + (long long)ddx * H + ddy);
+            uint32_t old = 0;
+            if (act) act = ng < __ldcg(field + nidx);
+            if (act) { old = atomicMin(field + nidx, ng); act = ng < old; }
+            if (act) {
+                if (old == FX_INF) dirty[nidx >> FX_DIRTY_SHIFT] = 1;
+                if (nidx == gidx) { atomicMin(&S.goal, ng); atomicMin(&S.U, ng); }
+            }
+            const unsigned nb = ng / WS;  // k+1 or k+2
+            const bool push = act && (old == FX_INF || old / WS != nb);
+            const bool p1 = push && nb == k + 1, p2 = push && nb != k + 1;
+            const unsigned m1 = __ballot_sync(0xFFFFFFFFu, p1), m2 = __ballot_sync(0xFFFFFFFFu, p2);
+            if (m1) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&S.tail[(k + 1) & 3], __popc(m1));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (p1) {
+                    unsigned pos = base + __popc(m1 & ((1u << lane) - 1u));
+                    if (pos < qcap) __stcg(q1 + pos, ((uint32_t)nx << 16) | (uint32_t)ny);
+                }
+            }
+            if (m2) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&S.tail[(k + 2) & 3], __popc(m2));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (p2) {
+                    unsigned pos = base + __popc(m2 & ((1u << lane) - 1u));
+                    if (pos < qcap) __stcg(q2 + pos, ((uint32_t)nx << 16) | (uint32_t)ny);
+                }
+            }
+        }
+        __syncthreads();
+        k++;
+    }
+    // every thread leaves the loop at the same k with the same decision (all read the same shared state
+    // after the same barrier); one more barrier so that nobody is still reading S when it is re-initialised
+    __syncthreads();
+    if (my_settled) atomicAdd(&S.settled, (unsigned long long)my_settled);
+    if (tid == 0) S.levels += k;
+    return result;
+}
+
+// reset every 128-byte field line this query touched
+__device__ void reset_slot(uint32_t *__restrict__ field, uint8_t *__restrict__ dirty, size_t dirty_n, size_t cells)
+{
+    const size_t n16 = dirty_n / 16;  // dirty_n is padded to a multiple of 16
+    uint4 *d4 = reinterpret_cast<uint4 *>(dirty);
+    const uint4 inf4 = make_uint4(FX_INF, FX_INF, FX_INF, FX_INF);
+    for (size_t i = threadIdx.x; i < n16; i += blockDim.x) {
+        uint4 v = __ldcg(d4 + i);
+        if ((v.x | v.y | v.z | v.w) == 0u) continue;
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            if (!w[a]) continue;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                if (!((w[a] >> (8 * b)) & 0xFFu)) continue;
+                size_t chunk = i * 16 + a * 4 + b;
+                size_t c0 = chunk << FX_DIRTY_SHIFT;
+                if (c0 + 32 <= cells) {
+                    uint4 *f4 = reinterpret_cast<uint4 *>(field + c0);
+#pragma unroll
+                    for (int t = 0; t < 8; t++) __stcg(f4 + t, inf4);
+                } else {
+                    for (size_t c = c0; c < cells; c++) __stcg(field + c, FX_INF);
+                }
+            }
+        }
+        __stcg(d4 + i, make_uint4(0, 0, 0, 0));
+    }
+    __syncthreads();
+}
+
+// Warp 0 walks goal -> start through cost-consistent predecessors and records turning points into tmp
+// (goal first).  Returns the number of points (may exceed cap: only cap are stored); straight/diagonal
+// step counts in *na, *nb (lane 0 values are authoritative; all lanes hold the same).
+template <int METRIC>
+__device__ int extract_path(const SearchParams &P, const uint32_t *__restrict__ field, int sx, int sy, int gx, int gy,
+                            int32_t *__restrict__ tmp, int cap, unsigned *na, unsigned *nb)
+{
+    constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
+    const int H = P.H, W = P.W, lane = threadIdx.x & 31;
+    const uint8_t *__restrict__ moves = P.moves;
+    int vx = gx, vy = gy;
+    uint32_t gv = __ldcg(field + (size_t)vx * H + vy);
+    int npts = 0, prev_d = -1;
+    unsigned a = 0, b = 0;
+    if (lane == 0 && cap > 0) { tmp[0] = vx; tmp[1] = vy; }
+    npts = 1;
+    // bounded by the number of cells: every iteration strictly decreases gv
+    while (!(vx == sx && vy == sy)) {
+        // 1) which directions d have a predecessor u = v - dir(d) with g(u) + w(d) == g(v) and move u->v legal
+        bool ok = false;
+        if (lane < 8) {
+            int ux = vx - fx_dx(lane), uy = vy - fx_dy(lane);
+            if (ux >= 0 && ux < W && uy >= 0 && uy < H) {
+                size_t u = (size_t)ux * H + uy;
+                uint32_t gu = __ldcg(field + u);
+                uint32_t w = lane < 4 ? WS : WD;
+                ok = gu != FX_INF && gu + w == gv && ((__ldg(moves + u) >> lane) & 1u);
+            }
+        }
+        unsigned cand = __ballot_sync(0xFFFFFFFFu, ok) & 0xFFu;
+        if (cand == 0) return -1;  // inconsistent field (cannot happen after a successful pass)
+        int d = (prev_d >= 0 && ((cand >> prev_d) & 1u)) ? prev_d : (__ffs(cand) - 1);
+        if (prev_d >= 0 && d != prev_d) {  // v is a turning point
+            if (lane == 0 && npts < cap) { tmp[2 * npts] = vx; tmp[2 * npts + 1] = vy; }
+            npts++;
+        }
+        prev_d = d;
+        // 2) follow direction d for up to 32 cells in one round trip
+        const int ddx = fx_dx(d), ddy = fx_dy(d);
+        const uint32_t w = d < 4 ? WS : WD;
+        int ux = vx - (lane + 1) * ddx, uy = vy - (lane + 1) * ddy;
+        bool run_ok = false;
+        if (ux >= 0 && ux < W && uy >= 0 && uy < H) {
+            size_t u = (size_t)ux * H + uy;
+            uint32_t gu = __ldcg(field + u);
+            uint64_t want = (uint64_t)gu + (uint64_t)w * (uint32_t)(lane + 1);
+            run_ok = gu != FX_INF && want == (uint64_t)gv && ((__ldg(moves + u) >> d) & 1u);
+        }
+        unsigned runmask = __ballot_sync(0xFFFFFFFFu, run_ok);
+        int run = __ffs(~runmask) - 1;  // leading valid lanes
+        if (runmask == 0xFFFFFFFFu) run = 32;
+        if (run <= 0) return -1;
+        // do not run past the start: if the start lies on the run, stop there
+        // (cells beyond it can still satisfy the equalities only if gv keeps decreasing below 0: impossible,
+        //  g(start) == 0 is the minimum, so the run ends at the start automatically)
+        vx -= run * ddx; vy -= run * ddy;
+        gv -= w * (uint32_t)run;
+        if (d < 4) a += run; else b += run;
+    }
+    if (lane == 0 && npts < cap) { tmp[2 * npts] = sx; tmp[2 * npts + 1] = sy; }
+    npts++;
+    *na = a; *nb = b;
+    return npts;
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(FX_SEARCH_THREADS) k_search_batch(const SearchParams P)
+{
+    constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
+    __shared__ CtaState S;
+    __shared__ int s_npts;
+    __shared__ unsigned s_ab[2];
+    const int tid = threadIdx.x;
+    const int slot = blockIdx.x;
+    uint32_t *field = P.fields + (size_t)slot * P.cells;
+    uint8_t *dirty = P.dirty + (size_t)slot * P.dirty_n;
+    uint32_t *queue = P.queues + (size_t)slot * 4 * P.qcap;
+    int32_t *tmp = P.tmp_path + (size_t)slot * P.path_cap * 2;
+    const int W = P.W, H = P.H;
+    if (tid == 0) { S.settled = 0; S.levels = 0; S.flags = 0; }
+    unsigned long long passes = 0, band_only = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { S.q = (int)atomicAdd(P.counters + 0, 1ull); S.flags = 0; }
+        __syncthreads();
+        const int q = S.q;
+        if (q >= P.Q) break;
+        const int sx = P.starts[2 * q], sy = P.starts[2 * q + 1], gx = P.goals[2 * q], gy = P.goals[2 * q + 1];
+        int32_t out_cost = FX_COST_UNREACHABLE;
+        bool trivial = true;
+        const bool s_in = sx >= 0 && sx < W && sy >= 0 && sy < H, g_in = gx >= 0 && gx < W && gy >= 0 && gy < H;
+        if (!s_in) out_cost = FX_COST_START_OOB;
+        else if (!g_in) out_cost = FX_COST_UNREACHABLE;
+        else if (sx == gx && sy == gy) out_cost = 0;                                       // jps1.py:199-208
+        else if (P.grid[(size_t)gx * H + gy] == 1) out_cost = FX_COST_UNREACHABLE;         // jump() tests the cell first
+        else if (P.moves[(size_t)sx * H + sy] == 0) out_cost = FX_COST_UNREACHABLE;        // start cannot move
+        else {
+            // can anything step INTO the goal?  (cheap rejection of sealed-off goals)
+            bool any = false;
+            for (int d = 0; d < 8; d++) {
+                int ux = gx - fx_dx(d), uy = gy - fx_dy(d);
+                if (ux >= 0 && ux < W && uy >= 0 && uy < H && ((P.moves[(size_t)ux * H + uy] >> d) & 1)) any = true;
+            }
+            if (any) trivial = false;
+        }
+        if (trivial) {
+            if (tid == 0) {
+                P.cost_i[q] = out_cost;
+                if (P.cost_f) P.cost_f[q] = out_cost == 0 ? 0.0 : -1.0;
+                if (P.path_len) P.path_len[q] = out_cost == 0 ? 1 : out_cost;
+                if (out_cost == 0 && P.path_xy && P.max_path > 0) {
+                    P.path_xy[(size_t)q * P.max_path * 2] = sx; P.path_xy[(size_t)q * P.max_path * 2 + 1] = sy;
+                }
+            }
+            continue;
+        }
+
+        const uint32_t h0 = octile(abs(sx - gx), abs(sy - gy), WS, WD - WS);
+        const float L = (float)max(abs(gx - sx), abs(gy - sy));
+        uint32_t best = FX_INF;
+        bool exact = false, overflow = false;
+        // pass A: narrow band, generous bound -> an upper bound on the cost; escalate if the band is sealed
+        float band = (float)P.band0;
+        uint32_t slack = h0 / 16 + 64 * WS;
+        for (int attempt = 0; attempt < 3; attempt++) {
+            const bool last = attempt == 2;
+            uint64_t U64 = (uint64_t)h0 + slack;
+            uint32_t U0 = (last || U64 > 0x7FFFFFFFull) ? 0x7FFFFFFFu : (uint32_t)U64;
+            float bandL = last ? -1.f : band * L;
+            best = run_pass<METRIC>(P, S, field, dirty, queue, sx, sy, gx, gy, U0, bandL);
+            passes++;
+            overflow = (S.flags & FLAG_OVERFLOW) != 0;
+            if (overflow) break;
+            if (best != FX_INF) { exact = last || best == h0; if (attempt == 0 && exact) band_only++; break; }
+            if (last) break;
+            reset_slot(field, dirty, P.dirty_n, P.cells);
+            band *= 8.f; slack = slack * 4;
+        }
+        // pass B: no band, U = the upper bound -> exact
+        if (!overflow && best != FX_INF && !exact) {
+            reset_slot(field, dirty, P.dirty_n, P.cells);
+            best = run_pass<METRIC>(P, S, field, dirty, queue, sx, sy, gx, gy, best, -1.f);
+            passes++;
+            overflow = (S.flags & FLAG_OVERFLOW) != 0;
+        }
+        if (overflow || (best != FX_INF && best > 0x7FFFFFFFu)) {
+            if (tid == 0) {
+                P.cost_i[q] = FX_COST_OVERFLOW;
+                if (P.cost_f) P.cost_f[q] = -3.0;
+                if (P.path_len) P.path_len[q] = FX_COST_OVERFLOW;
+            }
+        } else if (best == FX_INF) {
+            if (tid == 0) {
+                P.cost_i[q] = FX_COST_UNREACHABLE;
+                if (P.cost_f) P.cost_f[q] = -1.0;
+                if (P.path_len) P.path_len[q] = FX_COST_UNREACHABLE;
+            }
+        } else {
+            if (tid < 32) {
+                unsigned a = 0, b = 0;
+                int npts = extract_path<METRIC>(P, field, sx, sy, gx, gy, tmp, P.path_cap, &a, &b);
+                if (tid == 0) { s_npts = npts; s_ab[0] = a; s_ab[1] = b; }
+            }
+            __syncthreads();
+            const int npts = s_npts;
+            if (tid == 0) {
+                P.cost_i[q] = npts < 0 ? FX_COST_OVERFLOW : (int32_t)best;
+                if (P.cost_f)
+                    P.cost_f[q] = METRIC == 1 ? (double)best : (double)s_ab[0] + (double)s_ab[1] * 1.4142135623730951;
+                if (P.path_len) P.path_len[q] = npts < 0 ? FX_COST_OVERFLOW : npts;
+            }
+            if (P.path_xy && npts > 0) {
+                const int stored = min(npts, P.path_cap);
+                const int nout = min(stored, P.max_path);
+                // tmp holds goal..start; output start..goal.  If npts > stored the points nearest the start were
+                // dropped: path_len > max_path tells the caller to retry with a larger max_path.
+                int32_t *out = P.path_xy + (size_t)q * P.max_path * 2;
+                for (int i = tid; i < nout; i += blockDim.x) {
+                    int src = stored - 1 - i;
+                    out[2 * i] = __ldcg(tmp + 2 * src); out[2 * i + 1] = __ldcg(tmp + 2 * src + 1);
+                }
+            }
+        }
+        __syncthreads();
+        reset_slot(field, dirty, P.dirty_n, P.cells);
+    }
+    if (tid == 0) {
+        atomicAdd(P.counters + 1, S.settled);
+        atomicAdd(P.counters + 2, S.levels);
+        atomicAdd(P.counters + 3, passes);
+        atomicAdd(P.counters + 4, band_only);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int fx_search_reserve(fx_context *ctx, int W, int H, int max_path)
+{
+    size_t cells = (size_t)W * H;
+    int path_cap = max_path > 0 ? max_path : 1;
+    if (ctx->fields && ctx->sW == W && ctx->sH == H && ctx->path_cap >= path_cap) return FX_OK;
+    if (ctx->fields) cudaFree(ctx->fields);
+    if (ctx->dirty) cudaFree(ctx->dirty);
+    if (ctx->queues) cudaFree(ctx->queues);
+    if (ctx->tmp_path) cudaFree(ctx->tmp_path);
+    ctx->fields = nullptr; ctx->dirty = nullptr; ctx->queues = nullptr; ctx->tmp_path = nullptr;
+    ctx->sW = ctx->sH = 0;
+
+    size_t dirty_n = ((cells >> FX_DIRTY_SHIFT) + 1 + 15) / 16 * 16;
+    int qcap = 8 * (W + H) + 1024;
+    size_t per_slot = cells * 4 + dirty_n + (size_t)qcap * 16 + (size_t)path_cap * 8;
+    size_t free_b = 0, total_b = 0;
+    FX_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    int slots = ctx->cfg_slots > 0 ? ctx->cfg_slots : ctx->sm_count * 4;
+    size_t budget = free_b / 2;  // leave half of what is free to the caller
+    if ((size_t)slots * per_slot > budget) slots = (int)(budget / per_slot);
+    if (slots < 1) return fx_set_err(ctx, FX_ERR_NOMEM, "search scratch for a %dx%d grid does not fit (%zu B per slot, %zu free)", W, H, per_slot, free_b);
+    // field rows must start 16-byte aligned for the uint4 reset
+    size_t cells_al = (cells + 31) / 32 * 32;
+    FX_CUDA(ctx, cudaMalloc(&ctx->fields, (size_t)slots * cells_al * 4));
+    FX_CUDA(ctx, cudaMalloc(&ctx->dirty, (size_t)slots * dirty_n));
+    FX_CUDA(ctx, cudaMalloc(&ctx->queues, (size_t)slots * 4 * qcap * 4));
+    FX_CUDA(ctx, cudaMalloc(&ctx->tmp_path, (size_t)slots * path_cap * 8));
+    FX_CUDA(ctx, cudaMemset(ctx->fields, 0xFF, (size_t)slots * cells_al * 4));
+    FX_CUDA(ctx, cudaMemset(ctx->dirty, 0, (size_t)slots * dirty_n));
+    ctx->sW = W; ctx->sH = H; ctx->slots = slots; ctx->qcap = qcap; ctx->path_cap = path_cap;
+    ctx->cells = cells_al; ctx->dirty_n = dirty_n;
+    return FX_OK;
+}
+
+extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int H, const int32_t *starts_xy,
+                               const int32_t *goals_xy, int Q, int metric, int32_t *cost_i, double *cost_f,
+                               int32_t *path_xy, int32_t *path_len, int max_path, void *stream)
+{
+    if (!ctx) return FX_ERR_ARG;
+    if (!grid || W <= 0 || H <= 0 || Q < 0 || (Q > 0 && (!starts_xy || !goals_xy || !cost_i)) || max_path < 0 ||
+        (metric != 1 && metric != 2))
+        return fx_set_err(ctx, FX_ERR_ARG, "fx_search_batch: bad argument");
+    if (W > 32767 || H > 32767) return fx_set_err(ctx, FX_ERR_UNSUPPORTED, "fx_search_batch: W,H must be <= 32767");
+    if (Q == 0) return FX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    FX_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = fx_search_reserve(ctx, W, H, path_xy ? max_path : 1);
+    if (rc) return rc;
+    rc = fx_build_moves(ctx, grid, W, H, st);
+    if (rc) return rc;
+    FX_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), st));
+    SearchParams P;
+    P.grid = grid; P.moves = ctx->moves; P.W = W; P.H = H;
+    P.starts = starts_xy; P.goals = goals_xy; P.Q = Q;
+    P.cost_i = cost_i; P.cost_f = cost_f; P.path_xy = path_xy; P.path_len = path_len;
+    P.max_path = path_xy ? max_path : 0;
+    P.fields = ctx->fields; P.dirty = ctx->dirty; P.queues = ctx->queues; P.tmp_path = ctx->tmp_path;
+    P.cells = ctx->cells; P.dirty_n = ctx->dirty_n; P.qcap = ctx->qcap; P.path_cap = ctx->path_cap;
+    P.counters = ctx->counters;
+    P.band0 = ctx->cfg_band0 > 0 ? ctx->cfg_band0 : 16;
+    int blocks = ctx->slots < Q ? ctx->slots : Q;
+    if (metric == 1) k_search_batch<1><<<blocks, FX_SEARCH_THREADS, 0, st>>>(P);
+    else k_search_batch<2><<<blocks, FX_SEARCH_THREADS, 0, st>>>(P);
+    FX_LAUNCH_CHECK(ctx);
+    return FX_OK;
+}
+
+extern "C" int fx_search_stats(fx_context *ctx, int64_t *h_stats4)
+{
+    if (!ctx || !h_stats4) return FX_ERR_ARG;
+    unsigned long long c[8];
+    FX_CUDA(ctx, cudaSetDevice(ctx->device));
+    FX_CUDA(ctx, cudaDeviceSynchronize());
+    FX_CUDA(ctx, cudaMemcpy(c, ctx->counters, sizeof(c), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; i++) h_stats4[i] = (int64_t)c[i + 1];
+    return FX_OK;
+}

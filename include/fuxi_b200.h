@@ -1,0 +1,141 @@
+/*
+ * fuxi_b200.h -- C ABI of libfuxi_b200.so: the B200 (sm_100a) implementation of FUXI's
+ * global-planning hot path.  This is the drop-in boundary: plain pointers and sizes, no C++ or
+ * torch types.  Every entry point cites the reference code it replaces (paths relative to the
+ * chenhanpolyu/fuxi-planner repo).  The ctypes binding a maintainer adds is in INTEGRATION.md.
+ *
+ * Conventions
+ *   - grids are uint8 [W][H], index x*H + y (y fastest) == the reference's matrix[x][y]
+ *     (scripts/global_planner_st.py:16-18).  For the search, value 1 is an obstacle and every other
+ *     value is free, exactly like `matrix[x][y] == 1` in scripts/jps1.py:20-29.
+ *   - every function returns 0 on success or a negative FX_ERR_* code; fx_last_error(ctx) gives text.
+ *     No C++ exception crosses the boundary.
+ *   - pointers are DEVICE pointers unless the parameter name starts with h_ (host).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device-pointer
+ *     entry points only enqueue work; they never synchronise the host.
+ *   - a context is bound to one device and is not re-entrant: one caller thread at a time
+ *     (the reference planners are single-threaded 80 Hz loops, global_planner_st.py:157).
+ */
+#ifndef FUXI_B200_H
+#define FUXI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FX_OK                  0
+#define FX_ERR_ARG            -1   /* bad argument */
+#define FX_ERR_CUDA           -2   /* CUDA runtime error (text in fx_last_error) */
+#define FX_ERR_NOMEM          -3   /* device or host allocation failed */
+#define FX_ERR_UNSUPPORTED    -4   /* e.g. W or H > 65535 for the search */
+#define FX_ERR_NCCL           -5
+
+/* per-query values written to cost_i / path_len */
+#define FX_COST_UNREACHABLE   -1   /* reference returns (0, t): scripts/jps1.py:230 */
+#define FX_COST_START_OOB     -2   /* reference raises IndexError (start outside the array) */
+#define FX_COST_OVERFLOW      -3   /* internal queue or 31-bit cost range exceeded; query not answered */
+
+/* fixed-point Euclidean metric (metric 2): straight = 2^16, diagonal = round(sqrt(2) * 2^16) */
+#define FX_EUCLID_WS 65536
+#define FX_EUCLID_WD 92682
+
+typedef struct fx_context fx_context;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int         fx_create(int device, fx_context **ctx);
+int         fx_destroy(fx_context *ctx);
+const char *fx_last_error(fx_context *ctx);     /* ctx may be NULL: last creation error */
+int         fx_version(void);                   /* ABI version, currently 1 */
+/* number of kernels this library launched through ctx since creation (bench.py: gpu_launches) */
+int64_t     fx_launch_count(fx_context *ctx);
+/* tuning: number of concurrent search slots (0 = auto: 4 per SM, bounded by free memory) and the
+ * half-width in cells of the first (band-limited) search attempt (0 = default 16) */
+int         fx_set_search_tuning(fx_context *ctx, int slots, int band0);
+
+/* ---- (1) point cloud -> 2D occupancy grid ---------------------------------------------------
+ * Replaces: the camera->earth transform + height filter of scripts/plc_point2_st.py:244-256
+ * (= plc_point2_ccst.py:311-326) fused with the 3D->2D projection the reference delegates to
+ * octomap_server / ccmapping (launch/map_st.launch:3, launch/map_ccst.launch:2; consumed at
+ * scripts/global_planner_st.py:54-56).  Semantics (float32, one rounding per op, no FMA):
+ *     e_k = ((a_k0*x + a_k1*y) + a_k2*z) + a_k3          h_affine3x4 = 12 floats, row major (HOST)
+ *     fx = floorf((e_x - ox) / reso), fy likewise
+ *     grid[fx*H + fy] = 1  iff  zmin < e_z <= zmax, 0 <= fx < W, 0 <= fy < H
+ * pts: n points, stride_floats = 3 (packed xyz, the PointCloud2 layout of plc_point2_st.py:112-138)
+ * or 4 (float4, w ignored; pointer must be 16-byte aligned).  clear_first != 0 zeroes grid first.
+ */
+int fx_project(fx_context *ctx, const float *pts, int64_t n, int stride_floats, const float *h_affine3x4,
+               float zmin, float zmax, float ox, float oy, float reso, int W, int H,
+               uint8_t *grid, int clear_first, void *stream);
+
+/* ---- (2) obstacle inflation -----------------------------------------------------------------
+ * Replaces: scripts/global_planner_st.py:256-262 (step == radius: 9-point stencil {-r,0,+r}^2) and
+ * scripts/global_planner_ccst.py:442-448 (step == 1: dense (2r+1)^2 square).  Sources are cells > 0;
+ * out = 1 where any source lies in the stencil, else 0.  Stencil targets outside the grid are dropped
+ * (the reference pads the grid so that none exist, global_planner_st.py:230-250).  in != out.
+ */
+int fx_inflate(fx_context *ctx, const uint8_t *in, uint8_t *out, int W, int H, int radius, int step,
+               void *stream);
+
+/* Exact squared Euclidean distance (in cells^2) to the nearest cell > 0; INT32_MAX if the grid has
+ * none.  Not in the reference (north-star addition); oracle = scipy.ndimage.distance_transform_edt. */
+int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W, int H, void *stream);
+
+/* ---- (3) shortest paths on the 8-connected grid ------------------------------------------------
+ * Replaces: scripts/jps1.py:183-230 `method(matrix, start, goal, hchoice)` and everything it calls
+ * (:3-179, :232-246), for Q independent (start, goal) queries per launch.  Edges are exactly
+ * `not blocked(c, d)` of scripts/jps1.py:14-31 (target != 1; diagonal also needs not both orthogonal
+ * cells == 1; the source cell is never tested; outside the array is blocked).
+ *   metric 1: weights 10 / 14 (hchoice 1) -> cost_i[q] is the integer the reference prints (jps1.py:207)
+ *   metric 2: Euclidean (hchoice 2)       -> cost_i[q] in 2^-16 fixed point (FX_EUCLID_WS/WD),
+ *                                            cost_f[q] = straight + diagonal*sqrt(2) of the path found
+ * starts_xy / goals_xy: int32 [Q][2].  cost_i: int32 [Q] (or FX_COST_*).  cost_f: double [Q] or NULL.
+ * path_xy: int32 [Q][max_path][2] turning points, start first, goal last (consecutive points are
+ * joined by a straight 8-direction run -- same contract as the reference's jump-point list), or NULL;
+ * path_len: int32 [Q] number of turning points (may exceed max_path: only max_path were stored;
+ * FX_COST_* when there is no path), or NULL.
+ */
+int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int H,
+                    const int32_t *starts_xy, const int32_t *goals_xy, int Q, int metric,
+                    int32_t *cost_i, double *cost_f, int32_t *path_xy, int32_t *path_len, int max_path,
+                    void *stream);
+
+/* Cost-from-source field: field[x*H+y] = cost of the cheapest legal path source -> (x,y), -1 if none
+ * (int32, same units as cost_i).  The source may sit on an obstacle (jps1.py never tests it). */
+int fx_field(fx_context *ctx, const uint8_t *grid, int W, int H, int sx, int sy, int metric,
+             int32_t *field, void *stream);
+
+/* Row-tiled variant for grids split into x-slabs across ranks: relaxes `field` (int32, -1 = unknown,
+ * already holding seeds: the source and/or halo rows received from neighbours) to its local fixpoint.
+ * grid/field cover slab rows [0, Wloc) where rows 0 and Wloc-1 may be ghost rows.  *d_changed (device
+ * int) is set to 1 if any cell improved.  See fuxi_planner_b200/tiled.py for the exchange loop. */
+int fx_field_relax(fx_context *ctx, const uint8_t *grid, int Wloc, int H, int metric,
+                   int32_t *field, int32_t *d_changed, void *stream);
+
+/* Synchronises and reports whether the last fx_field / fx_field_relax on ctx completed (FX_OK) or overflowed
+ * an internal queue / the 31-bit cost range (FX_ERR_UNSUPPORTED).  Optional outputs: wavefront levels run and
+ * cells settled. */
+int fx_field_status(fx_context *ctx, int64_t *h_levels, int64_t *h_settled);
+
+/* Search statistics of the last fx_search_batch / fx_plan_host on this ctx (host sync):
+ * h_stats[0] = cells settled (popped and expanded), [1] = wavefront levels, [2] = search passes,
+ * [3] = queries answered in the band-limited first pass alone. */
+int fx_search_stats(fx_context *ctx, int64_t *h_stats4);
+
+/* ---- host-buffer convenience = what the Python drop-in `jps1.method` calls ---------------------
+ * Same as fx_search_batch but all buffers are HOST memory; copies in, runs, copies out and
+ * synchronises.  Uses pinned staging owned by ctx. */
+int fx_plan_host(fx_context *ctx, const uint8_t *h_grid, int W, int H,
+                 const int32_t *h_starts_xy, const int32_t *h_goals_xy, int Q, int metric,
+                 int32_t *h_cost_i, double *h_cost_f, int32_t *h_path_xy, int32_t *h_path_len, int max_path);
+
+/* host-buffer map pipeline: project + inflate in one call (HOST in, HOST out), for the ROS-side glue */
+int fx_map_host(fx_context *ctx, const float *h_pts, int64_t n, int stride_floats, const float *h_affine3x4,
+                float zmin, float zmax, float ox, float oy, float reso, int W, int H,
+                int radius, int step, uint8_t *h_grid_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUXI_B200_H */

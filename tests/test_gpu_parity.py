@@ -1,0 +1,332 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the committed golden
+vectors produced by the unmodified reference.  Bit-exact for grids, masks, fields and integer costs;
+1e-5 relative for Euclidean path lengths (the north-star tolerance)."""
+import numpy as np
+import pytest
+
+from conftest import unpack_grid, large_grid
+from util import validate_path, random_queries
+
+pytestmark = pytest.mark.gpu
+SQRT2 = 1.4142135623730951
+RTOL = 1e-5   # north-star tolerance for float path lengths
+
+
+@pytest.fixture(scope="module")
+def fx():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import __graft_entry__ as ge
+    ge.build()
+    import fuxi_planner_b200 as fx
+    return fx
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+    return torch.device("cuda:0")
+
+
+def _t(a, dev):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+# ------------------------------------------------------------------------------------------ projection
+@pytest.mark.parametrize("stride,n", [(3, 100003), (4, 100003), (3, 7), (4, 1), (3, 1 << 20)])
+def test_project_bit_exact(fx, dev, oracle, stride, n):
+    rng = np.random.default_rng(stride * 1000 + n % 97)
+    pts = np.zeros((n, stride), dtype=np.float32)
+    pts[:, 0:2] = rng.uniform(-110, 110, (n, 2))
+    pts[:, 2] = rng.uniform(-0.5, 3.0, n)
+    if n > 100:
+        pts[5] = np.nan
+        pts[6, 0] = np.inf
+        pts[7, :3] = (-102.4, -102.4, 0.3)       # exactly on the low edges / z threshold
+        pts[8, :3] = (102.4, 0.0, 1.0)           # exactly on the high edge -> outside
+        pts[9:40, 0] = (np.arange(31) * 0.2 - 3.0).astype(np.float32)   # on cell boundaries
+    A = oracle.hostref.cloud_affine((0.03, -0.02, 0.7), (1.0, -2.0, 0.4), dt=0.01, ang_vel=(0.1, 0.2, -0.1), line_vel=(1, 0, 0))
+    for affine in (None, A):
+        want = oracle.hostref.project(pts[:, :3], np.eye(3, 4) if affine is None else affine, 0.3, np.inf, -102.4, -102.4, 0.2, 1024, 1024)
+        got = fx.project(_t(pts, dev), affine, 0.3, np.inf, (-102.4, -102.4), 0.2, (1024, 1024))
+        assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_project_unaligned_and_accumulate(fx, dev, oracle):
+    import torch
+    rng = np.random.default_rng(3)
+    pts = rng.uniform(-10, 10, (1001, 3)).astype(np.float32)
+    buf = torch.zeros(1001 * 3 + 1, dtype=torch.float32, device=dev)
+    buf[1:] = _t(pts.reshape(-1), dev)
+    view = buf[1:].view(1001, 3)            # 4-byte aligned only -> generic kernel
+    want = oracle.hostref.project(pts, np.eye(3, 4), -1.0, 5.0, -10, -10, 0.5, 40, 56)
+    got = fx.project(view, None, -1.0, 5.0, (-10, -10), 0.5, (40, 56))
+    assert np.array_equal(got.cpu().numpy(), want)
+    pts2 = rng.uniform(-10, 10, (500, 3)).astype(np.float32)
+    fx.project(_t(pts2, dev), None, -1.0, 5.0, (-10, -10), 0.5, out=got, clear=False)
+    want2 = want | oracle.hostref.project(pts2, np.eye(3, 4), -1.0, 5.0, -10, -10, 0.5, 40, 56)
+    assert np.array_equal(got.cpu().numpy(), want2)
+
+
+# ------------------------------------------------------------------------------------------ inflation
+@pytest.mark.parametrize("shape", [(1024, 1024), (300, 528), (148, 52), (1, 16), (17, 1), (2048, 4096)])
+@pytest.mark.parametrize("radius,variant", [(1, "st"), (2, "ccst"), (3, "st"), (5, "ccst"), (16, "ccst"), (20, "ccst"), (0, "ccst")])
+def test_inflate_bit_exact(fx, dev, oracle, shape, radius, variant):
+    if shape == (2048, 4096) and radius not in (2, 3):
+        pytest.skip("large case only for the reference radii")
+    rng = np.random.default_rng(radius * 7 + shape[0])
+    m = ((rng.random(shape) < 0.03) * rng.integers(1, 101, shape)).astype(np.uint8)   # occupancy values 1..100 count (> 0)
+    step = 1 if variant == "ccst" else max(radius, 1)
+    want = oracle.inflate(m, radius, step)
+    got = fx.inflate(_t(m, dev), radius, variant)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_inflate_matches_reference_formulation_on_padded_map(fx, dev, oracle, maps):
+    # the exact numpy fancy-index formulation of the planners, on a map padded as global_planner_st.py:230-250 does
+    for ifa, fn, variant in ((1, oracle.hostref.inflate_st, "st"), (2, oracle.hostref.inflate_ccst, "ccst"), (3, oracle.hostref.inflate_st, "st")):
+        core = maps["-16.20-11.40_out.png"]
+        m = np.zeros((core.shape[0] + 6 * ifa, core.shape[1] + 6 * ifa))
+        m[2 * ifa:2 * ifa + core.shape[0], 2 * ifa:2 * ifa + core.shape[1]] = core * 100      # OccupancyGrid-style 100
+        want = fn(m, ifa)
+        got = fx.inflate(_t((m > 0).astype(np.uint8) * 100, dev), ifa, variant)
+        assert np.array_equal(got.cpu().numpy().astype(np.float64), want)
+
+
+# ------------------------------------------------------------------------------------------ EDT
+@pytest.mark.parametrize("shape,fill", [((512, 512), 0.2), ((300, 272), 0.001), ((64, 48), 0.0), ((1000, 37), 0.01),
+                                        ((1, 100), 0.05), ((2048, 1024), 0.00001)])
+def test_edt_exact(fx, dev, oracle, shape, fill):
+    rng = np.random.default_rng(int(fill * 1e6) + shape[0])
+    m = (rng.random(shape) < fill).astype(np.uint8)
+    want = oracle.edt(m)
+    got = fx.edt(_t(m, dev)).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
+def test_edt_vs_scipy(fx, dev):
+    from scipy.ndimage import distance_transform_edt
+    rng = np.random.default_rng(12)
+    m = (rng.random((700, 400)) < 0.002).astype(np.uint8)
+    m[0, 0] = 1
+    ref = np.rint(distance_transform_edt(m == 0) ** 2).astype(np.int64)
+    assert np.array_equal(fx.edt(_t(m, dev)).cpu().numpy().astype(np.int64), ref)
+
+
+# ------------------------------------------------------------------------------------------ search
+def _check_batch(fx, dev, oracle, m, recs, max_path=1024):
+    """recs: golden records (start, goal, h, cost).  Costs: metric 1 bit-exact, metric 2 within RTOL; paths legal."""
+    import torch
+    for h in (1, 2):
+        rs = [r for r in recs if r["h"] == h]
+        if not rs:
+            continue
+        s = np.array([r["start"] for r in rs], dtype=np.int32)
+        g = np.array([r["goal"] for r in rs], dtype=np.int32)
+        res = fx.plan_batch(_t(m, dev), _t(s, dev), _t(g, dev), metric=h, max_path=max_path)
+        torch.cuda.synchronize()
+        ci, cf, pl = res.cost_i.cpu().numpy(), res.cost_f.cpu().numpy(), res.path_len.cpu().numpy()
+        pxy = res.path_xy.cpu().numpy()
+        for q, r in enumerate(rs):
+            if r["cost"] is None:
+                assert ci[q] == -1 and pl[q] == -1, (r, ci[q])
+                continue
+            want = float(r["cost"])
+            if h == 1:
+                assert ci[q] == int(want), (r, ci[q])
+                assert cf[q] == want
+            else:
+                assert abs(cf[q] - want) <= RTOL * max(want, 1e-12), (r, cf[q])
+            n = pl[q]
+            assert 1 <= n <= max_path, (r, n)
+            path = [tuple(p) for p in pxy[q, :n].tolist()]
+            if r["start"] == r["goal"]:
+                assert path == [tuple(r["start"])]
+                continue
+            a, b = validate_path(m, path, r["start"], r["goal"])
+            if h == 1:
+                assert 10 * a + 14 * b == ci[q]
+            else:
+                assert a * 65536 + b * 92682 == ci[q]
+                assert cf[q] == a + b * SQRT2
+            # turning points really turn
+            for p0, p1, p2 in zip(path[:-2], path[1:-1], path[2:]):
+                d1 = (np.sign(p1[0] - p0[0]), np.sign(p1[1] - p0[1]))
+                d2 = (np.sign(p2[0] - p1[0]), np.sign(p2[1] - p1[1]))
+                assert d1 != d2
+
+
+def test_search_all_reference_maps(fx, dev, oracle, golden, maps):
+    for name, recs in golden["maps"].items():
+        _check_batch(fx, dev, oracle, maps[name], recs)
+
+
+def test_search_cfg1_300_pairs(fx, dev, oracle, golden, maps):
+    _check_batch(fx, dev, oracle, maps["-16.40-4.80_out.png"], golden["cfg1"])
+
+
+def test_search_edge_cases(fx, dev, oracle, golden):
+    for rec in golden["edge"]:
+        m = (np.array(rec["grid"]) == 1).astype(np.uint8)
+        _check_batch(fx, dev, oracle, m, [rec])
+
+
+def test_search_random_small(fx, dev, oracle, golden):
+    for g in golden["random_small"]:
+        _check_batch(fx, dev, oracle, unpack_grid(g), g["queries"])
+
+
+def test_search_large_golden(fx, dev, oracle, golden):
+    for g in golden["large"]:
+        _check_batch(fx, dev, oracle, large_grid(g), g["queries"], max_path=4096)
+
+
+def test_search_start_oob_and_goal_oob(fx, dev):
+    import torch
+    m = np.zeros((8, 8), dtype=np.uint8)
+    s = np.array([[8, 0], [0, 0], [-1, 3]], dtype=np.int32)
+    g = np.array([[1, 1], [9, 9], [2, 2]], dtype=np.int32)
+    res = fx.plan_batch(_t(m, dev), _t(s, dev), _t(g, dev), metric=1)
+    torch.cuda.synchronize()
+    assert res.cost_i.cpu().tolist() == [-2, -1, -2]
+
+
+@pytest.mark.parametrize("n,fill,Q", [(256, 0.2, 512), (512, 0.3, 256), (1024, 0.2, 256), (300, 0.42, 200)])
+def test_search_vs_oracle_random(fx, dev, oracle, n, fill, Q):
+    """cfg3-style: random-obstacle grid used as the final grid; GPU batch vs the restated JPS (threads on the host)."""
+    import torch
+    rng = np.random.default_rng(n + Q)
+    m = (rng.random((n, n + 16)) < fill).astype(np.uint8)
+    s, g = random_queries(m, Q, rng)
+    for h in (1, 2):
+        want, status, _ = oracle.jps_batch(m, s, g, h)
+        res = fx.plan_batch(_t(m, dev), _t(s, dev), _t(g, dev), metric=h, max_path=8192)
+        torch.cuda.synchronize()
+        ci, cf, pl = res.cost_i.cpu().numpy(), res.cost_f.cpu().numpy(), res.path_len.cpu().numpy()
+        pxy = res.path_xy.cpu().numpy()
+        assert ((status == 1) == (ci >= 0)).all()
+        ok = status == 1
+        if h == 1:
+            assert np.array_equal(ci[ok].astype(np.float64), want[ok])
+        else:
+            assert (np.abs(cf[ok] - want[ok]) <= RTOL * np.maximum(want[ok], 1e-12)).all()
+        for q in np.flatnonzero(ok)[:64]:
+            path = [tuple(p) for p in pxy[q, :pl[q]].tolist()]
+            if tuple(s[q]) != tuple(g[q]):
+                validate_path(m, path, s[q], g[q])
+
+
+def test_search_maze_needs_wide_passes(fx, dev, oracle):
+    """Serpentine walls: the band-limited first pass must fail and escalate; the result is still exact."""
+    import torch
+    n = 96
+    m = np.zeros((n, n), dtype=np.uint8)
+    for i, x in enumerate(range(4, n - 4, 4)):
+        m[x, :] = 1
+        if i % 2 == 0:
+            m[x, n - 3:n - 1] = 0
+        else:
+            m[x, 1:3] = 0
+    s = np.array([[0, 0], [0, n // 2], [n - 1, n - 1]], dtype=np.int32)
+    g = np.array([[n - 1, n - 1], [n - 1, n // 2], [0, 0]], dtype=np.int32)
+    for h in (1, 2):
+        want, status, _ = oracle.jps_batch(m, s, g, h)
+        assert (status == 1).all()
+        res = fx.plan_batch(_t(m, dev), _t(s, dev), _t(g, dev), metric=h, max_path=1024)
+        torch.cuda.synchronize()
+        if h == 1:
+            assert res.cost_i.cpu().tolist() == [int(v) for v in want]
+        else:
+            assert np.allclose(res.cost_f.cpu().numpy(), want, rtol=RTOL, atol=0)
+
+
+# ------------------------------------------------------------------------------------------ field
+def test_field_bit_exact(fx, dev, oracle, maps):
+    rng = np.random.default_rng(9)
+    cases = [(maps["-16.20-11.40_out.png"], (0, 0)), (maps["-16.00-8.80_out.png"], (144, 71))]
+    m = (rng.random((384, 272)) < 0.25).astype(np.uint8)
+    free = np.argwhere(m == 0)
+    cases.append((m, tuple(free[len(free) // 2])))
+    occ_src = np.argwhere(m == 1)[10]
+    cases.append((m, tuple(occ_src)))           # source on an obstacle may leave it (jps1.py never tests the source)
+    for grid, src in cases:
+        for metric in (1, 2):
+            want = oracle.sssp_field(grid, src, metric)
+            got = fx.field(_t(grid, dev), src, metric).cpu().numpy()
+            assert np.array_equal(got.astype(np.int64), want)
+
+
+def test_field_relax_two_slabs(fx, dev, oracle):
+    """Row-tiled mode with two virtual ranks on one GPU: slabs + one ghost row each, halo exchange until
+    nothing changes; the stitched field must equal the single-GPU field bit for bit."""
+    import torch
+    rng = np.random.default_rng(21)
+    W, H = 200, 144
+    m = (rng.random((W, H)) < 0.3).astype(np.uint8)
+    src = tuple(np.argwhere(m == 0)[5])
+    want = oracle.sssp_field(m, src, 1)
+    cut = 90
+    # slab 0 owns rows [0,cut), holds [0,cut+1); slab 1 owns [cut,W), holds [cut-1,W)
+    g0, g1 = _t(m[:cut + 1], dev), _t(m[cut - 1:], dev)
+    f0 = torch.full((cut + 1, H), -1, dtype=torch.int32, device=dev)
+    f1 = torch.full((W - cut + 1, H), -1, dtype=torch.int32, device=dev)
+    if src[0] < cut:
+        f0[src[0], src[1]] = 0
+    else:
+        f1[src[0] - cut + 1, src[1]] = 0
+    umin = lambda a, b: torch.minimum(a.view(torch.int32).to(torch.int64) & 0xFFFFFFFF, b.to(torch.int64) & 0xFFFFFFFF)
+    for it in range(64):
+        c0 = fx.field_relax(g0, f0, 1)
+        c1 = fx.field_relax(g1, f1, 1)
+        torch.cuda.synchronize()
+        if it > 0 and int(c0) == 0 and int(c1) == 0:
+            break
+        # exchange: each side's ghost row <- min(own ghost, neighbour's owned boundary row), both directions
+        a = umin(f0[cut], f1[1]); b = umin(f0[cut - 1], f1[0])
+        a = torch.where(a == 0xFFFFFFFF, torch.full_like(a, -1), a).to(torch.int32)
+        b = torch.where(b == 0xFFFFFFFF, torch.full_like(b, -1), b).to(torch.int32)
+        f0[cut] = a; f1[1] = a; f0[cut - 1] = b; f1[0] = b
+    else:
+        raise AssertionError("tiled relaxation did not converge")
+    got = torch.cat([f0[:cut], f1[1:]]).cpu().numpy().astype(np.int64)
+    assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------------------------------ drop-in
+def test_jps1_dropin_contract(fx, oracle, golden, maps, capsys):
+    from fuxi_planner_b200 import jps1
+    m = maps["-16.40-4.80_out.png"].astype(np.float64)
+    start = (np.int64(0), np.int64(0))
+    path, secs = jps1.method(m, start, (147, 51), 1)
+    out = capsys.readouterr().out.strip()
+    assert out == "1674.0" and isinstance(secs, float)
+    assert path[0] is start and path[-1] == (147, 51)
+    assert np.array(path).shape[1] == 2                       # callers do np.array(path1[0]) + [1,1]
+    validate_path(maps["-16.40-4.80_out.png"], [tuple(int(v) for v in p) for p in path], (0, 0), (147, 51))
+    path, _ = jps1.method(m, (0, 0), (147, 51), 2)
+    assert abs(float(capsys.readouterr().out.strip()) - 168.12489168102775) <= RTOL * 168.12489168102775
+    z = np.zeros((6, 6)); z[3, :] = 1
+    r = jps1.method(z, (0, 0), (5, 5), 2)
+    assert r[0] is 0                                          # noqa: F632  (the planners' identity test)
+    r = jps1.method(np.zeros((6, 6)), (2, 2), (2, 2), 2)
+    assert r[0] == [(2, 2)] and capsys.readouterr().out.strip() == "0"
+    m100 = np.zeros((5, 5)); m100[2, :] = 100                 # 100 is free: the test is == 1
+    r = jps1.method(m100, (0, 2), (4, 2), 1)
+    assert r[0] == [(0, 2), (4, 2)] and capsys.readouterr().out.strip() == "40.0"
+    with pytest.raises(IndexError):
+        jps1.method(np.zeros((6, 6)), (6, 0), (1, 1), 1)
+
+
+def test_host_pipeline_map_then_plan(fx, oracle):
+    rng = np.random.default_rng(5)
+    pts = np.c_[rng.uniform(-20, 20, (5000, 2)), rng.uniform(0, 2, 5000)].astype(np.float32)
+    g = fx.map_host(pts, None, 0.3, np.inf, (-25.6, -25.6), 0.2, (256, 256), radius=2, variant="ccst")
+    want = oracle.inflate(oracle.hostref.project(pts, np.eye(3, 4), 0.3, np.inf, -25.6, -25.6, 0.2, 256, 256), 2, 1)
+    assert np.array_equal(g, want)
+    s, t = random_queries(g, 32, rng)
+    ci, cf, pxy, pl = fx.plan_host(g, s, t, metric=1, max_path=512)
+    wantc, status, _ = oracle.jps_batch(g, s, t, 1)
+    assert ((status == 1) == (ci >= 0)).all()
+    assert np.array_equal(ci[status == 1].astype(np.float64), wantc[status == 1])
