@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS) k_search_batch(const Search
             if (tid == 0) {
                 P.cost_i[q] = npts < 0 ? FX_COST_OVERFLOW : (int32_t)best;
                 if (P.cost_f)
-                    P.cost_f[q] = METRIC == 1 ? (double)best : (double)s_ab[0] + (double)s_ab[1] * 1.4142135623730951;
+                    P.cost_f[q] = METRIC == 1 ? (double)best : __dadd_rn((double)s_ab[0], __dmul_rn((double)s_ab[1], 1.4142135623730951));
                 if (P.path_len) P.path_len[q] = npts < 0 ? FX_COST_OVERFLOW : npts;
             }
             if (P.path_xy && npts > 0) {
