@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the FUXI global-planning hot path on B200.
+
+Metric (BASELINE.json): planning queries/s on a 4096^2 random-obstacle grid (20 % fill), batched
+start/goal queries sharded query-parallel over N GPUs (cfg4 of SURVEY.md §8d: 65 536 queries at N = 8,
+i.e. 8 192 queries per GPU, "weak" scaling), plus p50 single-replan latency of the drop-in
+``jps1.method``.  One "step" = one fx_search_batch launch over this rank's batch of queries
+(move-mask build + search + path extraction), Euclidean metric (hchoice 2, what the planners use).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # this repo's CUDA path
+    python bench.py --impl reference ...                                # CPU arm (see below)
+    torchrun --nproc-per-node N bench.py --gpus N ...                   # N > 1
+
+`value`   queries/s with grid and queries resident in HBM, CUDA-event timed, max over ranks.
+`e2e`     the same queries through the host-buffer C-ABI call (fx_plan_host): H2D of the grid and the
+          queries and D2H of costs + paths inside the timed region.
+`roofline`  of the dominant kernel (k_search_batch); `kernels` = the map-side kernels (projection,
+          inflation, EDT) at the BASELINE sizes and at HBM-exercising scaled sizes.
+`cpu_baseline` / `--impl reference`: the reference itself is Python (scripts/jps1.py) and
+          /root/reference does not exist on the GPU box, so the CPU arm is the C restatement of jps1.py in
+          oracle/ (kind "port"), OpenMP over all host threads, on a bounded sample of the same queries.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC_NAME = "planning queries/s, 4096^2 grid (20% fill), batched start/goal queries, Euclidean metric"
+L2_FLUSH_BYTES = 512 << 20
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--grid", type=int, default=4096, help="grid edge in cells")
+    ap.add_argument("--queries", type=int, default=8192, help="queries per GPU per step")
+    ap.add_argument("--hchoice", type=int, default=2, choices=[1, 2])
+    ap.add_argument("--max-path", type=int, default=1024)
+    ap.add_argument("--no-extras", action="store_true", help="skip map-kernel rooflines, latency and cpu_baseline")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work for the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ workload
+def make_workload(n, q_total):
+    """cfg4 of SURVEY.md §8d: grid default_rng(4) at 20 % fill, queries default_rng(5) over free cells."""
+    m = (np.random.default_rng(4).random((n, n)) < 0.2).astype(np.uint8)
+    free = np.argwhere(m == 0)
+    rng = np.random.default_rng(5)
+    s = free[rng.integers(len(free), size=q_total)].astype(np.int32)
+    g = free[rng.integers(len(free), size=q_total)].astype(np.int32)
+    return m, s, g
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(power))}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_sample(m, s, g, hchoice, target_s, oracle):
+    """Times the C restatement of jps1.py over all host threads on the first S queries; S is doubled until
+    the sample costs about target_s seconds of wall clock (bounded: S <= 64 x threads)."""
+    threads = oracle.num_threads()
+    S = min(len(s), max(threads, 8))
+    while True:
+        t0 = time.perf_counter()
+        cost, status, used = oracle.jps_batch(m, s[:S], g[:S], hchoice)
+        dt = time.perf_counter() - t0
+        if dt >= target_s / 3 or S >= len(s) or S >= 64 * threads:
+            return S, dt, used, cost, status
+        S = min(len(s), S * 2)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle
+    oracle.build()
+    n, Q = args.grid, args.queries
+    m, s, g = make_workload(n, Q * args.gpus)
+    threads = oracle.num_threads()
+    # one step = a bounded sample of the workload: 2 queries per host thread (≈ 1.5 s per query per core at 4096^2)
+    S = min(len(s), 2 * threads)
+    for _ in range(args.warmup):
+        oracle.jps_batch(m, s[:S], g[:S], args.hchoice)
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        oracle.jps_batch(m, s[:S], g[:S], args.hchoice)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = S * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.queries),
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": threads, "kind": "port",
+                         "sample": "first %d of the workload's queries per step, C restatement of scripts/jps1.py "
+                                   "(oracle/fuxi_oracle.c), OpenMP over %d host threads" % (S, threads)},
+        "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, q_per_step):
+    return {"workload": "cfg4 shard: %d start/goal queries per GPU per step on a %dx%d random-obstacle grid "
+                        "(20%% fill, default_rng(4)/(5)), hchoice %d" % (q_per_step, args.grid, args.grid, args.hchoice),
+            "grid": [args.grid, args.grid], "queries_per_gpu": q_per_step, "global_queries": q_per_step * args.gpus,
+            "parallelism": "query-parallel x%d (grid replicated, no data-path collective)" % args.gpus,
+            "l2": "flushed between timed steps (%d MiB write)" % (L2_FLUSH_BYTES >> 20)}
+
+
+# ------------------------------------------------------------------------------------------ map kernels
+def time_kernel(torch, fn, flush, reps=5, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.mean(ts)), float(np.min(ts))
+
+
+def map_kernel_rooflines(torch, fx, dev, flush, peak):
+    """Projection / inflation / EDT at the BASELINE sizes (cfg2: 1 M points, 1024^2) and at scaled sizes where
+    HBM is exercised (64 M points, 16384^2).  Algorithmic bytes: projection N*16 + W*H (float4
+    points) or N*12 + W*H (packed xyz); inflation 2*W*H; EDT 5*W*H."""
+    out = {}
+    rng = np.random.default_rng(1)
+
+    def entry(name, alg_bytes, fn):
+        mean_ms, min_ms = time_kernel(torch, fn, flush)
+        gbs = alg_bytes / (mean_ms * 1e-3) / 1e9
+        out[name] = {"ms": mean_ms, "ms_min": min_ms, "alg_bytes": int(alg_bytes), "achieved_gbs": gbs, "frac": gbs / peak}
+
+    for label, N, n in (("cfg2", 1 << 20, 1024), ("scaled", 64 << 20, 16384)):
+        half = n * 0.1
+        pts = torch.empty((N, 4), dtype=torch.float32, device=dev)
+        pts[:, 0:2].uniform_(-half, half)
+        pts[:, 2].uniform_(-0.5, 3.0)
+        pts[:, 3] = 0
+        grid = torch.empty((n, n), dtype=torch.uint8, device=dev)
+        entry("project_f4_%s" % label, N * 16 + n * n,
+              lambda: fx.project(pts, None, 0.3, float("inf"), (-half, -half), 0.2, out=grid))
+        p3 = pts[:, :3].contiguous()
+        entry("project_xyz_%s" % label, N * 12 + n * n,
+              lambda: fx.project(p3, None, 0.3, float("inf"), (-half, -half), 0.2, out=grid))
+        del pts, p3
+        occ = (torch.rand((n, n), device=dev) < 0.02).to(torch.uint8)
+        o2 = torch.empty_like(occ)
+        entry("inflate_r2_%s" % label, 2 * n * n, lambda: fx.inflate(occ, 2, "ccst", out=o2))
+        entry("inflate_r1_%s" % label, 2 * n * n, lambda: fx.inflate(occ, 1, "st", out=o2))
+        d2 = torch.empty((n, n), dtype=torch.int32, device=dev)
+        entry("edt_%s" % label, 5 * n * n, lambda: fx.edt(occ, out=d2))
+        del occ, o2, d2, grid
+        torch.cuda.empty_cache()
+    del rng
+    return out
+
+
+def latency_probe(fx, m4096, s, g, hchoice):
+    """p50 of one drop-in replan: jps1.method(matrix, start, goal, 2) wall clock, host buffers in and out."""
+    import contextlib
+    import io
+    res = {}
+    z = np.load(os.path.join(ROOT, "tests", "golden", "maps.npz"))
+    m1 = z["-16.40-4.80_out.png"].astype(np.float64)
+    free = np.argwhere(m1 == 0)
+    rng = np.random.default_rng(0)
+    pairs = [(tuple(free[rng.integers(len(free))]), tuple(free[rng.integers(len(free))])) for _ in range(300)]
+    sink = io.StringIO()
+
+    def run(mat, pairs, warm):
+        ts = []
+        with contextlib.redirect_stdout(sink):
+            for i, (a, b) in enumerate(pairs):
+                t0 = time.perf_counter()
+                fx.jps1.method(mat, a, b, hchoice)
+                dt = time.perf_counter() - t0
+                if i >= warm:
+                    ts.append(dt)
+        ts = np.array(ts) * 1e3
+        return {"p50_ms": float(np.percentile(ts, 50)), "p90_ms": float(np.percentile(ts, 90)),
+                "p99_ms": float(np.percentile(ts, 99)), "n": len(ts)}
+
+    res["cfg1_map_148x52"] = run(m1, pairs, 20)
+    m4 = m4096.astype(np.float64)
+    pairs4 = [(tuple(int(v) for v in s[i]), tuple(int(v) for v in g[i])) for i in range(40)]
+    res["grid_%dx%d" % m4096.shape] = run(m4, pairs4, 8)
+    return res
+
+
+# ------------------------------------------------------------------------------------------ main arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    import fuxi_planner_b200 as fx
+    ctx = fx.default_context(local)
+
+    n, Q = args.grid, args.queries
+    m, s_all, g_all = make_workload(n, Q * world)
+    s, g = s_all[rank * Q:(rank + 1) * Q], g_all[rank * Q:(rank + 1) * Q]
+    d_m = torch.from_numpy(m).to(dev)
+    d_s, d_g = torch.from_numpy(s).to(dev), torch.from_numpy(g).to(dev)
+    flush_buf = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def flush():
+        flush_buf.fill_(1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return fx.plan_batch(d_m, d_s, d_g, metric=args.hchoice, max_path=args.max_path)
+
+    for _ in range(args.warmup):
+        res = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in ev:
+        flush()
+        a.record()
+        res = step()
+        b.record()
+    barrier()
+    launches = ctx.launches - launches0
+    t_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    settled, levels, passes, band_only = fx.search_stats(ctx)
+    tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+    st = torch.tensor([float(settled)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(st, op=dist.ReduceOp.SUM)
+    t_ms_max = float(tt.item())
+    value = Q * world * args.steps / (t_ms_max * 1e-3)
+    answered = int((res.cost_i >= 0).sum().item())
+
+    # ---- e2e: host buffers through fx_plan_host (H2D grid + queries, D2H costs + paths), wall clock, max over ranks
+    e2e_steps = args.steps
+    fx.plan_host(m, s, g, metric=args.hchoice, max_path=args.max_path, ctx=ctx)   # warm (allocates staging)
+    fx.plan_host(m, s, g, metric=args.hchoice, max_path=args.max_path, ctx=ctx)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ci, cf, pxy, pl = fx.plan_host(m, s, g, metric=args.hchoice, max_path=args.max_path, ctx=ctx)
+    torch.cuda.synchronize()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_value = Q * world * e2e_steps / float(e2e_t.item())
+    assert np.array_equal(ci, res.cost_i.cpu().numpy()), "host-buffer path and device path disagree"
+    h2d = m.nbytes + s.nbytes + g.nbytes
+    d2h = Q * (4 + 4 + 8) + Q * args.max_path * 8
+
+    peak, peak_src = measured_peak()
+    settled_all = float(st.item())
+    ms_step = t_ms_max / args.steps
+    alg_bytes = settled / 1.0 * 5.0            # this rank's last step: settled cells x (1 B occupancy + 4 B cost)
+    achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+    line = {
+        "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32 fixed point (2^-16 cells)" if args.hchoice == 2 else "u32",
+        "data": "synthetic", "config": workload_config(args, Q),
+        "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "api": "fx_plan_host (fuxi_planner_b200.plan_host), host numpy buffers"},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "k_search_batch", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes": "settled cells x 5 B (SURVEY §8d early-exit form)",
+                     "full_field_form_gbs": Q * n * n * 5.0 / (ms_step * 1e-3) / 1e9},
+        "search": {"settled_cells_per_step_rank0": int(settled), "nodes_per_s": settled_all / (ms_step * 1e-3),
+                   "levels": int(levels), "passes": int(passes), "band_only": int(band_only),
+                   "answered_rank0": answered, "queries_rank0": Q},
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_extras:
+        line["kernels"] = map_kernel_rooflines(torch, fx, dev, flush, peak)
+        line["latency"] = latency_probe(fx, m, s, g, args.hchoice)
+        import oracle
+        oracle.build()
+        S, dt, used, cost, status = cpu_sample(m, s, g, args.hchoice, args.cpu_seconds, oracle)
+        line["cpu_baseline"] = {"value": S / dt, "unit": "queries/s", "cores": int(used), "kind": "port",
+                                "sample": "first %d queries of the step's batch, C restatement of scripts/jps1.py "
+                                          "(oracle/fuxi_oracle.c) over %d OpenMP threads, %.1f s" % (S, used, dt)}
+        # the sample doubles as a parity spot-check of the timed batch
+        got = cf[:S]
+        ok = status == 1
+        bad = np.abs(got[ok] - cost[ok]) > 1e-5 * np.maximum(cost[ok], 1e-12) if args.hchoice == 2 else ci[:S][ok] != cost[ok]
+        line["cpu_baseline"]["parity_mismatches"] = int(bad.sum()) + int(((ci[:S] >= 0) != ok).sum())
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(run_reference(a) if a.impl == "reference" else run_b200(a))
