@@ -8,6 +8,7 @@ from ._lib import Context, FuxiError, default_context, load, SO_PATH  # noqa: F4
 from .api import (PlanResult, edt, field, field_relax, field_status, inflate, map_host, plan_batch, plan_host,  # noqa: F401
                   project, search_stats)
 from . import jps1  # noqa: F401
+from . import tiled  # noqa: F401
 
 __all__ = ["Context", "FuxiError", "default_context", "load", "SO_PATH", "PlanResult", "edt", "field", "field_relax",
-           "field_status", "inflate", "map_host", "plan_batch", "plan_host", "project", "search_stats", "jps1"]
+           "field_status", "inflate", "map_host", "plan_batch", "plan_host", "project", "search_stats", "jps1", "tiled"]

@@ -16,7 +16,7 @@ FX_EUCLID_WD = 92682
 # every symbol include/fuxi_b200.h declares (tests/test_boundary.py checks the .so exports all of them)
 SYMBOLS = ["fx_create", "fx_destroy", "fx_last_error", "fx_version", "fx_launch_count", "fx_set_search_tuning",
            "fx_project", "fx_inflate", "fx_edt", "fx_search_batch", "fx_field", "fx_field_relax", "fx_field_status",
-           "fx_search_stats", "fx_plan_host", "fx_map_host"]
+           "fx_search_stats", "fx_plan_host", "fx_map_host", "fx_halo_merge"]
 
 _lib = None
 
@@ -49,6 +49,7 @@ def load():
     lib.fx_search_batch.argtypes = [vp, vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp, i32, vp]
     lib.fx_field.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
     lib.fx_field_relax.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
+    lib.fx_halo_merge.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.fx_field_status.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     lib.fx_search_stats.argtypes = [vp, C.POINTER(i64)]
     lib.fx_plan_host.argtypes = [vp, vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp, i32]

@@ -348,6 +348,32 @@ extern "C" int fx_field_relax(fx_context *ctx, const uint8_t *grid, int Wloc, in
     return field_common(ctx, grid, Wloc, H, metric, field, d_changed, 0, 0, true, (cudaStream_t)stream);
 }
 
+// halo merge for the row-tiled mode: dst[i] = min(dst[i], src[i]) with -1 (unknown) as +inf; *d_changed |= improved
+__global__ void __launch_bounds__(256) k_halo_merge(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, size_t n,
+                                                    int32_t *changed)
+{
+    bool any = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t a = dst[i], b = src[i];
+        if (b < a) { dst[i] = b; any = true; }
+    }
+    if (__any_sync(0xFFFFFFFFu, any) && (threadIdx.x & 31) == 0 && changed) *changed = 1;
+}
+
+extern "C" int fx_halo_merge(fx_context *ctx, int32_t *dst, const int32_t *src, int64_t n, int32_t *d_changed, void *stream)
+{
+    if (!ctx) return FX_ERR_ARG;
+    if (n < 0 || (n > 0 && (!dst || !src))) return fx_set_err(ctx, FX_ERR_ARG, "fx_halo_merge: bad argument");
+    if (n == 0) return FX_OK;
+    FX_CUDA(ctx, cudaSetDevice(ctx->device));
+    long long blocks = (n + 255) / 256;
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    k_halo_merge<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint32_t *>(dst),
+                                                                 reinterpret_cast<const uint32_t *>(src), (size_t)n, d_changed);
+    FX_LAUNCH_CHECK(ctx);
+    return FX_OK;
+}
+
 extern "C" int fx_field_status(fx_context *ctx, int64_t *h_levels, int64_t *h_settled)
 {
     if (!ctx) return FX_ERR_ARG;

@@ -113,6 +113,11 @@ int fx_field(fx_context *ctx, const uint8_t *grid, int W, int H, int sx, int sy,
 int fx_field_relax(fx_context *ctx, const uint8_t *grid, int Wloc, int H, int metric,
                    int32_t *field, int32_t *d_changed, void *stream);
 
+/* Halo merge of the row-tiled mode: dst[i] = min(dst[i], src[i]) over n int32 cells, -1 (unknown) counting as
+ * +infinity; *d_changed (device int, may be NULL) is set to 1 if any dst cell improved.  dst is a boundary row of
+ * this rank's slab, src the same row as received from the neighbouring rank (ncclSend/ncclRecv). */
+int fx_halo_merge(fx_context *ctx, int32_t *dst, const int32_t *src, int64_t n, int32_t *d_changed, void *stream);
+
 /* Synchronises and reports whether the last fx_field / fx_field_relax on ctx completed (FX_OK) or overflowed
  * an internal queue / the 31-bit cost range (FX_ERR_UNSUPPORTED).  Optional outputs: wavefront levels run and
  * cells settled. */

@@ -330,3 +330,31 @@ def test_host_pipeline_map_then_plan(fx, oracle):
     wantc, status, _ = oracle.jps_batch(g, s, t, 1)
     assert ((status == 1) == (ci >= 0)).all()
     assert np.array_equal(ci[status == 1].astype(np.float64), wantc[status == 1])
+
+
+# ------------------------------------------------------------------------------------------ multi-GPU building blocks
+def test_halo_merge_kernel(fx, dev):
+    import torch
+    from fuxi_planner_b200 import tiled
+    rng = np.random.default_rng(5)
+    a = rng.integers(-1, 1000, size=(2, 1000)).astype(np.int32)
+    b = rng.integers(-1, 1000, size=(2, 1000)).astype(np.int32)
+    want = np.minimum(a.view(np.uint32), b.view(np.uint32)).view(np.int32)
+    da, db = _t(a, dev), _t(b, dev)
+    ch = torch.zeros(1, dtype=torch.int32, device=dev)
+    tiled.CudaOps().merge(da, db, ch)
+    assert np.array_equal(da.cpu().numpy(), want) and int(ch) == 1
+    ch.zero_()
+    tiled.CudaOps().merge(da, db, ch)           # idempotent: nothing improves the second time
+    assert np.array_equal(da.cpu().numpy(), want) and int(ch) == 0
+
+
+def test_field_tiled_single_rank_equals_field(fx, dev, oracle):
+    """field_tiled with one rank (no process group) is the plain relax-to-fixpoint path used by every rank."""
+    from fuxi_planner_b200 import tiled
+    m = (np.random.default_rng(33).random((300, 200)) < 0.25).astype(np.uint8)
+    src = tuple(int(v) for v in np.argwhere(m == 0)[3])
+    for metric in (1, 2):
+        fld, rounds = tiled.field_tiled(_t(m, dev), 300, src, metric)
+        assert rounds == 1
+        assert np.array_equal(fld.cpu().numpy().astype(np.int64), oracle.sssp_field(m, src, metric))
