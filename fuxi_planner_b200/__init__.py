@@ -9,6 +9,9 @@ from .api import (PlanResult, edt, field, field_relax, field_status, inflate, ma
                   project, search_stats)
 from . import jps1  # noqa: F401
 from . import tiled  # noqa: F401
+from . import cloud, planner  # noqa: F401
+from .cloud import cloud_affine, cloud_to_grid  # noqa: F401
+from .planner import inflate_host, replan  # noqa: F401
 
 __all__ = ["Context", "FuxiError", "default_context", "load", "SO_PATH", "PlanResult", "edt", "field", "field_relax",
-           "field_status", "inflate", "map_host", "plan_batch", "plan_host", "project", "search_stats", "jps1", "tiled"]
+           "field_status", "inflate", "map_host", "plan_batch", "plan_host", "project", "search_stats", "jps1", "tiled", "cloud", "planner", "cloud_affine", "cloud_to_grid", "inflate_host", "replan"]

@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libfuxi_b200.so")
+# FUXI_B200_SO: tuning experiments only (a differently-compiled build of the same sources, scripts/build_variants.sh)
+SO_PATH = os.environ.get("FUXI_B200_SO") or os.path.join(_HERE, "libfuxi_b200.so")
 
 FX_OK = 0
 FX_COST_UNREACHABLE = -1

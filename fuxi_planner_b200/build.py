@@ -20,16 +20,24 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """extra_flags / out: tuning experiments only (scripts/build_variants.sh builds libfuxi_b200_<tag>.so beside the
+    default library; FUXI_B200_SO selects one at load time)."""
+    global SO
+    if out is not None:
+        force = True
     if not force and not needs_build():
         return SO
+    so = out or SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for f in SOURCES:
         o = os.path.join(HERE, "build", f.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, f), "-o", o]
+        if out is not None:
+            o = o.replace(".o", "." + os.path.basename(out) + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, f), "-o", o]
         procs.append((f, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     failed = False
@@ -41,9 +49,11 @@ def build(force=False, verbose=False):
             failed = True
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.run([nvcc, "-shared", "-o", SO] + objs + ["-lcudart"], check=True)
-    return SO
+    subprocess.run([nvcc, "-shared", "-o", so] + objs + ["-lcudart"], check=True)
+    return so
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose="-v" in sys.argv))
+    extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[len("--out="):] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force=True, verbose="-v" in sys.argv, extra_flags=extra, out=os.path.join(HERE, outs[0]) if outs else None))

@@ -8,7 +8,12 @@
 #include "../../include/fuxi_b200.h"
 
 #define FX_INF 0xFFFFFFFFu
+#ifndef FX_SEARCH_THREADS
 #define FX_SEARCH_THREADS 256
+#endif
+#ifndef FX_SEARCH_MINB
+#define FX_SEARCH_MINB 3 /* resident search CTAs per SM the register budget is compiled for */
+#endif
 #define FX_DIRTY_SHIFT 5 /* one dirty flag per 32 field cells (one 128 B line) */
 
 struct fx_context {
@@ -40,6 +45,9 @@ struct fx_context {
     uint2 *seeds_sorted;
     unsigned int *seed_hist;
     size_t seed_cap, seed_hist_cap;
+    // projection scratch: bit-packed grid for the large-grid scatter
+    unsigned *proj_bits;
+    size_t proj_bits_cap;
     // EDT scratch
     uint16_t *edt_g;
     uint16_t *edt_s, *edt_t;

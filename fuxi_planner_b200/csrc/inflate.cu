@@ -15,6 +15,7 @@
 #define INF_TY 512     /* cells per tile row (32 lanes x 16 B) */
 #define INF_MAXR 16
 #define INF_MAXTX 64
+#define INF_UNROLL 4
 
 __device__ __forceinline__ unsigned bytes_to_bits16(uint4 v)
 {
@@ -38,7 +39,7 @@ __device__ __forceinline__ uint4 bits16_to_bytes(unsigned b)
     return v;
 }
 
-__global__ void __launch_bounds__(256) k_inflate_tiled(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
+__global__ void __launch_bounds__(256, 5) k_inflate_tiled(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
                                                        int W, int H, int r, int step, int TX)
 {
     __shared__ unsigned short rowbits[INF_MAXTX + 2 * INF_MAXR][32];
@@ -46,24 +47,33 @@ __global__ void __launch_bounds__(256) k_inflate_tiled(const uint8_t *__restrict
     const int x0 = blockIdx.y * TX, y0 = blockIdx.x * INF_TY;
     const int rows = TX + 2 * r;
     const int yl = y0 + 16 * lane;
-    // pass 1: y dilation, one row per warp iteration
-    for (int rr = warp; rr < rows; rr += nwarps) {
-        const int x = x0 - r + rr;
-        unsigned b = 0, extra = 0;
-        if (x >= 0 && x < W) {
-            const uint8_t *row = in + (size_t)x * H;
-            if (yl < H) b = bytes_to_bits16(__ldg(reinterpret_cast<const uint4 *>(row + yl)));
-            const int ye = lane == 0 ? y0 - 16 : y0 + INF_TY;
-            if ((lane == 0 || lane == 31) && ye >= 0 && ye < H)
-                extra = bytes_to_bits16(__ldg(reinterpret_cast<const uint4 *>(row + ye)));
+    // pass 1: y dilation, one row per warp and step; INF_UNROLL rows are loaded before any is used so that every
+    // lane keeps INF_UNROLL independent 16-byte loads in flight (HBM latency x bandwidth needs ~40 KB per SM)
+    for (int rr0 = warp; rr0 < rows; rr0 += nwarps * INF_UNROLL) {
+        uint4 v[INF_UNROLL], e[INF_UNROLL];
+#pragma unroll
+        for (int u = 0; u < INF_UNROLL; u++) {
+            const int rr = rr0 + u * nwarps, x = x0 - r + rr;
+            v[u] = make_uint4(0, 0, 0, 0); e[u] = make_uint4(0, 0, 0, 0);
+            if (rr < rows && x >= 0 && x < W) {
+                const uint8_t *row = in + (size_t)x * H;
+                if (yl < H) v[u] = __ldcs(reinterpret_cast<const uint4 *>(row + yl));
+                const int ye = lane == 0 ? y0 - 16 : y0 + INF_TY;
+                if ((lane == 0 || lane == 31) && ye >= 0 && ye < H) e[u] = __ldg(reinterpret_cast<const uint4 *>(row + ye));
+            }
         }
-        unsigned prev = __shfl_up_sync(0xFFFFFFFFu, b, 1), next = __shfl_down_sync(0xFFFFFFFFu, b, 1);
-        if (lane == 0) prev = extra;
-        if (lane == 31) next = extra;
-        const unsigned long long win = (unsigned long long)prev | ((unsigned long long)b << 16) | ((unsigned long long)next << 32);
-        unsigned acc = 0;
-        for (int s = -r; s <= r; s += step) acc |= (unsigned)(win >> (16 + s));
-        rowbits[rr][lane] = (unsigned short)(acc & 0xFFFFu);
+#pragma unroll
+        for (int u = 0; u < INF_UNROLL; u++) {
+            const int rr = rr0 + u * nwarps;
+            const unsigned b = bytes_to_bits16(v[u]), extra = bytes_to_bits16(e[u]);
+            unsigned prev = __shfl_up_sync(0xFFFFFFFFu, b, 1), next = __shfl_down_sync(0xFFFFFFFFu, b, 1);
+            if (lane == 0) prev = extra;
+            if (lane == 31) next = extra;
+            const unsigned long long win = (unsigned long long)prev | ((unsigned long long)b << 16) | ((unsigned long long)next << 32);
+            unsigned acc = 0;
+            for (int s = -r; s <= r; s += step) acc |= (unsigned)(win >> (16 + s));
+            if (rr < rows) rowbits[rr][lane] = (unsigned short)(acc & 0xFFFFu);
+        }
     }
     __syncthreads();
     // pass 2: x dilation + expand + store

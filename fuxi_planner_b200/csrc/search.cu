@@ -21,6 +21,12 @@
 #include "common.cuh"
 
 #define FLAG_OVERFLOW 1u
+#define FX_POCKET_BUDGET 4096u /* queue pops of the bounded flood from the goal */
+// neighbour probe before the atomic: a stale (too large) value only costs a redundant atomicMin, never a wrong
+// result, so the probe may be served by L1 (FX_LDF = __ldca); the popped cell's own cost is always read with __ldcg.
+#ifndef FX_LDF
+#define FX_LDF __ldcg
+#endif
 
 template <int METRIC> struct Wt;
 template <> struct Wt<1> { static constexpr uint32_t WS = 10, WD = 14; };
@@ -105,6 +111,7 @@ struct __align__(16) CtaState {
     unsigned goal;   // best known cost of the goal cell (FX_INF = not reached)
     unsigned U;      // prune bound on g + h
     unsigned flags;
+    unsigned pruned;  // this pass rejected a legal move by the ellipse or the band (so a drained queue proves nothing)
     int q;
     unsigned long long settled, levels;
 };
@@ -117,10 +124,11 @@ __device__ __forceinline__ uint32_t octile(int ax, int ay, uint32_t ws, uint32_t
 }
 
 // One search pass.  Returns (to every thread) the goal cost or FX_INF.  bandL < 0 disables the band.
+// budget > 0 stops the pass (returning FX_INF with *budget_hit = true) once more than `budget` queue entries were popped.
 template <int METRIC>
 __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__restrict__ field,
                              uint8_t *__restrict__ dirty, uint32_t *__restrict__ queue,
-                             int sx, int sy, int gx, int gy, uint32_t U0, float bandL)
+                             int sx, int sy, int gx, int gy, uint32_t U0, float bandL, unsigned budget, bool *budget_hit)
 {
     constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
     const int H = P.H, W = P.W;
@@ -133,7 +141,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__res
 
     if (tid == 0) {
         S.tail[0] = 1; S.tail[1] = 0; S.tail[2] = 0; S.tail[3] = 0;
-        S.goal = FX_INF; S.U = U0;
+        S.goal = FX_INF; S.U = U0; S.pruned = 0;
         __stcg(queue, ((uint32_t)sx << 16) | (uint32_t)sy);
         __stcg(field + sidx, 0u);
         dirty[sidx >> FX_DIRTY_SHIFT] = 1;
@@ -141,71 +149,98 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__res
     __syncthreads();
 
     unsigned my_settled = 0;
-    unsigned k = 0;
+    unsigned k = 0, popped = 0;
+    bool my_pruned = false;
     uint32_t result = FX_INF;
+    *budget_hit = false;
     for (;;) {
         const unsigned n = S.tail[k & 3], n1 = S.tail[(k + 1) & 3];
         const unsigned goalc = S.goal;
         if (goalc != FX_INF && goalc / WS <= k) { result = goalc; break; }
         if ((n == 0 && n1 == 0) || (S.flags & FLAG_OVERFLOW)) break;
+        popped += n;
+        if (budget && popped > budget) { *budget_hit = true; break; }
         if (n > qcap || n1 > qcap) { if (tid == 0) S.flags |= FLAG_OVERFLOW; break; }
         if (tid == 0) S.tail[(k + 3) & 3] = 0;  // bucket k-1 is done; levels k+1.. will refill this slot
         const uint32_t U = S.U;
         const uint32_t *__restrict__ qk = queue + (size_t)(k & 3) * qcap;
         uint32_t *__restrict__ q1 = queue + (size_t)((k + 1) & 3) * qcap;
         uint32_t *__restrict__ q2 = queue + (size_t)((k + 2) & 3) * qcap;
-        const unsigned total = n * 8u;
-        for (unsigned i0 = (unsigned)(tid - lane); i0 < total; i0 += (unsigned)nthreads) {
+        // one thread per frontier cell; its eight neighbour probes are independent loads in flight together
+        for (unsigned i0 = (unsigned)(tid - lane); i0 < n; i0 += (unsigned)nthreads) {
             const unsigned i = i0 + lane;
-            bool act = i < total;
-            const int d = (int)(i & 7u);
-            uint32_t xy = act ? __ldcg(qk + (i >> 3)) : 0u;
+            bool act = i < n;
+            const uint32_t xy = act ? __ldcg(qk + i) : 0u;
             const int x = (int)(xy >> 16), y = (int)(xy & 0xFFFFu);
             const size_t idx = (size_t)x * H + y;
-            const uint32_t g = act ? __ldcg(field + idx) : FX_INF;
+            uint32_t g = FX_INF;
+            unsigned m = 0;
+            if (act) { g = __ldcg(field + idx); m = (unsigned)__ldg(moves + idx); }
             act = act && g != FX_INF && (g / WS) == k;  // stale entry: the cell moved to an earlier bucket
-            if (act && d == 0) my_settled++;
-            const unsigned m = act ? (unsigned)__ldg(moves + idx) : 0u;
-            act = act && ((m >> d) & 1u);
-            const int ddx = fx_dx(d), ddy = fx_dy(d);
-            const int nx = x + ddx, ny = y + ddy;
-            const uint32_t ng = g + (d < 4 ? WS : WD);
-            if (act) {
-                const uint32_t h = octile(abs(nx - gx), abs(ny - gy), WS, WD - WS);
-                act = ((uint64_t)ng + h) <= (uint64_t)U;
-                if (bandL >= 0.f) {
-                    float lat = (float)(nx - sx) * qdy - (float)(ny - sy) * qdx;
-                    act = act && fabsf(lat) <= bandL;
+            if (act) my_settled++; else m = 0;
+            // candidates: legal move, inside the ellipse g + h <= U, inside the band
+            uint32_t cur[8];
+#pragma unroll
+            for (int d = 0; d < 8; d++) {
+                const int nx = x + fx_dx(d), ny = y + fx_dy(d);
+                const uint32_t ng = g + (d < 4 ? WS : WD);
+                bool c = (m >> d) & 1u;
+                if (c) {
+                    const uint32_t h = octile(abs(nx - gx), abs(ny - gy), WS, WD - WS);
+                    c = ((uint64_t)ng + h) <= (uint64_t)U;
+                    if (bandL >= 0.f) {
+                        float lat = (float)(nx - sx) * qdy - (float)(ny - sy) * qdx;
+                        c = c && fabsf(lat) <= bandL;
+                    }
+                    if (!c) my_pruned = true;
+                }
+                if (!c) m &= ~(1u << d);
+                cur[d] = c ? FX_LDF(field + (size_t)((long long)idx + (long long)fx_dx(d) * H + fx_dy(d))) : 0u;
+            }
+            unsigned push1 = 0, push2 = 0;  // direction masks of the cells to append to bucket k+1 / k+2
+#pragma unroll
+            for (int d = 0; d < 8; d++) {
+                const uint32_t ng = g + (d < 4 ? WS : WD);
+                if (((m >> d) & 1u) && ng < cur[d]) {
+                    const size_t nidx = (size_t)((long long)idx + (long long)fx_dx(d) * H + fx_dy(d));
+                    const uint32_t old = atomicMin(field + nidx, ng);
+                    if (ng < old) {
+                        if (old == FX_INF) dirty[nidx >> FX_DIRTY_SHIFT] = 1;
+                        if (nidx == gidx) { atomicMin(&S.goal, ng); atomicMin(&S.U, ng); }
+                        const unsigned nb = ng / WS;  // k+1 or k+2
+                        if (old == FX_INF || old / WS != nb) {
+                            if (nb == k + 1) push1 |= 1u << d; else push2 |= 1u << d;
+                        }
+                    }
                 }
             }
-            const size_t nidx = (size_t)((long long)idx + (long long)ddx * H + ddy);
-            uint32_t old = 0;
-            if (act) act = ng < __ldcg(field + nidx);
-            if (act) { old = atomicMin(field + nidx, ng); act = ng < old; }
-            if (act) {
-                if (old == FX_INF) dirty[nidx >> FX_DIRTY_SHIFT] = 1;
-                if (nidx == gidx) { atomicMin(&S.goal, ng); atomicMin(&S.U, ng); }
+            // warp-aggregated append: inclusive scan of both counts (packed 16|16), one shared atomic per bucket
+            const unsigned cnt = (unsigned)__popc(push1) | ((unsigned)__popc(push2) << 16);
+            unsigned incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += t;
             }
-            const unsigned nb = ng / WS;  // k+1 or k+2
-            const bool push = act && (old == FX_INF || old / WS != nb);
-            const bool p1 = push && nb == k + 1, p2 = push && nb != k + 1;
-            const unsigned m1 = __ballot_sync(0xFFFFFFFFu, p1), m2 = __ballot_sync(0xFFFFFFFFu, p2);
-            if (m1) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(&S.tail[(k + 1) & 3], __popc(m1));
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                if (p1) {
-                    unsigned pos = base + __popc(m1 & ((1u << lane) - 1u));
-                    if (pos < qcap) __stcg(q1 + pos, ((uint32_t)nx << 16) | (uint32_t)ny);
+            const unsigned tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if (tot) {
+                unsigned base1 = 0, base2 = 0;
+                if (lane == 31) {
+                    if (tot & 0xFFFFu) base1 = atomicAdd(&S.tail[(k + 1) & 3], tot & 0xFFFFu);
+                    if (tot >> 16) base2 = atomicAdd(&S.tail[(k + 2) & 3], tot >> 16);
                 }
-            }
-            if (m2) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(&S.tail[(k + 2) & 3], __popc(m2));
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                if (p2) {
-                    unsigned pos = base + __popc(m2 & ((1u << lane) - 1u));
-                    if (pos < qcap) __stcg(q2 + pos, ((uint32_t)nx << 16) | (uint32_t)ny);
+                base1 = __shfl_sync(0xFFFFFFFFu, base1, 31);
+                base2 = __shfl_sync(0xFFFFFFFFu, base2, 31);
+                unsigned pos1 = base1 + ((incl - cnt) & 0xFFFFu), pos2 = base2 + ((incl - cnt) >> 16);
+                while (push1) {
+                    const int d = __ffs(push1) - 1; push1 &= push1 - 1;
+                    if (pos1 < qcap) __stcg(q1 + pos1, ((uint32_t)(x + fx_dx(d)) << 16) | (uint32_t)(y + fx_dy(d)));
+                    pos1++;
+                }
+                while (push2) {
+                    const int d = __ffs(push2) - 1; push2 &= push2 - 1;
+                    if (pos2 < qcap) __stcg(q2 + pos2, ((uint32_t)(x + fx_dx(d)) << 16) | (uint32_t)(y + fx_dy(d)));
+                    pos2++;
                 }
             }
         }
@@ -214,6 +249,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__res
     }
     // every thread leaves the loop at the same k with the same decision (all read the same shared state
     // after the same barrier); one more barrier so that nobody is still reading S when it is re-initialised
+    if (my_pruned) S.pruned = 1;  // S.pruned was zeroed before the first barrier of this pass; nobody reads it until the next one
     __syncthreads();
     if (my_settled) atomicAdd(&S.settled, (unsigned long long)my_settled);
     if (tid == 0) S.levels += k;
@@ -318,7 +354,7 @@ __device__ int extract_path(const SearchParams &P, const uint32_t *__restrict__ 
 }
 
 template <int METRIC>
-__global__ void __launch_bounds__(FX_SEARCH_THREADS) k_search_batch(const SearchParams P)
+__global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_batch(const SearchParams P)
 {
     constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
     __shared__ CtaState S;
@@ -374,27 +410,55 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS) k_search_batch(const Search
         const float L = (float)max(abs(gx - sx), abs(gy - sy));
         uint32_t best = FX_INF;
         bool exact = false, overflow = false;
+        bool hit = false, unreachable = false;
+        // pocket check: a bounded flood FROM THE GOAL.  Among free cells the move graph is symmetric (a diagonal
+        // tests the same two orthogonal cells both ways), so if the flood drains below the budget the goal sits in a
+        // small sealed component: unless it met the start (or, for a start on an obstacle, a cell the start can
+        // step into) the query is unreachable and the forward search need not flood the start's whole component.
+        // If the flood reaches the start its cost is the exact answer and pass A is skipped.
+        {
+            uint32_t back = run_pass<METRIC>(P, S, field, dirty, queue, gx, gy, sx, sy, 0x7FFFFFFFu, -1.f, FX_POCKET_BUDGET, &hit);
+            passes++;
+            overflow = (S.flags & FLAG_OVERFLOW) != 0;
+            const bool start_free = P.grid[(size_t)sx * H + sy] != 1;
+            if (!overflow && !hit) {
+                if (back != FX_INF && start_free) { best = back; }        // symmetric cost; pass B with U = best proves it
+                else if (back == FX_INF) {
+                    bool touch = false;
+                    if (!start_free) {
+                        const unsigned ms = P.moves[(size_t)sx * H + sy];
+                        for (int d = 0; d < 8; d++)
+                            if (((ms >> d) & 1u) && __ldcg(field + (size_t)(sx + fx_dx(d)) * H + (sy + fx_dy(d))) != FX_INF) touch = true;
+                    }
+                    unreachable = !touch;
+                }
+            }
+            __syncthreads();
+            reset_slot(field, dirty, P.dirty_n, P.cells);
+        }
         // pass A: narrow band, generous bound -> an upper bound on the cost; escalate if the band is sealed
         float band = (float)P.band0;
         uint32_t slack = h0 / 16 + 64 * WS;
-        for (int attempt = 0; attempt < 3; attempt++) {
+        for (int attempt = 0; attempt < 3 && !overflow && !unreachable && best == FX_INF; attempt++) {
             const bool last = attempt == 2;
             uint64_t U64 = (uint64_t)h0 + slack;
             uint32_t U0 = (last || U64 > 0x7FFFFFFFull) ? 0x7FFFFFFFu : (uint32_t)U64;
             float bandL = last ? -1.f : band * L;
-            best = run_pass<METRIC>(P, S, field, dirty, queue, sx, sy, gx, gy, U0, bandL);
+            best = run_pass<METRIC>(P, S, field, dirty, queue, sx, sy, gx, gy, U0, bandL, 0u, &hit);
             passes++;
             overflow = (S.flags & FLAG_OVERFLOW) != 0;
             if (overflow) break;
             if (best != FX_INF) { exact = last || best == h0; if (attempt == 0 && exact) band_only++; break; }
-            if (last) break;
+            if (last || !S.pruned) break;  // nothing was pruned and the queue drained: the start's component is exhausted
+            __syncthreads();
             reset_slot(field, dirty, P.dirty_n, P.cells);
             band *= 8.f; slack = slack * 4;
         }
         // pass B: no band, U = the upper bound -> exact
-        if (!overflow && best != FX_INF && !exact) {
+        if (!overflow && !unreachable && best != FX_INF && !exact) {
+            __syncthreads();
             reset_slot(field, dirty, P.dirty_n, P.cells);
-            best = run_pass<METRIC>(P, S, field, dirty, queue, sx, sy, gx, gy, best, -1.f);
+            best = run_pass<METRIC>(P, S, field, dirty, queue, sx, sy, gx, gy, best, -1.f, 0u, &hit);
             passes++;
             overflow = (S.flags & FLAG_OVERFLOW) != 0;
         }
@@ -467,7 +531,7 @@ int fx_search_reserve(fx_context *ctx, int W, int H, int max_path)
     size_t per_slot = cells * 4 + dirty_n + (size_t)qcap * 16 + (size_t)path_cap * 8;
     size_t free_b = 0, total_b = 0;
     FX_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-    int slots = ctx->cfg_slots > 0 ? ctx->cfg_slots : ctx->sm_count * 4;
+    int slots = ctx->cfg_slots > 0 ? ctx->cfg_slots : ctx->sm_count * FX_SEARCH_MINB;
     size_t budget = free_b / 2;  // leave half of what is free to the caller
     if ((size_t)slots * per_slot > budget) slots = (int)(budget / per_slot);
     if (slots < 1) return fx_set_err(ctx, FX_ERR_NOMEM, "search scratch for a %dx%d grid does not fit (%zu B per slot, %zu free)", W, H, per_slot, free_b);

@@ -358,3 +358,35 @@ def test_field_tiled_single_rank_equals_field(fx, dev, oracle):
         fld, rounds = tiled.field_tiled(_t(m, dev), 300, src, metric)
         assert rounds == 1
         assert np.array_equal(fld.cpu().numpy().astype(np.int64), oracle.sssp_field(m, src, metric))
+
+
+def test_search_pockets_and_obstacle_start(fx, dev, oracle):
+    """Sealed pockets (goal side: bounded flood from the goal; start side: drained queue with nothing pruned) must
+    come back unreachable without flooding the whole map, and a start on an obstacle next to / inside a pocket
+    keeps the reference's semantics (the source cell is never tested, jps1.py:14-31)."""
+    n = 600
+    m = np.zeros((n, n), dtype=np.uint8)
+    m[100:107, 100] = 1; m[100:107, 106] = 1; m[100, 100:107] = 1; m[106, 100:107] = 1      # sealed 5x5 room A
+    m[400:407, 300] = 1; m[400:407, 306] = 1; m[400, 300:307] = 1; m[406, 300:307] = 1      # sealed 5x5 room B
+    m[(np.random.default_rng(8).random((n, n)) < 0.1) & (m == 0)] = 1
+    m[101:106, 101:106] = 0; m[401:406, 301:306] = 0
+    q = [((5, 5), (103, 103)),        # goal in a pocket
+         ((103, 103), (5, 5)),        # start in a pocket
+         ((102, 102), (104, 104)),    # both inside the same pocket: reachable, met by the flood from the goal
+         ((103, 103), (403, 303)),    # different pockets
+         ((100, 103), (104, 104)),    # start ON the wall of room A, goal inside: reachable
+         ((100, 103), (90, 103)),     # start on the wall, goal outside: reachable too (steps out)
+         ((100, 103), (403, 303)),    # wall start, goal in the other pocket: unreachable
+         ((7, 9), (590, 580))]        # ordinary long query
+    s = np.array([a for a, _ in q], dtype=np.int32)
+    g = np.array([b for _, b in q], dtype=np.int32)
+    for metric in (1, 2):
+        want = oracle.sssp_batch(m, s, g, metric)
+        res = fx.plan_batch(_t(m, dev), _t(s, dev), _t(g, dev), metric=metric, max_path=2048)
+        got = res.cost_i.cpu().numpy().astype(np.int64)
+        assert np.array_equal(got, want), (metric, got, want)
+        assert list(want[[0, 1, 3, 6]]) == [-1] * 4 and (want[[2, 4, 5, 7]] > 0).all()
+        for i in np.flatnonzero(want > 0):
+            validate_path(m, res.path(int(i)), tuple(s[i]), tuple(g[i]))
+    settled = fx.search_stats()[0]
+    assert settled < 8 * 40000, "pocket queries flooded the map (%d cells settled)" % settled

@@ -1,0 +1,84 @@
+"""Product host glue (fuxi_planner_b200/cloud.py, planner.py) against the oracle's line-by-line restatements of the
+reference's inline blocks (oracle/hostref.py, themselves pinned to the reference functions that are importable,
+tests/golden/hostfn_golden.npz).  CPU only: these are the small host computations around the kernels."""
+import numpy as np
+import pytest
+
+from fuxi_planner_b200 import cloud, planner
+
+
+def test_cloud_affine_matches_reference_transform(oracle):
+    rng = np.random.default_rng(0)
+    for _ in range(100):
+        rpy, pos = rng.uniform(-1.2, 1.2, 3), rng.uniform(-20, 20, 3)
+        dt, av, lv = rng.uniform(0, 0.1), rng.uniform(-3, 3, 3), rng.uniform(-2, 2, 3)
+        A = cloud.cloud_affine(rpy, pos, dt, av, lv)
+        pts = rng.uniform(-6, 6, (50, 3))
+        want = oracle.hostref.transform_cloud(pts, rpy, pos, dt, av, lv)        # plc_point2_st.py:244-251
+        got = pts @ A[:, :3].T + A[:, 3]
+        assert np.allclose(got, want, rtol=0, atol=1e-12)
+        assert np.allclose(cloud.rotation_zyx(*rpy), oracle.hostref.body_to_earth_frame(*rpy), rtol=0, atol=1e-15)
+
+
+def test_rotation_matches_reference_utils_golden(hostfn_golden):
+    """rpy -> R pairs produced by the UNMODIFIED scripts/utils.py:21-28 (tests/golden/make_golden.py)."""
+    for rpy, R in zip(hostfn_golden["rpy"], hostfn_golden["R"]):
+        assert np.allclose(cloud.rotation_zyx(*rpy), R, rtol=0, atol=1e-15)
+
+
+def test_pointcloud2_roundtrip(oracle):
+    rng = np.random.default_rng(1)
+    pts = rng.normal(size=(1000, 3))
+    msg = cloud.xyz_to_pointcloud2_fields(pts)
+    ref = oracle.hostref.pack_pointcloud2(pts)                                   # plc_point2_st.py:112-138
+    assert msg == ref
+    back = cloud.pointcloud2_to_xyz(msg["data"])
+    assert back.dtype == np.float32 and np.array_equal(back, pts.astype(np.float32))
+    # a 16-byte point step with xyz at 0/4/8 (e.g. an extra intensity field)
+    rec = np.zeros((1000, 4), dtype="<f4"); rec[:, :3] = pts
+    assert np.array_equal(cloud.pointcloud2_to_xyz(rec.tobytes(), point_step=16), pts.astype(np.float32))
+
+
+def test_occupancy_grid_codec(oracle):
+    rng = np.random.default_rng(2)
+    w, h = 37, 21
+    data = rng.choice(np.array([-1, 0, 100, 50, 1], dtype=np.int8), size=w * h)
+    a = planner.occupancy_grid_to_array(data, w, h)
+    assert np.array_equal(a, oracle.hostref.decode_occupancy_grid(data, w, h))   # global_planner_st.py:15-20
+    assert a.shape == (w, h)
+    assert np.array_equal(planner.array_to_occupancy_grid(a), oracle.hostref.encode_occupancy_grid(a))
+
+
+@pytest.mark.parametrize("variant", ["st", "ccst"])
+def test_plan_assembly_matches_reference_blocks(oracle, variant):
+    rng = np.random.default_rng(3)
+    for _ in range(400):
+        W0, H0 = (int(v) for v in rng.integers(5, 80, 2))
+        m = (rng.random((W0, H0)) < 0.2).astype(np.int64)
+        o, reso, ifa = rng.uniform(-20, 20, 2), 0.2, int(rng.integers(1, 4))
+        s = o + np.array([rng.uniform(-4, W0 * reso + 4), rng.uniform(-4, H0 * reso + 4)])
+        g = o + np.array([rng.uniform(-4, W0 * reso + 4), rng.uniform(-4, H0 * reso + 4)])
+        ref_grid, ref_s, ref_g, ref_o, ref_d = oracle.hostref.assemble_grid(m, o, reso, s, g, ifa, variant)
+        a = planner.plan_assembly(m.shape, o, reso, s, g, ifa, variant)
+        assert a.shape == ref_grid.shape
+        assert a.start == tuple(int(v) for v in ref_s) and a.goal == tuple(int(v) for v in ref_g)
+        assert a.paste_at == tuple(int(v) for v in ref_d)
+        assert np.allclose(a.origin, ref_o, rtol=0, atol=1e-12)
+
+
+def test_relocate_goal_and_path_to_world(oracle):
+    rng = np.random.default_rng(4)
+    for _ in range(300):
+        m = (rng.random((30, 20)) < 0.5).astype(np.float64)
+        if rng.random() < 0.2:
+            m[int(rng.integers(30)), :] = 1                      # a full row: forces the column fallback
+        g = (int(rng.integers(30)), int(rng.integers(20)))
+        if m[g[0], g[1]] == 1 and not (m[g[0], :] == 0).any() and not (m[:, g[1]] == 0).any():
+            continue
+        want, occ = oracle.hostref.relocate_goal(m, g)           # global_planner_st.py:268-275
+        got, moved = planner.relocate_goal(m, g)
+        assert got == tuple(int(v) for v in want) and moved == bool(occ)
+    path = [(3, 4), (7, 8), (7, 20)]
+    for v in ("st", "ccst"):
+        assert np.array_equal(planner.path_cells_to_world(path, 0.2, (-3.0, 5.0), v),
+                              oracle.hostref.path_to_world(path, 0.2, np.array([-3.0, 5.0]), v))
