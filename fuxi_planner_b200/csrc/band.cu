@@ -1,0 +1,237 @@
+// band.cu -- per-query upper bounds for the batched search (sm_100a), one WARP per query.
+//
+// The exact pass of search.cu prunes with the ellipse g + octile(c, goal) <= U, so it needs an upper bound U on
+// the cost of each query.  A wavefront restricted to a +-15-cell band around the start-goal line finds one: any
+// path inside the band is a real path.  Its frontier is ~30 cells wide -- one warp's worth -- and a level costs one
+// chain of dependent L2 round trips whatever the width, so giving it a whole CTA (as the first version did) left
+// three quarters of the warps waiting at the block barrier for ~half of all levels (ncu r01: 45 % barrier stalls).
+// Here every warp runs its own query: no block barrier, bucket queues in shared memory, and a cost field in *band
+// coordinates* (t = position along the major axis, v = offset from the line, 32 cells = one 128-byte line per t)
+// so that a slot needs (max(W,H) + 2*margin) * 128 bytes instead of a full W x H field and is reset with
+// streaming stores.
+//
+// Also here: the longest-processing-time-first query order (k_order_queries).  Query work spans four orders of
+// magnitude (it grows with the area of the start-goal parallelogram); handing out the big ones first keeps the
+// tail of the batch short.
+#include "common.cuh"
+
+#define BAND_B 16                 /* |offset from the line| <= BAND_B - 1 */
+#define BAND_M 24                 /* rows allowed before the start / after the goal along the major axis */
+#define BAND_Q 256                /* queue entries per bucket and warp (shared memory) */
+#define BAND_WARPS 8
+
+struct BandParams {
+    const uint8_t *grid, *moves;
+    int W, H;
+    const int32_t *starts, *goals;
+    int Q;
+    const uint32_t *order;
+    uint32_t *ubound;
+    uint32_t *bfields;
+    size_t bcap;
+    unsigned long long *counter;
+};
+
+// ---- LPT order: 64 log-scale buckets of estimated work, largest first ---------------------------------------
+__device__ __forceinline__ unsigned work_bucket(int sx, int sy, int gx, int gy)
+{
+    const unsigned dx = (unsigned)abs(gx - sx), dy = (unsigned)abs(gy - sy);
+    const unsigned mn = min(dx, dy), mx = max(dx, dy);
+    unsigned long long est = (unsigned long long)mn * (mx - mn) + 64ull * mx + 1ull;  // parallelogram area + band
+    if (est > 0x7FFFFFFFull) est = 0x7FFFFFFFull;
+    const unsigned e = (unsigned)est, lg = 31u - (unsigned)__clz(e);
+    return 2u * lg + ((lg > 0) ? ((e >> (lg - 1)) & 1u) : 0u);  // 0..61
+}
+
+__global__ void __launch_bounds__(1024) k_order_queries(const int32_t *__restrict__ starts, const int32_t *__restrict__ goals, int Q,
+                                                        uint32_t *__restrict__ order)
+{
+    __shared__ unsigned hist[64], offs[64];
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int q = threadIdx.x; q < Q; q += blockDim.x)
+        atomicAdd(&hist[work_bucket(starts[2 * q], starts[2 * q + 1], goals[2 * q], goals[2 * q + 1])], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned acc = 0;
+        for (int b = 63; b >= 0; b--) { offs[b] = acc; acc += hist[b]; }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+        const unsigned b = work_bucket(starts[2 * q], starts[2 * q + 1], goals[2 * q], goals[2 * q + 1]);
+        order[atomicAdd(&offs[b], 1u)] = (uint32_t)q;
+    }
+}
+
+// ---- band pass ------------------------------------------------------------------------------------------------
+template <int METRIC>
+__global__ void __launch_bounds__(BAND_WARPS * 32, 4) k_band_bound(const BandParams P)
+{
+    constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
+    __shared__ uint32_t s_queue[BAND_WARPS][3][BAND_Q];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int H = P.H, W = P.W;
+    uint32_t *__restrict__ field = P.bfields + (size_t)(blockIdx.x * BAND_WARPS + warp) * P.bcap;
+    const uint8_t *__restrict__ moves = P.moves;
+    uint32_t(*queue)[BAND_Q] = s_queue[warp];
+
+    for (;;) {
+        unsigned long long it = 0;
+        if (lane == 0) it = atomicAdd(P.counter, 1ull);
+        it = __shfl_sync(0xFFFFFFFFu, it, 0);
+        if (it >= (unsigned long long)P.Q) break;
+        const int q = P.order ? (int)P.order[it] : (int)it;
+        const int sx = P.starts[2 * q], sy = P.starts[2 * q + 1], gx = P.goals[2 * q], gy = P.goals[2 * q + 1];
+        uint32_t result = FX_INF;
+        const bool ok = sx >= 0 && sx < W && sy >= 0 && sy < H && gx >= 0 && gx < W && gy >= 0 && gy < H && !(sx == gx && sy == gy);
+        if (!ok || P.grid[(size_t)gx * H + gy] == 1 || moves[(size_t)sx * H + sy] == 0) {  // search.cu answers these itself
+            if (lane == 0) P.ubound[q] = FX_INF;
+            continue;
+        }
+        // band coordinates: a = major axis, b = minor axis
+        const int ddx = gx - sx, ddy = gy - sy;
+        const bool xmajor = abs(ddx) >= abs(ddy);
+        const int L = xmajor ? abs(ddx) : abs(ddy);
+        const int sgn = (xmajor ? ddx : ddy) >= 0 ? 1 : -1;
+        const int as = xmajor ? sx : sy, bs = xmajor ? sy : sx;
+        const long long slope = ((long long)(xmajor ? ddy : ddx) * 65536) / L;  // minor offset per major step, 2^-16
+        const int tmax = L + 2 * BAND_M;
+        auto off = [&](int tt) { return (int)(((long long)tt * slope + 32768) >> 16); };
+        const uint32_t h0 = octile(abs(ddx), abs(ddy), WS, WD - WS);
+        const uint64_t U64 = (uint64_t)h0 + h0 / 16 + 64 * WS;
+        uint32_t U = U64 > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)U64;
+
+        if (lane == 0) {
+            queue[0][0] = ((uint32_t)sx << 16) | (uint32_t)sy;
+            __stcg(field + ((size_t)BAND_M << 5) + (BAND_B - 1), 0u);  // start: t = BAND_M, deviation 0
+        }
+        __syncwarp();
+        unsigned n = 1, n1 = 0, n2 = 0;  // entries in buckets k, k+1, k+2
+        int bk = 0;                      // buffer of bucket k; k+1 -> (bk+1)%3, k+2 -> (bk+2)%3
+        uint32_t goalc = FX_INF;
+        bool overflow = false;
+        for (unsigned k = 0;; k++) {
+            if (goalc != FX_INF && goalc / WS <= k) { result = goalc; break; }
+            if ((n == 0 && n1 == 0) || overflow) break;
+            const int b1 = bk == 2 ? 0 : bk + 1, b2 = b1 == 2 ? 0 : b1 + 1;
+            uint32_t lane_goal = FX_INF;
+            for (unsigned i0 = 0; i0 < n; i0 += 32) {
+                const unsigned i = i0 + lane;
+                bool act = i < n;
+                const uint32_t xy = act ? queue[bk][i] : 0u;
+                const int x = (int)(xy >> 16), y = (int)(xy & 0xFFFFu);
+                const int tt = ((xmajor ? x : y) - as) * sgn;
+                const int bcur = xmajor ? y : x;
+                const int o_m = off(tt - 1), o_0 = off(tt), o_p = off(tt + 1);
+                const size_t idx = (size_t)x * H + y;
+                uint32_t g = FX_INF;
+                unsigned m = 0;
+                if (act) { g = __ldcg(field + ((size_t)(tt + BAND_M) << 5) + (bcur - bs - o_0 + BAND_B - 1)); m = (unsigned)__ldg(moves + idx); }
+                act = act && g != FX_INF && (g / WS) == k;
+                if (!act) m = 0;
+                uint32_t cur[8];
+                int nfi[8];
+#pragma unroll
+                for (int d = 0; d < 8; d++) {
+                    const int nx = x + fx_dx(d), ny = y + fx_dy(d);
+                    const uint32_t ng = g + (d < 4 ? WS : WD);
+                    const int da = (xmajor ? fx_dx(d) : fx_dy(d)) * sgn;   // step along the major axis: -1, 0, +1
+                    const int nb = xmajor ? ny : nx;
+                    const int ntt = tt + da;
+                    const int dev = nb - bs - (da < 0 ? o_m : (da > 0 ? o_p : o_0));
+                    bool c = (m >> d) & 1u;
+                    c = c && ntt + BAND_M >= 0 && ntt + BAND_M <= tmax && dev >= -(BAND_B - 1) && dev <= BAND_B - 1;
+                    if (c) {
+                        const uint32_t h = octile(abs(nx - gx), abs(ny - gy), WS, WD - WS);
+                        c = ((uint64_t)ng + h) <= (uint64_t)U;
+                    }
+                    if (!c) m &= ~(1u << d);
+                    nfi[d] = ((ntt + BAND_M) << 5) + (dev + BAND_B - 1);
+                    cur[d] = c ? __ldcg(field + nfi[d]) : 0u;
+                }
+                unsigned push1 = 0, push2 = 0;
+#pragma unroll
+                for (int d = 0; d < 8; d++) {
+                    const uint32_t ng = g + (d < 4 ? WS : WD);
+                    if (((m >> d) & 1u) && ng < cur[d]) {
+                        const uint32_t old = atomicMin(field + nfi[d], ng);
+                        if (ng < old) {
+                            if (x + fx_dx(d) == gx && y + fx_dy(d) == gy) lane_goal = min(lane_goal, ng);
+                            const unsigned nbk = ng / WS;
+                            if (old == FX_INF || old / WS != nbk) {
+                                if (nbk == k + 1) push1 |= 1u << d; else push2 |= 1u << d;
+                            }
+                        }
+                    }
+                }
+                const unsigned cnt = (unsigned)__popc(push1) | ((unsigned)__popc(push2) << 16);
+                unsigned incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const unsigned tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                unsigned pos1 = n1 + ((incl - cnt) & 0xFFFFu), pos2 = n2 + ((incl - cnt) >> 16);
+                n1 += tot & 0xFFFFu; n2 += tot >> 16;
+                if (n1 > BAND_Q || n2 > BAND_Q) overflow = true;
+                while (push1) {
+                    const int d = __ffs(push1) - 1; push1 &= push1 - 1;
+                    if (pos1 < BAND_Q) queue[b1][pos1] = ((uint32_t)(x + fx_dx(d)) << 16) | (uint32_t)(y + fx_dy(d));
+                    pos1++;
+                }
+                while (push2) {
+                    const int d = __ffs(push2) - 1; push2 &= push2 - 1;
+                    if (pos2 < BAND_Q) queue[b2][pos2] = ((uint32_t)(x + fx_dx(d)) << 16) | (uint32_t)(y + fx_dy(d));
+                    pos2++;
+                }
+            }
+            lane_goal = __reduce_min_sync(0xFFFFFFFFu, lane_goal);
+            if (lane_goal < goalc) { goalc = lane_goal; U = min(U, goalc); }
+            __syncwarp();
+            n = n1; n1 = n2; n2 = 0; bk = b1;
+        }
+        if (lane == 0) P.ubound[q] = overflow ? FX_INF : result;
+        // reset the rows this query could touch (one 128-byte line per t)
+        {
+            uint4 *f4 = reinterpret_cast<uint4 *>(field);
+            const uint4 inf4 = make_uint4(FX_INF, FX_INF, FX_INF, FX_INF);
+            const size_t n16 = ((size_t)tmax + 1) * 8;
+            for (size_t i = lane; i < n16; i += 32) __stcg(f4 + i, inf4);
+        }
+        __syncwarp();
+    }
+}
+
+int fx_band_bounds(fx_context *ctx, const uint8_t *grid, int W, int H, const int32_t *starts_xy, const int32_t *goals_xy, int Q,
+                   int metric, cudaStream_t st)
+{
+    if (ctx->q_cap < (size_t)Q) {
+        if (ctx->q_order) cudaFree(ctx->q_order);
+        if (ctx->q_ubound) cudaFree(ctx->q_ubound);
+        ctx->q_order = ctx->q_ubound = nullptr; ctx->q_cap = 0;
+        FX_CUDA(ctx, cudaMalloc(&ctx->q_order, (size_t)Q * sizeof(uint32_t)));
+        FX_CUDA(ctx, cudaMalloc(&ctx->q_ubound, (size_t)Q * sizeof(uint32_t)));
+        ctx->q_cap = (size_t)Q;
+    }
+    const size_t bcap = ((size_t)(W > H ? W : H) + 2 * BAND_M + 1) * 32;
+    const int bslots = ctx->sm_count * 4 * BAND_WARPS;
+    if (ctx->bcap < bcap || ctx->bslots < bslots) {
+        if (ctx->bfields) cudaFree(ctx->bfields);
+        ctx->bfields = nullptr; ctx->bcap = 0; ctx->bslots = 0;
+        FX_CUDA(ctx, cudaMalloc(&ctx->bfields, (size_t)bslots * bcap * sizeof(uint32_t)));
+        FX_CUDA(ctx, cudaMemsetAsync(ctx->bfields, 0xFF, (size_t)bslots * bcap * sizeof(uint32_t), st));
+        ctx->bcap = bcap; ctx->bslots = bslots;
+    }
+    k_order_queries<<<1, 1024, 0, st>>>(starts_xy, goals_xy, Q, ctx->q_order);
+    FX_LAUNCH_CHECK(ctx);
+    BandParams P;
+    P.grid = grid; P.moves = ctx->moves; P.W = W; P.H = H; P.starts = starts_xy; P.goals = goals_xy; P.Q = Q;
+    P.order = ctx->q_order; P.ubound = ctx->q_ubound; P.bfields = ctx->bfields; P.bcap = ctx->bcap; P.counter = ctx->counters + 6;
+    int blocks = (Q + BAND_WARPS - 1) / BAND_WARPS;
+    if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
+    if (metric == 1) k_band_bound<1><<<blocks, BAND_WARPS * 32, 0, st>>>(P);
+    else k_band_bound<2><<<blocks, BAND_WARPS * 32, 0, st>>>(P);
+    FX_LAUNCH_CHECK(ctx);
+    return FX_OK;
+}

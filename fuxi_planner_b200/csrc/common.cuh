@@ -9,10 +9,10 @@
 
 #define FX_INF 0xFFFFFFFFu
 #ifndef FX_SEARCH_THREADS
-#define FX_SEARCH_THREADS 256
+#define FX_SEARCH_THREADS 128
 #endif
 #ifndef FX_SEARCH_MINB
-#define FX_SEARCH_MINB 3 /* resident search CTAs per SM the register budget is compiled for */
+#define FX_SEARCH_MINB 6 /* resident search CTAs per SM the register budget is compiled for */
 #endif
 #define FX_DIRTY_SHIFT 5 /* one dirty flag per 32 field cells (one 128 B line) */
 
@@ -37,6 +37,12 @@ struct fx_context {
     uint8_t *moves;     // [cells] legal-move mask per cell
     size_t moves_cap;
     unsigned long long *counters;  // [8]: 0 work counter, 1 settled, 2 levels, 3 passes, 4 band-only, 5 flags
+    // band pass scratch (band.cu)
+    uint32_t *q_order;   // [Q] query indices, largest estimated work first
+    uint32_t *q_ubound;  // [Q] upper bound on the cost from the band pass, FX_INF = none
+    size_t q_cap;
+    uint32_t *bfields;   // [bslots][bcap] band-coordinate cost fields
+    size_t bcap; int bslots;
     // full-field (cooperative) scratch
     uint32_t *fq;       // [4][fqcap]
     size_t fqcap;
@@ -47,6 +53,7 @@ struct fx_context {
     size_t seed_cap, seed_hist_cap;
     // projection scratch: bit-packed grid for the large-grid scatter
     unsigned *proj_bits;
+    int inflate_attr_set;
     size_t proj_bits_cap;
     // EDT scratch
     uint16_t *edt_g;
@@ -88,5 +95,20 @@ static_assert(fx_dx(2) == 0 && fx_dy(2) == -1 && fx_dx(3) == 0 && fx_dy(3) == 1,
 static_assert(fx_dx(4) == -1 && fx_dy(4) == -1 && fx_dx(5) == -1 && fx_dy(5) == 1, "dir table");
 static_assert(fx_dx(6) == 1 && fx_dy(6) == -1 && fx_dx(7) == 1 && fx_dy(7) == 1, "dir table");
 
+// edge weights: metric 1 = the reference's hchoice 1 (10 / 14, scripts/jps1.py:3-12,232-246); metric 2 = Euclidean in 2^-16 fixed point
+template <int METRIC> struct Wt;
+template <> struct Wt<1> { static constexpr uint32_t WS = 10, WD = 14; };
+template <> struct Wt<2> { static constexpr uint32_t WS = FX_EUCLID_WS, WD = FX_EUCLID_WD; };
+
+__device__ __forceinline__ uint32_t octile(int ax, int ay, uint32_t ws, uint32_t wdiff)
+{
+    // ax, ay >= 0.  ws*max + (wd-ws)*min; fits 32 bits for W,H <= 32767 (checked on the host side)
+    int mx = max(ax, ay), mn = min(ax, ay);
+    return ws * (uint32_t)mx + wdiff * (uint32_t)mn;
+}
+
 int fx_search_reserve(fx_context *ctx, int W, int H, int max_path);
+// band.cu: LPT query order + per-query upper bounds from the band pass (one warp per query)
+int fx_band_bounds(fx_context *ctx, const uint8_t *grid, int W, int H, const int32_t *starts_xy, const int32_t *goals_xy, int Q,
+                   int metric, cudaStream_t st);
 int fx_build_moves(fx_context *ctx, const uint8_t *grid, int W, int H, cudaStream_t st);

@@ -149,6 +149,54 @@ __global__ void __launch_bounds__(256) k_edt_cols_window(const uint16_t *__restr
     if (open) *flag = 1;
 }
 
+// ---- pass 2a, tiled: the same window scan out of shared memory ------------------------------------
+// One CTA owns EDT_TX x EDT_TYC output cells and stages the (EDT_TX + 2*EDT_WIN) x EDT_TYC block of g it can
+// need (coalesced 16-byte loads, every g value is read from HBM/L2 once per tile instead of once per probe).
+// All arithmetic fits 32 unsigned bits: g <= 65534 -> g*g + EDT_WIN^2 < 2^32.
+#define EDT_TX 64
+#define EDT_TYC 128
+__global__ void __launch_bounds__(256) k_edt_cols_tile(const uint16_t *__restrict__ g, int32_t *__restrict__ out, int W, int H,
+                                                       int *__restrict__ flag)
+{
+    __shared__ __align__(16) uint16_t tile[EDT_TX + 2 * EDT_WIN][EDT_TYC];
+    const int x0 = blockIdx.y * EDT_TX, y0 = blockIdx.x * EDT_TYC;
+    constexpr int ROWS = EDT_TX + 2 * EDT_WIN;
+    // stage: 16 threads x 16 bytes per row, 16 rows per step
+    {
+        const int cchunk = (threadIdx.x & 15) * 8, r0 = threadIdx.x >> 4;
+        for (int rr = r0; rr < ROWS; rr += 16) {
+            const int x = x0 - EDT_WIN + rr;
+            uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            if (x >= 0 && x < W && y0 + cchunk < H) v = __ldcs(reinterpret_cast<const uint4 *>(g + (size_t)x * H + y0 + cchunk));
+            *reinterpret_cast<uint4 *>(&tile[rr][cchunk]) = v;
+        }
+    }
+    __syncthreads();
+    const int c = threadIdx.x & (EDT_TYC - 1);
+    bool open = false;
+    if (y0 + c < H) {
+        for (int r = threadIdx.x >> 7; r < EDT_TX; r += 2) {
+            const int x = x0 + r;
+            if (x >= W) break;
+            const int tr = r + EDT_WIN;
+            const unsigned g0 = tile[tr][c];
+            unsigned best = g0 == EDT_NONE ? 0xFFFFFFFFu : g0 * g0;
+            int d = 1;
+            for (; d <= EDT_WIN; d++) {
+                const unsigned dd = (unsigned)(d * d);
+                if (dd >= best) break;
+                if (x - d < 0 && x + d >= W) break;  // nothing left on either side
+                const unsigned ga = tile[tr - d][c], gb = tile[tr + d][c];  // rows outside the grid were staged as NONE
+                if (ga != EDT_NONE) best = min(best, dd + ga * ga);
+                if (gb != EDT_NONE) best = min(best, dd + gb * gb);
+            }
+            if (d > EDT_WIN && (unsigned)(d * d) < best && !(x - d < 0 && x + d >= W)) open = true;
+            __stcs(out + (size_t)x * H + y0 + c, best > 0x7FFFFFFFu ? 0x7FFFFFFF : (int32_t)best);
+        }
+    }
+    if (open) *flag = 1;
+}
+
 // ---- pass 2b: Meijster et al. lower envelope, one thread per column ------------------------------
 __device__ __forceinline__ long long edt_f(int x, int i, long long gi2) { return (long long)(x - i) * (x - i) + gi2; }
 __global__ void __launch_bounds__(128) k_edt_cols_exact(const uint16_t *__restrict__ g, int32_t *__restrict__ out, int W, int H,
@@ -226,7 +274,12 @@ extern "C" int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W
     FX_LAUNCH_CHECK(ctx);
     int b2 = (int)((cells + 255) / 256);
     if (b2 > ctx->sm_count * 16) b2 = ctx->sm_count * 16;
-    k_edt_cols_window<<<b2, 256, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_flag);
+    if (H % 8 == 0) {
+        dim3 gt((H + EDT_TYC - 1) / EDT_TYC, (W + EDT_TX - 1) / EDT_TX);
+        k_edt_cols_tile<<<gt, 256, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_flag);
+    } else {
+        k_edt_cols_window<<<b2, 256, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_flag);
+    }
     FX_LAUNCH_CHECK(ctx);
     k_edt_cols_exact<<<(H + 127) / 128, 128, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_s, ctx->edt_t, ctx->edt_flag);
     FX_LAUNCH_CHECK(ctx);

@@ -28,10 +28,6 @@
 #define FX_LDF __ldcg
 #endif
 
-template <int METRIC> struct Wt;
-template <> struct Wt<1> { static constexpr uint32_t WS = 10, WD = 14; };
-template <> struct Wt<2> { static constexpr uint32_t WS = FX_EUCLID_WS, WD = FX_EUCLID_WD; };
-
 struct SearchParams {
     const uint8_t *grid;
     const uint8_t *moves;
@@ -51,6 +47,8 @@ struct SearchParams {
     int qcap, path_cap;
     unsigned long long *counters;
     int band0;
+    const uint32_t *order;   // LPT query order (band.cu) or NULL
+    const uint32_t *ubound;  // per-query upper bound from the band pass or NULL
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -111,17 +109,11 @@ struct __align__(16) CtaState {
     unsigned goal;   // best known cost of the goal cell (FX_INF = not reached)
     unsigned U;      // prune bound on g + h
     unsigned flags;
+    int xlo, xhi;     // x-rows this query has touched since the last reset (bounds the dirty-flag scan)
     unsigned pruned;  // this pass rejected a legal move by the ellipse or the band (so a drained queue proves nothing)
     int q;
     unsigned long long settled, levels;
 };
-
-__device__ __forceinline__ uint32_t octile(int ax, int ay, uint32_t ws, uint32_t wdiff)
-{
-    // ax, ay >= 0.  ws*max + (wd-ws)*min; fits 32 bits for W,H <= 32767 (checked on the host side)
-    int mx = max(ax, ay), mn = min(ax, ay);
-    return ws * (uint32_t)mx + wdiff * (uint32_t)mn;
-}
 
 // One search pass.  Returns (to every thread) the goal cost or FX_INF.  bandL < 0 disables the band.
 // budget > 0 stops the pass (returning FX_INF with *budget_hit = true) once more than `budget` queue entries were popped.
@@ -142,6 +134,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__res
     if (tid == 0) {
         S.tail[0] = 1; S.tail[1] = 0; S.tail[2] = 0; S.tail[3] = 0;
         S.goal = FX_INF; S.U = U0; S.pruned = 0;
+        S.xlo = min(S.xlo, sx - 1); S.xhi = max(S.xhi, sx + 1);
         __stcg(queue, ((uint32_t)sx << 16) | (uint32_t)sy);
         __stcg(field + sidx, 0u);
         dirty[sidx >> FX_DIRTY_SHIFT] = 1;
@@ -149,6 +142,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__res
     __syncthreads();
 
     unsigned my_settled = 0;
+    int my_xlo = 0x7FFFFFFF, my_xhi = -1;
     unsigned k = 0, popped = 0;
     bool my_pruned = false;
     uint32_t result = FX_INF;
@@ -177,7 +171,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__res
             unsigned m = 0;
             if (act) { g = __ldcg(field + idx); m = (unsigned)__ldg(moves + idx); }
             act = act && g != FX_INF && (g / WS) == k;  // stale entry: the cell moved to an earlier bucket
-            if (act) my_settled++; else m = 0;
+            if (act) { my_settled++; my_xlo = min(my_xlo, x); my_xhi = max(my_xhi, x); } else m = 0;
             // candidates: legal move, inside the ellipse g + h <= U, inside the band
             uint32_t cur[8];
 #pragma unroll
@@ -249,6 +243,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__res
     }
     // every thread leaves the loop at the same k with the same decision (all read the same shared state
     // after the same barrier); one more barrier so that nobody is still reading S when it is re-initialised
+    if (my_xhi >= 0) { atomicMin(&S.xlo, my_xlo - 1); atomicMax(&S.xhi, my_xhi + 1); }
     if (my_pruned) S.pruned = 1;  // S.pruned was zeroed before the first barrier of this pass; nobody reads it until the next one
     __syncthreads();
     if (my_settled) atomicAdd(&S.settled, (unsigned long long)my_settled);
@@ -256,13 +251,20 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__res
     return result;
 }
 
-// reset every 128-byte field line this query touched
-__device__ void reset_slot(uint32_t *__restrict__ field, uint8_t *__restrict__ dirty, size_t dirty_n, size_t cells)
+// reset every 128-byte field line this query touched: only the dirty flags of the x-rows [xlo, xhi] are scanned
+__device__ void reset_slot(CtaState &S, uint32_t *__restrict__ field, uint8_t *__restrict__ dirty, size_t dirty_n, size_t cells, int H)
 {
+    __syncthreads();
+    const int xlo = max(S.xlo, 0), xhi = S.xhi;
+    __syncthreads();
+    if (threadIdx.x == 0) { S.xlo = 0x7FFFFFFF; S.xhi = -1; }
+    if (xhi < xlo) { __syncthreads(); return; }
+    size_t i0 = (((size_t)xlo * H) >> FX_DIRTY_SHIFT) / 16, i1 = ((((size_t)(xhi + 1) * H) >> FX_DIRTY_SHIFT) + 16) / 16;
     const size_t n16 = dirty_n / 16;  // dirty_n is padded to a multiple of 16
+    if (i1 > n16) i1 = n16;
     uint4 *d4 = reinterpret_cast<uint4 *>(dirty);
     const uint4 inf4 = make_uint4(FX_INF, FX_INF, FX_INF, FX_INF);
-    for (size_t i = threadIdx.x; i < n16; i += blockDim.x) {
+    for (size_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
         uint4 v = __ldcg(d4 + i);
         if ((v.x | v.y | v.z | v.w) == 0u) continue;
         uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -367,15 +369,15 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_ba
     uint32_t *queue = P.queues + (size_t)slot * 4 * P.qcap;
     int32_t *tmp = P.tmp_path + (size_t)slot * P.path_cap * 2;
     const int W = P.W, H = P.H;
-    if (tid == 0) { S.settled = 0; S.levels = 0; S.flags = 0; }
+    if (tid == 0) { S.settled = 0; S.levels = 0; S.flags = 0; S.xlo = 0x7FFFFFFF; S.xhi = -1; }
     unsigned long long passes = 0, band_only = 0;
 
     for (;;) {
         __syncthreads();
         if (tid == 0) { S.q = (int)atomicAdd(P.counters + 0, 1ull); S.flags = 0; }
         __syncthreads();
-        const int q = S.q;
-        if (q >= P.Q) break;
+        if (S.q >= P.Q) break;
+        const int q = P.order ? (int)P.order[S.q] : S.q;
         const int sx = P.starts[2 * q], sy = P.starts[2 * q + 1], gx = P.goals[2 * q], gy = P.goals[2 * q + 1];
         int32_t out_cost = FX_COST_UNREACHABLE;
         bool trivial = true;
@@ -434,9 +436,24 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_ba
                 }
             }
             __syncthreads();
-            reset_slot(field, dirty, P.dirty_n, P.cells);
+            reset_slot(S, field, dirty, P.dirty_n, P.cells, H);
         }
-        // pass A: narrow band, generous bound -> an upper bound on the cost; escalate if the band is sealed
+        // upper bound from the warp-per-query band pass (band.cu).  If it equals the octile lower bound it is the
+        // answer and only the path is still needed: one pass inside the same band with U = h0 recovers it (the band
+        // of band.cu is a subset of this one, so the pass finds a path of that cost).  Otherwise it seeds pass B.
+        const uint32_t hint = P.ubound ? P.ubound[q] : FX_INF;
+        if (!overflow && !unreachable && best == FX_INF && hint != FX_INF) {
+            if (hint == h0) {
+                best = run_pass<METRIC>(P, S, field, dirty, queue, sx, sy, gx, gy, h0, (float)P.band0 * L, 0u, &hit);
+                passes++;
+                overflow = (S.flags & FLAG_OVERFLOW) != 0;
+                if (best != FX_INF) { exact = true; band_only++; }
+                else if (!overflow) reset_slot(S, field, dirty, P.dirty_n, P.cells, H);
+            } else {
+                best = hint;
+            }
+        }
+        // pass A (only without a usable hint): narrow band, generous bound; escalate if the band is sealed
         float band = (float)P.band0;
         uint32_t slack = h0 / 16 + 64 * WS;
         for (int attempt = 0; attempt < 3 && !overflow && !unreachable && best == FX_INF; attempt++) {
@@ -451,13 +468,13 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_ba
             if (best != FX_INF) { exact = last || best == h0; if (attempt == 0 && exact) band_only++; break; }
             if (last || !S.pruned) break;  // nothing was pruned and the queue drained: the start's component is exhausted
             __syncthreads();
-            reset_slot(field, dirty, P.dirty_n, P.cells);
+            reset_slot(S, field, dirty, P.dirty_n, P.cells, H);
             band *= 8.f; slack = slack * 4;
         }
         // pass B: no band, U = the upper bound -> exact
         if (!overflow && !unreachable && best != FX_INF && !exact) {
             __syncthreads();
-            reset_slot(field, dirty, P.dirty_n, P.cells);
+            reset_slot(S, field, dirty, P.dirty_n, P.cells, H);
             best = run_pass<METRIC>(P, S, field, dirty, queue, sx, sy, gx, gy, best, -1.f, 0u, &hit);
             passes++;
             overflow = (S.flags & FLAG_OVERFLOW) != 0;
@@ -501,7 +518,7 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_ba
             }
         }
         __syncthreads();
-        reset_slot(field, dirty, P.dirty_n, P.cells);
+        reset_slot(S, field, dirty, P.dirty_n, P.cells, H);
     }
     if (tid == 0) {
         atomicAdd(P.counters + 1, S.settled);
@@ -574,6 +591,9 @@ extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int 
     P.cells = ctx->cells; P.dirty_n = ctx->dirty_n; P.qcap = ctx->qcap; P.path_cap = ctx->path_cap;
     P.counters = ctx->counters;
     P.band0 = ctx->cfg_band0 > 0 ? ctx->cfg_band0 : 16;
+    rc = fx_band_bounds(ctx, grid, W, H, starts_xy, goals_xy, Q, metric, st);
+    if (rc) return rc;
+    P.order = ctx->q_order; P.ubound = ctx->q_ubound;
     int blocks = ctx->slots < Q ? ctx->slots : Q;
     if (metric == 1) k_search_batch<1><<<blocks, FX_SEARCH_THREADS, 0, st>>>(P);
     else k_search_batch<2><<<blocks, FX_SEARCH_THREADS, 0, st>>>(P);

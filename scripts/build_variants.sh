@@ -6,10 +6,12 @@ rm -f fuxi_planner_b200/libfuxi_b200_*.so
 b() { tag=$1; shift; python fuxi_planner_b200/build.py --out=libfuxi_b200_$tag.so "$@" > /dev/null 2>&1; echo built $tag "$@"; }
 for v in "$@"; do
   case $v in
-    t256b3_ca) b $v -DFX_SEARCH_THREADS=256 -DFX_SEARCH_MINB=3 -DFX_LDF=__ldca;;
+    t256b3_cg) b $v -DFX_SEARCH_THREADS=256 -DFX_SEARCH_MINB=3;;
+    t128b6_ca) b $v -DFX_SEARCH_THREADS=128 -DFX_SEARCH_MINB=6 -DFX_LDF=__ldca;;
     t256b4_cg) b $v -DFX_SEARCH_THREADS=256 -DFX_SEARCH_MINB=4;;
     t128b6_cg) b $v -DFX_SEARCH_THREADS=128 -DFX_SEARCH_MINB=6;;
     t128b8_cg) b $v -DFX_SEARCH_THREADS=128 -DFX_SEARCH_MINB=8;;
+    t128b12_cg) b $v -DFX_SEARCH_THREADS=128 -DFX_SEARCH_MINB=12;;
     t64b12_cg) b $v -DFX_SEARCH_THREADS=64 -DFX_SEARCH_MINB=12;;
     t512b1_cg) b $v -DFX_SEARCH_THREADS=512 -DFX_SEARCH_MINB=1;;
     *) echo unknown variant $v; exit 1;;
