@@ -149,18 +149,24 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, 4) k_band_bound(const BandPar
                     nfi[d] = ((ntt + BAND_M) << 5) + (dev + BAND_B - 1);
                     cur[d] = c ? __ldcg(field + nfi[d]) : 0u;
                 }
+                uint32_t old[8];
+                unsigned tried = 0;
+#pragma unroll
+                for (int d = 0; d < 8; d++) {  // all atomics in flight together, results consumed afterwards
+                    const uint32_t ng = g + (d < 4 ? WS : WD);
+                    const bool t = ((m >> d) & 1u) && ng < cur[d];
+                    old[d] = t ? atomicMin(field + nfi[d], ng) : 0u;
+                    tried |= (t ? 1u : 0u) << d;
+                }
                 unsigned push1 = 0, push2 = 0;
 #pragma unroll
                 for (int d = 0; d < 8; d++) {
                     const uint32_t ng = g + (d < 4 ? WS : WD);
-                    if (((m >> d) & 1u) && ng < cur[d]) {
-                        const uint32_t old = atomicMin(field + nfi[d], ng);
-                        if (ng < old) {
-                            if (x + fx_dx(d) == gx && y + fx_dy(d) == gy) lane_goal = min(lane_goal, ng);
-                            const unsigned nbk = ng / WS;
-                            if (old == FX_INF || old / WS != nbk) {
-                                if (nbk == k + 1) push1 |= 1u << d; else push2 |= 1u << d;
-                            }
+                    if (((tried >> d) & 1u) && ng < old[d]) {
+                        if (x + fx_dx(d) == gx && y + fx_dy(d) == gy) lane_goal = min(lane_goal, ng);
+                        const unsigned nbk = ng / WS;
+                        if (old[d] == FX_INF || old[d] / WS != nbk) {
+                            if (nbk == k + 1) push1 |= 1u << d; else push2 |= 1u << d;
                         }
                     }
                 }

@@ -27,6 +27,9 @@
 #ifndef FX_LDF
 #define FX_LDF __ldcg
 #endif
+#ifndef FX_EAGER_PROBE
+#define FX_EAGER_PROBE 1
+#endif
 
 struct SearchParams {
     const uint8_t *grid;
@@ -161,50 +164,77 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__res
         uint32_t *__restrict__ q1 = queue + (size_t)((k + 1) & 3) * qcap;
         uint32_t *__restrict__ q2 = queue + (size_t)((k + 2) & 3) * qcap;
         // one thread per frontier cell; its eight neighbour probes are independent loads in flight together
+        uint32_t xy_next = (unsigned)tid < n ? __ldcg(qk + tid) : 0u;
         for (unsigned i0 = (unsigned)(tid - lane); i0 < n; i0 += (unsigned)nthreads) {
             const unsigned i = i0 + lane;
             bool act = i < n;
-            const uint32_t xy = act ? __ldcg(qk + i) : 0u;
+            const uint32_t xy = xy_next;
+            if (i + nthreads < n) xy_next = __ldcg(qk + i + nthreads);  // the next round's queue entry is already on its way
             const int x = (int)(xy >> 16), y = (int)(xy & 0xFFFFu);
-            const size_t idx = (size_t)x * H + y;
+            const int idx = x * H + y;  // W*H < 2^30 (W, H <= 32767)
             uint32_t g = FX_INF;
             unsigned m = 0;
-            if (act) { g = __ldcg(field + idx); m = (unsigned)__ldg(moves + idx); }
-            act = act && g != FX_INF && (g / WS) == k;  // stale entry: the cell moved to an earlier bucket
-            if (act) { my_settled++; my_xlo = min(my_xlo, x); my_xhi = max(my_xhi, x); } else m = 0;
-            // candidates: legal move, inside the ellipse g + h <= U, inside the band
             uint32_t cur[8];
+#if FX_EAGER_PROBE
+            // the cell's own cost, its move mask and all eight neighbour costs leave in ONE round trip: the probes do
+            // not wait for the move mask (an in-bounds test keeps the addresses valid; legality is applied afterwards)
+            {
+                unsigned inb = 0;
+                if (act) {
+                    const unsigned xm = x > 0, xp = x < W - 1, ym = y > 0, yp = y < H - 1;
+                    inb = xm | (xp << 1) | (ym << 2) | (yp << 3) | ((xm & ym) << 4) | ((xm & yp) << 5) | ((xp & ym) << 6) | ((xp & yp) << 7);
+                    g = __ldcg(field + idx);
+                    m = (unsigned)__ldg(moves + idx);
+                }
+#pragma unroll
+                for (int d = 0; d < 8; d++)
+                    cur[d] = ((inb >> d) & 1u) ? FX_LDF(field + (idx + fx_dx(d) * H + fx_dy(d))) : 0u;
+            }
+#else
+            if (act) { g = __ldcg(field + idx); m = (unsigned)__ldg(moves + idx); }
+#endif
+            act = act && g != FX_INF && (g / WS) == k;  // stale entry: the cell moved to an earlier bucket
+            if (act) {
+                // prune at POP time: a cell outside the ellipse g + h <= U (or outside the band) keeps its cost but is
+                // not expanded -- one heuristic per settled cell instead of one per probed neighbour.  Every cell of a
+                // path of cost <= U satisfies g*(c) + h(c) <= U, so all of them are still expanded: exactness holds.
+                const uint32_t h = octile(abs(x - gx), abs(y - gy), WS, WD - WS);
+                bool keep = ((uint64_t)g + h) <= (uint64_t)U;
+                if (bandL >= 0.f) {
+                    const float lat = (float)(x - sx) * qdy - (float)(y - sy) * qdx;
+                    keep = keep && fabsf(lat) <= bandL;
+                }
+                if (!keep) { my_pruned = true; act = false; }
+            }
+            if (act) { my_settled++; my_xlo = min(my_xlo, x); my_xhi = max(my_xhi, x); } else m = 0;
+#if !FX_EAGER_PROBE
+#pragma unroll
+            for (int d = 0; d < 8; d++)
+                cur[d] = ((m >> d) & 1u) ? FX_LDF(field + (idx + fx_dx(d) * H + fx_dy(d))) : 0u;
+#endif
+            // all improving atomics are issued back to back (no branch depends on a result until every one is in
+            // flight): one L2 round trip for the lot instead of up to eight dependent ones (ncu r01: the serialised
+            // atomicMin results were > 50 % of the long-scoreboard stalls)
+            uint32_t old[8];
+            unsigned tried = 0;
 #pragma unroll
             for (int d = 0; d < 8; d++) {
-                const int nx = x + fx_dx(d), ny = y + fx_dy(d);
                 const uint32_t ng = g + (d < 4 ? WS : WD);
-                bool c = (m >> d) & 1u;
-                if (c) {
-                    const uint32_t h = octile(abs(nx - gx), abs(ny - gy), WS, WD - WS);
-                    c = ((uint64_t)ng + h) <= (uint64_t)U;
-                    if (bandL >= 0.f) {
-                        float lat = (float)(nx - sx) * qdy - (float)(ny - sy) * qdx;
-                        c = c && fabsf(lat) <= bandL;
-                    }
-                    if (!c) my_pruned = true;
-                }
-                if (!c) m &= ~(1u << d);
-                cur[d] = c ? FX_LDF(field + (size_t)((long long)idx + (long long)fx_dx(d) * H + fx_dy(d))) : 0u;
+                const bool t = ((m >> d) & 1u) && ng < cur[d];
+                old[d] = t ? atomicMin(field + (idx + fx_dx(d) * H + fx_dy(d)), ng) : 0u;
+                tried |= (t ? 1u : 0u) << d;
             }
             unsigned push1 = 0, push2 = 0;  // direction masks of the cells to append to bucket k+1 / k+2
 #pragma unroll
             for (int d = 0; d < 8; d++) {
                 const uint32_t ng = g + (d < 4 ? WS : WD);
-                if (((m >> d) & 1u) && ng < cur[d]) {
-                    const size_t nidx = (size_t)((long long)idx + (long long)fx_dx(d) * H + fx_dy(d));
-                    const uint32_t old = atomicMin(field + nidx, ng);
-                    if (ng < old) {
-                        if (old == FX_INF) dirty[nidx >> FX_DIRTY_SHIFT] = 1;
-                        if (nidx == gidx) { atomicMin(&S.goal, ng); atomicMin(&S.U, ng); }
-                        const unsigned nb = ng / WS;  // k+1 or k+2
-                        if (old == FX_INF || old / WS != nb) {
-                            if (nb == k + 1) push1 |= 1u << d; else push2 |= 1u << d;
-                        }
+                if (((tried >> d) & 1u) && ng < old[d]) {
+                    const int nidx = idx + fx_dx(d) * H + fx_dy(d);
+                    if (old[d] == FX_INF) dirty[nidx >> FX_DIRTY_SHIFT] = 1;
+                    if (nidx == (int)gidx) { atomicMin(&S.goal, ng); atomicMin(&S.U, ng); }
+                    const unsigned nb = ng / WS;  // k+1 or k+2
+                    if (old[d] == FX_INF || old[d] / WS != nb) {
+                        if (nb == k + 1) push1 |= 1u << d; else push2 |= 1u << d;
                     }
                 }
             }
