@@ -203,6 +203,18 @@ def map_kernel_rooflines(torch, fx, dev, flush, peak):
         gbs = alg_bytes / (mean_ms * 1e-3) / 1e9
         out[name] = {"ms": mean_ms, "ms_min": min_ms, "alg_bytes": int(alg_bytes), "achieved_gbs": gbs, "frac": gbs / peak}
 
+    # 64 Mi points into cfg4's 4096^2 grid: the grid (16 MiB) stays in L2, so this isolates the streaming side of the
+    # projection kernel (byte-store form); the 16384^2 case below adds the L2-resident bit-packed scatter (RED.OR).
+    N, n = 64 << 20, 4096
+    half = n * 0.1
+    pts = torch.empty((N, 4), dtype=torch.float32, device=dev)
+    pts[:, 0:2].uniform_(-half, half)
+    pts[:, 2].uniform_(-0.5, 3.0)
+    pts[:, 3] = 0
+    grid = torch.empty((n, n), dtype=torch.uint8, device=dev)
+    entry("project_f4_64Mpts_4096", N * 16 + n * n, lambda: fx.project(pts, None, 0.3, float("inf"), (-half, -half), 0.2, out=grid))
+    del pts, grid
+    torch.cuda.empty_cache()
     for label, N, n in (("cfg2", 1 << 20, 1024), ("scaled", 64 << 20, 16384)):
         half = n * 0.1
         pts = torch.empty((N, 4), dtype=torch.float32, device=dev)

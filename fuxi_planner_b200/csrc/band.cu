@@ -22,7 +22,7 @@
 
 struct BandParams {
     const uint8_t *grid, *moves;
-    int W, H;
+    int W, H, TY;
     const int32_t *starts, *goals;
     int Q;
     const uint32_t *order;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, 4) k_band_bound(const BandPar
         const int sx = P.starts[2 * q], sy = P.starts[2 * q + 1], gx = P.goals[2 * q], gy = P.goals[2 * q + 1];
         uint32_t result = FX_INF;
         const bool ok = sx >= 0 && sx < W && sy >= 0 && sy < H && gx >= 0 && gx < W && gy >= 0 && gy < H && !(sx == gx && sy == gy);
-        if (!ok || P.grid[(size_t)gx * H + gy] == 1 || moves[(size_t)sx * H + sy] == 0) {  // search.cu answers these itself
+        if (!ok || P.grid[(size_t)gx * H + gy] == 1 || moves[fx_cidx(sx, sy, H, P.TY)] == 0) {  // search.cu answers these itself
             if (lane == 0) P.ubound[q] = FX_INF;
             continue;
         }
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, 4) k_band_bound(const BandPar
                 const int tt = ((xmajor ? x : y) - as) * sgn;
                 const int bcur = xmajor ? y : x;
                 const int o_m = off(tt - 1), o_0 = off(tt), o_p = off(tt + 1);
-                const size_t idx = (size_t)x * H + y;
+                const int idx = fx_cidx(x, y, H, P.TY);
                 uint32_t g = FX_INF;
                 unsigned m = 0;
                 if (act) { g = __ldcg(field + ((size_t)(tt + BAND_M) << 5) + (bcur - bs - o_0 + BAND_B - 1)); m = (unsigned)__ldg(moves + idx); }
@@ -232,7 +232,7 @@ int fx_band_bounds(fx_context *ctx, const uint8_t *grid, int W, int H, const int
     k_order_queries<<<1, 1024, 0, st>>>(starts_xy, goals_xy, Q, ctx->q_order);
     FX_LAUNCH_CHECK(ctx);
     BandParams P;
-    P.grid = grid; P.moves = ctx->moves; P.W = W; P.H = H; P.starts = starts_xy; P.goals = goals_xy; P.Q = Q;
+    P.grid = grid; P.moves = ctx->moves; P.W = W; P.H = H; P.TY = fx_tiles_y(H); P.starts = starts_xy; P.goals = goals_xy; P.Q = Q;
     P.order = ctx->q_order; P.ubound = ctx->q_ubound; P.bfields = ctx->bfields; P.bcap = ctx->bcap; P.counter = ctx->counters + 6;
     int blocks = (Q + BAND_WARPS - 1) / BAND_WARPS;
     if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;

@@ -107,8 +107,35 @@ __device__ __forceinline__ uint32_t octile(int ax, int ay, uint32_t ws, uint32_t
     return ws * (uint32_t)mx + wdiff * (uint32_t)mn;
 }
 
+// Cell index inside the search scratch (cost fields, move masks).  FX_TILED: 8x8-cell tiles, tile-row major
+// (a tile is 64 cells = 256 B of costs = 2 lines; a tile row of 8 cells is one 32-byte sector), so that the eight
+// neighbours of a cell and the cells of a wavefront arc share sectors and lines in BOTH grid directions.  The
+// row-major form is used by the whole-grid field kernel, whose output is the caller's [W][H] array.
+#ifndef FX_TILED
+#define FX_TILED 1
+#endif
+__host__ __device__ __forceinline__ int fx_tiles_y(int H) { return (H + 7) >> 3; }
+__host__ __device__ __forceinline__ size_t fx_scratch_cells(int W, int H)
+{
+#if FX_TILED
+    return (size_t)((W + 7) >> 3) * (size_t)fx_tiles_y(H) * 64;
+#else
+    return ((size_t)W * H + 63) / 64 * 64;
+#endif
+}
+__device__ __forceinline__ int fx_cidx(int x, int y, int H, int TY)
+{
+#if FX_TILED
+    (void)H;
+    return ((((x >> 3) * TY) + (y >> 3)) << 6) | ((x & 7) << 3) | (y & 7);
+#else
+    (void)TY;
+    return x * H + y;
+#endif
+}
+
 int fx_search_reserve(fx_context *ctx, int W, int H, int max_path);
 // band.cu: LPT query order + per-query upper bounds from the band pass (one warp per query)
 int fx_band_bounds(fx_context *ctx, const uint8_t *grid, int W, int H, const int32_t *starts_xy, const int32_t *goals_xy, int Q,
                    int metric, cudaStream_t st);
-int fx_build_moves(fx_context *ctx, const uint8_t *grid, int W, int H, cudaStream_t st);
+int fx_build_moves(fx_context *ctx, const uint8_t *grid, int W, int H, bool tiled, cudaStream_t st);

@@ -293,7 +293,7 @@ static int field_common(fx_context *ctx, const uint8_t *grid, int W, int H, int 
     FX_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = field_reserve(ctx, W, H, relax);
     if (rc) return rc;
-    rc = fx_build_moves(ctx, grid, W, H, st);
+    rc = fx_build_moves(ctx, grid, W, H, false, st);
     if (rc) return rc;
     const size_t cells = (size_t)W * H;
     FX_CUDA(ctx, cudaMemsetAsync(ctx->fstate, 0, ST_WORDS * sizeof(unsigned), st));

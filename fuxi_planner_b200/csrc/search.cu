@@ -34,7 +34,7 @@
 struct SearchParams {
     const uint8_t *grid;
     const uint8_t *moves;
-    int W, H;
+    int W, H, TY;
     const int32_t *starts, *goals;
     int Q;
     int32_t *cost_i;
@@ -57,9 +57,11 @@ struct SearchParams {
 // ------------------------------------------------------------------------------------------------
 // legal-move mask: bit d of moves[c] == not blocked(c, dir d)   (scripts/jps1.py:14-31)
 // ------------------------------------------------------------------------------------------------
+template <bool TILED>
 __global__ void __launch_bounds__(256) k_build_moves(const uint8_t *__restrict__ grid, int W, int H,
                                                      uint8_t *__restrict__ moves)
 {
+    const int TY = fx_tiles_y(H);
     size_t total = (size_t)W * H;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         int x = (int)(i / H), y = (int)(i - (size_t)x * H);
@@ -83,23 +85,25 @@ __global__ void __launch_bounds__(256) k_build_moves(const uint8_t *__restrict__
             if (d >= 4) ok = ok && !(B(a, 0) && B(0, b));
             m |= (ok ? 1u : 0u) << d;
         }
-        moves[i] = (uint8_t)m;
+        moves[TILED ? (size_t)fx_cidx(x, y, H, TY) : i] = (uint8_t)m;
     }
 }
 
-int fx_build_moves(fx_context *ctx, const uint8_t *grid, int W, int H, cudaStream_t st)
+int fx_build_moves(fx_context *ctx, const uint8_t *grid, int W, int H, bool tiled, cudaStream_t st)
 {
     size_t total = (size_t)W * H;
-    if (ctx->moves_cap < total) {
+    const size_t need = fx_scratch_cells(W, H) > total ? fx_scratch_cells(W, H) : total;
+    if (ctx->moves_cap < need) {
         if (ctx->moves) cudaFree(ctx->moves);
         ctx->moves = nullptr; ctx->moves_cap = 0;
-        FX_CUDA(ctx, cudaMalloc(&ctx->moves, total));
-        ctx->moves_cap = total;
+        FX_CUDA(ctx, cudaMalloc(&ctx->moves, need));
+        ctx->moves_cap = need;
     }
     int blocks = (int)((total + 255) / 256);
     int maxb = ctx->sm_count * 16;
     if (blocks > maxb) blocks = maxb;
-    k_build_moves<<<blocks, 256, 0, st>>>(grid, W, H, ctx->moves);
+    if (tiled && FX_TILED) k_build_moves<true><<<blocks, 256, 0, st>>>(grid, W, H, ctx->moves);
+    else k_build_moves<false><<<blocks, 256, 0, st>>>(grid, W, H, ctx->moves);
     FX_LAUNCH_CHECK(ctx);
     return FX_OK;
 }
@@ -129,7 +133,8 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__res
     const int H = P.H, W = P.W;
     const int tid = threadIdx.x, lane = tid & 31, nthreads = blockDim.x;
     const unsigned qcap = (unsigned)P.qcap;
-    const size_t sidx = (size_t)sx * H + sy, gidx = (size_t)gx * H + gy;
+    const int TY = P.TY;
+    const int sidx = fx_cidx(sx, sy, H, TY), gidx = fx_cidx(gx, gy, H, TY);
     const float qdx = (float)(gx - sx), qdy = (float)(gy - sy);
     const uint8_t *__restrict__ moves = P.moves;
     (void)W;
@@ -171,7 +176,10 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__res
             const uint32_t xy = xy_next;
             if (i + nthreads < n) xy_next = __ldcg(qk + i + nthreads);  // the next round's queue entry is already on its way
             const int x = (int)(xy >> 16), y = (int)(xy & 0xFFFFu);
-            const int idx = x * H + y;  // W*H < 2^30 (W, H <= 32767)
+            const int idx = fx_cidx(x, y, H, TY);  // < 2^30 (W, H <= 32767)
+            int nidx[8];
+#pragma unroll
+            for (int d = 0; d < 8; d++) nidx[d] = fx_cidx(x + fx_dx(d), y + fx_dy(d), H, TY);  // only used where in bounds
             uint32_t g = FX_INF;
             unsigned m = 0;
             uint32_t cur[8];
@@ -188,7 +196,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__res
                 }
 #pragma unroll
                 for (int d = 0; d < 8; d++)
-                    cur[d] = ((inb >> d) & 1u) ? FX_LDF(field + (idx + fx_dx(d) * H + fx_dy(d))) : 0u;
+                    cur[d] = ((inb >> d) & 1u) ? FX_LDF(field + nidx[d]) : 0u;
             }
 #else
             if (act) { g = __ldcg(field + idx); m = (unsigned)__ldg(moves + idx); }
@@ -210,7 +218,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__res
 #if !FX_EAGER_PROBE
 #pragma unroll
             for (int d = 0; d < 8; d++)
-                cur[d] = ((m >> d) & 1u) ? FX_LDF(field + (idx + fx_dx(d) * H + fx_dy(d))) : 0u;
+                cur[d] = ((m >> d) & 1u) ? FX_LDF(field + nidx[d]) : 0u;
 #endif
             // all improving atomics are issued back to back (no branch depends on a result until every one is in
             // flight): one L2 round trip for the lot instead of up to eight dependent ones (ncu r01: the serialised
@@ -221,7 +229,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__res
             for (int d = 0; d < 8; d++) {
                 const uint32_t ng = g + (d < 4 ? WS : WD);
                 const bool t = ((m >> d) & 1u) && ng < cur[d];
-                old[d] = t ? atomicMin(field + (idx + fx_dx(d) * H + fx_dy(d)), ng) : 0u;
+                old[d] = t ? atomicMin(field + nidx[d], ng) : 0u;
                 tried |= (t ? 1u : 0u) << d;
             }
             unsigned push1 = 0, push2 = 0;  // direction masks of the cells to append to bucket k+1 / k+2
@@ -229,42 +237,39 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__res
             for (int d = 0; d < 8; d++) {
                 const uint32_t ng = g + (d < 4 ? WS : WD);
                 if (((tried >> d) & 1u) && ng < old[d]) {
-                    const int nidx = idx + fx_dx(d) * H + fx_dy(d);
-                    if (old[d] == FX_INF) dirty[nidx >> FX_DIRTY_SHIFT] = 1;
-                    if (nidx == (int)gidx) { atomicMin(&S.goal, ng); atomicMin(&S.U, ng); }
+                    if (old[d] == FX_INF) dirty[nidx[d] >> FX_DIRTY_SHIFT] = 1;
+                    if (nidx[d] == gidx) { atomicMin(&S.goal, ng); atomicMin(&S.U, ng); }
                     const unsigned nb = ng / WS;  // k+1 or k+2
                     if (old[d] == FX_INF || old[d] / WS != nb) {
                         if (nb == k + 1) push1 |= 1u << d; else push2 |= 1u << d;
                     }
                 }
             }
-            // warp-aggregated append: inclusive scan of both counts (packed 16|16), one shared atomic per bucket
-            const unsigned cnt = (unsigned)__popc(push1) | ((unsigned)__popc(push2) << 16);
-            unsigned incl = cnt;
+            // warp-aggregated append, grouped BY DIRECTION: the children of adjacent parents in one direction are
+            // adjacent cells and land next to each other in the queue, so the next level's warps read, probe and
+            // relax neighbouring cells (same sectors / lines) instead of a shuffled set
+            unsigned tot1 = 0, tot2 = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += t;
+            for (int d = 0; d < 8; d++) {
+                tot1 += __popc(__ballot_sync(0xFFFFFFFFu, (push1 >> d) & 1u));
+                tot2 += __popc(__ballot_sync(0xFFFFFFFFu, (push2 >> d) & 1u));
             }
-            const unsigned tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            if (tot) {
+            if (tot1 | tot2) {
                 unsigned base1 = 0, base2 = 0;
-                if (lane == 31) {
-                    if (tot & 0xFFFFu) base1 = atomicAdd(&S.tail[(k + 1) & 3], tot & 0xFFFFu);
-                    if (tot >> 16) base2 = atomicAdd(&S.tail[(k + 2) & 3], tot >> 16);
+                if (lane == 0) {
+                    if (tot1) base1 = atomicAdd(&S.tail[(k + 1) & 3], tot1);
+                    if (tot2) base2 = atomicAdd(&S.tail[(k + 2) & 3], tot2);
                 }
-                base1 = __shfl_sync(0xFFFFFFFFu, base1, 31);
-                base2 = __shfl_sync(0xFFFFFFFFu, base2, 31);
-                unsigned pos1 = base1 + ((incl - cnt) & 0xFFFFu), pos2 = base2 + ((incl - cnt) >> 16);
-                while (push1) {
-                    const int d = __ffs(push1) - 1; push1 &= push1 - 1;
-                    if (pos1 < qcap) __stcg(q1 + pos1, ((uint32_t)(x + fx_dx(d)) << 16) | (uint32_t)(y + fx_dy(d)));
-                    pos1++;
-                }
-                while (push2) {
-                    const int d = __ffs(push2) - 1; push2 &= push2 - 1;
-                    if (pos2 < qcap) __stcg(q2 + pos2, ((uint32_t)(x + fx_dx(d)) << 16) | (uint32_t)(y + fx_dy(d)));
-                    pos2++;
+                base1 = __shfl_sync(0xFFFFFFFFu, base1, 0);
+                base2 = __shfl_sync(0xFFFFFFFFu, base2, 0);
+                const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+                for (int d = 0; d < 8; d++) {
+                    const unsigned b1 = __ballot_sync(0xFFFFFFFFu, (push1 >> d) & 1u), b2 = __ballot_sync(0xFFFFFFFFu, (push2 >> d) & 1u);
+                    const uint32_t child = ((uint32_t)(x + fx_dx(d)) << 16) | (uint32_t)(y + fx_dy(d));
+                    if ((push1 >> d) & 1u) { const unsigned pos = base1 + __popc(b1 & lt); if (pos < qcap) __stcg(q1 + pos, child); }
+                    if ((push2 >> d) & 1u) { const unsigned pos = base2 + __popc(b2 & lt); if (pos < qcap) __stcg(q2 + pos, child); }
+                    base1 += __popc(b1); base2 += __popc(b2);
                 }
             }
         }
@@ -289,7 +294,12 @@ __device__ void reset_slot(CtaState &S, uint32_t *__restrict__ field, uint8_t *_
     __syncthreads();
     if (threadIdx.x == 0) { S.xlo = 0x7FFFFFFF; S.xhi = -1; }
     if (xhi < xlo) { __syncthreads(); return; }
-    size_t i0 = (((size_t)xlo * H) >> FX_DIRTY_SHIFT) / 16, i1 = ((((size_t)(xhi + 1) * H) >> FX_DIRTY_SHIFT) + 16) / 16;
+#if FX_TILED
+    const size_t c_lo = (size_t)(xlo >> 3) * fx_tiles_y(H) * 64, c_hi = (size_t)((xhi >> 3) + 1) * fx_tiles_y(H) * 64;
+#else
+    const size_t c_lo = (size_t)xlo * H, c_hi = (size_t)(xhi + 1) * H;
+#endif
+    size_t i0 = (c_lo >> FX_DIRTY_SHIFT) / 16, i1 = ((c_hi >> FX_DIRTY_SHIFT) + 16) / 16;
     const size_t n16 = dirty_n / 16;  // dirty_n is padded to a multiple of 16
     if (i1 > n16) i1 = n16;
     uint4 *d4 = reinterpret_cast<uint4 *>(dirty);
@@ -328,10 +338,10 @@ __device__ int extract_path(const SearchParams &P, const uint32_t *__restrict__ 
                             int32_t *__restrict__ tmp, int cap, unsigned *na, unsigned *nb)
 {
     constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
-    const int H = P.H, W = P.W, lane = threadIdx.x & 31;
+    const int H = P.H, W = P.W, TY = P.TY, lane = threadIdx.x & 31;
     const uint8_t *__restrict__ moves = P.moves;
     int vx = gx, vy = gy;
-    uint32_t gv = __ldcg(field + (size_t)vx * H + vy);
+    uint32_t gv = __ldcg(field + fx_cidx(vx, vy, H, TY));
     int npts = 0, prev_d = -1;
     unsigned a = 0, b = 0;
     if (lane == 0 && cap > 0) { tmp[0] = vx; tmp[1] = vy; }
@@ -343,7 +353,7 @@ __device__ int extract_path(const SearchParams &P, const uint32_t *__restrict__ 
         if (lane < 8) {
             int ux = vx - fx_dx(lane), uy = vy - fx_dy(lane);
             if (ux >= 0 && ux < W && uy >= 0 && uy < H) {
-                size_t u = (size_t)ux * H + uy;
+                const int u = fx_cidx(ux, uy, H, TY);
                 uint32_t gu = __ldcg(field + u);
                 uint32_t w = lane < 4 ? WS : WD;
                 ok = gu != FX_INF && gu + w == gv && ((__ldg(moves + u) >> lane) & 1u);
@@ -363,7 +373,7 @@ __device__ int extract_path(const SearchParams &P, const uint32_t *__restrict__ 
         int ux = vx - (lane + 1) * ddx, uy = vy - (lane + 1) * ddy;
         bool run_ok = false;
         if (ux >= 0 && ux < W && uy >= 0 && uy < H) {
-            size_t u = (size_t)ux * H + uy;
+            const int u = fx_cidx(ux, uy, H, TY);
             uint32_t gu = __ldcg(field + u);
             uint64_t want = (uint64_t)gu + (uint64_t)w * (uint32_t)(lane + 1);
             run_ok = gu != FX_INF && want == (uint64_t)gv && ((__ldg(moves + u) >> d) & 1u);
@@ -416,13 +426,13 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_ba
         else if (!g_in) out_cost = FX_COST_UNREACHABLE;
         else if (sx == gx && sy == gy) out_cost = 0;                                       // jps1.py:199-208
         else if (P.grid[(size_t)gx * H + gy] == 1) out_cost = FX_COST_UNREACHABLE;         // jump() tests the cell first
-        else if (P.moves[(size_t)sx * H + sy] == 0) out_cost = FX_COST_UNREACHABLE;        // start cannot move
+        else if (P.moves[fx_cidx(sx, sy, H, P.TY)] == 0) out_cost = FX_COST_UNREACHABLE;        // start cannot move
         else {
             // can anything step INTO the goal?  (cheap rejection of sealed-off goals)
             bool any = false;
             for (int d = 0; d < 8; d++) {
                 int ux = gx - fx_dx(d), uy = gy - fx_dy(d);
-                if (ux >= 0 && ux < W && uy >= 0 && uy < H && ((P.moves[(size_t)ux * H + uy] >> d) & 1)) any = true;
+                if (ux >= 0 && ux < W && uy >= 0 && uy < H && ((P.moves[fx_cidx(ux, uy, H, P.TY)] >> d) & 1)) any = true;
             }
             if (any) trivial = false;
         }
@@ -458,9 +468,9 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_ba
                 else if (back == FX_INF) {
                     bool touch = false;
                     if (!start_free) {
-                        const unsigned ms = P.moves[(size_t)sx * H + sy];
+                        const unsigned ms = P.moves[fx_cidx(sx, sy, H, P.TY)];
                         for (int d = 0; d < 8; d++)
-                            if (((ms >> d) & 1u) && __ldcg(field + (size_t)(sx + fx_dx(d)) * H + (sy + fx_dy(d))) != FX_INF) touch = true;
+                            if (((ms >> d) & 1u) && __ldcg(field + fx_cidx(sx + fx_dx(d), sy + fx_dy(d), H, P.TY)) != FX_INF) touch = true;
                     }
                     unreachable = !touch;
                 }
@@ -563,7 +573,7 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_ba
 // ------------------------------------------------------------------------------------------------
 int fx_search_reserve(fx_context *ctx, int W, int H, int max_path)
 {
-    size_t cells = (size_t)W * H;
+    size_t cells = fx_scratch_cells(W, H);
     int path_cap = max_path > 0 ? max_path : 1;
     if (ctx->fields && ctx->sW == W && ctx->sH == H && ctx->path_cap >= path_cap) return FX_OK;
     if (ctx->fields) cudaFree(ctx->fields);
@@ -609,11 +619,11 @@ extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int 
     FX_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = fx_search_reserve(ctx, W, H, path_xy ? max_path : 1);
     if (rc) return rc;
-    rc = fx_build_moves(ctx, grid, W, H, st);
+    rc = fx_build_moves(ctx, grid, W, H, true, st);
     if (rc) return rc;
     FX_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), st));
     SearchParams P;
-    P.grid = grid; P.moves = ctx->moves; P.W = W; P.H = H;
+    P.grid = grid; P.moves = ctx->moves; P.W = W; P.H = H; P.TY = fx_tiles_y(H);
     P.starts = starts_xy; P.goals = goals_xy; P.Q = Q;
     P.cost_i = cost_i; P.cost_f = cost_f; P.path_xy = path_xy; P.path_len = path_len;
     P.max_path = path_xy ? max_path : 0;

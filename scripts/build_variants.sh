@@ -10,7 +10,10 @@ for v in "$@"; do
     t128b6_ca) b $v -DFX_SEARCH_THREADS=128 -DFX_SEARCH_MINB=6 -DFX_LDF=__ldca;;
     t256b4_cg) b $v -DFX_SEARCH_THREADS=256 -DFX_SEARCH_MINB=4;;
     t128b6_cg) b $v -DFX_SEARCH_THREADS=128 -DFX_SEARCH_MINB=6;;
+    t64b10_cg) b $v -DFX_SEARCH_THREADS=64 -DFX_SEARCH_MINB=10;;
     lazy) b $v -DFX_EAGER_PROBE=0;;
+    t128b5_cg) b $v -DFX_SEARCH_THREADS=128 -DFX_SEARCH_MINB=5;;
+    rowmajor) b $v -DFX_TILED=0;;
     t128b8_cg) b $v -DFX_SEARCH_THREADS=128 -DFX_SEARCH_MINB=8;;
     t128b12_cg) b $v -DFX_SEARCH_THREADS=128 -DFX_SEARCH_MINB=12;;
     t64b12_cg) b $v -DFX_SEARCH_THREADS=64 -DFX_SEARCH_MINB=12;;

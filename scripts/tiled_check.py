@@ -1,6 +1,6 @@
 """Multi-GPU check + timing of the row-tiled and query-parallel modes (run under torchrun, one rank per GPU):
 
-    torchrun --standalone --local-addr 127.0.0.1 --nproc-per-node N scripts/tiled_check.py [--n 8192] [--out file.json]
+    torchrun --standalone --local-addr 127.0.0.1 --nproc-per-node N scripts/tiled_check.py [--size 8192] [--out file.json]
 
 * row-tiled single-source field (BASELINE cfg5 shape: grid default_rng(6), 20 % fill, first free -> last free cell)
   over N x-slabs with NCCL halo exchange; rank 0 also computes the single-GPU field (when the grid fits its scratch)
@@ -23,7 +23,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=8192)
+    ap.add_argument("--size", dest="n", type=int, default=8192)
     ap.add_argument("--queries", type=int, default=1024)
     ap.add_argument("--out", default="")
     ap.add_argument("--no-verify", action="store_true")
