@@ -293,6 +293,8 @@ def run_b200(args):
         dist.barrier()
     import fuxi_planner_b200 as fx
     ctx = fx.default_context(local)
+    if os.environ.get("FUXI_SLOTS"):  # tuning experiments only: concurrent search slots
+        ctx.check(ctx.lib.fx_set_search_tuning(ctx.handle, int(os.environ["FUXI_SLOTS"]), 0), "fx_set_search_tuning")
 
     n, Q = args.grid, args.queries
     m, s_all, g_all = make_workload(n, Q * world)
@@ -366,7 +368,7 @@ def run_b200(args):
     line = {
         "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32 fixed point (2^-16 cells)" if args.hchoice == 2 else "u32",
+        "vs_baseline": None, "dtype": "u32 (cost in 1/2378 cell, packed with the arrival direction)" if args.hchoice == 2 else "u32",
         "data": "synthetic", "config": workload_config(args, Q),
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "api": "fx_plan_host (fuxi_planner_b200.plan_host), host numpy buffers"},

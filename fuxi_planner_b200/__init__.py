@@ -4,7 +4,8 @@ point cloud -> 2D occupancy grid -> obstacle inflation -> batched shortest paths
 Everything compute runs in hand-written CUDA behind the C ABI in include/fuxi_b200.h
 (libfuxi_b200.so, built in-tree by fuxi_planner_b200/build.py).  There is no CPU fallback.
 """
-from ._lib import Context, FuxiError, default_context, load, SO_PATH  # noqa: F401
+from ._lib import (Context, FuxiError, default_context, load, SO_PATH,  # noqa: F401
+                   FX_EUCLID_WS, FX_EUCLID_WD)
 from .api import (PlanResult, edt, field, field_relax, field_status, inflate, map_host, plan_batch, plan_host,  # noqa: F401
                   project, search_stats)
 from . import jps1  # noqa: F401

@@ -11,8 +11,8 @@ FX_OK = 0
 FX_COST_UNREACHABLE = -1
 FX_COST_START_OOB = -2
 FX_COST_OVERFLOW = -3
-FX_EUCLID_WS = 65536
-FX_EUCLID_WD = 92682
+FX_EUCLID_WS = 2378
+FX_EUCLID_WD = 3363
 
 # every symbol include/fuxi_b200.h declares (tests/test_boundary.py checks the .so exports all of them)
 SYMBOLS = ["fx_create", "fx_destroy", "fx_last_error", "fx_version", "fx_launch_count", "fx_set_search_tuning",

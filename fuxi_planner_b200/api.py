@@ -88,7 +88,7 @@ def edt(grid, out=None, ctx=None):
 
 @dataclass
 class PlanResult:
-    cost_i: torch.Tensor    # int32 [Q]   metric 1: 10/14 cost; metric 2: 2^-16 fixed point; <0: FX_COST_*
+    cost_i: torch.Tensor    # int32 [Q]   metric 1: 10/14 cost; metric 2: units of 1/FX_EUCLID_WS cell; <0: FX_COST_*
     cost_f: torch.Tensor    # float64 [Q] metric 2: straight + diagonal*sqrt(2); metric 1: float(cost_i)
     path_xy: torch.Tensor   # int32 [Q, max_path, 2] turning points (start .. goal) or None
     path_len: torch.Tensor  # int32 [Q]   number of turning points (<0: FX_COST_*)

@@ -48,8 +48,8 @@ extern "C" int fx_create(int device, fx_context **out)
     }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
-    e = cudaMalloc(&ctx->counters, 8 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemset(ctx->counters, 0, 8 * sizeof(unsigned long long));
+    e = cudaMalloc(&ctx->counters, 16 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ctx->counters, 0, 16 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->fstate, 32 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(ctx->fstate, 0, 32 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->edt_flag, sizeof(int));

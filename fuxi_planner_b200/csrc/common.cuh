@@ -12,7 +12,7 @@
 #define FX_SEARCH_THREADS 128
 #endif
 #ifndef FX_SEARCH_MINB
-#define FX_SEARCH_MINB 6 /* resident search CTAs per SM the register budget is compiled for */
+#define FX_SEARCH_MINB 8 /* resident search CTAs per SM the register budget is compiled for (64 registers) */
 #endif
 #define FX_DIRTY_SHIFT 5 /* one dirty flag per 32 field cells (one 128 B line) */
 
@@ -105,6 +105,49 @@ __device__ __forceinline__ uint32_t octile(int ax, int ay, uint32_t ws, uint32_t
     // ax, ay >= 0.  ws*max + (wd-ws)*min; fits 32 bits for W,H <= 32767 (checked on the host side)
     int mx = max(ax, ay), mn = min(ax, ay);
     return ws * (uint32_t)mx + wdiff * (uint32_t)mn;
+}
+
+// ---- canonical successor generation (batched search) -----------------------------------------------------------
+// Packed cost-field entry: (cost << 4) | arrival direction (0..7, FX_CODE_START for the source); FX_INF = unreached.
+// Costs therefore live in 28 bits: 32767 * 3363 < 2^27 covers any monotone path on the largest grid, longer (maze)
+// paths up to 2^28 / WS = 112 k straight steps; beyond that the query reports FX_COST_OVERFLOW.
+#define FX_CODE_START 8u
+#define FX_COST_MAX28 0x0FFFFFFEu
+__device__ __forceinline__ uint32_t fx_pack(uint32_t g, unsigned code) { return (g << 4) | code; }
+__host__ __device__ constexpr int fx_dir_of(int dx, int dy)
+{
+    return dy == 0 ? (dx < 0 ? 0 : 1) : dx == 0 ? (dy < 0 ? 2 : 3) : 4 + (dx > 0 ? 2 : 0) + (dy > 0 ? 1 : 0);
+}
+static_assert(fx_dir_of(-1, 0) == 0 && fx_dir_of(1, 0) == 1 && fx_dir_of(0, -1) == 2 && fx_dir_of(0, 1) == 3, "dir_of");
+static_assert(fx_dir_of(-1, -1) == 4 && fx_dir_of(-1, 1) == 5 && fx_dir_of(1, -1) == 6 && fx_dir_of(1, 1) == 7, "dir_of");
+// Successors of a cell whose legal-move mask is m and which was reached by a move in direction `code`: the natural
+// and forced neighbours of scripts/jps1.py:49-93 (nodeNeighbours) in single-step form.
+//   source (code 8): every legal move (:51-56)
+//   straight d:  d itself; the diagonal d+s for each side s whose cell is blocked (:75-92)
+//   diagonal (dx,dy): (dx,0), (0,dy), (dx,dy); (-dx,dy) if (-dx,0) is blocked; (dx,-dy) if (0,-dy) is blocked (:59-73)
+// each only if the move is legal (bit set in m).  "Blocked side cell" == the straight move onto it is illegal
+// (jps1.blocked is True outside the array, so borders force neighbours exactly like the reference).
+__host__ __device__ inline unsigned fx_canon_succ(unsigned code, unsigned m)
+{
+    if (code >= 8u) return m;
+    const int dx = fx_dx((int)code), dy = fx_dy((int)code);
+    auto bit = [](int a, int b) { return 1u << fx_dir_of(a, b); };
+    unsigned s;
+    if (code < 4u) {
+        s = m & (1u << code);
+        if (dx != 0) {
+            if (!(m & bit(0, 1))) s |= m & bit(dx, 1);
+            if (!(m & bit(0, -1))) s |= m & bit(dx, -1);
+        } else {
+            if (!(m & bit(1, 0))) s |= m & bit(1, dy);
+            if (!(m & bit(-1, 0))) s |= m & bit(-1, dy);
+        }
+    } else {
+        s = m & (bit(dx, 0) | bit(0, dy) | (1u << code));
+        if (!(m & bit(-dx, 0))) s |= m & bit(-dx, dy);
+        if (!(m & bit(0, -dy))) s |= m & bit(dx, -dy);
+    }
+    return s;
 }
 
 // Cell index inside the search scratch (cost fields, move masks).  FX_TILED: 8x8-cell tiles, tile-row major

@@ -22,14 +22,41 @@
 
 #define FLAG_OVERFLOW 1u
 #define FX_POCKET_BUDGET 4096u /* queue pops of the bounded flood from the goal */
-// neighbour probe before the atomic: a stale (too large) value only costs a redundant atomicMin, never a wrong
-// result, so the probe may be served by L1 (FX_LDF = __ldca); the popped cell's own cost is always read with __ldcg.
-#ifndef FX_LDF
-#define FX_LDF __ldcg
+
+// -DFX_PHASE_CLOCKS: tuning build that accumulates, for warp 0 of every CTA, the cycles spent in each dependent step of
+// a level (counters[8..15]; read with fx_search_phase_clocks).  Not compiled into the default library.
+#ifdef FX_PHASE_CLOCKS
+__device__ __forceinline__ long long fx_clk_after(uint32_t dep)
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(dep) : "memory");
+    return t;
+}
+#define PH_DECL long long ph_t = 0, ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PH_START(dep) ph_t = fx_clk_after(dep);
+#define PH_MARK(i, dep) { const long long t__ = fx_clk_after(dep); ph_acc[i] += t__ - ph_t; ph_t = t__; }
+#define PH_COUNT(i, n) ph_acc[i] += (n);
+#define PH_FLUSH if (threadIdx.x == 0) { for (int i__ = 0; i__ < 8; i__++) atomicAdd(P.counters + 8 + i__, (unsigned long long)ph_acc[i__]); }
+#else
+#define PH_DECL
+#define PH_START(dep)
+#define PH_MARK(i, dep)
+#define PH_COUNT(i, n)
+#define PH_FLUSH
 #endif
-#ifndef FX_EAGER_PROBE
-#define FX_EAGER_PROBE 1
-#endif
+
+__device__ __forceinline__ void fx_red_min(uint32_t *p, uint32_t v)
+{
+    asm volatile("red.relaxed.gpu.global.min.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// shared-memory atomic add through PTX: keeps ptxas from rewriting it into a warp-aggregated shuffle sequence
+__device__ __forceinline__ unsigned fx_atoms_add(unsigned *p, unsigned v)
+{
+    unsigned old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+    return old;
+}
 
 struct SearchParams {
     const uint8_t *grid;
@@ -44,7 +71,7 @@ struct SearchParams {
     int max_path;
     uint32_t *fields;
     uint8_t *dirty;
-    uint32_t *queues;
+    uint2 *queues;      // [slots][4][qcap] (packed xy, packed cost|direction)
     int32_t *tmp_path;
     size_t cells, dirty_n;
     int qcap, path_cap;
@@ -113,7 +140,8 @@ int fx_build_moves(fx_context *ctx, const uint8_t *grid, int W, int H, bool tile
 // ------------------------------------------------------------------------------------------------
 struct __align__(16) CtaState {
     unsigned tail[4];
-    unsigned goal;   // best known cost of the goal cell (FX_INF = not reached)
+    unsigned goal;   // cost of the goal cell once it has been popped (FX_INF = not yet)
+    unsigned ovf_level;  // level + 1 in which a cost left the 28-bit range (0 = never)
     unsigned U;      // prune bound on g + h
     unsigned flags;
     int xlo, xhi;     // x-rows this query has touched since the last reset (bounds the dirty-flag scan)
@@ -124,27 +152,39 @@ struct __align__(16) CtaState {
 
 // One search pass.  Returns (to every thread) the goal cost or FX_INF.  bandL < 0 disables the band.
 // budget > 0 stops the pass (returning FX_INF with *budget_hit = true) once more than `budget` queue entries were popped.
+//
+// Successor generation is CANONICAL (the pruning of scripts/jps1.py:49-93 `nodeNeighbours`, applied at every cell
+// instead of only at jump points): a cell popped with arrival direction `code` relaxes only its natural and forced
+// neighbours, s_lut[code][moves] (fx_canon_succ) -- ~1.4 relaxations per settled cell instead of 8.  The cost field
+// packs (cost << 4 | arrival direction) so that one atomic min keeps cost and parent together; ties on cost resolve
+// to the lower direction code, which the pruning tolerates (every optimal parent works: the JPS argument; checked
+// against plain Dijkstra with random tie-breaking on whole fields).
+//
+// No memory round trip sits between popping a cell and pushing its children: a relaxation is a fire-and-forget
+// RED.MIN on the packed word plus an unconditional queue entry (child xy, packed value) in the bucket of the new
+// cost.  Whether the relaxation won is decided when the entry is POPPED: it is expanded iff the field still holds
+// exactly the entry's value (the writer of the final minimum is unique), so losers and superseded entries drop out
+// there.  A level is therefore: queue load -> field + move-mask load -> ALU -> stores, then one block barrier.
 template <int METRIC>
-__device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__restrict__ field,
-                             uint8_t *__restrict__ dirty, uint32_t *__restrict__ queue,
+__device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *__restrict__ s_lut,
+                             uint32_t *__restrict__ field, uint8_t *__restrict__ dirty, uint2 *__restrict__ queue,
                              int sx, int sy, int gx, int gy, uint32_t U0, float bandL, unsigned budget, bool *budget_hit)
 {
     constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
-    const int H = P.H, W = P.W;
+    const int H = P.H;
     const int tid = threadIdx.x, lane = tid & 31, nthreads = blockDim.x;
     const unsigned qcap = (unsigned)P.qcap;
     const int TY = P.TY;
     const int sidx = fx_cidx(sx, sy, H, TY), gidx = fx_cidx(gx, gy, H, TY);
     const float qdx = (float)(gx - sx), qdy = (float)(gy - sy);
     const uint8_t *__restrict__ moves = P.moves;
-    (void)W;
 
     if (tid == 0) {
         S.tail[0] = 1; S.tail[1] = 0; S.tail[2] = 0; S.tail[3] = 0;
-        S.goal = FX_INF; S.U = U0; S.pruned = 0;
+        S.goal = FX_INF; S.U = U0; S.pruned = 0; S.ovf_level = 0;
         S.xlo = min(S.xlo, sx - 1); S.xhi = max(S.xhi, sx + 1);
-        __stcg(queue, ((uint32_t)sx << 16) | (uint32_t)sy);
-        __stcg(field + sidx, 0u);
+        __stcg(queue, make_uint2(((uint32_t)sx << 16) | (uint32_t)sy, fx_pack(0u, FX_CODE_START)));
+        __stcg(field + sidx, fx_pack(0u, FX_CODE_START));
         dirty[sidx >> FX_DIRTY_SHIFT] = 1;
     }
     __syncthreads();
@@ -155,57 +195,51 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__res
     bool my_pruned = false;
     uint32_t result = FX_INF;
     *budget_hit = false;
+    PH_DECL
     for (;;) {
         const unsigned n = S.tail[k & 3], n1 = S.tail[(k + 1) & 3];
+        PH_START(n)
+        // Shared state read here must look the same to a warp that is still at the top of level k and to one that is
+        // already inside it: S.goal (written when the goal is popped, in the level of its bucket) only counts once
+        // its level is over; S.ovf_level likewise; n is complete since the last barrier; n1 is still growing but
+        // only matters when n == 0, i.e. when nobody pushes in this level.
         const unsigned goalc = S.goal;
-        if (goalc != FX_INF && goalc / WS <= k) { result = goalc; break; }
+        if (goalc != FX_INF && goalc / WS < k) { result = goalc; break; }  // the goal was popped in an earlier level: final
+        const unsigned ovl = S.ovf_level;
+        if (ovl != 0 && ovl <= k) { if (tid == 0) S.flags |= FLAG_OVERFLOW; break; }
         if ((n == 0 && n1 == 0) || (S.flags & FLAG_OVERFLOW)) break;
         popped += n;
         if (budget && popped > budget) { *budget_hit = true; break; }
-        if (n > qcap || n1 > qcap) { if (tid == 0) S.flags |= FLAG_OVERFLOW; break; }
+        if (n > qcap) { if (tid == 0) S.flags |= FLAG_OVERFLOW; break; }  // entries beyond qcap were dropped at push time
         if (tid == 0) S.tail[(k + 3) & 3] = 0;  // bucket k-1 is done; levels k+1.. will refill this slot
         const uint32_t U = S.U;
-        const uint32_t *__restrict__ qk = queue + (size_t)(k & 3) * qcap;
-        uint32_t *__restrict__ q1 = queue + (size_t)((k + 1) & 3) * qcap;
-        uint32_t *__restrict__ q2 = queue + (size_t)((k + 2) & 3) * qcap;
-        // one thread per frontier cell; its eight neighbour probes are independent loads in flight together
-        uint32_t xy_next = (unsigned)tid < n ? __ldcg(qk + tid) : 0u;
+        const uint2 *__restrict__ qk = queue + (size_t)(k & 3) * qcap;
+        uint2 *__restrict__ q1 = queue + (size_t)((k + 1) & 3) * qcap;
+        uint2 *__restrict__ q2 = queue + (size_t)((k + 2) & 3) * qcap;
+        const uint32_t kbase = k * WS;
+        uint2 e_next = (unsigned)tid < n ? __ldcg(qk + tid) : make_uint2(0u, 0u);
         for (unsigned i0 = (unsigned)(tid - lane); i0 < n; i0 += (unsigned)nthreads) {
             const unsigned i = i0 + lane;
             bool act = i < n;
-            const uint32_t xy = xy_next;
-            if (i + nthreads < n) xy_next = __ldcg(qk + i + nthreads);  // the next round's queue entry is already on its way
-            const int x = (int)(xy >> 16), y = (int)(xy & 0xFFFFu);
+            const uint2 e = e_next;
+            if (i + nthreads < n) e_next = __ldcg(qk + i + nthreads);  // the next round's entry is already on its way
+            const int x = (int)(e.x >> 16), y = (int)(e.x & 0xFFFFu);
+            PH_MARK(0, e.x)  // queue entry arrived
             const int idx = fx_cidx(x, y, H, TY);  // < 2^30 (W, H <= 32767)
-            int nidx[8];
-#pragma unroll
-            for (int d = 0; d < 8; d++) nidx[d] = fx_cidx(x + fx_dx(d), y + fx_dy(d), H, TY);  // only used where in bounds
-            uint32_t g = FX_INF;
+            uint32_t v = FX_INF;
             unsigned m = 0;
-            uint32_t cur[8];
-#if FX_EAGER_PROBE
-            // the cell's own cost, its move mask and all eight neighbour costs leave in ONE round trip: the probes do
-            // not wait for the move mask (an in-bounds test keeps the addresses valid; legality is applied afterwards)
-            {
-                unsigned inb = 0;
-                if (act) {
-                    const unsigned xm = x > 0, xp = x < W - 1, ym = y > 0, yp = y < H - 1;
-                    inb = xm | (xp << 1) | (ym << 2) | (yp << 3) | ((xm & ym) << 4) | ((xm & yp) << 5) | ((xp & ym) << 6) | ((xp & yp) << 7);
-                    g = __ldcg(field + idx);
-                    m = (unsigned)__ldg(moves + idx);
-                }
-#pragma unroll
-                for (int d = 0; d < 8; d++)
-                    cur[d] = ((inb >> d) & 1u) ? FX_LDF(field + nidx[d]) : 0u;
-            }
-#else
-            if (act) { g = __ldcg(field + idx); m = (unsigned)__ldg(moves + idx); }
-#endif
-            act = act && g != FX_INF && (g / WS) == k;  // stale entry: the cell moved to an earlier bucket
             if (act) {
+                v = __ldcg(field + idx);
+                m = (unsigned)__ldg(moves + idx);
+            }
+            PH_MARK(1, v + m)  // cost + move mask arrived
+            const uint32_t g = e.y >> 4;
+            act = act && v == e.y;  // this entry's relaxation won and nothing improved the cell since
+            if (act) {
+                if (idx == gidx) S.goal = g;  // unique winner: plain store
                 // prune at POP time: a cell outside the ellipse g + h <= U (or outside the band) keeps its cost but is
-                // not expanded -- one heuristic per settled cell instead of one per probed neighbour.  Every cell of a
-                // path of cost <= U satisfies g*(c) + h(c) <= U, so all of them are still expanded: exactness holds.
+                // not expanded.  Every cell of a path of cost <= U satisfies g*(c) + h(c) <= U (h is consistent), and so
+                // do the cells of the alternative paths the canonical pruning relies on: exactness holds.
                 const uint32_t h = octile(abs(x - gx), abs(y - gy), WS, WD - WS);
                 bool keep = ((uint64_t)g + h) <= (uint64_t)U;
                 if (bandL >= 0.f) {
@@ -214,68 +248,46 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, uint32_t *__res
                 }
                 if (!keep) { my_pruned = true; act = false; }
             }
-            if (act) { my_settled++; my_xlo = min(my_xlo, x); my_xhi = max(my_xhi, x); } else m = 0;
-#if !FX_EAGER_PROBE
-#pragma unroll
-            for (int d = 0; d < 8; d++)
-                cur[d] = ((m >> d) & 1u) ? FX_LDF(field + nidx[d]) : 0u;
-#endif
-            // all improving atomics are issued back to back (no branch depends on a result until every one is in
-            // flight): one L2 round trip for the lot instead of up to eight dependent ones (ncu r01: the serialised
-            // atomicMin results were > 50 % of the long-scoreboard stalls)
-            uint32_t old[8];
-            unsigned tried = 0;
-#pragma unroll
-            for (int d = 0; d < 8; d++) {
-                const uint32_t ng = g + (d < 4 ? WS : WD);
-                const bool t = ((m >> d) & 1u) && ng < cur[d];
-                old[d] = t ? atomicMin(field + nidx[d], ng) : 0u;
-                tried |= (t ? 1u : 0u) << d;
+            unsigned succ = 0;
+            if (act) {
+                my_settled++; my_xlo = min(my_xlo, x); my_xhi = max(my_xhi, x);
+                succ = s_lut[((e.y & 15u) << 8) | m];
+                if (g + WD > FX_COST_MAX28) { S.ovf_level = k + 1; succ = 0; }  // 28-bit cost range (benign race: same value)
             }
-            unsigned push1 = 0, push2 = 0;  // direction masks of the cells to append to bucket k+1 / k+2
-#pragma unroll
-            for (int d = 0; d < 8; d++) {
-                const uint32_t ng = g + (d < 4 ? WS : WD);
-                if (((tried >> d) & 1u) && ng < old[d]) {
-                    if (old[d] == FX_INF) dirty[nidx[d] >> FX_DIRTY_SHIFT] = 1;
-                    if (nidx[d] == gidx) { atomicMin(&S.goal, ng); atomicMin(&S.U, ng); }
-                    const unsigned nb = ng / WS;  // k+1 or k+2
-                    if (old[d] == FX_INF || old[d] / WS != nb) {
-                        if (nb == k + 1) push1 |= 1u << d; else push2 |= 1u << d;
-                    }
-                }
+            PH_MARK(2, succ)  // successor mask ready
+            unsigned pos1 = 0, pos2 = 0;
+            // a straight child lands in bucket k+1; all diagonal children of this cell land in the same bucket, k+1 or k+2
+            const bool diag2 = (g - kbase) + WD >= 2u * WS;
+            if (succ) {
+                // queue space: one shared-memory atomic per lane and bucket (the unit serialises same-address lanes in
+                // ~1-2 cycles each; cheaper than a warp scan + broadcast, and no warp-collective in the loop body)
+                const unsigned ns = (unsigned)__popc(succ & 0x0Fu), nd = (unsigned)__popc(succ & 0xF0u);
+                const unsigned c1 = ns + (diag2 ? 0u : nd), c2 = diag2 ? nd : 0u;
+                if (c1) pos1 = fx_atoms_add(&S.tail[(k + 1) & 3], c1);
+                if (c2) pos2 = fx_atoms_add(&S.tail[(k + 2) & 3], c2);
             }
-            // warp-aggregated append, grouped BY DIRECTION: the children of adjacent parents in one direction are
-            // adjacent cells and land next to each other in the queue, so the next level's warps read, probe and
-            // relax neighbouring cells (same sectors / lines) instead of a shuffled set
-            unsigned tot1 = 0, tot2 = 0;
-#pragma unroll
-            for (int d = 0; d < 8; d++) {
-                tot1 += __popc(__ballot_sync(0xFFFFFFFFu, (push1 >> d) & 1u));
-                tot2 += __popc(__ballot_sync(0xFFFFFFFFu, (push2 >> d) & 1u));
+            PH_MARK(3, pos1 + pos2)  // queue space reserved
+            while (succ) {
+                const int d = __ffs(succ) - 1;
+                succ &= succ - 1;
+                const int nx = x + fx_dx(d), ny = y + fx_dy(d);
+                const int nidx = fx_cidx(nx, ny, H, TY);
+                const uint32_t nv = fx_pack(g + (d < 4 ? WS : WD), (unsigned)d);
+                fx_red_min(field + nidx, nv);
+                dirty[nidx >> FX_DIRTY_SHIFT] = 1;
+                const uint2 child = make_uint2(((uint32_t)nx << 16) | (uint32_t)ny, nv);
+                if (d < 4 || !diag2) { if (pos1 < qcap) __stcg(q1 + pos1, child); pos1++; }
+                else { if (pos2 < qcap) __stcg(q2 + pos2, child); pos2++; }
             }
-            if (tot1 | tot2) {
-                unsigned base1 = 0, base2 = 0;
-                if (lane == 0) {
-                    if (tot1) base1 = atomicAdd(&S.tail[(k + 1) & 3], tot1);
-                    if (tot2) base2 = atomicAdd(&S.tail[(k + 2) & 3], tot2);
-                }
-                base1 = __shfl_sync(0xFFFFFFFFu, base1, 0);
-                base2 = __shfl_sync(0xFFFFFFFFu, base2, 0);
-                const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-                for (int d = 0; d < 8; d++) {
-                    const unsigned b1 = __ballot_sync(0xFFFFFFFFu, (push1 >> d) & 1u), b2 = __ballot_sync(0xFFFFFFFFu, (push2 >> d) & 1u);
-                    const uint32_t child = ((uint32_t)(x + fx_dx(d)) << 16) | (uint32_t)(y + fx_dy(d));
-                    if ((push1 >> d) & 1u) { const unsigned pos = base1 + __popc(b1 & lt); if (pos < qcap) __stcg(q1 + pos, child); }
-                    if ((push2 >> d) & 1u) { const unsigned pos = base2 + __popc(b2 & lt); if (pos < qcap) __stcg(q2 + pos, child); }
-                    base1 += __popc(b1); base2 += __popc(b2);
-                }
-            }
+            PH_MARK(4, pos1)  // children relaxed and appended
+            PH_COUNT(6, 1)    // rounds (warp 0)
         }
         __syncthreads();
+        PH_MARK(5, k)  // barrier (includes waiting for the other warps' rounds)
+        PH_COUNT(7, 1)  // levels
         k++;
     }
+    PH_FLUSH
     // every thread leaves the loop at the same k with the same decision (all read the same shared state
     // after the same barrier); one more barrier so that nobody is still reading S when it is re-initialised
     if (my_xhi >= 0) { atomicMin(&S.xlo, my_xlo - 1); atomicMax(&S.xhi, my_xhi + 1); }
@@ -330,63 +342,42 @@ __device__ void reset_slot(CtaState &S, uint32_t *__restrict__ field, uint8_t *_
     __syncthreads();
 }
 
-// Warp 0 walks goal -> start through cost-consistent predecessors and records turning points into tmp
-// (goal first).  Returns the number of points (may exceed cap: only cap are stored); straight/diagonal
-// step counts in *na, *nb (lane 0 values are authoritative; all lanes hold the same).
+// Warp 0 walks goal -> start along the arrival directions stored in the packed field and records turning points
+// into tmp (goal first).  Returns the number of points (may exceed cap: only cap are stored), -1 if the field is
+// inconsistent (cannot happen after a successful pass); straight/diagonal step counts in *na, *nb.
 template <int METRIC>
 __device__ int extract_path(const SearchParams &P, const uint32_t *__restrict__ field, int sx, int sy, int gx, int gy,
                             int32_t *__restrict__ tmp, int cap, unsigned *na, unsigned *nb)
 {
-    constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
     const int H = P.H, W = P.W, TY = P.TY, lane = threadIdx.x & 31;
-    const uint8_t *__restrict__ moves = P.moves;
     int vx = gx, vy = gy;
-    uint32_t gv = __ldcg(field + fx_cidx(vx, vy, H, TY));
-    int npts = 0, prev_d = -1;
+    uint32_t v = __ldcg(field + fx_cidx(vx, vy, H, TY));
+    int npts = 1, prev_d = -1;
     unsigned a = 0, b = 0;
     if (lane == 0 && cap > 0) { tmp[0] = vx; tmp[1] = vy; }
-    npts = 1;
-    // bounded by the number of cells: every iteration strictly decreases gv
+    const unsigned long long max_steps = (unsigned long long)W * H;
+    unsigned long long steps = 0;
     while (!(vx == sx && vy == sy)) {
-        // 1) which directions d have a predecessor u = v - dir(d) with g(u) + w(d) == g(v) and move u->v legal
-        bool ok = false;
-        if (lane < 8) {
-            int ux = vx - fx_dx(lane), uy = vy - fx_dy(lane);
-            if (ux >= 0 && ux < W && uy >= 0 && uy < H) {
-                const int u = fx_cidx(ux, uy, H, TY);
-                uint32_t gu = __ldcg(field + u);
-                uint32_t w = lane < 4 ? WS : WD;
-                ok = gu != FX_INF && gu + w == gv && ((__ldg(moves + u) >> lane) & 1u);
-            }
-        }
-        unsigned cand = __ballot_sync(0xFFFFFFFFu, ok) & 0xFFu;
-        if (cand == 0) return -1;  // inconsistent field (cannot happen after a successful pass)
-        int d = (prev_d >= 0 && ((cand >> prev_d) & 1u)) ? prev_d : (__ffs(cand) - 1);
+        const int d = (int)(v & 15u);
+        if (v == FX_INF || d > 7 || steps > max_steps) return -1;
         if (prev_d >= 0 && d != prev_d) {  // v is a turning point
             if (lane == 0 && npts < cap) { tmp[2 * npts] = vx; tmp[2 * npts + 1] = vy; }
             npts++;
         }
         prev_d = d;
-        // 2) follow direction d for up to 32 cells in one round trip
+        // the parent of v is u_1 = v - dir(d); u_j keeps the run going while it arrived in direction d as well.
+        // Lane j reads u_(j+1): 32 cells of a straight run per round trip.
         const int ddx = fx_dx(d), ddy = fx_dy(d);
-        const uint32_t w = d < 4 ? WS : WD;
-        int ux = vx - (lane + 1) * ddx, uy = vy - (lane + 1) * ddy;
-        bool run_ok = false;
-        if (ux >= 0 && ux < W && uy >= 0 && uy < H) {
-            const int u = fx_cidx(ux, uy, H, TY);
-            uint32_t gu = __ldcg(field + u);
-            uint64_t want = (uint64_t)gu + (uint64_t)w * (uint32_t)(lane + 1);
-            run_ok = gu != FX_INF && want == (uint64_t)gv && ((__ldg(moves + u) >> d) & 1u);
-        }
-        unsigned runmask = __ballot_sync(0xFFFFFFFFu, run_ok);
-        int run = __ffs(~runmask) - 1;  // leading valid lanes
-        if (runmask == 0xFFFFFFFFu) run = 32;
-        if (run <= 0) return -1;
-        // do not run past the start: if the start lies on the run, stop there
-        // (cells beyond it can still satisfy the equalities only if gv keeps decreasing below 0: impossible,
-        //  g(start) == 0 is the minimum, so the run ends at the start automatically)
+        const int ux = vx - (lane + 1) * ddx, uy = vy - (lane + 1) * ddy;
+        uint32_t uv = FX_INF;
+        if (ux >= 0 && ux < W && uy >= 0 && uy < H) uv = __ldcg(field + fx_cidx(ux, uy, H, TY));
+        const unsigned cont = __ballot_sync(0xFFFFFFFFu, uv != FX_INF && (int)(uv & 15u) == d);
+        int lead = __ffs(~cont) - 1;  // u_1 .. u_lead arrived in direction d
+        if (cont == 0xFFFFFFFFu) lead = 31;  // move to u_32 and look again
+        const int run = lead + 1;
+        v = __shfl_sync(0xFFFFFFFFu, uv, lead);
         vx -= run * ddx; vy -= run * ddy;
-        gv -= w * (uint32_t)run;
+        steps += (unsigned)run;
         if (d < 4) a += run; else b += run;
     }
     if (lane == 0 && npts < cap) { tmp[2 * npts] = sx; tmp[2 * npts + 1] = sy; }
@@ -400,16 +391,18 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_ba
 {
     constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
     __shared__ CtaState S;
+    __shared__ uint8_t s_lut[9 * 256];
     __shared__ int s_npts;
     __shared__ unsigned s_ab[2];
     const int tid = threadIdx.x;
     const int slot = blockIdx.x;
     uint32_t *field = P.fields + (size_t)slot * P.cells;
     uint8_t *dirty = P.dirty + (size_t)slot * P.dirty_n;
-    uint32_t *queue = P.queues + (size_t)slot * 4 * P.qcap;
+    uint2 *queue = P.queues + (size_t)slot * 4 * P.qcap;
     int32_t *tmp = P.tmp_path + (size_t)slot * P.path_cap * 2;
     const int W = P.W, H = P.H;
     if (tid == 0) { S.settled = 0; S.levels = 0; S.flags = 0; S.xlo = 0x7FFFFFFF; S.xhi = -1; }
+    for (int i = tid; i < 9 * 256; i += blockDim.x) s_lut[i] = (uint8_t)fx_canon_succ((unsigned)(i >> 8), (unsigned)(i & 255));
     unsigned long long passes = 0, band_only = 0;
 
     for (;;) {
@@ -459,7 +452,7 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_ba
         // step into) the query is unreachable and the forward search need not flood the start's whole component.
         // If the flood reaches the start its cost is the exact answer and pass A is skipped.
         {
-            uint32_t back = run_pass<METRIC>(P, S, field, dirty, queue, gx, gy, sx, sy, 0x7FFFFFFFu, -1.f, FX_POCKET_BUDGET, &hit);
+            uint32_t back = run_pass<METRIC>(P, S, s_lut, field, dirty, queue, gx, gy, sx, sy, 0x7FFFFFFFu, -1.f, FX_POCKET_BUDGET, &hit);
             passes++;
             overflow = (S.flags & FLAG_OVERFLOW) != 0;
             const bool start_free = P.grid[(size_t)sx * H + sy] != 1;
@@ -484,7 +477,7 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_ba
         const uint32_t hint = P.ubound ? P.ubound[q] : FX_INF;
         if (!overflow && !unreachable && best == FX_INF && hint != FX_INF) {
             if (hint == h0) {
-                best = run_pass<METRIC>(P, S, field, dirty, queue, sx, sy, gx, gy, h0, (float)P.band0 * L, 0u, &hit);
+                best = run_pass<METRIC>(P, S, s_lut, field, dirty, queue, sx, sy, gx, gy, h0, (float)P.band0 * L, 0u, &hit);
                 passes++;
                 overflow = (S.flags & FLAG_OVERFLOW) != 0;
                 if (best != FX_INF) { exact = true; band_only++; }
@@ -501,7 +494,7 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_ba
             uint64_t U64 = (uint64_t)h0 + slack;
             uint32_t U0 = (last || U64 > 0x7FFFFFFFull) ? 0x7FFFFFFFu : (uint32_t)U64;
             float bandL = last ? -1.f : band * L;
-            best = run_pass<METRIC>(P, S, field, dirty, queue, sx, sy, gx, gy, U0, bandL, 0u, &hit);
+            best = run_pass<METRIC>(P, S, s_lut, field, dirty, queue, sx, sy, gx, gy, U0, bandL, 0u, &hit);
             passes++;
             overflow = (S.flags & FLAG_OVERFLOW) != 0;
             if (overflow) break;
@@ -515,7 +508,7 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_ba
         if (!overflow && !unreachable && best != FX_INF && !exact) {
             __syncthreads();
             reset_slot(S, field, dirty, P.dirty_n, P.cells, H);
-            best = run_pass<METRIC>(P, S, field, dirty, queue, sx, sy, gx, gy, best, -1.f, 0u, &hit);
+            best = run_pass<METRIC>(P, S, s_lut, field, dirty, queue, sx, sy, gx, gy, best, -1.f, 0u, &hit);
             passes++;
             overflow = (S.flags & FLAG_OVERFLOW) != 0;
         }
@@ -585,7 +578,7 @@ int fx_search_reserve(fx_context *ctx, int W, int H, int max_path)
 
     size_t dirty_n = ((cells >> FX_DIRTY_SHIFT) + 1 + 15) / 16 * 16;
     int qcap = 8 * (W + H) + 1024;
-    size_t per_slot = cells * 4 + dirty_n + (size_t)qcap * 16 + (size_t)path_cap * 8;
+    size_t per_slot = cells * 4 + dirty_n + (size_t)qcap * 32 + (size_t)path_cap * 8;
     size_t free_b = 0, total_b = 0;
     FX_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
     int slots = ctx->cfg_slots > 0 ? ctx->cfg_slots : ctx->sm_count * FX_SEARCH_MINB;
@@ -596,7 +589,7 @@ int fx_search_reserve(fx_context *ctx, int W, int H, int max_path)
     size_t cells_al = (cells + 31) / 32 * 32;
     FX_CUDA(ctx, cudaMalloc(&ctx->fields, (size_t)slots * cells_al * 4));
     FX_CUDA(ctx, cudaMalloc(&ctx->dirty, (size_t)slots * dirty_n));
-    FX_CUDA(ctx, cudaMalloc(&ctx->queues, (size_t)slots * 4 * qcap * 4));
+    FX_CUDA(ctx, cudaMalloc(&ctx->queues, (size_t)slots * 4 * qcap * sizeof(uint2)));
     FX_CUDA(ctx, cudaMalloc(&ctx->tmp_path, (size_t)slots * path_cap * 8));
     FX_CUDA(ctx, cudaMemset(ctx->fields, 0xFF, (size_t)slots * cells_al * 4));
     FX_CUDA(ctx, cudaMemset(ctx->dirty, 0, (size_t)slots * dirty_n));
@@ -621,13 +614,13 @@ extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int 
     if (rc) return rc;
     rc = fx_build_moves(ctx, grid, W, H, true, st);
     if (rc) return rc;
-    FX_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), st));
+    FX_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, 16 * sizeof(unsigned long long), st));
     SearchParams P;
     P.grid = grid; P.moves = ctx->moves; P.W = W; P.H = H; P.TY = fx_tiles_y(H);
     P.starts = starts_xy; P.goals = goals_xy; P.Q = Q;
     P.cost_i = cost_i; P.cost_f = cost_f; P.path_xy = path_xy; P.path_len = path_len;
     P.max_path = path_xy ? max_path : 0;
-    P.fields = ctx->fields; P.dirty = ctx->dirty; P.queues = ctx->queues; P.tmp_path = ctx->tmp_path;
+    P.fields = ctx->fields; P.dirty = ctx->dirty; P.queues = reinterpret_cast<uint2 *>(ctx->queues); P.tmp_path = ctx->tmp_path;
     P.cells = ctx->cells; P.dirty_n = ctx->dirty_n; P.qcap = ctx->qcap; P.path_cap = ctx->path_cap;
     P.counters = ctx->counters;
     P.band0 = ctx->cfg_band0 > 0 ? ctx->cfg_band0 : 16;
@@ -638,6 +631,18 @@ extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int 
     if (metric == 1) k_search_batch<1><<<blocks, FX_SEARCH_THREADS, 0, st>>>(P);
     else k_search_batch<2><<<blocks, FX_SEARCH_THREADS, 0, st>>>(P);
     FX_LAUNCH_CHECK(ctx);
+    return FX_OK;
+}
+
+/* tuning builds only (-DFX_PHASE_CLOCKS): cycles per dependent step, summed over warp 0 of every CTA */
+extern "C" int fx_search_phase_clocks(fx_context *ctx, int64_t *h_8)
+{
+    if (!ctx || !h_8) return FX_ERR_ARG;
+    unsigned long long c[16];
+    FX_CUDA(ctx, cudaSetDevice(ctx->device));
+    FX_CUDA(ctx, cudaDeviceSynchronize());
+    FX_CUDA(ctx, cudaMemcpy(c, ctx->counters, sizeof(c), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; i++) h_8[i] = (int64_t)c[8 + i];
     return FX_OK;
 }
 

@@ -35,11 +35,12 @@ extern "C" {
 /* per-query values written to cost_i / path_len */
 #define FX_COST_UNREACHABLE   -1   /* reference returns (0, t): scripts/jps1.py:230 */
 #define FX_COST_START_OOB     -2   /* reference raises IndexError (start outside the array) */
-#define FX_COST_OVERFLOW      -3   /* internal queue or 31-bit cost range exceeded; query not answered */
+#define FX_COST_OVERFLOW      -3   /* internal queue or 28-bit cost range exceeded; query not answered */
 
-/* fixed-point Euclidean metric (metric 2): straight = 2^16, diagonal = round(sqrt(2) * 2^16) */
-#define FX_EUCLID_WS 65536
-#define FX_EUCLID_WD 92682
+/* integer Euclidean metric (metric 2): straight : diagonal = 2378 : 3363, a convergent of sqrt(2)
+ * (3363/2378 = sqrt(2) * (1 + 4.4e-8)); small enough that cost and arrival direction share one 32-bit word */
+#define FX_EUCLID_WS 2378
+#define FX_EUCLID_WD 3363
 
 typedef struct fx_context fx_context;
 
@@ -88,7 +89,7 @@ int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W, int H, vo
  * `not blocked(c, d)` of scripts/jps1.py:14-31 (target != 1; diagonal also needs not both orthogonal
  * cells == 1; the source cell is never tested; outside the array is blocked).
  *   metric 1: weights 10 / 14 (hchoice 1) -> cost_i[q] is the integer the reference prints (jps1.py:207)
- *   metric 2: Euclidean (hchoice 2)       -> cost_i[q] in 2^-16 fixed point (FX_EUCLID_WS/WD),
+ *   metric 2: Euclidean (hchoice 2)       -> cost_i[q] in units of 1/FX_EUCLID_WS cell (FX_EUCLID_WS/WD),
  *                                            cost_f[q] = straight + diagonal*sqrt(2) of the path found
  * starts_xy / goals_xy: int32 [Q][2].  cost_i: int32 [Q] (or FX_COST_*).  cost_f: double [Q] or NULL.
  * path_xy: int32 [Q][max_path][2] turning points, start first, goal last (consecutive points are

@@ -10,9 +10,9 @@ _SRC = os.path.join(_HERE, "fuxi_oracle.c")
 _SO = os.path.join(_HERE, "libfuxi_oracle.so")
 _lib = None
 
-# fixed-point Euclidean weights shared with the CUDA path (DESIGN.md "metric 2"): 2^16 and round(sqrt(2)*2^16)
-FX_WS = 65536
-FX_WD = 92682
+# integer Euclidean weights shared with the CUDA path (DESIGN.md "metric 2"): 2378 : 3363 ~ 1 : sqrt(2) (rel. error 4.4e-8)
+FX_WS = 2378
+FX_WD = 3363
 
 
 def lib_path():

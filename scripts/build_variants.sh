@@ -18,6 +18,9 @@ for v in "$@"; do
     t128b12_cg) b $v -DFX_SEARCH_THREADS=128 -DFX_SEARCH_MINB=12;;
     t64b12_cg) b $v -DFX_SEARCH_THREADS=64 -DFX_SEARCH_MINB=12;;
     t512b1_cg) b $v -DFX_SEARCH_THREADS=512 -DFX_SEARCH_MINB=1;;
+    t128b10_cg) b $v -DFX_SEARCH_THREADS=128 -DFX_SEARCH_MINB=10;;
+    t256b5_cg) b $v -DFX_SEARCH_THREADS=256 -DFX_SEARCH_MINB=5;;
+    clk128) b $v -DFX_PHASE_CLOCKS -DFX_SEARCH_MINB=8;;
     *) echo unknown variant $v; exit 1;;
   esac
 done

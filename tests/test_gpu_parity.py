@@ -149,7 +149,7 @@ def _check_batch(fx, dev, oracle, m, recs, max_path=1024):
             if h == 1:
                 assert 10 * a + 14 * b == ci[q]
             else:
-                assert a * 65536 + b * 92682 == ci[q]
+                assert a * fx.FX_EUCLID_WS + b * fx.FX_EUCLID_WD == ci[q]
                 assert cf[q] == a + b * SQRT2
             # turning points really turn
             for p0, p1, p2 in zip(path[:-2], path[1:-1], path[2:]):

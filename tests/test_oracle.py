@@ -94,13 +94,13 @@ def test_dijkstra_equals_jps_metric1(oracle, golden, maps):
 
 
 def _true_len(oracle, m, rec):
-    """Euclidean length of the path that is optimal in the 2^16 fixed-point metric."""
+    """Euclidean length of the path that is optimal in the integer (2378 : 3363) metric."""
     c, _ = oracle.sssp_cost(m, rec["start"], rec["goal"], 2)
     return c
 
 
 def test_fixed_point_metric2_within_tolerance(oracle, golden, maps):
-    """The 2^16 fixed-point Euclidean metric used on the GPU reproduces jps1's float cost to << 1e-5."""
+    """The integer (2378 : 3363) Euclidean metric used on the GPU reproduces jps1's float cost to << 1e-5."""
     from oracle.capi import FX_WS
     worst = 0.0
     for g in golden["large"]:
