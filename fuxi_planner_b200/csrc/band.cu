@@ -17,7 +17,7 @@
 
 #define BAND_B 16                 /* |offset from the line| <= BAND_B - 1 */
 #define BAND_M 24                 /* rows allowed before the start / after the goal along the major axis */
-#define BAND_Q 256                /* queue entries per bucket and warp (shared memory) */
+#define BAND_Q 128                /* queue entries (8 bytes) per bucket and warp (shared memory) */
 #define BAND_WARPS 8
 
 struct BandParams {
@@ -64,16 +64,34 @@ __global__ void __launch_bounds__(1024) k_order_queries(const int32_t *__restric
 }
 
 // ---- band pass ------------------------------------------------------------------------------------------------
+// Same relaxation scheme as search.cu (canonical successors from the shared LUT, packed cost|direction words,
+// fire-and-forget RED.MIN, entries validated when popped), run by ONE WARP per query on a field in band coordinates.
+__device__ __forceinline__ void band_red_min(uint32_t *p, uint32_t v)
+{
+    asm volatile("red.relaxed.gpu.global.min.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned band_atoms_add(unsigned *p, unsigned v)
+{
+    unsigned old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+    return old;
+}
+
 template <int METRIC>
 __global__ void __launch_bounds__(BAND_WARPS * 32, 4) k_band_bound(const BandParams P)
 {
     constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
-    __shared__ uint32_t s_queue[BAND_WARPS][3][BAND_Q];
+    __shared__ uint2 s_queue[BAND_WARPS][3][BAND_Q];
+    __shared__ unsigned s_cnt[BAND_WARPS][4];
+    __shared__ uint8_t s_lut[9 * 256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int H = P.H, W = P.W;
     uint32_t *__restrict__ field = P.bfields + (size_t)(blockIdx.x * BAND_WARPS + warp) * P.bcap;
     const uint8_t *__restrict__ moves = P.moves;
-    uint32_t(*queue)[BAND_Q] = s_queue[warp];
+    uint2(*queue)[BAND_Q] = s_queue[warp];
+    unsigned *cnt = s_cnt[warp];
+    for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x) s_lut[i] = (uint8_t)fx_canon_succ((unsigned)(i >> 8), (unsigned)(i & 255));
+    __syncthreads();
 
     for (;;) {
         unsigned long long it = 0;
@@ -97,109 +115,74 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, 4) k_band_bound(const BandPar
         const long long slope = ((long long)(xmajor ? ddy : ddx) * 65536) / L;  // minor offset per major step, 2^-16
         const int tmax = L + 2 * BAND_M;
         auto off = [&](int tt) { return (int)(((long long)tt * slope + 32768) >> 16); };
+        // field slot of cell (x, y), or -1 outside the band
+        auto slot_of = [&](int x, int y) {
+            const int tt = ((xmajor ? x : y) - as) * sgn;
+            const int dev = (xmajor ? y : x) - bs - off(tt);
+            const bool in = tt + BAND_M >= 0 && tt + BAND_M <= tmax && dev >= -(BAND_B - 1) && dev <= BAND_B - 1;
+            return in ? ((tt + BAND_M) << 5) + (dev + BAND_B - 1) : -1;
+        };
         const uint32_t h0 = octile(abs(ddx), abs(ddy), WS, WD - WS);
         const uint64_t U64 = (uint64_t)h0 + h0 / 16 + 64 * WS;
-        uint32_t U = U64 > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)U64;
+        const uint32_t U = U64 > 0x0FFFE000ull ? 0x0FFFE000u : (uint32_t)U64;  // also keeps every child cost inside 28 bits
 
         if (lane == 0) {
-            queue[0][0] = ((uint32_t)sx << 16) | (uint32_t)sy;
-            __stcg(field + ((size_t)BAND_M << 5) + (BAND_B - 1), 0u);  // start: t = BAND_M, deviation 0
+            queue[0][0] = make_uint2(((uint32_t)sx << 16) | (uint32_t)sy, fx_pack(0u, FX_CODE_START));
+            __stcg(field + ((size_t)BAND_M << 5) + (BAND_B - 1), fx_pack(0u, FX_CODE_START));  // start: t = BAND_M, deviation 0
+            cnt[0] = 1; cnt[1] = 0; cnt[2] = 0;
         }
         __syncwarp();
-        unsigned n = 1, n1 = 0, n2 = 0;  // entries in buckets k, k+1, k+2
-        int bk = 0;                      // buffer of bucket k; k+1 -> (bk+1)%3, k+2 -> (bk+2)%3
-        uint32_t goalc = FX_INF;
+        int bk = 0;  // buffer of bucket k; k+1 -> (bk+1)%3, k+2 -> (bk+2)%3
         bool overflow = false;
         for (unsigned k = 0;; k++) {
-            if (goalc != FX_INF && goalc / WS <= k) { result = goalc; break; }
-            if ((n == 0 && n1 == 0) || overflow) break;
             const int b1 = bk == 2 ? 0 : bk + 1, b2 = b1 == 2 ? 0 : b1 + 1;
-            uint32_t lane_goal = FX_INF;
+            const unsigned n = cnt[bk], n1 = cnt[b1];
+            if (n > BAND_Q) { overflow = true; break; }
+            if (n == 0 && n1 == 0) break;
+            __syncwarp();
+            if (lane == 0) cnt[b2] = 0;  // bucket k+2 starts empty (its buffer held bucket k-1)
+            __syncwarp();
+            const uint32_t kbase = k * WS;
+            uint32_t found = FX_INF;
             for (unsigned i0 = 0; i0 < n; i0 += 32) {
                 const unsigned i = i0 + lane;
                 bool act = i < n;
-                const uint32_t xy = act ? queue[bk][i] : 0u;
-                const int x = (int)(xy >> 16), y = (int)(xy & 0xFFFFu);
-                const int tt = ((xmajor ? x : y) - as) * sgn;
-                const int bcur = xmajor ? y : x;
-                const int o_m = off(tt - 1), o_0 = off(tt), o_p = off(tt + 1);
-                const int idx = fx_cidx(x, y, H, P.TY);
-                uint32_t g = FX_INF;
+                const uint2 e = act ? queue[bk][i] : make_uint2(0u, 0u);
+                const int x = (int)(e.x >> 16), y = (int)(e.x & 0xFFFFu);
+                uint32_t v = FX_INF;
                 unsigned m = 0;
-                if (act) { g = __ldcg(field + ((size_t)(tt + BAND_M) << 5) + (bcur - bs - o_0 + BAND_B - 1)); m = (unsigned)__ldg(moves + idx); }
-                act = act && g != FX_INF && (g / WS) == k;
-                if (!act) m = 0;
-                uint32_t cur[8];
-                int nfi[8];
-#pragma unroll
-                for (int d = 0; d < 8; d++) {
+                if (act) {
+                    v = __ldcg(field + slot_of(x, y));  // entries are only created for in-band cells
+                    m = (unsigned)__ldg(moves + fx_cidx(x, y, H, P.TY));
+                }
+                const uint32_t g = e.y >> 4;
+                act = act && v == e.y;  // this entry's relaxation won and nothing improved the cell since
+                if (act && x == gx && y == gy) found = g;
+                if (act) act = ((uint64_t)g + octile(abs(x - gx), abs(y - gy), WS, WD - WS)) <= (uint64_t)U;
+                unsigned succ = act ? (unsigned)s_lut[((e.y & 15u) << 8) | m] : 0u;
+                const bool diag2 = (g - kbase) + WD >= 2u * WS;
+                while (succ) {
+                    const int d = __ffs(succ) - 1;
+                    succ &= succ - 1;
                     const int nx = x + fx_dx(d), ny = y + fx_dy(d);
-                    const uint32_t ng = g + (d < 4 ? WS : WD);
-                    const int da = (xmajor ? fx_dx(d) : fx_dy(d)) * sgn;   // step along the major axis: -1, 0, +1
-                    const int nb = xmajor ? ny : nx;
-                    const int ntt = tt + da;
-                    const int dev = nb - bs - (da < 0 ? o_m : (da > 0 ? o_p : o_0));
-                    bool c = (m >> d) & 1u;
-                    c = c && ntt + BAND_M >= 0 && ntt + BAND_M <= tmax && dev >= -(BAND_B - 1) && dev <= BAND_B - 1;
-                    if (c) {
-                        const uint32_t h = octile(abs(nx - gx), abs(ny - gy), WS, WD - WS);
-                        c = ((uint64_t)ng + h) <= (uint64_t)U;
-                    }
-                    if (!c) m &= ~(1u << d);
-                    nfi[d] = ((ntt + BAND_M) << 5) + (dev + BAND_B - 1);
-                    cur[d] = c ? __ldcg(field + nfi[d]) : 0u;
-                }
-                uint32_t old[8];
-                unsigned tried = 0;
-#pragma unroll
-                for (int d = 0; d < 8; d++) {  // all atomics in flight together, results consumed afterwards
-                    const uint32_t ng = g + (d < 4 ? WS : WD);
-                    const bool t = ((m >> d) & 1u) && ng < cur[d];
-                    old[d] = t ? atomicMin(field + nfi[d], ng) : 0u;
-                    tried |= (t ? 1u : 0u) << d;
-                }
-                unsigned push1 = 0, push2 = 0;
-#pragma unroll
-                for (int d = 0; d < 8; d++) {
-                    const uint32_t ng = g + (d < 4 ? WS : WD);
-                    if (((tried >> d) & 1u) && ng < old[d]) {
-                        if (x + fx_dx(d) == gx && y + fx_dy(d) == gy) lane_goal = min(lane_goal, ng);
-                        const unsigned nbk = ng / WS;
-                        if (old[d] == FX_INF || old[d] / WS != nbk) {
-                            if (nbk == k + 1) push1 |= 1u << d; else push2 |= 1u << d;
-                        }
-                    }
-                }
-                const unsigned cnt = (unsigned)__popc(push1) | ((unsigned)__popc(push2) << 16);
-                unsigned incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                const unsigned tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                unsigned pos1 = n1 + ((incl - cnt) & 0xFFFFu), pos2 = n2 + ((incl - cnt) >> 16);
-                n1 += tot & 0xFFFFu; n2 += tot >> 16;
-                if (n1 > BAND_Q || n2 > BAND_Q) overflow = true;
-                while (push1) {
-                    const int d = __ffs(push1) - 1; push1 &= push1 - 1;
-                    if (pos1 < BAND_Q) queue[b1][pos1] = ((uint32_t)(x + fx_dx(d)) << 16) | (uint32_t)(y + fx_dy(d));
-                    pos1++;
-                }
-                while (push2) {
-                    const int d = __ffs(push2) - 1; push2 &= push2 - 1;
-                    if (pos2 < BAND_Q) queue[b2][pos2] = ((uint32_t)(x + fx_dx(d)) << 16) | (uint32_t)(y + fx_dy(d));
-                    pos2++;
+                    const int ns = slot_of(nx, ny);
+                    if (ns < 0) continue;
+                    const uint32_t nv = fx_pack(g + (d < 4 ? WS : WD), (unsigned)d);
+                    band_red_min(field + ns, nv);
+                    const int nb = (d < 4 || !diag2) ? b1 : b2;
+                    const unsigned pos = band_atoms_add(&cnt[nb], 1u);
+                    if (pos < BAND_Q) queue[nb][pos] = make_uint2(((uint32_t)nx << 16) | (uint32_t)ny, nv);
                 }
             }
-            lane_goal = __reduce_min_sync(0xFFFFFFFFu, lane_goal);
-            if (lane_goal < goalc) { goalc = lane_goal; U = min(U, goalc); }
+            found = __reduce_min_sync(0xFFFFFFFFu, found);
+            if (found != FX_INF) { result = found; break; }  // the goal was popped: its cost inside the band is final
             __syncwarp();
-            n = n1; n1 = n2; n2 = 0; bk = b1;
+            bk = b1;
         }
         if (lane == 0) P.ubound[q] = overflow ? FX_INF : result;
         // reset the rows this query could touch (one 128-byte line per t)
         {
+            __syncwarp();
             uint4 *f4 = reinterpret_cast<uint4 *>(field);
             const uint4 inf4 = make_uint4(FX_INF, FX_INF, FX_INF, FX_INF);
             const size_t n16 = ((size_t)tmax + 1) * 8;
