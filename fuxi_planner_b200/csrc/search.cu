@@ -19,6 +19,9 @@
 //   Path: warp-parallel descent from the goal along cost-consistent predecessors, 32 cells of a
 //   straight run per round trip, emitting turning points.
 #include "common.cuh"
+#if !FX_TILED
+#error "search.cu relies on the 8x8-tiled scratch layout (step tables)"
+#endif
 
 #define FLAG_OVERFLOW 1u
 #define FX_POCKET_BUDGET 4096u /* queue pops of the bounded flood from the goal */
@@ -139,7 +142,7 @@ int fx_build_moves(fx_context *ctx, const uint8_t *grid, int W, int H, bool tile
 // per-CTA shared state
 // ------------------------------------------------------------------------------------------------
 struct __align__(16) CtaState {
-    unsigned tail[4];
+    unsigned tailS[4], tailD[4];  // entries per bucket: cells that arrived by a straight / by a diagonal move
     unsigned goal;   // cost of the goal cell once it has been popped (FX_INF = not yet)
     unsigned ovf_level;  // level + 1 in which a cost left the 28-bit range (0 = never)
     unsigned U;      // prune bound on g + h
@@ -166,21 +169,22 @@ struct __align__(16) CtaState {
 // exactly the entry's value (the writer of the final minimum is unique), so losers and superseded entries drop out
 // there.  A level is therefore: queue load -> field + move-mask load -> ALU -> stores, then one block barrier.
 template <int METRIC>
-__device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *__restrict__ s_lut,
+__device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *__restrict__ s_lut, const int *__restrict__ s_step,
                              uint32_t *__restrict__ field, uint8_t *__restrict__ dirty, uint2 *__restrict__ queue,
                              int sx, int sy, int gx, int gy, uint32_t U0, float bandL, unsigned budget, bool *budget_hit)
 {
     constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
     const int H = P.H;
     const int tid = threadIdx.x, lane = tid & 31, nthreads = blockDim.x;
-    const unsigned qcap = (unsigned)P.qcap;
+    const unsigned qcap = (unsigned)P.qcap, qhalf = qcap >> 1;
     const int TY = P.TY;
     const int sidx = fx_cidx(sx, sy, H, TY), gidx = fx_cidx(gx, gy, H, TY);
     const float qdx = (float)(gx - sx), qdy = (float)(gy - sy);
     const uint8_t *__restrict__ moves = P.moves;
 
     if (tid == 0) {
-        S.tail[0] = 1; S.tail[1] = 0; S.tail[2] = 0; S.tail[3] = 0;
+        S.tailS[0] = 1; S.tailS[1] = 0; S.tailS[2] = 0; S.tailS[3] = 0;
+        S.tailD[0] = 0; S.tailD[1] = 0; S.tailD[2] = 0; S.tailD[3] = 0;
         S.goal = FX_INF; S.U = U0; S.pruned = 0; S.ovf_level = 0;
         S.xlo = min(S.xlo, sx - 1); S.xhi = max(S.xhi, sx + 1);
         __stcg(queue, make_uint2(((uint32_t)sx << 16) | (uint32_t)sy, fx_pack(0u, FX_CODE_START)));
@@ -197,7 +201,11 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
     *budget_hit = false;
     PH_DECL
     for (;;) {
-        const unsigned n = S.tail[k & 3], n1 = S.tail[(k + 1) & 3];
+        // A bucket's array holds the straight-arrival entries in its first half and the diagonal-arrival entries in
+        // its second half: a straight arrival has 1 natural (+ <= 2 forced) successor, a diagonal one 3 (+ <= 2), so
+        // warps that pop one class run the relaxation loop about the same number of times in every lane.
+        const unsigned nS = S.tailS[k & 3], nD = S.tailD[k & 3], n = nS + nD;
+        const unsigned n1 = S.tailS[(k + 1) & 3] + S.tailD[(k + 1) & 3];
         PH_START(n)
         // Shared state read here must look the same to a warp that is still at the top of level k and to one that is
         // already inside it: S.goal (written when the goal is popped, in the level of its bucket) only counts once
@@ -210,19 +218,20 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
         if ((n == 0 && n1 == 0) || (S.flags & FLAG_OVERFLOW)) break;
         popped += n;
         if (budget && popped > budget) { *budget_hit = true; break; }
-        if (n > qcap) { if (tid == 0) S.flags |= FLAG_OVERFLOW; break; }  // entries beyond qcap were dropped at push time
-        if (tid == 0) S.tail[(k + 3) & 3] = 0;  // bucket k-1 is done; levels k+1.. will refill this slot
+        if (nS > qhalf || nD > qhalf) { if (tid == 0) S.flags |= FLAG_OVERFLOW; break; }  // entries beyond a half were dropped at push time
+        if (tid == 0) { S.tailS[(k + 3) & 3] = 0; S.tailD[(k + 3) & 3] = 0; }  // bucket k-1 is done; levels k+1.. will refill this slot
         const uint32_t U = S.U;
         const uint2 *__restrict__ qk = queue + (size_t)(k & 3) * qcap;
         uint2 *__restrict__ q1 = queue + (size_t)((k + 1) & 3) * qcap;
         uint2 *__restrict__ q2 = queue + (size_t)((k + 2) & 3) * qcap;
         const uint32_t kbase = k * WS;
-        uint2 e_next = (unsigned)tid < n ? __ldcg(qk + tid) : make_uint2(0u, 0u);
+        auto slot_of = [&](unsigned i) { return i < nS ? i : qhalf + (i - nS); };
+        uint2 e_next = (unsigned)tid < n ? __ldcg(qk + slot_of((unsigned)tid)) : make_uint2(0u, 0u);
         for (unsigned i0 = (unsigned)(tid - lane); i0 < n; i0 += (unsigned)nthreads) {
             const unsigned i = i0 + lane;
             bool act = i < n;
             const uint2 e = e_next;
-            if (i + nthreads < n) e_next = __ldcg(qk + i + nthreads);  // the next round's entry is already on its way
+            if (i + nthreads < n) e_next = __ldcg(qk + slot_of(i + nthreads));  // the next round's entry is already on its way
             const int x = (int)(e.x >> 16), y = (int)(e.x & 0xFFFFu);
             PH_MARK(0, e.x)  // queue entry arrived
             const int idx = fx_cidx(x, y, H, TY);  // < 2^30 (W, H <= 32767)
@@ -231,6 +240,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
             if (act) {
                 v = __ldcg(field + idx);
                 m = (unsigned)__ldg(moves + idx);
+                dirty[idx >> FX_DIRTY_SHIFT] = 1;  // every relaxed cell has an entry: lines are marked when entries are popped
             }
             PH_MARK(1, v + m)  // cost + move mask arrived
             const uint32_t g = e.y >> 4;
@@ -255,31 +265,35 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
                 if (g + WD > FX_COST_MAX28) { S.ovf_level = k + 1; succ = 0; }  // 28-bit cost range (benign race: same value)
             }
             PH_MARK(2, succ)  // successor mask ready
-            unsigned pos1 = 0, pos2 = 0;
+            unsigned posS = 0, posD = 0;
             // a straight child lands in bucket k+1; all diagonal children of this cell land in the same bucket, k+1 or k+2
             const bool diag2 = (g - kbase) + WD >= 2u * WS;
             if (succ) {
-                // queue space: one shared-memory atomic per lane and bucket (the unit serialises same-address lanes in
+                // queue space: one shared-memory atomic per lane and class (the unit serialises same-address lanes in
                 // ~1-2 cycles each; cheaper than a warp scan + broadcast, and no warp-collective in the loop body)
                 const unsigned ns = (unsigned)__popc(succ & 0x0Fu), nd = (unsigned)__popc(succ & 0xF0u);
-                const unsigned c1 = ns + (diag2 ? 0u : nd), c2 = diag2 ? nd : 0u;
-                if (c1) pos1 = fx_atoms_add(&S.tail[(k + 1) & 3], c1);
-                if (c2) pos2 = fx_atoms_add(&S.tail[(k + 2) & 3], c2);
+                if (ns) posS = fx_atoms_add(&S.tailS[(k + 1) & 3], ns);
+                if (nd) posD = qhalf + fx_atoms_add(&S.tailD[(k + (diag2 ? 2 : 1)) & 3], nd);
+                if (posS + ns > qhalf || posD + nd > qcap) succ = 0;  // no room: the tail counts flag the overflow at the next level
             }
-            PH_MARK(3, pos1 + pos2)  // queue space reserved
+            PH_MARK(3, posS + posD)  // queue space reserved
+            // the loop below runs as often as the busiest lane of the warp has successors, so it is kept short: the
+            // child's packed xy, its tiled index and its packed value are one table lookup + one add each
+            uint2 *__restrict__ qS = q1 + posS;
+            uint2 *__restrict__ qD = (diag2 ? q2 : q1) + posD;
+            const uint32_t nvS = fx_pack(g + WS, 0u), nvD = fx_pack(g + WD, 0u);
+            const int *__restrict__ stp = s_step + 2 * (idx & 63);  // tile-local position (x & 7) << 3 | (y & 7)
             while (succ) {
                 const int d = __ffs(succ) - 1;
                 succ &= succ - 1;
-                const int nx = x + fx_dx(d), ny = y + fx_dy(d);
-                const int nidx = fx_cidx(nx, ny, H, TY);
-                const uint32_t nv = fx_pack(g + (d < 4 ? WS : WD), (unsigned)d);
-                fx_red_min(field + nidx, nv);
-                dirty[nidx >> FX_DIRTY_SHIFT] = 1;
-                const uint2 child = make_uint2(((uint32_t)nx << 16) | (uint32_t)ny, nv);
-                if (d < 4 || !diag2) { if (pos1 < qcap) __stcg(q1 + pos1, child); pos1++; }
-                else { if (pos2 < qcap) __stcg(q2 + pos2, child); pos2++; }
+                const int2 st = *reinterpret_cast<const int2 *>(stp + 2 * 64 * d);  // (packed xy step, tiled index step)
+                const uint32_t nv = (d < 4 ? nvS : nvD) | (unsigned)d;
+                fx_red_min(field + (idx + st.y), nv);
+                const uint2 child = make_uint2(e.x + (uint32_t)st.x, nv);
+                if (d < 4) __stcg(qS++, child);
+                else __stcg(qD++, child);
             }
-            PH_MARK(4, pos1)  // children relaxed and appended
+            PH_MARK(4, posS)  // children relaxed and appended
             PH_COUNT(6, 1)    // rounds (warp 0)
         }
         __syncthreads();
@@ -288,6 +302,15 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
         k++;
     }
     PH_FLUSH
+    // entries that were never popped (buckets k and k+1; k+2 is still empty at the top of a level): mark their lines too
+    for (unsigned b = k; b <= k + 1; b++) {
+        const uint2 *__restrict__ qb = queue + (size_t)(b & 3) * qcap;
+        const unsigned mS = min(S.tailS[b & 3], qhalf), mD = min(S.tailD[b & 3], qhalf);
+        for (unsigned i = (unsigned)tid; i < mS + mD; i += (unsigned)nthreads) {
+            const uint32_t xy = __ldcg(qb + (i < mS ? i : qhalf + (i - mS))).x;
+            dirty[fx_cidx((int)(xy >> 16), (int)(xy & 0xFFFFu), H, TY) >> FX_DIRTY_SHIFT] = 1;
+        }
+    }
     // every thread leaves the loop at the same k with the same decision (all read the same shared state
     // after the same barrier); one more barrier so that nobody is still reading S when it is re-initialised
     if (my_xhi >= 0) { atomicMin(&S.xlo, my_xlo - 1); atomicMax(&S.xhi, my_xhi + 1); }
@@ -303,6 +326,8 @@ __device__ void reset_slot(CtaState &S, uint32_t *__restrict__ field, uint8_t *_
 {
     __syncthreads();
     const int xlo = max(S.xlo, 0), xhi = S.xhi;
+    // after an overflow some relaxed cells have no queue entry (and so no dirty flag): reset every line of the x-range
+    const bool force = (S.flags & FLAG_OVERFLOW) != 0;
     __syncthreads();
     if (threadIdx.x == 0) { S.xlo = 0x7FFFFFFF; S.xhi = -1; }
     if (xhi < xlo) { __syncthreads(); return; }
@@ -318,6 +343,7 @@ __device__ void reset_slot(CtaState &S, uint32_t *__restrict__ field, uint8_t *_
     const uint4 inf4 = make_uint4(FX_INF, FX_INF, FX_INF, FX_INF);
     for (size_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
         uint4 v = __ldcg(d4 + i);
+        if (force) v = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
         if ((v.x | v.y | v.z | v.w) == 0u) continue;
         uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -392,6 +418,7 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_ba
     constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
     __shared__ CtaState S;
     __shared__ uint8_t s_lut[9 * 256];
+    __shared__ __align__(8) int s_step[8 * 64 * 2];  // [direction][x&7][y&7] -> (step of the packed xy, step of the tiled index)
     __shared__ int s_npts;
     __shared__ unsigned s_ab[2];
     const int tid = threadIdx.x;
@@ -403,6 +430,13 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_ba
     const int W = P.W, H = P.H;
     if (tid == 0) { S.settled = 0; S.levels = 0; S.flags = 0; S.xlo = 0x7FFFFFFF; S.xhi = -1; }
     for (int i = tid; i < 9 * 256; i += blockDim.x) s_lut[i] = (uint8_t)fx_canon_succ((unsigned)(i >> 8), (unsigned)(i & 255));
+    for (int i = tid; i < 8 * 64; i += blockDim.x) {
+        const int d = i >> 6, xi = (i >> 3) & 7, yi = i & 7, dx = fx_dx(d), dy = fx_dy(d);
+        // stepping over a tile edge changes the tile part of the index by TY (x) or 1 (y) tiles and wraps the in-tile part
+        const int tx = (xi + dx) >> 3, ty = (yi + dy) >> 3;  // -1, 0, +1 (arithmetic shift)
+        s_step[2 * i] = dx * 65536 + dy;  // (x << 16 | y) + this == (x + dx) << 16 | (y + dy) for in-range children
+        s_step[2 * i + 1] = (tx * P.TY + ty) * 64 + ((((xi + dx) & 7) - xi) << 3) + (((yi + dy) & 7) - yi);
+    }
     unsigned long long passes = 0, band_only = 0;
 
     for (;;) {
@@ -452,7 +486,7 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_ba
         // step into) the query is unreachable and the forward search need not flood the start's whole component.
         // If the flood reaches the start its cost is the exact answer and pass A is skipped.
         {
-            uint32_t back = run_pass<METRIC>(P, S, s_lut, field, dirty, queue, gx, gy, sx, sy, 0x7FFFFFFFu, -1.f, FX_POCKET_BUDGET, &hit);
+            uint32_t back = run_pass<METRIC>(P, S, s_lut, s_step, field, dirty, queue, gx, gy, sx, sy, 0x7FFFFFFFu, -1.f, FX_POCKET_BUDGET, &hit);
             passes++;
             overflow = (S.flags & FLAG_OVERFLOW) != 0;
             const bool start_free = P.grid[(size_t)sx * H + sy] != 1;
@@ -477,7 +511,7 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_ba
         const uint32_t hint = P.ubound ? P.ubound[q] : FX_INF;
         if (!overflow && !unreachable && best == FX_INF && hint != FX_INF) {
             if (hint == h0) {
-                best = run_pass<METRIC>(P, S, s_lut, field, dirty, queue, sx, sy, gx, gy, h0, (float)P.band0 * L, 0u, &hit);
+                best = run_pass<METRIC>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, h0, (float)P.band0 * L, 0u, &hit);
                 passes++;
                 overflow = (S.flags & FLAG_OVERFLOW) != 0;
                 if (best != FX_INF) { exact = true; band_only++; }
@@ -494,7 +528,7 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_ba
             uint64_t U64 = (uint64_t)h0 + slack;
             uint32_t U0 = (last || U64 > 0x7FFFFFFFull) ? 0x7FFFFFFFu : (uint32_t)U64;
             float bandL = last ? -1.f : band * L;
-            best = run_pass<METRIC>(P, S, s_lut, field, dirty, queue, sx, sy, gx, gy, U0, bandL, 0u, &hit);
+            best = run_pass<METRIC>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, U0, bandL, 0u, &hit);
             passes++;
             overflow = (S.flags & FLAG_OVERFLOW) != 0;
             if (overflow) break;
@@ -508,7 +542,7 @@ __global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_ba
         if (!overflow && !unreachable && best != FX_INF && !exact) {
             __syncthreads();
             reset_slot(S, field, dirty, P.dirty_n, P.cells, H);
-            best = run_pass<METRIC>(P, S, s_lut, field, dirty, queue, sx, sy, gx, gy, best, -1.f, 0u, &hit);
+            best = run_pass<METRIC>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, best, -1.f, 0u, &hit);
             passes++;
             overflow = (S.flags & FLAG_OVERFLOW) != 0;
         }
