@@ -15,7 +15,7 @@ FX_EUCLID_WS = 2378
 FX_EUCLID_WD = 3363
 
 # every symbol include/fuxi_b200.h declares (tests/test_boundary.py checks the .so exports all of them)
-SYMBOLS = ["fx_create", "fx_destroy", "fx_last_error", "fx_version", "fx_launch_count", "fx_set_search_tuning",
+SYMBOLS = ["fx_create", "fx_destroy", "fx_last_error", "fx_version", "fx_launch_count", "fx_set_search_tuning", "fx_canon_successors",
            "fx_project", "fx_inflate", "fx_edt", "fx_search_batch", "fx_field", "fx_field_relax", "fx_field_status",
            "fx_search_stats", "fx_plan_host", "fx_map_host", "fx_halo_merge"]
 

@@ -668,6 +668,12 @@ extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int 
     return FX_OK;
 }
 
+extern "C" int fx_canon_successors(int code, int moves)
+{
+    if (code < 0 || code > 8 || moves < 0 || moves > 255) return FX_ERR_ARG;
+    return (int)fx_canon_succ((unsigned)code, (unsigned)moves);
+}
+
 /* tuning builds only (-DFX_PHASE_CLOCKS): cycles per dependent step, summed over warp 0 of every CTA */
 extern "C" int fx_search_phase_clocks(fx_context *ctx, int64_t *h_8)
 {

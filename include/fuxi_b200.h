@@ -102,6 +102,13 @@ int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int H,
                     int32_t *cost_i, double *cost_f, int32_t *path_xy, int32_t *path_len, int max_path,
                     void *stream);
 
+/* Successor rule of the batched search, exposed for parity tests (pure host function, no GPU needed).
+ * Replaces: scripts/jps1.py:49-93 `nodeNeighbours` (natural + forced neighbours of a cell given the direction it
+ * was reached by), in single-step form.  code: 0..7 = arrival direction in the order (-1,0) (+1,0) (0,-1) (0,+1)
+ * (-1,-1) (-1,+1) (+1,-1) (+1,+1), 8 = the start cell; moves: bit d set iff `not blocked(c, direction d)`
+ * (scripts/jps1.py:14-31).  Returns the bit mask of directions the cell relaxes, or FX_ERR_ARG. */
+int fx_canon_successors(int code, int moves);
+
 /* Cost-from-source field: field[x*H+y] = cost of the cheapest legal path source -> (x,y), -1 if none
  * (int32, same units as cost_i).  The source may sit on an obstacle (jps1.py never tests it). */
 int fx_field(fx_context *ctx, const uint8_t *grid, int W, int H, int sx, int sy, int metric,
