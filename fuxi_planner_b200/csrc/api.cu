@@ -52,7 +52,7 @@ extern "C" int fx_create(int device, fx_context **out)
     if (e == cudaSuccess) e = cudaMemset(ctx->counters, 0, 16 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->fstate, 32 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(ctx->fstate, 0, 32 * sizeof(unsigned));
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->edt_flag, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->edt_flag, 4 * sizeof(int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         fx_set_err(nullptr, FX_ERR_CUDA, "context allocation: %s", cudaGetErrorString(e));

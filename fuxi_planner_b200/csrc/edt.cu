@@ -18,8 +18,9 @@
 
 // ---- pass 1 -------------------------------------------------------------------------------------
 // one warp per row; smem per warp: (H+31)/32 mask words + 2 * that for the prefix arrays
-__global__ void __launch_bounds__(256) k_edt_rows(const uint8_t *__restrict__ occ, uint16_t *__restrict__ g, int W, int H)
+__global__ void __launch_bounds__(256) k_edt_rows(const uint8_t *__restrict__ occ, uint16_t *__restrict__ g, int W, int H, const int *__restrict__ run_flag)
 {
+    if (run_flag && *run_flag == 0) return;  // fallback of the bit-parallel path: only when it gave up
     extern __shared__ unsigned sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int nwords = (H + 31) / 32;
@@ -156,8 +157,9 @@ __global__ void __launch_bounds__(256) k_edt_cols_window(const uint16_t *__restr
 #define EDT_TX 64
 #define EDT_TYC 128
 __global__ void __launch_bounds__(256) k_edt_cols_tile(const uint16_t *__restrict__ g, int32_t *__restrict__ out, int W, int H,
-                                                       int *__restrict__ flag)
+                                                       int *__restrict__ flag, const int *__restrict__ run_flag)
 {
+    if (run_flag && *run_flag == 0) return;
     __shared__ __align__(16) uint16_t tile[EDT_TX + 2 * EDT_WIN][EDT_TYC];
     const int x0 = blockIdx.y * EDT_TX, y0 = blockIdx.x * EDT_TYC;
     constexpr int ROWS = EDT_TX + 2 * EDT_WIN;
@@ -244,6 +246,229 @@ __global__ void __launch_bounds__(128) k_edt_cols_exact(const uint16_t *__restri
     }
 }
 
+// ---- dense-map fast path: bit-parallel exact EDT ----------------------------------------------------
+// dist^2(x,y) = min over row offsets d of d^2 + g(x+-d, y)^2 with g the integer distance to the nearest occupied cell
+// in that row, so dist^2 <= D  <=>  some (d, r) with d^2 + r^2 <= D has B_r(x+-d, y) set, where B_r is the row's
+// occupancy mask dilated by r along y.  Walking the distinct values D = d^2 + r^2 in increasing order and OR-ing the
+// masks of the pairs with d^2 + r^2 == D settles 32 cells per operation: the level at which a cell's bit first turns
+// on IS its exact squared distance.  Up to EDT_R (cells farther than that from every obstacle are rare on the maps
+// this path is for: they go to a fix-up list; if that list overflows the grid is redone by the windowed path above).
+//   k_edt_pack: occupancy bytes -> bit words along y (268 MB -> 33 MB at 16384^2)
+//   k_edt_bits: one CTA per 64 x 256-cell tile; shared memory holds B_0..B_R for the tile's rows + R halo rows
+//               (built from three-word windows with funnel shifts), the per-cell level index, and the output is
+//               written with 16-byte streaming stores.  Traffic: bits in, int32 out -- the algorithmic 5 B/cell.
+//   k_edt_fix:  brute-force search on the bit grid for the listed cells.
+#define EDT_R 10
+#define EDT_BT_ROWS 64
+#define EDT_BT_WORDS 8
+#define EDT_MAX_PAIRS 128
+#define EDT_MAX_LEVELS 80
+#define EDT_BITS_SMEM (4 * (EDT_R + 1) * (EDT_BT_ROWS + 2 * EDT_R) * EDT_BT_WORDS + 4 * (EDT_BT_ROWS + 2 * EDT_R) * (EDT_BT_WORDS + 2))
+// distinct D = d^2 + r^2 (0 <= d, r <= EDT_R) in increasing order, limited to D <= EDT_R^2 (beyond that a pair with a
+// larger d or r, which the tile does not hold, could win); built at compile time so that the level walk is straight-line
+// code with immediate shared-memory offsets
+struct EdtLevels {
+    int nlevels, npairs;
+    int D[EDT_MAX_LEVELS];
+    int start[EDT_MAX_LEVELS + 1];
+    int pd[EDT_MAX_PAIRS], pr[EDT_MAX_PAIRS];
+};
+__host__ __device__ constexpr EdtLevels edt_make_levels()
+{
+    EdtLevels h{};
+    int np = 0, nl = 0;
+    for (int D = 0; D <= EDT_R * EDT_R; D++) {
+        bool any = false;
+        for (int d = 0; d <= EDT_R; d++)
+            for (int r = 0; r <= EDT_R; r++)
+                if (d * d + r * r == D) {
+                    if (!any) { h.D[nl] = D; h.start[nl] = np; any = true; }
+                    h.pd[np] = d; h.pr[np] = r; np++;
+                }
+        if (any) nl++;
+    }
+    h.start[nl] = np;
+    h.nlevels = nl; h.npairs = np;
+    return h;
+}
+static_assert(edt_make_levels().nlevels <= EDT_MAX_LEVELS && edt_make_levels().npairs <= EDT_MAX_PAIRS, "EDT level table sizes");
+
+// OR of the masks of pairs [P, PEND): base points at T[0][tile row][word]
+template <int P, int PEND>
+__device__ __forceinline__ unsigned edt_pairs(const unsigned *__restrict__ base)
+{
+    if constexpr (P >= PEND) return 0u;
+    else {
+        constexpr EdtLevels tab = edt_make_levels();
+        constexpr int ROWS = EDT_BT_ROWS + 2 * EDT_R;
+        constexpr int d = tab.pd[P], r = tab.pr[P];
+        constexpr int offA = (r * ROWS - d) * EDT_BT_WORDS, offB = (r * ROWS + d) * EDT_BT_WORDS;
+        if constexpr (d == 0) return base[offA] | edt_pairs<P + 1, PEND>(base);
+        else return base[offA] | base[offB] | edt_pairs<P + 1, PEND>(base);
+    }
+}
+// level LV settles the cells in `nw`; their squared distance D (a compile-time constant) is recorded bit-sliced:
+// plane k collects the cells whose D has bit k set -- no per-cell work, no divergence
+template <int LV>
+__device__ __forceinline__ void edt_levels(const unsigned *__restrict__ base, unsigned &done, unsigned (&pl)[7])
+{
+    constexpr EdtLevels tab = edt_make_levels();
+    if constexpr (LV < tab.nlevels) {
+        const unsigned nw = edt_pairs<tab.start[LV], tab.start[LV + 1]>(base) & ~done;
+        done |= nw;
+        constexpr int D = tab.D[LV];
+        static_assert(D < 128, "seven bit planes");
+#pragma unroll
+        for (int k = 0; k < 7; k++)
+            if ((D >> k) & 1) pl[k] |= nw;
+        if (done != 0xFFFFFFFFu) edt_levels<LV + 1>(base, done, pl);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_edt_pack(const uint8_t *__restrict__ occ, unsigned *__restrict__ bits, size_t nwords)
+{
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (size_t)gridDim.x * blockDim.x) {
+        const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(occ) + 2 * w), b = __ldcs(reinterpret_cast<const uint4 *>(occ) + 2 * w + 1);
+        const unsigned v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        unsigned m = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const unsigned nz = __vcmpne4(v[i], 0u) & 0x01010101u;
+            m |= (((nz * 0x01020408u) >> 24) & 0xFu) << (4 * i);
+        }
+        bits[w] = m;
+    }
+}
+
+__global__ void __launch_bounds__(EDT_BT_ROWS * EDT_BT_WORDS) k_edt_bits(const unsigned *__restrict__ bits, int32_t *__restrict__ out, int W, int HW,
+                                                                         unsigned *__restrict__ fix_list, unsigned *__restrict__ fix_count, unsigned fix_cap,
+                                                                         int *__restrict__ flag)
+{
+    __shared__ unsigned s_cnt, s_base;
+    __shared__ unsigned s_list[1024];  // unresolved cells of this tile, (row << 8 | column); more than that: give up (flag)
+    if (threadIdx.x == 0) s_cnt = 0;
+    constexpr int ROWS = EDT_BT_ROWS + 2 * EDT_R, TW = EDT_BT_WORDS;
+    extern __shared__ __align__(16) unsigned char edt_smem[];
+    unsigned(*T)[ROWS][TW] = reinterpret_cast<unsigned(*)[ROWS][TW]>(edt_smem);                                   // [EDT_R + 1]
+    unsigned(*raw)[TW + 2] = reinterpret_cast<unsigned(*)[TW + 2]>(edt_smem + sizeof(unsigned) * (EDT_R + 1) * ROWS * TW);
+    const int x0 = blockIdx.y * EDT_BT_ROWS, w0 = blockIdx.x * TW;
+    const int tid = threadIdx.x;
+    // raw occupancy words of the tile + halo (zero outside the grid)
+    for (int i = tid; i < ROWS * (TW + 2); i += blockDim.x) {
+        const int rr = i / (TW + 2), ww = i - rr * (TW + 2);
+        const int x = x0 - EDT_R + rr, w = w0 - 1 + ww;
+        raw[rr][ww] = (x >= 0 && x < W && w >= 0 && w < HW) ? __ldg(bits + (size_t)x * HW + w) : 0u;
+    }
+    __syncthreads();
+    // B_r for r = 0..EDT_R from a three-word window (exact for the centre word while r <= 32)
+    for (int i = tid; i < ROWS * TW; i += blockDim.x) {
+        const int rr = i / TW, ww = i - rr * TW;
+        unsigned L = raw[rr][ww], C = raw[rr][ww + 1], R = raw[rr][ww + 2];
+        T[0][rr][ww] = C;
+#pragma unroll
+        for (int r = 1; r <= EDT_R; r++) {
+            const unsigned nl = L | (L << 1) | __funnelshift_r(L, C, 1);
+            const unsigned nc = C | __funnelshift_l(L, C, 1) | __funnelshift_r(C, R, 1);
+            const unsigned nr = R | __funnelshift_l(C, R, 1) | (R >> 1);
+            L = nl; C = nc; R = nr;
+            T[r][rr][ww] = C;
+        }
+    }
+    __syncthreads();
+    // level walk + write-out: thread = (row, word) = 32 cells = 128 contiguous output bytes
+    {
+        const int row = tid / TW, ww = tid - row * TW, tr = row + EDT_R;
+        const int x = x0 + row, w = w0 + ww;
+        if (x < W && w < HW) {
+            unsigned done = 0;
+            unsigned pl[7] = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            edt_levels<0>(&T[0][tr][ww], done, pl);
+            int4 *dst = reinterpret_cast<int4 *>(out + ((size_t)x * HW + w) * 32);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                unsigned acc = 0;  // four cells, one byte each
+#pragma unroll
+                for (int k = 0; k < 7; k++) acc |= ((((pl[k] >> (4 * j)) & 0xFu) * 0x00204081u) & 0x01010101u) << k;
+                const unsigned dn = done >> (4 * j);
+                int4 v;
+                v.x = (dn & 1u) ? (int)(acc & 0xFFu) : 0x7FFFFFFF;
+                v.y = (dn & 2u) ? (int)((acc >> 8) & 0xFFu) : 0x7FFFFFFF;
+                v.z = (dn & 4u) ? (int)((acc >> 16) & 0xFFu) : 0x7FFFFFFF;
+                v.w = (dn & 8u) ? (int)(acc >> 24) : 0x7FFFFFFF;
+                __stcs(dst + j, v);
+            }
+            unsigned um = ~done;  // farther than EDT_R from every obstacle: fix-up list
+            while (um) {
+                const int b = __ffs(um) - 1;
+                um &= um - 1;
+                const unsigned pos = atomicAdd(&s_cnt, 1u);
+                if (pos < 1024u) s_list[pos] = ((unsigned)row << 8) | (unsigned)(ww * 32 + b);
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned cnt = s_cnt;
+    if (cnt == 0) return;
+    if (cnt > 1024u) { if (tid == 0) *flag = 1; return; }  // a sparse tile: the windowed path redoes the grid
+    if (tid == 0) s_base = atomicAdd(fix_count, cnt);
+    __syncthreads();
+    for (unsigned i = tid; i < cnt; i += blockDim.x) {
+        const size_t pos = (size_t)s_base + i;
+        if (pos < fix_cap) {
+            fix_list[2 * pos] = (unsigned)(x0 + (int)(s_list[i] >> 8));
+            fix_list[2 * pos + 1] = (unsigned)(w0 * 32 + (int)(s_list[i] & 0xFFu));
+        }
+    }
+}
+
+// nearest set bit to column y in one row of the bit grid, looking no farther than `lim` cells; returns the distance or -1
+__device__ int edt_row_nearest(const unsigned *__restrict__ rowbits, int HW, int y, int lim)
+{
+    const int w = y >> 5, b = y & 31;
+    int best = -1;
+    {
+        const unsigned m = rowbits[w];
+        const unsigned below = m & (0xFFFFFFFFu >> (31 - b)), above = m >> b;
+        if (below) best = b - (31 - __clz(below));
+        if (above) { const int d = __ffs(above) - 1; if (best < 0 || d < best) best = d; }
+    }
+    for (int k = 1; (k - 1) * 32 < lim && (best < 0 || (k - 1) * 32 < best); k++) {
+        if (w - k >= 0) { const unsigned m = rowbits[w - k]; if (m) { const int d = y - ((w - k) * 32 + 31 - __clz(m)); if (best < 0 || d < best) best = d; } }
+        if (w + k < HW) { const unsigned m = rowbits[w + k]; if (m) { const int d = (w + k) * 32 + __ffs(m) - 1 - y; if (best < 0 || d < best) best = d; } }
+    }
+    return (best >= 0 && best <= lim) ? best : -1;
+}
+
+__global__ void __launch_bounds__(128) k_edt_fix(const unsigned *__restrict__ bits, int32_t *__restrict__ out, int W, int HW,
+                                                 const unsigned *__restrict__ fix_list, const unsigned *__restrict__ fix_count, unsigned fix_cap,
+                                                 int *__restrict__ flag)
+{
+    const unsigned n = *fix_count;
+    if (n > fix_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) *flag = 1; return; }  // too many: the windowed path redoes the grid
+    const int H = HW * 32;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int x = (int)fix_list[2 * (size_t)i], y = (int)fix_list[2 * (size_t)i + 1];
+        long long best = (long long)1 << 40;
+        for (int d = 0; (long long)d * d < best && (x - d >= 0 || x + d < W); d++) {
+            const long long room = best - (long long)d * d;
+            int lim = H;
+            if (room < (long long)H * H) { lim = (int)sqrtf((float)room) + 1; if (lim > H) lim = H; }
+            if (x - d >= 0) { const int g = edt_row_nearest(bits + (size_t)(x - d) * HW, HW, y, lim); if (g >= 0) best = min(best, (long long)d * d + (long long)g * g); }
+            if (d > 0 && x + d < W) { const int g = edt_row_nearest(bits + (size_t)(x + d) * HW, HW, y, lim); if (g >= 0) best = min(best, (long long)d * d + (long long)g * g); }
+        }
+        out[(size_t)x * H + y] = best > 0x7FFFFFFFLL ? 0x7FFFFFFF : (int32_t)best;
+    }
+}
+
+static int edt_upload_levels(fx_context *ctx)
+{
+    static bool done[64] = {false};
+    if (ctx->device >= 0 && ctx->device < 64 && done[ctx->device]) return FX_OK;
+    FX_CUDA(ctx, cudaFuncSetAttribute(k_edt_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, EDT_BITS_SMEM));
+    if (ctx->device >= 0 && ctx->device < 64) done[ctx->device] = true;
+    return FX_OK;
+}
+
 extern "C" int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W, int H, void *stream)
 {
     if (!ctx) return FX_ERR_ARG;
@@ -262,7 +487,43 @@ extern "C" int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W
         FX_CUDA(ctx, cudaMalloc(&ctx->edt_t, cells * 2));
         ctx->edt_cap = cells;
     }
-    FX_CUDA(ctx, cudaMemsetAsync(ctx->edt_flag, 0, sizeof(int), st));
+    FX_CUDA(ctx, cudaMemsetAsync(ctx->edt_flag, 0, 4 * sizeof(int), st));
+    if (H % 32 == 0 && ((uintptr_t)occ & 15u) == 0 && ((uintptr_t)dist2 & 15u) == 0) {
+        // dense-map fast path; falls through to the windowed path (conditionally, on the device flag) if too many
+        // cells are farther than EDT_R from every obstacle
+        int rc = edt_upload_levels(ctx);
+        if (rc) return rc;
+        const int HW = H / 32;
+        const size_t nw = (size_t)W * HW;
+        unsigned *bitsb = reinterpret_cast<unsigned *>(ctx->edt_s);        // scratch reuse: cells*2 bytes >= cells/8
+        unsigned *fix_list = reinterpret_cast<unsigned *>(ctx->edt_t);     // cells*2 bytes -> cells/4 entries of 8 bytes
+        unsigned *fix_count = reinterpret_cast<unsigned *>(ctx->edt_flag) + 1;
+        size_t cap = cells / 4; if (cap > (1u << 22)) cap = 1u << 22;
+        FX_CUDA(ctx, cudaMemsetAsync(fix_count, 0, sizeof(unsigned), st));
+        int pb = (int)((nw + 255) / 256); if (pb > ctx->sm_count * 16) pb = ctx->sm_count * 16;
+        k_edt_pack<<<pb, 256, 0, st>>>(occ, bitsb, nw);
+        FX_LAUNCH_CHECK(ctx);
+        dim3 gt((HW + EDT_BT_WORDS - 1) / EDT_BT_WORDS, (W + EDT_BT_ROWS - 1) / EDT_BT_ROWS);
+        k_edt_bits<<<gt, EDT_BT_ROWS * EDT_BT_WORDS, EDT_BITS_SMEM, st>>>(bitsb, dist2, W, HW, fix_list, fix_count, (unsigned)cap, ctx->edt_flag);
+        FX_LAUNCH_CHECK(ctx);
+        k_edt_fix<<<ctx->sm_count * 4, 128, 0, st>>>(bitsb, dist2, W, HW, fix_list, fix_count, (unsigned)cap, ctx->edt_flag);
+        FX_LAUNCH_CHECK(ctx);
+        // the windowed path below runs only if the flag was raised
+        const int nwords = (H + 31) / 32;
+        int warps = 8;
+        size_t smem = (size_t)warps * 3 * nwords * 4;
+        while (smem > 48 * 1024 && warps > 1) { warps >>= 1; smem = (size_t)warps * 3 * nwords * 4; }
+        int blocks = (W + warps - 1) / warps;
+        if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+        k_edt_rows<<<blocks, warps * 32, smem, st>>>(occ, ctx->edt_g, W, H, ctx->edt_flag);
+        FX_LAUNCH_CHECK(ctx);
+        dim3 g2((H + EDT_TYC - 1) / EDT_TYC, (W + EDT_TX - 1) / EDT_TX);
+        k_edt_cols_tile<<<g2, 256, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_flag + 2, ctx->edt_flag);
+        FX_LAUNCH_CHECK(ctx);
+        k_edt_cols_exact<<<(H + 127) / 128, 128, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_s, ctx->edt_t, ctx->edt_flag + 2);
+        FX_LAUNCH_CHECK(ctx);
+        return FX_OK;
+    }
     const int nwords = (H + 31) / 32;
     // warps per CTA limited by shared memory (3 arrays of nwords per warp)
     int warps = 8;
@@ -270,13 +531,13 @@ extern "C" int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W
     while (smem > 48 * 1024 && warps > 1) { warps >>= 1; smem = (size_t)warps * 3 * nwords * 4; }
     int blocks = (W + warps - 1) / warps;
     if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-    k_edt_rows<<<blocks, warps * 32, smem, st>>>(occ, ctx->edt_g, W, H);
+    k_edt_rows<<<blocks, warps * 32, smem, st>>>(occ, ctx->edt_g, W, H, nullptr);
     FX_LAUNCH_CHECK(ctx);
     int b2 = (int)((cells + 255) / 256);
     if (b2 > ctx->sm_count * 16) b2 = ctx->sm_count * 16;
     if (H % 8 == 0) {
         dim3 gt((H + EDT_TYC - 1) / EDT_TYC, (W + EDT_TX - 1) / EDT_TX);
-        k_edt_cols_tile<<<gt, 256, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_flag);
+        k_edt_cols_tile<<<gt, 256, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_flag, nullptr);
     } else {
         k_edt_cols_window<<<b2, 256, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_flag);
     }

@@ -97,13 +97,32 @@ def test_inflate_matches_reference_formulation_on_padded_map(fx, dev, oracle, ma
 
 # ------------------------------------------------------------------------------------------ EDT
 @pytest.mark.parametrize("shape,fill", [((512, 512), 0.2), ((300, 272), 0.001), ((64, 48), 0.0), ((1000, 37), 0.01),
-                                        ((1, 100), 0.05), ((2048, 1024), 0.00001)])
+                                        ((1, 100), 0.05), ((2048, 1024), 0.00001),
+                                        # H % 32 == 0: the bit-parallel path (dense: all resolved in-tile; 0.5-2 %: fix-up
+                                        # list; sparse tiles: falls back to the windowed path on the device flag)
+                                        ((1024, 1024), 0.02), ((256, 64), 0.05), ((1100, 2048), 0.005), ((96, 32), 0.3),
+                                        ((130, 96), 1.0), ((2048, 4096), 0.02), ((777, 1056), 0.0004)])
 def test_edt_exact(fx, dev, oracle, shape, fill):
     rng = np.random.default_rng(int(fill * 1e6) + shape[0])
     m = (rng.random(shape) < fill).astype(np.uint8)
     want = oracle.edt(m)
     got = fx.edt(_t(m, dev)).cpu().numpy()
     assert np.array_equal(got, want)
+
+
+def test_edt_single_obstacle_and_clusters(fx, dev, oracle):
+    m = np.zeros((128, 128), dtype=np.uint8)
+    m[5, 120] = 1
+    assert np.array_equal(fx.edt(_t(m, dev)).cpu().numpy(), oracle.edt(m))
+    # dense blobs next to large empty areas: resolved tiles, fix-up cells and (here) sparse tiles in one grid
+    rng = np.random.default_rng(3)
+    m = np.zeros((512, 1024), dtype=np.uint8)
+    m[:200, :300] = rng.random((200, 300)) < 0.1
+    m[300:330, 900:] = 1
+    assert np.array_equal(fx.edt(_t(m, dev)).cpu().numpy(), oracle.edt(m))
+    m[:, :] = 0
+    m[::9, ::11] = 1            # every cell within sqrt(4^2 + 5^2) of an obstacle: nothing left for the fix-up list
+    assert np.array_equal(fx.edt(_t(m, dev)).cpu().numpy(), oracle.edt(m))
 
 
 def test_edt_vs_scipy(fx, dev):
