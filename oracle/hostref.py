@@ -126,6 +126,22 @@ def map_line_col(p2, p1, mapu):
     return True
 
 
+def shortcut_path(path, mapu):
+    """scripts/global_planner_ccst.py:515-521: greedy line-of-sight shortcutting of the jump-point list -- drop the
+    middle point ii whenever map_line_col sees no occupied cell between its neighbours, looking only at the part of
+    the map inside their bounding box (exclusive upper edges, so axis-aligned pairs always "see" each other)."""
+    pts = np.array(path)
+    ii = 1
+    while ii < len(pts) - 1:
+        a, b = pts[ii - 1], pts[ii + 1]
+        crop = mapu[min(a[0], b[0]):max(a[0], b[0]), min(a[1], b[1]):max(a[1], b[1])]
+        if map_line_col(pts[ii + 1], pts[ii - 1], crop):
+            pts = np.delete(pts, ii, axis=0)
+        else:
+            ii += 1
+    return pts.tolist()
+
+
 # --------------------------------------------------------------------------- a15 / a16
 def body_to_earth_frame(ii, jj, kk):
     """scripts/utils.py:21-28: R = Rz(kk) * Ry(jj) * Rx(ii)."""

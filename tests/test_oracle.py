@@ -2,6 +2,8 @@
 (tests/golden/make_golden.py).  CPU only."""
 import hashlib
 
+import os
+
 import numpy as np
 import pytest
 
@@ -160,6 +162,23 @@ def test_hostref_vs_reference_functions(oracle, hostfn_golden):
             continue
         got = oracle.hostref.map_line_col(np.array(a[0:2], dtype=float), np.array(a[2:4], dtype=float), g)
         assert int(bool(got)) == want, a
+
+
+def test_shortcut_restatement_vs_reference_golden(oracle, maps):
+    """hostref.shortcut_path against the vectors made with the reference's own map_line_col (make_shortcut_golden.py)."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "shortcut_golden.json")))
+    n = 0
+    for name, rows in g["maps"].items():
+        m = maps[name].astype(np.float64)
+        for r in rows[::3]:
+            assert oracle.hostref.shortcut_path(r["path"], m) == r["out"], (name, r["path"])
+            n += 1
+    for r in g["random"]:
+        m = np.unpackbits(np.array(r["grid"], dtype=np.uint8))[:r["W"] * r["H"]].reshape(r["W"], r["H"]).astype(np.float64)
+        assert oracle.hostref.shortcut_path(r["path"], m) == r["out"], r["path"]
+        n += 1
+    assert n > 200
 
 
 def test_transform_affine_equivalence(oracle):
