@@ -17,7 +17,25 @@ FX_EUCLID_WD = 3363
 # every symbol include/fuxi_b200.h declares (tests/test_boundary.py checks the .so exports all of them)
 SYMBOLS = ["fx_create", "fx_destroy", "fx_last_error", "fx_version", "fx_launch_count", "fx_set_search_tuning", "fx_canon_successors",
            "fx_project", "fx_inflate", "fx_edt", "fx_search_batch", "fx_field", "fx_field_relax", "fx_field_status",
-           "fx_search_stats", "fx_plan_host", "fx_map_host", "fx_halo_merge"]
+           "fx_search_stats", "fx_plan_host", "fx_map_host", "fx_halo_merge",
+           "fx_grid_decode", "fx_grid_encode", "fx_grid_paste", "fx_grid_bbox", "fx_relocate_goal", "fx_path_post",
+           "fx_replan_host", "fx_replan_grid_host"]
+
+
+class ReplanIn(C.Structure):
+    """fx_replan_in of include/fuxi_b200.h"""
+    _fields_ = [("variant", C.c_int32), ("layout", C.c_int32), ("crop", C.c_int32), ("ifa", C.c_int32), ("hchoice", C.c_int32),
+                ("shortcut", C.c_int32), ("origin_x", C.c_double), ("origin_y", C.c_double), ("reso", C.c_double),
+                ("start_x", C.c_double), ("start_y", C.c_double), ("goal_x", C.c_double), ("goal_y", C.c_double),
+                ("drop_px", C.c_double), ("drop_py", C.c_double), ("drop_pz", C.c_double), ("drop_radius", C.c_double)]
+
+
+class ReplanOut(C.Structure):
+    """fx_replan_out of include/fuxi_b200.h"""
+    _fields_ = [("W", C.c_int32), ("H", C.c_int32), ("paste_x", C.c_int32), ("paste_y", C.c_int32), ("start_x", C.c_int32),
+                ("start_y", C.c_int32), ("goal_x", C.c_int32), ("goal_y", C.c_int32), ("goal_moved", C.c_int32),
+                ("end_occu", C.c_int32), ("skipped", C.c_int32), ("raw_len", C.c_int32), ("path_len", C.c_int32),
+                ("cost_i", C.c_int32), ("cost_f", C.c_double), ("origin_x", C.c_double), ("origin_y", C.c_double)]
 
 _lib = None
 
@@ -55,6 +73,15 @@ def load():
     lib.fx_search_stats.argtypes = [vp, C.POINTER(i64)]
     lib.fx_plan_host.argtypes = [vp, vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp, i32]
     lib.fx_map_host.argtypes = [vp, vp, i64, i32, C.POINTER(f32), f32, f32, f32, f32, f32, i32, i32, i32, i32, vp]
+    f64p = C.POINTER(C.c_double)
+    lib.fx_grid_decode.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp]
+    lib.fx_grid_encode.argtypes = [vp, vp, i32, i32, vp, vp]
+    lib.fx_grid_paste.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp]
+    lib.fx_grid_bbox.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    lib.fx_relocate_goal.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp]
+    lib.fx_path_post.argtypes = [vp, vp, i32, i32, vp, vp, i32, i32, i32, f64p, f64p, vp, vp, vp, vp]
+    lib.fx_replan_host.argtypes = [vp, vp, i32, i32, C.POINTER(ReplanIn), C.POINTER(ReplanOut), vp, vp, i32]
+    lib.fx_replan_grid_host.argtypes = [vp, vp, C.c_size_t, C.POINTER(i32), C.POINTER(i32)]
     for s in SYMBOLS:
         if s not in ("fx_last_error", "fx_launch_count"):
             getattr(lib, s).restype = i32

@@ -168,7 +168,122 @@ def field_status(ctx=None):
     return lv.value, st.value
 
 
+# ---------------------------------------------------------------------------------- grid assembly / path post-processing
+def grid_decode(msg, width, height, out=None, window=None, paste_at=(0, 0), ctx=None):
+    """OccupancyGrid.data (int8 CUDA tensor, index y*width + x) -> uint8 [x][y] with 100 -> 1, -1 -> 0
+    (map_callback, global_planner_st.py:15-20), optionally only ``window = (x0, y0, w, h)`` of it, pasted at
+    ``paste_at`` of ``out`` (which must then be pre-zeroed by the caller where the window does not reach)."""
+    if not (isinstance(msg, torch.Tensor) and msg.is_cuda and msg.dtype == torch.int8 and msg.numel() == width * height):
+        raise FuxiError("msg must be an int8 CUDA tensor of width*height elements")
+    msg = msg.contiguous()
+    ctx = _ctx(ctx, msg)
+    x0, y0, w, h = window if window is not None else (0, 0, int(width), int(height))
+    if out is None:
+        out = torch.zeros((w + paste_at[0], h + paste_at[1]), dtype=torch.uint8, device=msg.device)
+    ctx.check(ctx.lib.fx_grid_decode(ctx.handle, _ptr(msg), int(width), int(height), int(x0), int(y0), int(w), int(h), _ptr(out),
+                                     out.shape[0], out.shape[1], int(paste_at[0]), int(paste_at[1]), _stream()), "fx_grid_decode")
+    return out
+
+
+def grid_encode(grid, ctx=None):
+    """uint8 [x][y] -> OccupancyGrid.data int8 (publish_map, global_planner_st.py:102-115): 1 -> 100, y-major."""
+    grid = _u8_grid(grid)
+    ctx = _ctx(ctx, grid)
+    W, H = grid.shape
+    out = torch.empty(W * H, dtype=torch.int8, device=grid.device)
+    ctx.check(ctx.lib.fx_grid_encode(ctx.handle, _ptr(grid), W, H, _ptr(out), _stream()), "fx_grid_encode")
+    return out
+
+
+def grid_paste(src, dst, window=None, paste_at=(0, 0), ctx=None):
+    """dst[px+i, py+j] = src[x0+i, y0+j] (overwrite), the slice assignments of the pre-map merge / pad step."""
+    src, ctx = _u8_grid(src), _ctx(ctx, src)
+    if not (dst.is_cuda and dst.dtype == torch.uint8 and dst.dim() == 2 and dst.is_contiguous()):
+        raise FuxiError("dst must be a contiguous uint8 CUDA tensor [W][H]")
+    x0, y0, w, h = window if window is not None else (0, 0, src.shape[0], src.shape[1])
+    ctx.check(ctx.lib.fx_grid_paste(ctx.handle, _ptr(src), src.shape[0], src.shape[1], int(x0), int(y0), int(w), int(h), _ptr(dst),
+                                    dst.shape[0], dst.shape[1], int(paste_at[0]), int(paste_at[1]), _stream()), "fx_grid_paste")
+    return dst
+
+
+def grid_bbox(a, width=None, height=None, ctx=None):
+    """int32 CUDA tensor {min x, max x, min y, max y} of the non-zero cells: of a uint8 [x][y] array, or (width/height
+    given) of a raw int8 OccupancyGrid message (non-zero after the 100/-1 mapping)."""
+    ctx = _ctx(ctx, a)
+    out = torch.empty(4, dtype=torch.int32, device=a.device)
+    if width is None:
+        a = _u8_grid(a)
+        ctx.check(ctx.lib.fx_grid_bbox(ctx.handle, _ptr(a), a.shape[0], a.shape[1], 0, _ptr(out), _stream()), "fx_grid_bbox")
+    else:
+        a = a.contiguous()
+        ctx.check(ctx.lib.fx_grid_bbox(ctx.handle, _ptr(a), int(width), int(height), 1, _ptr(out), _stream()), "fx_grid_bbox")
+    return out
+
+
+def relocate_goal(grid, goal, ifa=1, variant="st", ctx=None):
+    """Goal on an obstacle -> nearest free cell of its row, else column (global_planner_st.py:268-275).
+    Returns an int32 CUDA tensor {gx, gy, moved, end_occu}."""
+    grid = _u8_grid(grid)
+    ctx = _ctx(ctx, grid)
+    g = torch.tensor([int(goal[0]), int(goal[1]), 0, 0], dtype=torch.int32, device=grid.device)
+    ctx.check(ctx.lib.fx_relocate_goal(ctx.handle, _ptr(grid), grid.shape[0], grid.shape[1], _ptr(g), int(ifa),
+                                       1 if variant == "ccst" else 0, _stream()), "fx_relocate_goal")
+    return g
+
+
+def path_post(grid, path_xy, path_len, shortcut=True, drop=None, world=None, ctx=None):
+    """Path post-processing of the ccmapping planner on Q paths at once (fx_path_post): optional near-vehicle drop
+    ``drop = (px, py, pz, radius)`` (ccst:507-513), line-of-sight shortcutting (ccst:258-283, 515-521), world
+    coordinates ``world = (reso, origin_x, origin_y, off_x, off_y)``.  Returns (out_xy, out_len, out_world | None)."""
+    grid = _u8_grid(grid)
+    ctx = _ctx(ctx, grid)
+    path_xy = path_xy.to(torch.int32).contiguous()
+    path_len = path_len.to(torch.int32).contiguous()
+    Q, max_path = path_xy.shape[0], path_xy.shape[1]
+    out_xy = torch.empty_like(path_xy)
+    out_len = torch.empty_like(path_len)
+    out_world = torch.empty((Q, max_path, 3), dtype=torch.float64, device=grid.device) if world is not None else None
+    d4 = (C.c_double * 4)(*[float(v) for v in drop]) if drop is not None else None
+    w5 = (C.c_double * 5)(*[float(v) for v in world]) if world is not None else None
+    if drop is not None and world is None:
+        raise FuxiError("drop= needs world= (the drop radius is in world units)")
+    ctx.check(ctx.lib.fx_path_post(ctx.handle, _ptr(grid), grid.shape[0], grid.shape[1], _ptr(path_xy), _ptr(path_len), Q, max_path,
+                                   1 if shortcut else 0, d4, w5, _ptr(out_xy), _ptr(out_len), _ptr(out_world), _stream()),
+              "fx_path_post")
+    return out_xy, out_len, out_world
+
+
 # ---------------------------------------------------------------------------------- host-buffer calls
+def replan_host(map_data, width, height, origin, reso, start_xy, goal_xy, ifa=1, variant="st", hchoice=2, layout="msg",
+                crop=False, shortcut=False, drop=None, max_path=1024, want_grid=False, ctx=None, device=0):
+    """One global replan through fx_replan_host: numpy in, numpy out, one H2D + one D2H + one sync.
+    ``map_data``: OccupancyGrid.data (int8, layout "msg") or a uint8 [x][y] array (layout "array", width = W, height = H).
+    Returns (ReplanOut struct, path cells int32 [k,2], path world float64 [k,3], grid uint8 [W][H] | None)."""
+    ctx = ctx or default_context(device)
+    if layout == "msg":
+        m = np.ascontiguousarray(map_data, dtype=np.int8).reshape(-1)
+    else:
+        m = np.ascontiguousarray(map_data, dtype=np.uint8).reshape(-1)
+    if m.size != int(width) * int(height):
+        raise FuxiError("map has %d cells, expected %d x %d" % (m.size, width, height))
+    rin = _lib.ReplanIn(1 if variant == "ccst" else 0, 0 if layout == "msg" else 1, 1 if crop else 0, int(ifa), int(hchoice),
+                        1 if shortcut else 0, float(origin[0]), float(origin[1]), float(reso), float(start_xy[0]),
+                        float(start_xy[1]), float(goal_xy[0]), float(goal_xy[1]), *(tuple(float(v) for v in drop) if drop else (0.0,) * 4))
+    rout = _lib.ReplanOut()
+    pxy = np.empty((max_path, 2), dtype=np.int32)
+    pw = np.empty((max_path, 3), dtype=np.float64)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    ctx.check(ctx.lib.fx_replan_host(ctx.handle, vp(m), int(width), int(height), C.byref(rin), C.byref(rout), vp(pxy), vp(pw),
+                                     int(max_path)), "fx_replan_host")
+    n = max(int(rout.path_len), 0)
+    grid = None
+    if want_grid and rout.skipped != 2:
+        grid = np.empty((rout.W, rout.H), dtype=np.uint8)
+        ctx.check(ctx.lib.fx_replan_grid_host(ctx.handle, vp(grid), grid.size, None, None), "fx_replan_grid_host")
+    return rout, pxy[:n].copy(), pw[:n].copy(), grid
+
+
+
 def plan_host(grid, starts, goals, metric=2, max_path=512, ctx=None, device=0):
     """numpy in / numpy out through fx_plan_host (H2D + search + D2H inside the call).
     Returns (cost_i int32[Q], cost_f float64[Q], path_xy int32[Q,max_path,2] or None, path_len int32[Q])."""

@@ -70,7 +70,8 @@ extern "C" int fx_destroy(fx_context *ctx)
     cudaDeviceSynchronize();
     void *dev[] = {ctx->fields, ctx->dirty, ctx->queues, ctx->tmp_path, ctx->moves, ctx->counters, ctx->fq, ctx->fstate,
                    ctx->seeds, ctx->seeds_sorted, ctx->seed_hist, ctx->edt_g, ctx->edt_s, ctx->edt_t, ctx->edt_flag,
-                   ctx->d_grid, ctx->d_grid2, ctx->d_q, ctx->d_out_i, ctx->d_out_f, ctx->d_path, ctx->d_pts, ctx->proj_bits, ctx->q_order, ctx->q_ubound, ctx->bfields};
+                   ctx->d_grid, ctx->d_grid2, ctx->d_q, ctx->d_out_i, ctx->d_out_f, ctx->d_path, ctx->d_pts, ctx->proj_bits, ctx->q_order, ctx->q_ubound, ctx->bfields,
+                   ctx->d_msg, ctx->d_rp};
     for (size_t i = 0; i < sizeof(dev) / sizeof(dev[0]); i++)
         if (dev[i]) cudaFree(dev[i]);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -97,17 +98,21 @@ extern "C" int fx_set_search_tuning(fx_context *ctx, int slots, int band0)
     return FX_OK;
 }
 
-template <typename T>
-static int grow(fx_context *ctx, T **p, size_t *cap, size_t want_bytes)
+int fx_grow_bytes(fx_context *ctx, void **p, size_t *cap, size_t want_bytes)
 {
     if (*cap >= want_bytes && *p) return FX_OK;
     if (*p) cudaFree(*p);
     *p = nullptr; *cap = 0;
-    FX_CUDA(ctx, cudaMalloc((void **)p, want_bytes));
+    FX_CUDA(ctx, cudaMalloc(p, want_bytes));
     *cap = want_bytes;
     return FX_OK;
 }
-static int grow_pinned(fx_context *ctx, size_t want)
+template <typename T>
+static int grow(fx_context *ctx, T **p, size_t *cap, size_t want_bytes)
+{
+    return fx_grow_bytes(ctx, (void **)p, cap, want_bytes);
+}
+int fx_grow_pinned(fx_context *ctx, size_t want)
 {
     if (ctx->h_pin_cap >= want && ctx->h_pin) return FX_OK;
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -116,6 +121,7 @@ static int grow_pinned(fx_context *ctx, size_t want)
     ctx->h_pin_cap = want;
     return FX_OK;
 }
+static int grow_pinned(fx_context *ctx, size_t want) { return fx_grow_pinned(ctx, want); }
 
 // Host-buffer planning call: H2D (grid + queries) -> search -> D2H (costs, path lengths, paths).
 // Replaces the whole of `jps1.method(...)` for Q queries (scripts/jps1.py:183-230) from the caller's view.

@@ -68,6 +68,10 @@ struct fx_context {
     int32_t *d_path;            size_t d_path_cap;
     float *d_pts;               size_t d_pts_cap;
     void *h_pin;                size_t h_pin_cap;
+    // fused replan (assemble.cu): raw OccupancyGrid message, small device block {bbox4, goal4, start2, path_len, cost_i, ...}
+    int8_t *d_msg;              size_t d_msg_cap;
+    int32_t *d_rp;              size_t d_rp_cap;
+    int rp_W, rp_H;             // shape of the last planning grid (kept in d_grid2)
     cudaStream_t own_stream;
 };
 
@@ -177,6 +181,8 @@ __device__ __forceinline__ int fx_cidx(int x, int y, int H, int TY)
 #endif
 }
 
+int fx_grow_bytes(fx_context *ctx, void **p, size_t *cap, size_t want_bytes);
+int fx_grow_pinned(fx_context *ctx, size_t want);
 int fx_search_reserve(fx_context *ctx, int W, int H, int max_path);
 // band.cu: LPT query order + per-query upper bounds from the band pass (one warp per query)
 int fx_band_bounds(fx_context *ctx, const uint8_t *grid, int W, int H, const int32_t *starts_xy, const int32_t *goals_xy, int Q,

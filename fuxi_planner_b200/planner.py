@@ -132,3 +132,32 @@ def replan(mapu, map_origin, reso, start_xy, goal_xy, ifa=1, variant="st", hchoi
     cells = res.path(0)
     cost = float(res.cost_i[0]) if hchoice == 1 else float(res.cost_f[0])
     return Replan(cells, path_cells_to_world(cells, reso, asm.origin, variant), cost, moved, asm, grid)
+
+
+def replan_fused(map_data, width, height, map_origin, reso, start_xy, goal_xy, ifa=1, variant="st", hchoice=2, layout="msg",
+                 crop=None, shortcut=None, drop_radius=None, pos_z=0.0, ctx=None, device=0, max_path=1024, want_grid=False):
+    """The same replan in ONE library call (fx_replan_host): the raw OccupancyGrid message goes to the device once,
+    crop / pad / decode / inflate / goal relocation / search / path post-processing run there back to back, and the
+    result comes back in one copy.  Defaults follow the two planners: "ccst" crops to the occupied bounding box
+    (global_planner_ccst.py:36-63), shortcuts the path (ccst:515-521) and drops points within 1.5 m of the vehicle
+    (ccst:507-513); "st" does none of these.  Returns a Replan (grid = host uint8 array when want_grid)."""
+    cc = variant == "ccst"
+    crop = cc if crop is None else crop
+    shortcut = cc if shortcut is None else shortcut
+    drop_radius = (1.5 if cc else 0.0) if drop_radius is None else drop_radius
+    drop = (float(start_xy[0]), float(start_xy[1]), float(pos_z), float(drop_radius)) if drop_radius > 0 else None
+    out, cells, world, grid = api.replan_host(map_data, width, height, map_origin, reso, start_xy, goal_xy, ifa=ifa, variant=variant,
+                                              hchoice=hchoice, layout=layout, crop=crop, shortcut=shortcut, drop=drop,
+                                              max_path=max_path, want_grid=want_grid, ctx=ctx, device=device)
+    asm = Assembly((out.W, out.H), (out.paste_x, out.paste_y), (out.origin_x, out.origin_y), (out.start_x, out.start_y),
+                   (out.goal_x, out.goal_y))
+    if out.skipped or out.path_len <= 0:
+        return Replan(0, None, None, out.goal_moved == 1, asm, grid)
+    cost = float(out.cost_i) if hchoice == 1 else float(out.cost_f)
+    return Replan([tuple(int(v) for v in p) for p in cells.tolist()], world, cost, out.goal_moved == 1, asm, grid)
+
+
+def waypoint_ccst(path_world, global_goal):
+    """global_planner_ccst.py:523-526: blend of the second and third path points, or the goal for short paths."""
+    p = np.asarray(path_world)
+    return (p[1] * 1.4 + p[2] * 0.6) / 2 if len(p) > 2 else np.asarray(global_goal)

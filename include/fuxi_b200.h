@@ -19,6 +19,7 @@
 #ifndef FUXI_B200_H
 #define FUXI_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -147,6 +148,77 @@ int fx_plan_host(fx_context *ctx, const uint8_t *h_grid, int W, int H,
 int fx_map_host(fx_context *ctx, const float *h_pts, int64_t n, int stride_floats, const float *h_affine3x4,
                 float zmin, float zmax, float ox, float oy, float reso, int W, int H,
                 int radius, int step, uint8_t *h_grid_out);
+
+/* ---- (4) planner-side grid assembly on the device ---------------------------------
+ * fx_grid_decode: nav_msgs/OccupancyGrid.data (int8, index y*width + x) -> uint8 array [x][y] with the value
+ * mapping of map_callback, scripts/global_planner_st.py:15-20 (= global_planner_ccst.py:17-24): 100 -> 1, -1 -> 0,
+ * everything else unchanged; fused with the slice paste of st:249-250: the source window
+ * [sx0, sx0+w) x [sy0, sy0+h) of the message lands at dst[px.., py..] of a dW x dH array (cells outside either
+ * array are skipped; dst cells outside the window are left as they are).
+ * fx_grid_encode: the inverse for publishing (publish_map, st:102-115): 1 -> 100, data = mapu.T.flatten().
+ * fx_grid_paste: dst[px+i][py+j] = src[sx0+i][sy0+j] between [x][y] arrays, overwriting -- the slice assignments of
+ * the pre-map merge (st:210-224) and of the pad / shift step.
+ * fx_grid_bbox: {min x, max x, min y, max y} of the non-zero cells (is_msg: of a raw message, value not in {0,-1});
+ * {INT32_MAX, -1, INT32_MAX, -1} if there are none.  Replaces X.nonzero()/np.unique/min/max in
+ * remove_zero_rowscols, scripts/global_planner_ccst.py:42-49.  d_bbox4: device int32[4].
+ * fx_relocate_goal: d_goal4 = device int32[4] {gx, gy, -, -} -> {gx', gy', moved, end_occu}; replaces
+ * st:268-275 / ccst:454-464: a goal on a cell == 1 moves to the nearest cell == 0 of its x-row (lower y on ties),
+ * else of its y-column; moved = -1 if neither has one (the reference raises), -2 if the goal is outside the grid.
+ * end_occu: st (ccst == 0) = moved; ccst = any cell == 1 in [gx-ifa, gx+ifa) x [gy-ifa, gy+ifa). */
+int fx_grid_decode(fx_context *ctx, const int8_t *msg, int width, int height, int sx0, int sy0, int w, int h,
+                   uint8_t *dst, int dW, int dH, int px, int py, void *stream);
+int fx_grid_encode(fx_context *ctx, const uint8_t *grid, int W, int H, int8_t *msg, void *stream);
+int fx_grid_paste(fx_context *ctx, const uint8_t *src, int sW, int sH, int sx0, int sy0, int w, int h,
+                  uint8_t *dst, int dW, int dH, int px, int py, void *stream);
+int fx_grid_bbox(fx_context *ctx, const void *a, int W, int H, int is_msg, int32_t *d_bbox4, void *stream);
+int fx_relocate_goal(fx_context *ctx, const uint8_t *grid, int W, int H, int32_t *d_goal4, int ifa, int ccst, void *stream);
+
+/* ---- (5) path post-processing -----------------------------------------------------
+ * Per path q (path_xy int32 [Q][max_path][2], path_len int32 [Q]; same layout as fx_search_batch writes):
+ *   h_drop4 = {px, py, pz, radius} (HOST, may be NULL; radius <= 0 = off): if the path has more than two points,
+ *     drop every point ii >= 1 whose world position (z = 0) is closer than radius to (px, py, pz)
+ *     -- scripts/global_planner_ccst.py:507-513 (radius 1.5 there);
+ *   shortcut != 0: greedy line-of-sight shortcutting `ii = 1; while ii < len-1: if map_line_col(path[ii+1],
+ *     path[ii-1], mapu[bounding box]) delete ii else ii += 1` -- ccst:258-283 + 515-521, same sampling
+ *     (one sample per integer x strictly between the points, y = rint(slope*x), half-open bounding box), cell == 1;
+ *   out_world (double [Q][max_path][3], may be NULL): (cell + off) * reso + origin, z = 0 -- st:291-296 /
+ *     ccst:487-491; h_world5 = {reso, origin_x, origin_y, off_x, off_y} (HOST; off = (1,1) st, (1,0) ccst).
+ * out_xy may alias path_xy.  out_len[q] = points kept (path_len[q] <= 0 is passed through).  Bit-exact. */
+int fx_path_post(fx_context *ctx, const uint8_t *grid, int W, int H, const int32_t *path_xy, const int32_t *path_len,
+                 int Q, int max_path, int shortcut, const double *h_drop4, const double *h_world5,
+                 int32_t *out_xy, int32_t *out_len, double *out_world, void *stream);
+
+/* ---- (6) one global replan in one call -----------------------------------------------------------
+ * What the planner loops do per iteration between receiving the map and publishing the path:
+ * scripts/global_planner_st.py:226-298 (variant 0) / scripts/global_planner_ccst.py:36-63 + 411-521 (variant 1):
+ * [crop] -> index/pad/shift -> decode+paste -> inflate -> goal relocation -> search -> [near-vehicle drop,
+ * shortcutting] -> world coordinates.  One H2D (the map), one D2H (the result), one synchronisation. */
+typedef struct fx_replan_in {
+    int32_t variant;    /* 0 = st (9-point stencil, index offset -1, path offset [1,1]); 1 = ccst (dense square, 0, [1,0]) */
+    int32_t layout;     /* 0 = h_map is OccupancyGrid.data (int8, y*width + x); 1 = uint8 array [x][y], W = width, H = height */
+    int32_t crop;       /* != 0: crop to the occupied bounding box first (remove_zero_rowscols, ccst:36-63) */
+    int32_t ifa;        /* inflation radius in cells (st: 1, ccst: 2 in the reference) */
+    int32_t hchoice;    /* 1: 10/14 integer metric, 2: Euclidean (the planners pass 2) */
+    int32_t shortcut;   /* != 0: line-of-sight shortcutting of the path (ccst:515-521) */
+    double origin_x, origin_y, reso;                 /* OccupancyGrid.info.origin / resolution */
+    double start_x, start_y, goal_x, goal_y;         /* world coordinates of the vehicle and the goal */
+    double drop_px, drop_py, drop_pz, drop_radius;   /* near-vehicle drop (ccst:507-513); radius <= 0 = off */
+} fx_replan_in;
+typedef struct fx_replan_out {
+    int32_t W, H;                 /* padded planning grid */
+    int32_t paste_x, paste_y;     /* the reference's map_d */
+    int32_t start_x, start_y, goal_x, goal_y;   /* cells in the planning grid; goal after relocation */
+    int32_t goal_moved, end_occu;
+    int32_t skipped;              /* 1: start beyond the map (st:280, no search); 2: empty map (ccst main loop skips) */
+    int32_t raw_len, path_len;    /* turning points found / points after post-processing (<= 0: FX_COST_*) */
+    int32_t cost_i;
+    double cost_f;                /* what jps1.method prints: gscore[goal] */
+    double origin_x, origin_y;    /* world position of cell [0][0] of the planning grid (the shifted map_o) */
+} fx_replan_out;
+int fx_replan_host(fx_context *ctx, const void *h_map, int width, int height, const fx_replan_in *in, fx_replan_out *out,
+                   int32_t *h_path_xy, double *h_path_world, int max_path);
+/* the inflated planning grid of the last fx_replan_host (uint8 [W][H]); h_out may be NULL to query W, H only */
+int fx_replan_grid_host(fx_context *ctx, uint8_t *h_out, size_t cap, int *W, int *H);
 
 #ifdef __cplusplus
 }

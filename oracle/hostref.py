@@ -142,6 +142,87 @@ def shortcut_path(path, mapu):
     return pts.tolist()
 
 
+def near_drop(path_cells, path_world, pos, radius=1.5):
+    """scripts/global_planner_ccst.py:507-513: if the path has more than two points, delete every point ii >= 1 whose
+    world position (z = 0, ``path3``) is closer than ``radius`` to the vehicle ``pos = (px, py, pz)``.
+    Returns (cells, world) after the deletion."""
+    path_cells = np.array(path_cells)
+    path_world = np.array(path_world)
+    del_path = []
+    if len(path_world) > 2:
+        for ii in range(1, len(path_world)):
+            if np.linalg.norm(path_world[ii] - np.array(pos)) < radius:
+                del_path.append(ii)
+        path_world = np.delete(path_world, del_path, axis=0)
+        path_cells = np.delete(path_cells, del_path, axis=0)
+    return path_cells, path_world
+
+
+def remove_zero_rowscols(X, px, py, map_o, map_reso):
+    """scripts/global_planner_ccst.py:36-63 (the arithmetic, without the ROS wait loop and the object state).
+
+    Returns None for an all-zero map (the reference returns 0), else (crop, map_c, map_r, new map_o): the crop window is
+    ``X[min(min_row, start_x):max_row, min(min_col, start_y):max_col]`` -- exclusive upper ends, so the last occupied
+    row and column are dropped -- while map_c / map_r are computed from the indices (they can differ from the crop's
+    shape when the start index is negative: numpy wraps a negative slice start)."""
+    X = np.asarray(X)
+    rows, cols = X.nonzero()
+    u_row, u_col = np.unique(rows), np.unique(cols)
+    if len(u_row) == 0:
+        return None
+    map_o = np.array(map_o, dtype=float)
+    map_start0 = ((np.array([px, py]) - map_o) / map_reso).astype(int)
+    map_mat_o = [min(u_row), min(u_col)]
+    r0, c0 = min(map_mat_o[0], map_start0[0]), min(map_mat_o[1], map_start0[1])
+    map_c = max(u_row) - r0
+    map_r = max(u_col) - c0
+    new_o = np.array([r0, c0]) * map_reso + map_o
+    x_row = X[r0:max(u_row)]
+    return x_row[:, c0:max(u_col)], int(map_c), int(map_r), new_o
+
+
+def replan_pipeline(mapu, map_o, map_reso, start_xy, goal_xy, ifa, variant="st", crop=False):
+    """The planner loop from the decoded map to the search call, restated: [crop ccst:36-63] -> index/pad/shift
+    (st:226-250 / ccst:411-436) -> inflation (st:256-262 / ccst:442-448) -> goal relocation and end_occu (st:266-275 /
+    ccst:452-464) -> the `start beyond the map` guard (st:280 / ccst:466).
+    Returns dict(grid float64 {0,1}-ish, start, goal, moved, end_occu, skipped, origin, map_d) or None (empty map)."""
+    mapu = np.asarray(mapu)
+    map_c, map_r = mapu.shape
+    map_o = np.array(map_o, dtype=float)
+    if crop:
+        r = remove_zero_rowscols(mapu, start_xy[0], start_xy[1], map_o, map_reso)
+        if r is None or not (r[1] * r[2] > 0):
+            return None
+        mapu, map_c, map_r, map_o = r
+    map_goal = ((np.array(goal_xy[0:2], dtype=float) - map_o) / map_reso).astype(int)
+    map_start = ((np.array(start_xy[0:2], dtype=float) - map_o) / map_reso).astype(int)
+    map_o2 = np.array([-2 * ifa, -2 * ifa])
+    if map_goal[0] < 0 or map_start[0] < 0:
+        map_o2[0] = min(map_goal[0], map_start[0]) + map_o2[0]
+    if map_goal[1] < 0 or map_start[1] < 0:
+        map_o2[1] = min(map_goal[1], map_start[1]) + map_o2[1]
+    map_d = abs(map_o2)
+    new_o = list(map_o2 * map_reso + np.array(map_o))
+    map_c = max(map_c, map_goal[0], map_start[0]) + map_d[0]
+    map_r = max(map_r, map_goal[1], map_start[1]) + map_d[1]
+    mapu0 = np.zeros([map_c + 4 * ifa, map_r + 4 * ifa])
+    mapu0[map_d[0]:len(mapu) + map_d[0], map_d[1]:(len(mapu[0]) if len(mapu) else 0) + map_d[1]] = mapu
+    mapu = inflate_st(mapu0, ifa) if variant == "st" else inflate_ccst(mapu0, ifa)
+    off = -1 if variant == "st" else 0
+    map_start = map_start + map_d + off
+    map_goal = map_goal + map_d + off
+    g0 = map_goal.copy()
+    map_goal, moved = relocate_goal(mapu, map_goal)
+    if variant == "st":
+        end_occu = moved
+    else:
+        end_occu = int((mapu[map_goal[0] - ifa:map_goal[0] + ifa, map_goal[1] - ifa:map_goal[1] + ifa] == 1).any())
+    skipped = bool(map_start[0] > map_c or map_start[1] > map_r)
+    return dict(grid=mapu, start=tuple(int(v) for v in map_start), goal=tuple(int(v) for v in map_goal),
+                goal0=tuple(int(v) for v in g0), moved=int(moved), end_occu=int(end_occu), skipped=skipped,
+                origin=[float(v) for v in new_o], map_d=tuple(int(v) for v in map_d))
+
+
 # --------------------------------------------------------------------------- a15 / a16
 def body_to_earth_frame(ii, jj, kk):
     """scripts/utils.py:21-28: R = Rz(kk) * Ry(jj) * Rx(ii)."""

@@ -204,3 +204,39 @@ def test_live_reference_agrees_with_golden(golden, maps):
                 assert path == 0
             else:
                 assert cost == float(rec["cost"]) and [list(map(int, p)) for p in path] == rec["path"]
+
+
+def _b64(s, dt, shape):
+    import base64
+    return np.frombuffer(base64.b64decode(s), dtype=dt).reshape(shape)
+
+
+def _crop_golden():
+    import json
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "crop_golden.json")))
+
+
+def test_crop_and_decode_restatements_vs_reference_golden(oracle):
+    """hostref.remove_zero_rowscols / decode_occupancy_grid against outputs of the reference's own methods
+    (tests/golden/make_crop_golden.py)."""
+    g = _crop_golden()
+    n = 0
+    for r in g["crop"]:
+        X = _b64(r["X"], np.uint8, (r["W"], r["H"])).astype(np.int64)
+        got = oracle.hostref.remove_zero_rowscols(X, r["p"][0], r["p"][1], r["map_o"], r["reso"])
+        if r["out"] is None:
+            assert got is None
+            continue
+        crop, map_c, map_r, new_o = got
+        o = r["out"]
+        assert list(crop.shape) == o["shape"] and (map_c, map_r) == (o["map_c"], o["map_r"])
+        assert np.array_equal(crop, _b64(o["crop"], np.uint8, o["shape"]))
+        assert [repr(float(v)) for v in new_o] == o["map_o"]
+        n += 1
+    assert n > 40
+    for r in g["decode"]:
+        data = _b64(r["data"], np.int8, (-1,))
+        got = oracle.hostref.decode_occupancy_grid(data, r["width"], r["height"])
+        assert np.array_equal(got, _b64(r["map"], np.uint8, r["shape"]))
+        assert np.array_equal(oracle.hostref.encode_occupancy_grid(got).astype(np.int64),
+                              np.where(got == 1, 100, got).T.reshape(-1))
