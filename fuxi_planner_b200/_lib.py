@@ -19,7 +19,8 @@ SYMBOLS = ["fx_create", "fx_destroy", "fx_last_error", "fx_version", "fx_launch_
            "fx_project", "fx_inflate", "fx_edt", "fx_search_batch", "fx_field", "fx_field_relax", "fx_field_status",
            "fx_search_stats", "fx_plan_host", "fx_map_host", "fx_halo_merge",
            "fx_grid_decode", "fx_grid_encode", "fx_grid_paste", "fx_grid_bbox", "fx_relocate_goal", "fx_path_post",
-           "fx_replan_host", "fx_replan_grid_host"]
+           "fx_replan_host", "fx_replan_grid_host",
+           "fx_cloud_reserve", "fx_cloud_filter", "fx_cloud_filter_host", "fx_distance_filter", "fx_distance_filter_host"]
 
 
 class ReplanIn(C.Structure):
@@ -36,6 +37,15 @@ class ReplanOut(C.Structure):
                 ("start_y", C.c_int32), ("goal_x", C.c_int32), ("goal_y", C.c_int32), ("goal_moved", C.c_int32),
                 ("end_occu", C.c_int32), ("skipped", C.c_int32), ("raw_len", C.c_int32), ("path_len", C.c_int32),
                 ("cost_i", C.c_int32), ("cost_f", C.c_double), ("origin_x", C.c_double), ("origin_y", C.c_double)]
+
+
+
+class CloudParams(C.Structure):
+    """fx_cloud_params of include/fuxi_b200.h (defaults = src/chen_filter_rgb.cpp:52-71)"""
+    _fields_ = [("stride_floats", C.c_int32), ("rgb_offset", C.c_int32), ("pass_lo", C.c_float), ("pass_hi", C.c_float),
+                ("leaf_x", C.c_float), ("leaf_y", C.c_float), ("leaf_z", C.c_float), ("min_neighbors", C.c_int32),
+                ("radius", C.c_double)]
+
 
 _lib = None
 
@@ -82,6 +92,11 @@ def load():
     lib.fx_path_post.argtypes = [vp, vp, i32, i32, vp, vp, i32, i32, i32, f64p, f64p, vp, vp, vp, vp]
     lib.fx_replan_host.argtypes = [vp, vp, i32, i32, C.POINTER(ReplanIn), C.POINTER(ReplanOut), vp, vp, i32]
     lib.fx_replan_grid_host.argtypes = [vp, vp, C.c_size_t, C.POINTER(i32), C.POINTER(i32)]
+    lib.fx_cloud_reserve.argtypes = [vp, i64]
+    lib.fx_cloud_filter.argtypes = [vp, vp, i64, C.POINTER(CloudParams), vp, i64, vp, vp]
+    lib.fx_cloud_filter_host.argtypes = [vp, vp, i64, C.POINTER(CloudParams), vp, i64, C.POINTER(i64)]
+    lib.fx_distance_filter.argtypes = [vp, vp, i64, C.c_double, vp, vp, vp]
+    lib.fx_distance_filter_host.argtypes = [vp, vp, i64, C.c_double, vp, C.POINTER(i64)]
     for s in SYMBOLS:
         if s not in ("fx_last_error", "fx_launch_count"):
             getattr(lib, s).restype = i32

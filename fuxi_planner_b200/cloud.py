@@ -5,12 +5,19 @@ fx_project (transform + height filter + scatter in one kernel).
   cloud_affine      camera->earth rigid transform of plc_point2_st.py:244-251 (+ utils.py:21-28) as ONE 3x4 matrix
   pointcloud2_xyz   PointCloud2 <-> float32 [N,3] (layout of plc_point2_st.py:112-138: x,y,z FLOAT32 at 0/4/8, step 12)
   cloud_to_grid     host cloud -> inflated grid through fx_map_host
+  cloud_filter(_host)     PassThrough -> VoxelGrid -> RadiusOutlierRemoval of src/chen_filter_rgb.cpp:52-71 (fx_cloud_filter)
+  distance_filter(_host)  convert_plc.distance_filter, plc_point2_st.py:139-148 (fx_distance_filter)
 """
+import ctypes as C
+
 import math
 
 import numpy as np
 
+import torch
+
 from . import api
+from ._lib import CloudParams, FuxiError, default_context
 
 CAMERA_LEVER_ARM = 0.12   # plc_point2_st.py:244  x_b = z_c + 0.12
 
@@ -68,3 +75,69 @@ def cloud_to_grid(points, rpy=None, pos=None, origin=(0.0, 0.0), reso=0.2, shape
     """Host cloud (camera frame if rpy/pos are given, else already in the earth frame) -> inflated uint8 grid [W][H]."""
     A = None if rpy is None else cloud_affine(rpy, pos if pos is not None else (0.0, 0.0, 0.0), dt, ang_vel, line_vel)
     return api.map_host(points, A, zmin, zmax, origin, reso, shape, radius, variant, ctx=ctx, device=device)
+
+
+def _cloud_params(stride, rgb_offset, pass_lim, leaf, radius, min_neighbors):
+    return CloudParams(int(stride), int(rgb_offset), float(pass_lim[0]), float(pass_lim[1]), float(leaf[0]), float(leaf[1]),
+                       float(leaf[2]), int(min_neighbors), float(radius))
+
+
+def cloud_filter(points, rgb_offset=-1, pass_lim=(0.0, 4.0), leaf=(0.17, 0.17, 0.2), radius=0.35, min_neighbors=13, ctx=None):
+    """PCL chain of src/chen_filter_rgb.cpp:52-71 on a float32 CUDA tensor [n, stride] (x, y, z first; rgb_offset = column
+    of PCL's packed rgb word or -1).  Returns (out float32 [n, 4] = x, y, z, rgb word; counts int64 CUDA tensor [4] =
+    {after PassThrough, voxels, kept, status}); rows [0, counts[2]) of out are valid.  Enqueues only (no host sync)."""
+    if not (isinstance(points, torch.Tensor) and points.is_cuda and points.dtype == torch.float32 and points.dim() == 2
+            and points.shape[1] >= 3):
+        raise FuxiError("points must be a float32 CUDA tensor [n, stride >= 3]")
+    points = points.contiguous()
+    ctx = api._ctx(ctx, points)
+    n, stride = points.shape
+    out = torch.empty((max(n, 1), 4), dtype=torch.float32, device=points.device)
+    counts = torch.empty(4, dtype=torch.int64, device=points.device)
+    prm = _cloud_params(stride, rgb_offset, pass_lim, leaf, radius, min_neighbors)
+    ctx.check(ctx.lib.fx_cloud_filter(ctx.handle, api._ptr(points), n, C.byref(prm), api._ptr(out), out.shape[0],
+                                      api._ptr(counts), api._stream()), "fx_cloud_filter")
+    return out, counts
+
+
+def cloud_filter_host(points, rgb_offset=-1, pass_lim=(0.0, 4.0), leaf=(0.17, 0.17, 0.2), radius=0.35, min_neighbors=13,
+                      ctx=None, device=0):
+    """Host numpy float32 [n, stride] -> (float32 [kept, 4], counts int64[4]) through fx_cloud_filter_host."""
+    p = np.ascontiguousarray(points, dtype=np.float32)
+    if p.ndim != 2 or p.shape[1] < 3:
+        raise FuxiError("points must be [n, stride >= 3]")
+    ctx = ctx or default_context(device)
+    n, stride = p.shape
+    out = np.empty((max(n, 1), 4), dtype=np.float32)
+    counts = np.zeros(4, dtype=np.int64)
+    prm = _cloud_params(stride, rgb_offset, pass_lim, leaf, radius, min_neighbors)
+    ctx.check(ctx.lib.fx_cloud_filter_host(ctx.handle, p.ctypes.data_as(C.c_void_p), n, C.byref(prm),
+                                           out.ctypes.data_as(C.c_void_p), out.shape[0],
+                                           counts.ctypes.data_as(C.POINTER(C.c_int64))), "fx_cloud_filter_host")
+    return out[:counts[2]].copy(), counts
+
+
+def distance_filter(points, dis, ctx=None):
+    """convert_plc.distance_filter (plc_point2_st.py:139-148) on a float64 CUDA tensor [n, 3]: returns (out float64
+    [n, 3], count int32 CUDA tensor [1]); rows [0, count) are the points with |p| < dis ordered by (|p|, z, y, x)."""
+    if not (isinstance(points, torch.Tensor) and points.is_cuda and points.dtype == torch.float64 and points.dim() == 2
+            and points.shape[1] == 3):
+        raise FuxiError("points must be a float64 CUDA tensor [n, 3]")
+    points = points.contiguous()
+    ctx = api._ctx(ctx, points)
+    out = torch.empty_like(points)
+    count = torch.empty(1, dtype=torch.int32, device=points.device)
+    ctx.check(ctx.lib.fx_distance_filter(ctx.handle, api._ptr(points), points.shape[0], float(dis), api._ptr(out),
+                                         api._ptr(count), api._stream()), "fx_distance_filter")
+    return out, count
+
+
+def distance_filter_host(plc, dis, ctx=None, device=0):
+    """Drop-in for ``convert_plc.distance_filter(plc, dis)``: host array in, float64 [m, 3] out."""
+    p = np.ascontiguousarray(np.asarray(plc, dtype=np.float64).reshape(-1, 3))
+    ctx = ctx or default_context(device)
+    out = np.empty_like(p)
+    cnt = C.c_int64(0)
+    ctx.check(ctx.lib.fx_distance_filter_host(ctx.handle, p.ctypes.data_as(C.c_void_p), p.shape[0], float(dis),
+                                              out.ctypes.data_as(C.c_void_p), C.byref(cnt)), "fx_distance_filter_host")
+    return out[:cnt.value].copy()

@@ -71,7 +71,8 @@ extern "C" int fx_destroy(fx_context *ctx)
     void *dev[] = {ctx->fields, ctx->dirty, ctx->queues, ctx->tmp_path, ctx->moves, ctx->counters, ctx->fq, ctx->fstate,
                    ctx->seeds, ctx->seeds_sorted, ctx->seed_hist, ctx->edt_g, ctx->edt_s, ctx->edt_t, ctx->edt_flag,
                    ctx->d_grid, ctx->d_grid2, ctx->d_q, ctx->d_out_i, ctx->d_out_f, ctx->d_path, ctx->d_pts, ctx->proj_bits, ctx->q_order, ctx->q_ubound, ctx->bfields,
-                   ctx->d_msg, ctx->d_rp};
+                   ctx->d_msg, ctx->d_rp, ctx->cl_bits, ctx->cl_gpref, ctx->cl_chunk, ctx->cl_vidx, ctx->cl_keep, ctx->cl_gpref2,
+                   ctx->cl_chunk2, ctx->cl_acc, ctx->cl_vox, ctx->cl_state, ctx->cl_out, ctx->df_rec};
     for (size_t i = 0; i < sizeof(dev) / sizeof(dev[0]); i++)
         if (dev[i]) cudaFree(dev[i]);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);

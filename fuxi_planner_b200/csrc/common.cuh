@@ -72,6 +72,14 @@ struct fx_context {
     int8_t *d_msg;              size_t d_msg_cap;
     int32_t *d_rp;              size_t d_rp_cap;
     int rp_W, rp_H;             // shape of the last planning grid (kept in d_grid2)
+    // cloud conditioning (cloud.cu): voxel bitmap + ranks, per-voxel accumulators / centroids, keep bitmap, sort records
+    unsigned *cl_bits, *cl_gpref, *cl_chunk, *cl_vidx, *cl_keep, *cl_gpref2, *cl_chunk2;
+    unsigned long long *cl_acc;
+    float4 *cl_vox;
+    void *cl_state, *cl_out, *df_rec;
+    size_t cl_bits_bytes, cl_gpref_bytes, cl_chunk_bytes, cl_vidx_bytes, cl_keep_bytes, cl_gpref2_bytes, cl_chunk2_bytes,
+        cl_acc_bytes, cl_vox_bytes, cl_state_bytes, cl_out_bytes, df_rec_bytes;
+    unsigned long long cl_cap_bits;  // voxel index space the bitmap is reserved for (fx_cloud_reserve)
     cudaStream_t own_stream;
 };
 

@@ -220,6 +220,43 @@ int fx_replan_host(fx_context *ctx, const void *h_map, int width, int height, co
 /* the inflated planning grid of the last fx_replan_host (uint8 [W][H]); h_out may be NULL to query W, H only */
 int fx_replan_grid_host(fx_context *ctx, uint8_t *h_out, size_t cap, int *W, int *H);
 
+/* ---- (7) upstream cloud conditioning ------------------------------------------------
+ * fx_cloud_filter: the PCL chain of src/chen_filter_rgb.cpp:52-71 in one call,
+ *     PassThrough("z", pass_lo, pass_hi) -> VoxelGrid(leaf_x, leaf_y, leaf_z) -> RadiusOutlierRemoval(radius, min_neighbors)
+ * (the reference: 0..4, 0.17/0.17/0.2, 0.35/13).  PCL is an un-vendored, unpinned dependency (CMakeLists.txt:10-18), so
+ * parity is against its published algorithm as restated in oracle/fuxi_oracle.c (fxo_cloud_filter), bit-exact:
+ *   PassThrough: keep a point iff x, y, z are finite and !(z < pass_lo || z > pass_hi);
+ *   VoxelGrid: inv = 1.0f/leaf; min_b = floor(min_p*inv), div_b = max_b - min_b + 1 over the kept points;
+ *     voxel = (int)(floorf(p*inv) - (float)min_b); idx = i + j*div_x + k*div_x*div_y; one output point per occupied
+ *     voxel in ascending idx.  Centroid: PCL sums floats in the order its (unstable) std::sort leaves them, which is
+ *     not reproducible; here coordinates accumulate as rint(p * 2^24) in int64 (order independent) and
+ *     centroid = (float)((double)sum / n * 2^-24); r, g, b = floor(channel sum / n) (downsample_all_data);
+ *   RadiusOutlierRemoval: k = #{q : ((cx-qx)^2 + (cy-qy)^2) + (cz-qz)^2 < (float)(radius*radius)} over the voxel
+ *     centroids, float32, the point itself included; kept iff k > min_neighbors.
+ * pts: n points of stride_floats floats each, x y z at 0 1 2; rgb_offset = float index of PCL's packed rgb word
+ * (4 for PointXYZRGB's 32-byte point_step) or -1.  out: float [cap][4] = x, y, z, rgb word (16-byte aligned);
+ * d_counts: device int64[4] = {points after PassThrough, voxels, points kept, status}; status 0 = ok, > 0 = voxel index
+ * space needed when it exceeds the reserved one (nothing is written; fx_cloud_reserve and call again), -1 = coordinates
+ * outside the int range.  PCL itself refuses a voxel index space above 2^31.  fx_cloud_filter_host: HOST buffers, grows
+ * the reservation and retries by itself, h_counts like d_counts. */
+typedef struct fx_cloud_params {
+    int32_t stride_floats, rgb_offset;
+    float pass_lo, pass_hi;
+    float leaf_x, leaf_y, leaf_z;
+    int32_t min_neighbors;
+    double radius;
+} fx_cloud_params;
+int fx_cloud_reserve(fx_context *ctx, int64_t max_voxel_space);   /* default 2^28 */
+int fx_cloud_filter(fx_context *ctx, const float *pts, int64_t n, const fx_cloud_params *h_params, float *out, int64_t cap,
+                    int64_t *d_counts, void *stream);
+int fx_cloud_filter_host(fx_context *ctx, const float *h_pts, int64_t n, const fx_cloud_params *h_params, float *h_out,
+                         int64_t cap, int64_t *h_counts);
+/* fx_distance_filter: convert_plc.distance_filter, scripts/plc_point2_st.py:139-148 (= plc_point2_ccst.py:178-193):
+ * d = sqrt((x*x + y*y) + z*z) in float64, keep d < dis, order by (d, z, y, x) like np.lexsort (stable).
+ * pts / out: double [n][3]; d_count: device int32 = rows written.  Bit-exact against the reference function. */
+int fx_distance_filter(fx_context *ctx, const double *pts, int64_t n, double dis, double *out, int32_t *d_count, void *stream);
+int fx_distance_filter_host(fx_context *ctx, const double *h_pts, int64_t n, double dis, double *h_out, int64_t *h_count);
+
 #ifdef __cplusplus
 }
 #endif

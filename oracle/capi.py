@@ -23,7 +23,7 @@ def build(force=False):
     """Compile the C oracle with gcc (needs nothing but libc/libm/libgomp)."""
     if not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= os.path.getmtime(_SRC):
         return _SO
-    cmd = ["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-std=c11", "-o", _SO, _SRC, "-lm"]
+    cmd = ["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-fopenmp", "-std=c11", "-o", _SO, _SRC, "-lm"]
     subprocess.run(cmd, check=True)
     return _SO
 
@@ -45,6 +45,10 @@ def _load():
     lib.fxo_sssp_batch.argtypes = [u8p, C.c_int, C.c_int, i32p, i32p, C.c_int, C.c_int64, C.c_int64, C.c_int, i64p]
     lib.fxo_inflate.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.fxo_edt.argtypes = [u8p, i32p, C.c_int, C.c_int]
+    f32p = C.POINTER(C.c_float)
+    lib.fxo_cloud_filter.argtypes = [f32p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                     C.c_double, C.c_int, f32p, C.c_int64, i64p]
+    lib.fxo_cloud_filter.restype = C.c_int
     for f in ("fxo_jps", "fxo_jps_batch", "fxo_sssp", "fxo_sssp_batch", "fxo_inflate", "fxo_edt", "fxo_num_threads"):
         getattr(lib, f).restype = C.c_int
     _lib = lib
@@ -167,3 +171,18 @@ def edt(grid):
     if r < 0:
         raise RuntimeError("fxo_edt failed: %d" % r)
     return out
+
+
+def cloud_filter(points, rgb_offset=-1, pass_lim=(0.0, 4.0), leaf=(0.17, 0.17, 0.2), radius=0.35, min_neighbors=13):
+    """PassThrough(z) -> VoxelGrid -> RadiusOutlierRemoval (src/chen_filter_rgb.cpp:52-71; PCL restated, parity unpinned).
+    points: float32 [n, stride]; returns (float32 [kept, 4] = x, y, z, rgb word, counts int64[4])."""
+    p = np.ascontiguousarray(points, dtype=np.float32)
+    n, stride = p.shape
+    out = np.zeros((max(n, 1), 4), dtype=np.float32)
+    counts = np.zeros(4, dtype=np.int64)
+    r = _load().fxo_cloud_filter(_p(p, C.c_float), n, stride, int(rgb_offset), float(pass_lim[0]), float(pass_lim[1]),
+                                 float(leaf[0]), float(leaf[1]), float(leaf[2]), float(radius), int(min_neighbors),
+                                 _p(out, C.c_float), n, _p(counts, C.c_int64))
+    if r < 0:
+        raise RuntimeError("fxo_cloud_filter failed: %d" % r)
+    return out[:counts[2]].copy(), counts

@@ -12,6 +12,8 @@
  *   - jump                     scripts/jps1.py:95-164  (jump)
  *   - A* over jump points      scripts/jps1.py:183-230 (method) + :232-246 (lenght) + :3-12 (heuristic)
  *   - square / 9-point dilation scripts/global_planner_st.py:256-262, global_planner_ccst.py:442-448
+ *   - PCL conditioning chain   src/chen_filter_rgb.cpp:52-71 (PassThrough, VoxelGrid, RadiusOutlierRemoval; PCL is
+ *                              un-vendored: published algorithm restated, PARITY UNPINNED)
  * plus a second, independent oracle: exact Dijkstra (Dial buckets) on the 8-connected
  * graph whose edges are "not blocked(c, d)" -- the graph-equivalence property SURVEY.md
  * section 0 verified against the reference.
@@ -540,6 +542,113 @@ int fxo_edt(const uint8_t *occ, int32_t *dist2, int W, int H)
         }
     }
     free(g); free(v); free(z); free(f);
+    return 0;
+}
+
+/* ---- upstream cloud conditioning: PassThrough -> VoxelGrid -> RadiusOutlierRemoval ------------------------------
+ * src/chen_filter_rgb.cpp:52-71 calls PCL (un-vendored, unpinned: CMakeLists.txt:10-18) -> PARITY UNPINNED.  This
+ * restates PCL's published algorithms (pcl/filters/impl/passthrough.hpp, voxel_grid.hpp, radius_outlier_removal.hpp,
+ * FLANN L2_Simple + RadiusResultSet) with the one deliberate change include/fuxi_b200.h documents: voxel centroids
+ * accumulate in 2^-24 fixed point (order independent) because PCL's own float sums depend on an unstable sort.
+ * out: float [cap][4] = x, y, z, packed rgb word; counts = {after PassThrough, voxels, kept, status}. */
+typedef struct { uint32_t idx; int32_t pt; } vox_ent_t;
+static int vox_cmp(const void *a, const void *b)
+{
+    const vox_ent_t *p = (const vox_ent_t *)a, *q = (const vox_ent_t *)b;
+    if (p->idx != q->idx) return p->idx < q->idx ? -1 : 1;
+    return (p->pt > q->pt) - (p->pt < q->pt);
+}
+int fxo_cloud_filter(const float *pts, int64_t n, int stride, int rgb_off, float lo, float hi, float leaf_x, float leaf_y,
+                     float leaf_z, double radius, int min_nb, float *out, int64_t cap, int64_t *counts)
+{
+    counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    vox_ent_t *e = (vox_ent_t *)malloc(sizeof(vox_ent_t) * (size_t)(n > 0 ? n : 1));
+    if (!e) return -3;
+    const float inv[3] = {1.0f / leaf_x, 1.0f / leaf_y, 1.0f / leaf_z};
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const float *p = pts + i * stride;
+        if (!isfinite(p[0]) || !isfinite(p[1]) || !isfinite(p[2])) continue;
+        if (p[2] < lo || p[2] > hi) continue; /* passthrough.hpp: removed iff value < min || value > max */
+        e[m++].pt = (int32_t)i;
+        for (int k = 0; k < 3; k++) {
+            if (p[k] < mn[k]) mn[k] = p[k];
+            if (p[k] > mx[k]) mx[k] = p[k];
+        }
+    }
+    counts[0] = m;
+    if (m == 0) { free(e); return 0; }
+    int min_b[3], div[3];
+    uint64_t total = 1;
+    for (int k = 0; k < 3; k++) {
+        float a = floorf(mn[k] * inv[k]), b = floorf(mx[k] * inv[k]);
+        if (!(fabsf(a) < 1.0e9f) || !(fabsf(b) < 1.0e9f)) { counts[3] = -1; free(e); return 0; }
+        min_b[k] = (int)a;
+        div[k] = (int)b - (int)a + 1;
+        total *= (uint64_t)div[k];
+        if (total > (1ull << 40)) break;
+    }
+    if (total > (1ull << 31)) { counts[3] = (int64_t)total; free(e); return 0; }
+    for (int64_t t = 0; t < m; t++) {
+        const float *p = pts + (int64_t)e[t].pt * stride;
+        int i = (int)(floorf(p[0] * inv[0]) - (float)min_b[0]);
+        int j = (int)(floorf(p[1] * inv[1]) - (float)min_b[1]);
+        int k = (int)(floorf(p[2] * inv[2]) - (float)min_b[2]);
+        e[t].idx = (uint32_t)i + (uint32_t)div[0] * ((uint32_t)j + (uint32_t)div[1] * (uint32_t)k);
+    }
+    qsort(e, (size_t)m, sizeof(vox_ent_t), vox_cmp);
+    float *vox = (float *)malloc(sizeof(float) * 4 * (size_t)m);
+    if (!vox) { free(e); return -3; }
+    int64_t nv = 0;
+    for (int64_t t = 0; t < m;) {
+        int64_t u = t, sx = 0, sy = 0, sz = 0;
+        uint64_t sr = 0, sg = 0, sb = 0;
+        for (; u < m && e[u].idx == e[t].idx; u++) {
+            const float *p = pts + (int64_t)e[u].pt * stride;
+            sx += llrint((double)p[0] * 16777216.0);
+            sy += llrint((double)p[1] * 16777216.0);
+            sz += llrint((double)p[2] * 16777216.0);
+            if (rgb_off >= 0) {
+                uint32_t c;
+                memcpy(&c, p + rgb_off, 4);
+                sr += (c >> 16) & 255u, sg += (c >> 8) & 255u, sb += c & 255u;
+            }
+        }
+        const double dn = (double)(u - t);
+        float *o = vox + 4 * nv++;
+        o[0] = (float)(((double)sx / dn) * (1.0 / 16777216.0));
+        o[1] = (float)(((double)sy / dn) * (1.0 / 16777216.0));
+        o[2] = (float)(((double)sz / dn) * (1.0 / 16777216.0));
+        uint32_t c = ((uint32_t)(sr / (uint64_t)(u - t)) << 16) | ((uint32_t)(sg / (uint64_t)(u - t)) << 8) | (uint32_t)(sb / (uint64_t)(u - t));
+        memcpy(o + 3, &c, 4);
+        t = u;
+    }
+    counts[1] = nv;
+    /* radius_outlier_removal.hpp: k = radiusSearch(point, radius) includes the point; outlier iff k <= min_pts */
+    const float r2 = (float)(radius * radius);
+    uint8_t *keep = (uint8_t *)calloc((size_t)nv, 1);
+    if (!keep) { free(e); free(vox); return -3; }
+#pragma omp parallel for schedule(static)
+    for (int64_t a = 0; a < nv; a++) {
+        int k = 0;
+        const float *c = vox + 4 * a;
+        for (int64_t b = 0; b < nv; b++) {
+            const float *q = vox + 4 * b;
+            const float ex = c[0] - q[0], ey = c[1] - q[1], ez = c[2] - q[2];
+            const float d2 = (ex * ex + ey * ey) + ez * ez;
+            k += d2 < r2;
+        }
+        keep[a] = k > min_nb;
+    }
+    int64_t kept = 0;
+    for (int64_t a = 0; a < nv; a++)
+        if (keep[a]) {
+            if (kept < cap) memcpy(out + 4 * kept, vox + 4 * a, 16);
+            kept++;
+        }
+    counts[2] = kept;
+    free(e); free(vox); free(keep);
     return 0;
 }
 

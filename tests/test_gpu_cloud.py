@@ -1,0 +1,165 @@
+"""GPU parity tests for the upstream cloud conditioning through the C ABI:
+fx_cloud_filter (PassThrough -> VoxelGrid -> RadiusOutlierRemoval of src/chen_filter_rgb.cpp:52-71) against the C
+restatement of PCL's published algorithms (oracle.cloud_filter; PCL is un-vendored -> parity unpinned), and
+fx_distance_filter against the reference's own convert_plc.distance_filter (golden vectors from the unmodified
+reference, plc_point2_st.py:139-148) and its numpy restatement.  Everything is bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fx():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import __graft_entry__ as ge
+    ge.build()
+    import fuxi_planner_b200 as fx
+    return fx
+
+
+def _scene(rng, n, rgb=False):
+    """Depth-camera-like cloud in the camera frame (z = depth): a wall, a floor strip, a box, sparse noise, bad points."""
+    k = n // 4
+    wall = np.c_[rng.uniform(-2.5, 2.5, k), rng.uniform(-1.5, 1.0, k), 3.0 + 0.03 * rng.standard_normal(k)]
+    floor = np.c_[rng.uniform(-2.0, 2.0, k), 1.2 + 0.02 * rng.standard_normal(k), rng.uniform(0.3, 4.5, k)]
+    box = np.c_[rng.uniform(0.2, 0.9, k), rng.uniform(-0.4, 0.6, k), rng.uniform(1.4, 1.9, k)]
+    noise = np.c_[rng.uniform(-4, 4, n - 3 * k), rng.uniform(-3, 3, n - 3 * k), rng.uniform(-1.0, 6.0, n - 3 * k)]
+    p = np.concatenate([wall, floor, box, noise]).astype(np.float32)
+    p = p[rng.permutation(len(p))]
+    bad = rng.integers(len(p), size=max(n // 200, 1))
+    p[bad[::3], 0] = np.nan
+    p[bad[1::3], 2] = np.inf
+    p[bad[2::3], 1] = -np.inf
+    if not rgb:
+        return p
+    q = np.zeros((len(p), 8), dtype=np.float32)      # PointXYZRGB: x y z pad | rgb pad pad pad (point_step 32)
+    q[:, :3] = p
+    q[:, 3] = 1.0
+    col = rng.integers(0, 256, size=(len(p), 3)).astype(np.uint32)
+    q[:, 4] = ((col[:, 0] << 16) | (col[:, 1] << 8) | col[:, 2]).view(np.float32)
+    return q
+
+
+def _check(fx, oracle, pts, **kw):
+    want, wc = oracle.cloud_filter(pts, **kw)
+    got, gc = fx.cloud.cloud_filter_host(pts, **kw)
+    assert gc.tolist() == wc.tolist(), (gc, wc)
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    return wc
+
+
+@pytest.mark.parametrize("n", [1, 37, 5000, 60000])
+def test_cloud_filter_scene(fx, oracle, n):
+    rng = np.random.default_rng(n)
+    c = _check(fx, oracle, _scene(rng, n))
+    if n >= 5000:
+        assert 0 < c[2] < c[1] < c[0] < n          # every stage removes something
+
+
+def test_cloud_filter_rgb_stride8(fx, oracle):
+    rng = np.random.default_rng(5)
+    c = _check(fx, oracle, _scene(rng, 30000, rgb=True), rgb_offset=4)
+    assert c[2] > 100
+
+
+def test_cloud_filter_device_entry_matches_host(fx, oracle):
+    import torch
+    rng = np.random.default_rng(6)
+    pts = _scene(rng, 20000)
+    want, wc = oracle.cloud_filter(pts)
+    out, counts = fx.cloud.cloud_filter(torch.from_numpy(pts).cuda())
+    torch.cuda.synchronize()
+    assert counts.cpu().numpy().tolist() == wc.tolist()
+    assert np.array_equal(out[:wc[2]].cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("params", [
+    dict(pass_lim=(0.5, 2.5), leaf=(0.1, 0.1, 0.1), radius=0.25, min_neighbors=5),
+    dict(pass_lim=(-10.0, 10.0), leaf=(0.3, 0.2, 0.45), radius=0.9, min_neighbors=20),
+    dict(leaf=(0.05, 0.05, 0.05), radius=0.12, min_neighbors=2),
+    dict(leaf=(0.17, 0.17, 0.2), radius=0.35, min_neighbors=0),
+])
+def test_cloud_filter_parameters(fx, oracle, params):
+    rng = np.random.default_rng(7)
+    _check(fx, oracle, _scene(rng, 20000), **params)
+
+
+def test_cloud_filter_edge_cases(fx, oracle):
+    rng = np.random.default_rng(8)
+    # nothing passes the z filter / everything non-finite / empty input
+    c = _check(fx, oracle, np.c_[rng.uniform(-1, 1, (100, 2)), rng.uniform(5, 6, 100)].astype(np.float32))
+    assert c.tolist() == [0, 0, 0, 0]
+    _check(fx, oracle, np.full((10, 3), np.nan, dtype=np.float32))
+    _check(fx, oracle, np.zeros((0, 3), dtype=np.float32))
+    # limits are inclusive (passthrough.hpp), duplicates share a voxel, negative coordinates floor downwards
+    pts = np.array([[0, 0, 0], [0, 0, 4], [0, 0, 4.0000005], [-0.01, -0.01, 0], [-0.01, -0.01, 0], [0.169, 0.0, -0.0]], dtype=np.float32)
+    c = _check(fx, oracle, pts, min_neighbors=0)
+    assert c[0] == 5
+    # one dense blob: 14 occupied voxels within the radius are needed
+    blob = (np.array([1.0, 1.0, 2.0]) + rng.uniform(-0.3, 0.3, (4000, 3))).astype(np.float32)
+    c = _check(fx, oracle, blob)
+    assert c[2] > 0
+
+
+def test_cloud_filter_grows_reservation(fx, oracle):
+    """A cloud whose bounding box needs more voxel index space than reserved: the device entry reports the need and
+    writes nothing, the host entry grows the reservation and retries."""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(9)
+    pts = np.concatenate([_scene(rng, 5000), np.array([[150.0, 120.0, 1.0], [-150.0, -120.0, 1.5]], dtype=np.float32)])
+    ctx = fx.Context(0)
+    ctx.check(ctx.lib.fx_cloud_reserve(ctx.handle, 1 << 16), "fx_cloud_reserve")
+    out, counts = fx.cloud.cloud_filter(torch.from_numpy(pts).cuda(), ctx=ctx)
+    torch.cuda.synchronize()
+    c = counts.cpu().numpy()
+    assert c[3] > (1 << 16) and c[1] == 0 and c[2] == 0
+    want, wc = oracle.cloud_filter(pts)
+    got, gc = fx.cloud.cloud_filter_host(pts, ctx=ctx)
+    assert gc.tolist() == wc.tolist() and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # beyond PCL's own 2^31 limit: refused loudly
+    far = np.array([[1.0e5, 1.0e5, 1.0], [-1.0e5, -1.0e5, 2.0]], dtype=np.float32)
+    with pytest.raises(fx.FuxiError):
+        fx.cloud.cloud_filter_host(far, ctx=ctx)
+    ctx.close()
+
+
+def test_distance_filter_golden(fx, hostfn_golden):
+    got = fx.cloud.distance_filter_host(hostfn_golden["df_in"], 4.0)
+    assert got.shape == hostfn_golden["df_out"].shape
+    assert np.array_equal(got.view(np.uint64), hostfn_golden["df_out"].view(np.uint64))
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 2048, 2049, 10000, 150000])
+def test_distance_filter_random(fx, oracle, n):
+    rng = np.random.default_rng(100 + n)
+    p = rng.uniform(-5, 5, (n, 3))
+    if n >= 5:
+        # ties on the primary key: duplicated points, sign flips and axis permutations share |p| exactly
+        p[1] = p[0]
+        p[2] = -p[0]
+        p[3] = p[0][[1, 0, 2]]
+        p[4] = [np.nan, 0.0, 0.0]
+    if n >= 10000:
+        q = rng.integers(-3, 4, (n // 2, 3)).astype(np.float64)          # many exact ties
+        p[: n // 2] = q
+    want = oracle.hostref.distance_filter(p, 4.0)
+    got = fx.cloud.distance_filter_host(p, 4.0)
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+
+
+def test_distance_filter_device_entry(fx, oracle):
+    import torch
+    rng = np.random.default_rng(11)
+    p = rng.uniform(-6, 6, (30000, 3))
+    want = oracle.hostref.distance_filter(p, 4.0)
+    out, count = fx.cloud.distance_filter(torch.from_numpy(p).cuda(), 4.0)
+    torch.cuda.synchronize()
+    m = int(count.item())
+    assert m == len(want)
+    assert np.array_equal(out[:m].cpu().numpy().view(np.uint64), want.view(np.uint64))

@@ -240,3 +240,39 @@ def test_crop_and_decode_restatements_vs_reference_golden(oracle):
         assert np.array_equal(got, _b64(r["map"], np.uint8, r["shape"]))
         assert np.array_equal(oracle.hostref.encode_occupancy_grid(got).astype(np.int64),
                               np.where(got == 1, 100, got).T.reshape(-1))
+
+
+# ---- upstream cloud conditioning: the C restatement of the PCL chain against an independent numpy/scipy
+# formulation.  PCL itself is un-vendored (parity unpinned); this guards the restatement's structure.
+def test_cloud_filter_oracle_against_numpy(oracle):
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(0)
+    n = 20000
+    p = np.c_[rng.uniform(-2, 2, n), rng.uniform(-1.5, 1.5, n), rng.uniform(-0.5, 4.5, n)].astype(np.float32)
+    p[::7, 2] = 2.0 + 0.05 * rng.standard_normal(len(p[::7]))          # a dense sheet so the radius filter keeps something
+    p[5] = np.nan
+    got, c = oracle.cloud_filter(p)
+    ok = np.isfinite(p).all(axis=1) & ~((p[:, 2] < 0.0) | (p[:, 2] > 4.0))
+    q = p[ok]
+    assert c[0] == len(q)
+    inv = np.float32(1.0) / np.array([0.17, 0.17, 0.2], dtype=np.float32)
+    ijk = np.floor(q * inv).astype(np.int64)
+    ijk -= np.floor(q.min(axis=0) * inv).astype(np.int64)
+    div = ijk.max(axis=0) + 1
+    idx = ijk[:, 0] + div[0] * (ijk[:, 1] + div[1] * ijk[:, 2])
+    uniq, inverse, cnt = np.unique(idx, return_inverse=True, return_counts=True)
+    assert c[1] == len(uniq)
+    cen = np.zeros((len(uniq), 3))
+    np.add.at(cen, inverse, q.astype(np.float64))
+    cen /= cnt[:, None]
+    tree = cKDTree(cen)
+    k = np.array([len(v) for v in tree.query_ball_point(cen, 0.35)])
+    # compare the kept set, ignoring centroids whose neighbour count could flip on a float32 rounding of a distance
+    d, _ = tree.query(cen, k=40, distance_upper_bound=0.36)
+    borderline = (np.abs(d - 0.35) < 1e-5).any(axis=1)
+    keep = k > 13
+    want = cen[keep & ~borderline]
+    dist, _ = cKDTree(got[:, :3].astype(np.float64)).query(want)
+    assert dist.max() < 1e-5
+    assert abs(int(c[2]) - int(keep.sum())) <= int(borderline.sum())
+    assert c[2] > 50
