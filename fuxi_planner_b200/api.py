@@ -195,6 +195,26 @@ def grid_encode(grid, ctx=None):
     return out
 
 
+def grid_to_image(grid, ctx=None):
+    """uint8 [x][y] -> 'L' image [H rows][W columns] as the planners save it (global_planner_st.py:368-372)."""
+    grid = _u8_grid(grid)
+    ctx = _ctx(ctx, grid)
+    W, H = grid.shape
+    img = torch.empty((H, W), dtype=torch.uint8, device=grid.device)
+    ctx.check(ctx.lib.fx_grid_to_image(ctx.handle, _ptr(grid), W, H, _ptr(img), _stream()), "fx_grid_to_image")
+    return img
+
+
+def image_to_grid(img, threshold=200, ctx=None):
+    """'L' image [H][W] uint8 CUDA tensor -> uint8 [x][y], pixel > threshold = free (pre-map loader, st:176-182)."""
+    img = _u8_grid(img)
+    ctx = _ctx(ctx, img)
+    H, W = img.shape
+    grid = torch.empty((W, H), dtype=torch.uint8, device=img.device)
+    ctx.check(ctx.lib.fx_image_to_grid(ctx.handle, _ptr(img), W, H, int(threshold), _ptr(grid), _stream()), "fx_image_to_grid")
+    return grid
+
+
 def grid_paste(src, dst, window=None, paste_at=(0, 0), ctx=None):
     """dst[px+i, py+j] = src[x0+i, y0+j] (overwrite), the slice assignments of the pre-map merge / pad step."""
     src, ctx = _u8_grid(src), _ctx(ctx, src)

@@ -206,6 +206,67 @@ extern "C" int fx_grid_encode(fx_context *ctx, const uint8_t *grid, int W, int H
     return FX_OK;
 }
 
+// ---- map image <-> [x][y] array ---------------------------------------------------------
+// Save block scripts/global_planner_st.py:368-372 (= global_planner_ccst.py:628-632): free (== 0) -> 255, anything
+// else -> 0, then `.T[::-1]`: image row r, column c holds cell [x = c][y = H-1-r] (image is H rows x W columns).
+// Load block st:176-182 (pre-map) / the fixture convention: cell = pixel > threshold ? 0 : 1, `img[::-1].T`.
+// DIR 0: grid -> image, DIR 1: image -> grid.  32x32 tiles through shared memory, coalesced on both sides.
+template <int DIR>
+__global__ void __launch_bounds__(256)
+k_grid_image(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int W, int H, int threshold)
+{
+    __shared__ uint8_t tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;  // bx: x of the grid / image column, by: y of the grid
+    if (DIR == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int x = bx + ty + 8 * k, y = by + tx;
+            tile[ty + 8 * k][tx] = (x < W && y < H) ? (src[(size_t)x * H + y] == 0 ? (uint8_t)255 : (uint8_t)0) : (uint8_t)0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int x = bx + tx, y = by + ty + 8 * k;
+            if (x < W && y < H) dst[(size_t)(H - 1 - y) * W + x] = tile[tx][ty + 8 * k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int x = bx + tx, y = by + ty + 8 * k;
+            tile[ty + 8 * k][tx] = (x < W && y < H) ? ((int)src[(size_t)(H - 1 - y) * W + x] > threshold ? (uint8_t)0 : (uint8_t)1) : (uint8_t)0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int x = bx + ty + 8 * k, y = by + tx;
+            if (x < W && y < H) dst[(size_t)x * H + y] = tile[tx][ty + 8 * k];
+        }
+    }
+}
+
+extern "C" int fx_grid_to_image(fx_context *ctx, const uint8_t *grid, int W, int H, uint8_t *img, void *stream)
+{
+    if (!ctx) return FX_ERR_ARG;
+    if (!grid || !img || W <= 0 || H <= 0) return fx_set_err(ctx, FX_ERR_ARG, "fx_grid_to_image: bad argument");
+    FX_CUDA(ctx, cudaSetDevice(ctx->device));
+    dim3 g((W + 31) / 32, (H + 31) / 32);
+    k_grid_image<0><<<g, 256, 0, (cudaStream_t)stream>>>(grid, img, W, H, 0);
+    FX_LAUNCH_CHECK(ctx);
+    return FX_OK;
+}
+
+extern "C" int fx_image_to_grid(fx_context *ctx, const uint8_t *img, int W, int H, int threshold, uint8_t *grid, void *stream)
+{
+    if (!ctx) return FX_ERR_ARG;
+    if (!grid || !img || W <= 0 || H <= 0) return fx_set_err(ctx, FX_ERR_ARG, "fx_image_to_grid: bad argument");
+    FX_CUDA(ctx, cudaSetDevice(ctx->device));
+    dim3 g((W + 31) / 32, (H + 31) / 32);
+    k_grid_image<1><<<g, 256, 0, (cudaStream_t)stream>>>(img, grid, W, H, threshold);
+    FX_LAUNCH_CHECK(ctx);
+    return FX_OK;
+}
+
 extern "C" int fx_grid_paste(fx_context *ctx, const uint8_t *src, int sW, int sH, int sx0, int sy0, int w, int h, uint8_t *dst,
                              int dW, int dH, int px, int py, void *stream)
 {

@@ -469,6 +469,22 @@ static int edt_upload_levels(fx_context *ctx)
     return FX_OK;
 }
 
+static int edt_reserve(fx_context *ctx, size_t cells)
+{
+    if (ctx->edt_cap >= cells) return FX_OK;
+    if (ctx->edt_g) cudaFree(ctx->edt_g);
+    if (ctx->edt_s) cudaFree(ctx->edt_s);
+    if (ctx->edt_t) cudaFree(ctx->edt_t);
+    ctx->edt_g = ctx->edt_s = ctx->edt_t = nullptr; ctx->edt_cap = 0;
+    FX_CUDA(ctx, cudaMalloc(&ctx->edt_g, cells * 2 + 64));
+    FX_CUDA(ctx, cudaMalloc(&ctx->edt_s, cells * 2));
+    FX_CUDA(ctx, cudaMalloc(&ctx->edt_t, cells * 2));
+    ctx->edt_cap = cells;
+    return FX_OK;
+}
+static int edt_rows_launch(fx_context *ctx, const uint8_t *occ, uint16_t *g, int W, int H, cudaStream_t st);
+static int edt_cols_launch(fx_context *ctx, const uint16_t *g, int32_t *dist2, int W, int H, cudaStream_t st);
+
 extern "C" int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W, int H, void *stream)
 {
     if (!ctx) return FX_ERR_ARG;
@@ -477,16 +493,8 @@ extern "C" int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W
     cudaStream_t st = (cudaStream_t)stream;
     FX_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t cells = (size_t)W * H;
-    if (ctx->edt_cap < cells) {
-        if (ctx->edt_g) cudaFree(ctx->edt_g);
-        if (ctx->edt_s) cudaFree(ctx->edt_s);
-        if (ctx->edt_t) cudaFree(ctx->edt_t);
-        ctx->edt_g = ctx->edt_s = ctx->edt_t = nullptr; ctx->edt_cap = 0;
-        FX_CUDA(ctx, cudaMalloc(&ctx->edt_g, cells * 2 + 64));
-        FX_CUDA(ctx, cudaMalloc(&ctx->edt_s, cells * 2));
-        FX_CUDA(ctx, cudaMalloc(&ctx->edt_t, cells * 2));
-        ctx->edt_cap = cells;
-    }
+    int rc0 = edt_reserve(ctx, cells);
+    if (rc0) return rc0;
     FX_CUDA(ctx, cudaMemsetAsync(ctx->edt_flag, 0, 4 * sizeof(int), st));
     if (H % 32 == 0 && ((uintptr_t)occ & 15u) == 0 && ((uintptr_t)dist2 & 15u) == 0) {
         // dense-map fast path; falls through to the windowed path (conditionally, on the device flag) if too many
@@ -524,6 +532,15 @@ extern "C" int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W
         FX_LAUNCH_CHECK(ctx);
         return FX_OK;
     }
+    int rc = edt_rows_launch(ctx, occ, ctx->edt_g, W, H, st);
+    if (rc) return rc;
+    return edt_cols_launch(ctx, ctx->edt_g, dist2, W, H, st);
+}
+
+// ---- the two separable passes as entry points: the row-tiled multi-GPU mode runs pass 1 on its x-slab, transposes
+// the row distances between ranks, and runs pass 2 on whole columns (tiled.edt_tiled) ------------------------------
+static int edt_rows_launch(fx_context *ctx, const uint8_t *occ, uint16_t *g, int W, int H, cudaStream_t st)
+{
     const int nwords = (H + 31) / 32;
     // warps per CTA limited by shared memory (3 arrays of nwords per warp)
     int warps = 8;
@@ -531,18 +548,46 @@ extern "C" int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W
     while (smem > 48 * 1024 && warps > 1) { warps >>= 1; smem = (size_t)warps * 3 * nwords * 4; }
     int blocks = (W + warps - 1) / warps;
     if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-    k_edt_rows<<<blocks, warps * 32, smem, st>>>(occ, ctx->edt_g, W, H, nullptr);
-    FX_LAUNCH_CHECK(ctx);
-    int b2 = (int)((cells + 255) / 256);
-    if (b2 > ctx->sm_count * 16) b2 = ctx->sm_count * 16;
-    if (H % 8 == 0) {
-        dim3 gt((H + EDT_TYC - 1) / EDT_TYC, (W + EDT_TX - 1) / EDT_TX);
-        k_edt_cols_tile<<<gt, 256, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_flag, nullptr);
-    } else {
-        k_edt_cols_window<<<b2, 256, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_flag);
-    }
-    FX_LAUNCH_CHECK(ctx);
-    k_edt_cols_exact<<<(H + 127) / 128, 128, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_s, ctx->edt_t, ctx->edt_flag);
+    k_edt_rows<<<blocks, warps * 32, smem, st>>>(occ, g, W, H, nullptr);
     FX_LAUNCH_CHECK(ctx);
     return FX_OK;
+}
+
+static int edt_cols_launch(fx_context *ctx, const uint16_t *g, int32_t *dist2, int W, int H, cudaStream_t st)
+{
+    const size_t cells = (size_t)W * H;
+    int b2 = (int)((cells + 255) / 256);
+    if (b2 > ctx->sm_count * 16) b2 = ctx->sm_count * 16;
+    if (H % 8 == 0 && ((uintptr_t)g & 15u) == 0) {
+        dim3 gt((H + EDT_TYC - 1) / EDT_TYC, (W + EDT_TX - 1) / EDT_TX);
+        k_edt_cols_tile<<<gt, 256, 0, st>>>(g, dist2, W, H, ctx->edt_flag, nullptr);
+    } else {
+        k_edt_cols_window<<<b2, 256, 0, st>>>(g, dist2, W, H, ctx->edt_flag);
+    }
+    FX_LAUNCH_CHECK(ctx);
+    k_edt_cols_exact<<<(H + 127) / 128, 128, 0, st>>>(g, dist2, W, H, ctx->edt_s, ctx->edt_t, ctx->edt_flag);
+    FX_LAUNCH_CHECK(ctx);
+    return FX_OK;
+}
+
+extern "C" int fx_edt_rows(fx_context *ctx, const uint8_t *occ, uint16_t *g, int W, int H, void *stream)
+{
+    if (!ctx) return FX_ERR_ARG;
+    if (!occ || !g || W <= 0 || H <= 0) return fx_set_err(ctx, FX_ERR_ARG, "fx_edt_rows: bad argument");
+    if (H > 65534) return fx_set_err(ctx, FX_ERR_UNSUPPORTED, "fx_edt_rows: H must be <= 65534");
+    FX_CUDA(ctx, cudaSetDevice(ctx->device));
+    return edt_rows_launch(ctx, occ, g, W, H, (cudaStream_t)stream);
+}
+
+extern "C" int fx_edt_cols(fx_context *ctx, const uint16_t *g, int32_t *dist2, int W, int H, void *stream)
+{
+    if (!ctx) return FX_ERR_ARG;
+    if (!g || !dist2 || W <= 0 || H <= 0) return fx_set_err(ctx, FX_ERR_ARG, "fx_edt_cols: bad argument");
+    if (W > 65534) return fx_set_err(ctx, FX_ERR_UNSUPPORTED, "fx_edt_cols: W must be <= 65534");
+    cudaStream_t st = (cudaStream_t)stream;
+    FX_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = edt_reserve(ctx, (size_t)W * H);
+    if (rc) return rc;
+    FX_CUDA(ctx, cudaMemsetAsync(ctx->edt_flag, 0, 4 * sizeof(int), st));
+    return edt_cols_launch(ctx, g, dist2, W, H, st);
 }

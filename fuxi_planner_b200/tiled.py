@@ -2,6 +2,11 @@
 
 * query-parallel: queries are independent units -> rank r takes a contiguous slice,
   the grid is replicated, there is NO collective on the data path (``shard_queries`` / ``plan_batch_sharded``).
+* projection of one cloud (§8e row 2): points are independent -> every rank bins its slice of the cloud into a full
+  grid and the grids are OR-ed with one all-reduce (MAX on uint8); bit-identical to one GPU (``project_sharded``).
+* EDT on row tiles (§8e row 4): pass 1 (along y) is local to an x-slab, pass 2 (along x) needs whole columns -> one
+  transpose of the uint16 row distances between ranks (grouped send/recv), the column pass on a y-block, and one
+  transpose of the int32 result back (``edt_tiled``).
 * row-tiled (cfg5): a grid too large for one GPU's scratch is cut into x-slabs (x-rows are contiguous in the
   ``[x][y]`` layout).  Inflation needs ONE halo exchange of ``radius`` rows; the single-source cost field needs an
   iterative exchange: every rank relaxes its slab to the local fixpoint (``fx_field_relax``, a Dial wavefront
@@ -84,6 +89,23 @@ class CudaOps:
 
     def inflate(self, grid, radius, variant):
         return api.inflate(grid, radius, variant, ctx=self.ctx)
+
+    def edt_rows(self, grid):
+        """uint8 [w][H] -> int16 view of uint16 row distances (0xFFFF = none); fx_edt_rows"""
+        ctx = api._ctx(self.ctx, grid)
+        g = torch.empty(grid.shape, dtype=torch.int16, device=grid.device)
+        ctx.check(ctx.lib.fx_edt_rows(ctx.handle, api._ptr(grid), api._ptr(g), grid.shape[0], grid.shape[1], api._stream()), "fx_edt_rows")
+        return g
+
+    def edt_cols(self, g):
+        """row distances for whole columns [W][hb] -> int32 squared distances [W][hb]; fx_edt_cols"""
+        ctx = api._ctx(self.ctx, g)
+        out = torch.empty(g.shape, dtype=torch.int32, device=g.device)
+        ctx.check(ctx.lib.fx_edt_cols(ctx.handle, api._ptr(g), api._ptr(out), g.shape[0], g.shape[1], api._stream()), "fx_edt_cols")
+        return out
+
+    def project(self, points, affine, zmin, zmax, origin, reso, shape):
+        return api.project(points, affine, zmin, zmax, origin, reso, shape, ctx=self.ctx)
 
 
 def _exchange(send_lo, send_hi, recv_lo, recv_hi, rank, n, group):
@@ -177,3 +199,60 @@ def field_tiled(own_rows, W, source, metric=1, group=None, ops=None, max_rounds=
         if int(flag.item()) == 0:
             break
     return field[off:off + h], rounds
+
+
+# ------------------------------------------------------------------------------------------ sharded projection
+def project_sharded(points, affine=None, zmin=0.3, zmax=float("inf"), origin=(0.0, 0.0), reso=0.2, shape=None, group=None,
+                    ops=None):
+    """points: THIS rank's slice of the cloud.  Every rank ends up with the full grid: local fx_project, then one
+    all-reduce (MAX) over the uint8 grids -- occupancy is a set union, so the result is bit-identical to projecting
+    the whole cloud on one GPU."""
+    ops = ops or CudaOps()
+    grid = ops.project(points, affine, zmin, zmax, origin, reso, shape)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(grid, op=dist.ReduceOp.MAX, group=group)
+    return grid
+
+
+# ------------------------------------------------------------------------------------------ row-tiled EDT
+def _peer(group, r):
+    return dist.get_global_rank(group, r) if group else r
+
+
+def _transpose_blocks(send, recv, rank, n, group):
+    """send[j] goes to rank j, recv[i] comes from rank i (one batch of P2P ops; the own block is copied locally)."""
+    recv[rank].copy_(send[rank])
+    ops = []
+    for k in range(1, n):
+        to, frm = (rank + k) % n, (rank - k) % n
+        ops.append(dist.P2POp(dist.isend, send[to], _peer(group, to), group))
+        ops.append(dist.P2POp(dist.irecv, recv[frm], _peer(group, frm), group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def edt_tiled(own_rows, W, group=None, ops=None):
+    """Exact squared EDT of a grid split into x-slabs: own_rows = uint8 [x1-x0, H] -> int32 [x1-x0, H], bit-identical
+    to fx_edt of the whole grid.  Two all-to-all transposes (uint16 in: W*H*2/n bytes per rank, int32 back)."""
+    ops = ops or CudaOps()
+    rank, n = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
+    x0, x1 = slab_bounds(W, n, rank)
+    h, H = own_rows.shape
+    if h != x1 - x0:
+        raise FuxiError("own_rows has %d rows, slab_bounds says %d" % (h, x1 - x0))
+    g = ops.edt_rows(own_rows.contiguous())
+    if n == 1:
+        return ops.edt_cols(g)
+    dev = own_rows.device
+    xb = [slab_bounds(W, n, r) for r in range(n)]
+    yb = [slab_bounds(H, n, r) for r in range(n)]
+    y0, y1 = yb[rank]
+    send = [g[:, a:b].contiguous() for a, b in yb]
+    recv = [torch.empty((b - a, y1 - y0), dtype=g.dtype, device=dev) for a, b in xb]
+    _transpose_blocks(send, recv, rank, n, group)
+    d = ops.edt_cols(torch.cat(recv).contiguous())          # [W][y1-y0]
+    send = [d[a:b].contiguous() for a, b in xb]
+    recv = [torch.empty((h, b - a), dtype=d.dtype, device=dev) for a, b in yb]
+    _transpose_blocks(send, recv, rank, n, group)
+    return torch.cat(recv, dim=1).contiguous()

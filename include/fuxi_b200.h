@@ -83,6 +83,12 @@ int fx_inflate(fx_context *ctx, const uint8_t *in, uint8_t *out, int W, int H, i
 /* Exact squared Euclidean distance (in cells^2) to the nearest cell > 0; INT32_MAX if the grid has
  * none.  Not in the reference (north-star addition); oracle = scipy.ndimage.distance_transform_edt. */
 int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W, int H, void *stream);
+/* The two separable passes of fx_edt on their own (row-tiled multi-GPU mode, tiled.edt_tiled): fx_edt_rows writes
+ * g[x][y] = distance along y to the nearest cell > 0 of row x (uint16, 0xFFFF = the row has none) -- local to an x-slab;
+ * fx_edt_cols takes g for WHOLE columns (uint16 [W][Hb], any column block) and writes dist2 = min over x' of
+ * (x-x')^2 + g(x',y)^2 (int32 [W][Hb], INT32_MAX when the grid has no occupied cell). */
+int fx_edt_rows(fx_context *ctx, const uint8_t *occ, uint16_t *g, int W, int H, void *stream);
+int fx_edt_cols(fx_context *ctx, const uint16_t *g, int32_t *dist2, int W, int H, void *stream);
 
 /* ---- (3) shortest paths on the 8-connected grid ------------------------------------------------
  * Replaces: scripts/jps1.py:183-230 `method(matrix, start, goal, hchoice)` and everything it calls
@@ -172,6 +178,13 @@ int fx_grid_paste(fx_context *ctx, const uint8_t *src, int sW, int sH, int sx0, 
                   uint8_t *dst, int dW, int dH, int px, int py, void *stream);
 int fx_grid_bbox(fx_context *ctx, const void *a, int W, int H, int is_msg, int32_t *d_bbox4, void *stream);
 int fx_relocate_goal(fx_context *ctx, const uint8_t *grid, int W, int H, int32_t *d_goal4, int ifa, int ccst, void *stream);
+/* Map image <-> array.  img: uint8 'L' image, H rows x W columns, row major.
+ * fx_grid_to_image: the save block scripts/global_planner_st.py:368-372 (= global_planner_ccst.py:628-632):
+ *   pixel[H-1-y][x] = grid[x][y] == 0 ? 255 : 0   (mapsave.T[::-1]).
+ * fx_image_to_grid: the pre-map loader st:176-182: grid[x][y] = img[H-1-y][x] > threshold ? 0 : 1  (img[::-1].T;
+ *   threshold 200 there; threshold 0 inverts fx_grid_to_image = the fixture convention `a[::-1].T == 0`). */
+int fx_grid_to_image(fx_context *ctx, const uint8_t *grid, int W, int H, uint8_t *img, void *stream);
+int fx_image_to_grid(fx_context *ctx, const uint8_t *img, int W, int H, int threshold, uint8_t *grid, void *stream);
 
 /* ---- (5) path post-processing -----------------------------------------------------
  * Per path q (path_xy int32 [Q][max_path][2], path_len int32 [Q]; same layout as fx_search_batch writes):

@@ -327,3 +327,26 @@ def grid_to_png_array(mapu):
     ms[mapu != 0] = 0
     ms[mapu == 0] = 255
     return np.uint8(ms.T[::-1])
+
+
+def load_premap(img_l, threshold=200):
+    """scripts/global_planner_st.py:176-182: img.point(lambda x: 0 if x > 200 else 1); map_pre = img[::-1].T."""
+    a = np.asarray(img_l)
+    return np.where(a > threshold, 0, 1).astype(np.uint8)[::-1].T
+
+
+def merge_premap(mapu, map_o, map_t, map_pre, ori_pre, reso):
+    """scripts/global_planner_st.py:210-224, line by line (float64 grid like np.zeros gives)."""
+    mapu = np.asarray(mapu)
+    map_c, map_r = mapu.shape
+    l1_pre, l2_pre = len(map_pre), len(map_pre[0])
+    t_pre = [ori_pre[0] + reso * l1_pre, ori_pre[1] + reso * l2_pre]
+    map_o1 = [min(map_o[0], ori_pre[0]), min(map_o[1], ori_pre[1])]
+    map_oi = ((np.array(map_o) - map_o1) / reso).astype(int)
+    ori_prei = ((np.array(ori_pre) - map_o1) / reso).astype(int)
+    map_c1 = int((max(t_pre[0], map_t[0]) - map_o1[0]) / reso)
+    map_r1 = int((max(t_pre[1], map_t[1]) - map_o1[1]) / reso)
+    mapu0 = np.zeros([map_c1, map_r1])
+    mapu0[ori_prei[0]:ori_prei[0] + l1_pre, ori_prei[1]:ori_prei[1] + l2_pre] = map_pre
+    mapu0[map_oi[0]:map_oi[0] + map_c, map_oi[1]:map_oi[1] + map_r] = mapu
+    return mapu0, map_o1

@@ -75,6 +75,35 @@ def main():
         dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
         res["inflate_r%d_%s" % (radius, variant)] = {"seconds": dt, "bit_exact_vs_single_gpu": bool(ok_t.item())}
         del full, inf
+    # row-tiled EDT (two transposes) and point-sharded projection (one all-reduce) against the single-GPU kernels
+    sparse = torch.from_numpy((np.random.default_rng(8).random((n, n)) < 0.002).astype(np.uint8))
+    for name, grid in (("edt_20pct", torch.from_numpy(m)), ("edt_0.2pct", sparse)):
+        own_e = grid[x0:x1].to(dev)
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        d = tiled.edt_tiled(own_e, n)
+        torch.cuda.synchronize(); dist.barrier()
+        dt = time.perf_counter() - t0
+        full = fx.edt(grid.to(dev))
+        ok_t = torch.tensor([int(torch.equal(full[x0:x1], d))], device=dev)
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+        res[name] = {"seconds": dt, "bit_exact_vs_single_gpu": bool(ok_t.item())}
+        del full, d, own_e
+    npts = 1 << 24
+    prng = np.random.default_rng(9)
+    pts = torch.from_numpy(np.c_[prng.uniform(0, n * 0.2, (npts, 2)), prng.uniform(-0.5, 3.0, npts)].astype(np.float32))
+    p0, p1 = tiled.shard_queries(npts, world, rank)
+    mine = pts[p0:p1].to(dev)
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    gr = tiled.project_sharded(mine, None, 0.3, float("inf"), (0.0, 0.0), 0.2, (n, n))
+    torch.cuda.synchronize(); dist.barrier()
+    dt = time.perf_counter() - t0
+    full = fx.project(pts.to(dev), None, 0.3, float("inf"), (0.0, 0.0), 0.2, (n, n))
+    ok_t = torch.tensor([int(torch.equal(full, gr))], device=dev)
+    dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+    res["project_sharded_16Mpts"] = {"seconds": dt, "bit_exact_vs_single_gpu": bool(ok_t.item()), "occupied": int(full.sum())}
+    del full, gr, mine
     # query-parallel
     rng = np.random.default_rng(7)
     Q = a.queries

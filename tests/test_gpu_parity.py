@@ -125,6 +125,21 @@ def test_edt_single_obstacle_and_clusters(fx, dev, oracle):
     assert np.array_equal(fx.edt(_t(m, dev)).cpu().numpy(), oracle.edt(m))
 
 
+@pytest.mark.parametrize("shape,fill", [((300, 200), 0.01), ((64, 1024), 0.2), ((257, 33), 0.001), ((128, 128), 0.0)])
+def test_edt_separable_passes(fx, dev, oracle, shape, fill):
+    """fx_edt_rows / fx_edt_cols (the entry points of the row-tiled mode) compose to fx_edt; the column pass also works
+    on a column block on its own (what a rank holds after the transpose)."""
+    from fuxi_planner_b200 import tiled
+    m = (np.random.default_rng(shape[0]).random(shape) < fill).astype(np.uint8)
+    want = oracle.edt(m)
+    ops = tiled.CudaOps()
+    g = ops.edt_rows(_t(m, dev))
+    assert np.array_equal(ops.edt_cols(g).cpu().numpy(), want)
+    a, b = shape[1] // 3, shape[1] // 3 + max(shape[1] // 2, 1)
+    assert np.array_equal(ops.edt_cols(g[:, a:b].contiguous()).cpu().numpy(), want[:, a:b])
+    assert np.array_equal(tiled.edt_tiled(_t(m, dev), shape[0]).cpu().numpy(), want)
+
+
 def test_edt_vs_scipy(fx, dev):
     from scipy.ndimage import distance_transform_edt
     rng = np.random.default_rng(12)

@@ -82,3 +82,13 @@ def test_relocate_goal_and_path_to_world(oracle):
     for v in ("st", "ccst"):
         assert np.array_equal(planner.path_cells_to_world(path, 0.2, (-3.0, 5.0), v),
                               oracle.hostref.path_to_world(path, 0.2, np.array([-3.0, 5.0]), v))
+
+
+def test_formats_host_side():
+    from fuxi_planner_b200 import formats
+    assert formats.map_png_name((-16.4, -4.8)) == "-16.40-4.80_out.png"
+    assert formats.map_png_name((4.6, 1.0)) == "4.601.00_out.png"
+    msg = formats.path_message([(1.0, 2.0, 0.0), (3.5, 4.5, 0.0)], stamp=12.5)
+    assert msg["header"]["frame_id"] == "map" and len(msg["poses"]) == 2
+    assert msg["poses"][1]["pose"]["position"] == {"x": 3.5, "y": 4.5, "z": 0.0}
+    assert msg["poses"][0]["header"] == {"frame_id": "map", "stamp": 12.5}

@@ -54,12 +54,42 @@ class CpuOps:
         return torch.from_numpy(oracle.inflate(grid.numpy(), radius, step))
 
 
+    def edt_rows(self, grid):
+        occ = grid.numpy() > 0
+        w, H = occ.shape
+        g = np.full((w, H), 0xFFFF, dtype=np.uint16)
+        ys = np.arange(H)
+        for x in range(w):
+            idx = np.flatnonzero(occ[x])
+            if len(idx):
+                g[x] = np.abs(ys[:, None] - idx[None, :]).min(axis=1)
+        return torch.from_numpy(g.view(np.int16))
+
+    def edt_cols(self, g):
+        gv = g.numpy().view(np.uint16).astype(np.int64)
+        W, hb = gv.shape
+        g2 = np.where(gv == 0xFFFF, 1 << 40, gv * gv)
+        xs = np.arange(W)
+        d = ((xs[:, None] - xs[None, :]) ** 2)[:, :, None] + g2[None, :, :]      # [x][x'][y]
+        return torch.from_numpy(np.minimum(d.min(axis=1), 0x7FFFFFFF).astype(np.int32))
+
+    def project(self, points, affine, zmin, zmax, origin, reso, shape):
+        import oracle
+        A = np.eye(3, 4) if affine is None else affine
+        return torch.from_numpy(oracle.hostref.project(points.numpy(), A, zmin, zmax, origin[0], origin[1], reso, shape[0], shape[1]))
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     p = s.getsockname()[1]
     s.close()
     return p
+
+
+def _cloud(seed, W, H):
+    rng = np.random.default_rng(seed + 1)
+    return np.c_[rng.uniform(-1, 0.5 * W + 1, 500), rng.uniform(-1, 0.5 * H + 1, 500), rng.uniform(-0.5, 3, 500)].astype(np.float32)
 
 
 def _worker(rank, world, port, W, H, seed, out_dir):
@@ -75,8 +105,12 @@ def _worker(rank, world, port, W, H, seed, out_dir):
         fld, rounds = tiled.field_tiled(own, W, src, metric=1, ops=CpuOps())
         inf = tiled.inflate_tiled(own, 2, "ccst", ops=CpuOps())
         inf_st = tiled.inflate_tiled(own, 3, "st", ops=CpuOps())
+        edt = tiled.edt_tiled(own, W, ops=CpuOps())
+        pts = _cloud(seed, W, H)
+        p0, p1 = tiled.shard_queries(len(pts), world, rank)
+        proj = tiled.project_sharded(torch.from_numpy(pts[p0:p1].copy()), None, 0.3, float("inf"), (0.0, 0.0), 0.5, (W, H), ops=CpuOps())
         np.savez(os.path.join(out_dir, "r%d.npz" % rank), field=fld.numpy(), inflate=inf.numpy(), inflate_st=inf_st.numpy(),
-                 rounds=rounds, x0=x0, x1=x1)
+                 rounds=rounds, x0=x0, x1=x1, edt=edt.numpy(), proj=proj.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -94,6 +128,9 @@ def test_row_tiled_field_and_inflation_match_single_device(tmp_path, oracle, wor
     assert np.array_equal(field, oracle.sssp_field(m, src, 1))
     assert np.array_equal(np.concatenate([p["inflate"] for p in parts]), oracle.inflate(m, 2, 1))
     assert np.array_equal(np.concatenate([p["inflate_st"] for p in parts]), oracle.inflate(m, 3, 3))
+    assert np.array_equal(np.concatenate([p["edt"] for p in parts]), oracle.edt(m))
+    want = oracle.hostref.project(_cloud(seed, W, H), np.eye(3, 4), 0.3, np.inf, 0.0, 0.0, 0.5, W, H)
+    assert want.sum() > 100 and all(np.array_equal(p["proj"], want) for p in parts)
     assert all(int(p["rounds"]) == int(parts[0]["rounds"]) for p in parts)     # every rank leaves the loop together
     assert int(parts[0]["rounds"]) >= 2
 
