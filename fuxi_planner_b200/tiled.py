@@ -225,8 +225,9 @@ def _transpose_blocks(send, recv, rank, n, group):
     ops = []
     for k in range(1, n):
         to, frm = (rank + k) % n, (rank - k) % n
-        ops.append(dist.P2POp(dist.isend, send[to], _peer(group, to), group))
-        ops.append(dist.P2POp(dist.irecv, recv[frm], _peer(group, frm), group))
+        # byte views: NCCL has no 16-bit integer type, and the payload is opaque to the transport anyway
+        ops.append(dist.P2POp(dist.isend, send[to].view(torch.uint8), _peer(group, to), group))
+        ops.append(dist.P2POp(dist.irecv, recv[frm].view(torch.uint8), _peer(group, frm), group))
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
