@@ -305,10 +305,13 @@ def replan_host(map_data, width, height, origin, reso, start_xy, goal_xy, ifa=1,
 
 
 def plan_host(grid, starts, goals, metric=2, max_path=512, ctx=None, device=0):
-    """numpy in / numpy out through fx_plan_host (H2D + search + D2H inside the call).
+    """numpy in / numpy out through fx_plan_host (H2D + search + D2H inside the call).  A float64 grid is taken as the
+    reference's matrix (obstacle iff == 1.0, fx_plan_host_f64); any other dtype is cast to uint8 occupancy.
     Returns (cost_i int32[Q], cost_f float64[Q], path_xy int32[Q,max_path,2] or None, path_len int32[Q])."""
     ctx = ctx or default_context(device)
-    g = np.ascontiguousarray(grid, dtype=np.uint8)
+    grid = np.asarray(grid)
+    f64 = grid.dtype == np.float64          # the reference's own matrix type: `== 1` is evaluated inside the library
+    g = np.ascontiguousarray(grid) if f64 else np.ascontiguousarray(grid, dtype=np.uint8)
     s = np.ascontiguousarray(starts, dtype=np.int32).reshape(-1, 2)
     t = np.ascontiguousarray(goals, dtype=np.int32).reshape(-1, 2)
     Q = len(s)
@@ -318,8 +321,8 @@ def plan_host(grid, starts, goals, metric=2, max_path=512, ctx=None, device=0):
     path_len = np.empty(Q, dtype=np.int32)
     path_xy = np.empty((Q, max_path, 2), dtype=np.int32) if max_path > 0 else None
     vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
-    rc = ctx.lib.fx_plan_host(ctx.handle, vp(g), W, H, vp(s), vp(t), Q, int(metric), vp(cost_i), vp(cost_f), vp(path_xy),
-                              vp(path_len), int(max_path))
+    fn = ctx.lib.fx_plan_host_f64 if f64 else ctx.lib.fx_plan_host
+    rc = fn(ctx.handle, vp(g), W, H, vp(s), vp(t), Q, int(metric), vp(cost_i), vp(cost_f), vp(path_xy), vp(path_len), int(max_path))
     ctx.check(rc, "fx_plan_host")
     return cost_i, cost_f, path_xy, path_len
 

@@ -2,6 +2,9 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
 
 static char g_create_err[512] = "";
@@ -47,6 +50,8 @@ extern "C" int fx_create(int device, fx_context **out)
         return FX_ERR_UNSUPPORTED;
     }
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->cfg_wide_below = -1;
+    if (const char *e = getenv("FUXI_B200_WIDE_BELOW")) ctx->cfg_wide_below = atoi(e);  // tuning experiments only
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
     e = cudaMalloc(&ctx->counters, 16 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(ctx->counters, 0, 16 * sizeof(unsigned long long));
@@ -126,12 +131,53 @@ static int grow_pinned(fx_context *ctx, size_t want) { return fx_grow_pinned(ctx
 
 // Host-buffer planning call: H2D (grid + queries) -> search -> D2H (costs, path lengths, paths).
 // Replaces the whole of `jps1.method(...)` for Q queries (scripts/jps1.py:183-230) from the caller's view.
+// The reference hands jps1.method a float64 matrix (np.zeros, scripts/global_planner_st.py:248) and tests `== 1`
+// (scripts/jps1.py:20-29).  Converting 16 Mi cells with numpy costs 15 ms on the host (r01f), more than the search:
+// the f64 entry point does `== 1.0 -> uint8` straight into the pinned staging buffer with a few host threads,
+// chunk by chunk, each chunk's H2D copy overlapping the conversion of the next.
+static void convert_f64_chunk(const double *src, uint8_t *dst, size_t n, int nthreads)
+{
+    auto work = [=](size_t a, size_t b) {
+        for (size_t i = a; i < b; i++) dst[i] = src[i] == 1.0 ? (uint8_t)1 : (uint8_t)0;
+    };
+    if (nthreads <= 1 || n < (1u << 18)) { work(0, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = (n + nthreads - 1) / nthreads;
+    for (int t = 1; t < nthreads; t++) {
+        const size_t a = (size_t)t * per, b = a + per < n ? a + per : n;
+        if (a < b) th.emplace_back(work, a, b);
+    }
+    work(0, per < n ? per : n);
+    for (auto &t : th) t.join();
+}
+
+static int plan_host_impl(fx_context *ctx, const uint8_t *h_grid, const double *h_matrix, int W, int H, const int32_t *h_starts_xy,
+                          const int32_t *h_goals_xy, int Q, int metric, int32_t *h_cost_i, double *h_cost_f,
+                          int32_t *h_path_xy, int32_t *h_path_len, int max_path);
+
 extern "C" int fx_plan_host(fx_context *ctx, const uint8_t *h_grid, int W, int H, const int32_t *h_starts_xy,
                             const int32_t *h_goals_xy, int Q, int metric, int32_t *h_cost_i, double *h_cost_f,
                             int32_t *h_path_xy, int32_t *h_path_len, int max_path)
 {
     if (!ctx) return FX_ERR_ARG;
-    if (!h_grid || W <= 0 || H <= 0 || Q < 0 || (Q > 0 && (!h_starts_xy || !h_goals_xy || !h_cost_i)) || max_path < 0)
+    if (!h_grid) return fx_set_err(ctx, FX_ERR_ARG, "fx_plan_host: bad argument");
+    return plan_host_impl(ctx, h_grid, nullptr, W, H, h_starts_xy, h_goals_xy, Q, metric, h_cost_i, h_cost_f, h_path_xy, h_path_len, max_path);
+}
+
+extern "C" int fx_plan_host_f64(fx_context *ctx, const double *h_matrix, int W, int H, const int32_t *h_starts_xy,
+                                const int32_t *h_goals_xy, int Q, int metric, int32_t *h_cost_i, double *h_cost_f,
+                                int32_t *h_path_xy, int32_t *h_path_len, int max_path)
+{
+    if (!ctx) return FX_ERR_ARG;
+    if (!h_matrix) return fx_set_err(ctx, FX_ERR_ARG, "fx_plan_host_f64: bad argument");
+    return plan_host_impl(ctx, nullptr, h_matrix, W, H, h_starts_xy, h_goals_xy, Q, metric, h_cost_i, h_cost_f, h_path_xy, h_path_len, max_path);
+}
+
+static int plan_host_impl(fx_context *ctx, const uint8_t *h_grid, const double *h_matrix, int W, int H, const int32_t *h_starts_xy,
+                          const int32_t *h_goals_xy, int Q, int metric, int32_t *h_cost_i, double *h_cost_f,
+                          int32_t *h_path_xy, int32_t *h_path_len, int max_path)
+{
+    if (W <= 0 || H <= 0 || Q < 0 || (Q > 0 && (!h_starts_xy || !h_goals_xy || !h_cost_i)) || max_path < 0)
         return fx_set_err(ctx, FX_ERR_ARG, "fx_plan_host: bad argument");
     if (Q == 0) return FX_OK;
     FX_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -158,10 +204,21 @@ extern "C" int fx_plan_host(fx_context *ctx, const uint8_t *h_grid, int W, int H
            off_pl = off_ci + (size_t)Q * 4, off_cf = (off_pl + (size_t)Q * 4 + 7) / 8 * 8, off_p = off_cf + (size_t)Q * 8;
     if ((rc = grow_pinned(ctx, off_p + path_bytes))) return rc;
     char *pin = (char *)ctx->h_pin;
-    memcpy(pin + off_grid, h_grid, cells);
     memcpy(pin + off_s, h_starts_xy, qb);
     memcpy(pin + off_g, h_goals_xy, qb);
-    FX_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid, pin + off_grid, cells, cudaMemcpyHostToDevice, st));
+    if (h_matrix) {
+        unsigned hc = std::thread::hardware_concurrency();
+        const int nthreads = (int)(hc == 0 ? 1 : (hc > 16 ? 16 : hc));
+        const size_t chunk = cells > (1u << 22) ? (cells + 3) / 4 : cells;
+        for (size_t a = 0; a < cells; a += chunk) {
+            const size_t nb = a + chunk < cells ? chunk : cells - a;
+            convert_f64_chunk(h_matrix + a, (uint8_t *)pin + off_grid + a, nb, nthreads);
+            FX_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid + a, pin + off_grid + a, nb, cudaMemcpyHostToDevice, st));
+        }
+    } else {
+        memcpy(pin + off_grid, h_grid, cells);
+        FX_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid, pin + off_grid, cells, cudaMemcpyHostToDevice, st));
+    }
     FX_CUDA(ctx, cudaMemcpyAsync(ctx->d_q, pin + off_s, 2 * qb, cudaMemcpyHostToDevice, st));
     int32_t *d_s = ctx->d_q, *d_g = ctx->d_q + (size_t)Q * 2;
     int32_t *d_ci = ctx->d_out_i, *d_pl = ctx->d_out_i + Q;

@@ -14,6 +14,9 @@
 #ifndef FX_SEARCH_MINB
 #define FX_SEARCH_MINB 8 /* resident search CTAs per SM the register budget is compiled for (64 registers) */
 #endif
+#ifndef FX_SEARCH_WIDE
+#define FX_SEARCH_WIDE 512 /* threads per CTA of the latency form (batches of at most sm_count queries) */
+#endif
 #define FX_DIRTY_SHIFT 5 /* one dirty flag per 32 field cells (one 128 B line) */
 
 struct fx_context {
@@ -26,6 +29,7 @@ struct fx_context {
     // tuning
     int cfg_slots;
     int cfg_band0;
+    int cfg_wide_below;  // batches of at most this many queries use the wide (latency) CTA form; -1 = sm_count
 
     // search scratch (sized for sW x sH, reallocated when the grid shape grows)
     int sW, sH, slots, qcap, path_cap;

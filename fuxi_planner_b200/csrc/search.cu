@@ -412,8 +412,11 @@ __device__ int extract_path(const SearchParams &P, const uint32_t *__restrict__ 
     return npts;
 }
 
-template <int METRIC>
-__global__ void __launch_bounds__(FX_SEARCH_THREADS, FX_SEARCH_MINB) k_search_batch(const SearchParams P)
+// THREADS / MINB: the throughput form (128 threads, 8 CTAs per SM hide each other's L2 round trips) and the latency
+// form for batches smaller than the machine (FX_SEARCH_WIDE threads: a whole level of a single query -- a few hundred
+// frontier cells -- is one round of loads instead of three).
+template <int METRIC, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchParams P)
 {
     constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
     __shared__ CtaState S;
@@ -662,8 +665,14 @@ extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int 
     if (rc) return rc;
     P.order = ctx->q_order; P.ubound = ctx->q_ubound;
     int blocks = ctx->slots < Q ? ctx->slots : Q;
-    if (metric == 1) k_search_batch<1><<<blocks, FX_SEARCH_THREADS, 0, st>>>(P);
-    else k_search_batch<2><<<blocks, FX_SEARCH_THREADS, 0, st>>>(P);
+    const int wide = ctx->cfg_wide_below >= 0 ? ctx->cfg_wide_below : ctx->sm_count;  // batches of at most this many queries
+    if (Q <= wide) {
+        if (metric == 1) k_search_batch<1, FX_SEARCH_WIDE, 1><<<blocks, FX_SEARCH_WIDE, 0, st>>>(P);
+        else k_search_batch<2, FX_SEARCH_WIDE, 1><<<blocks, FX_SEARCH_WIDE, 0, st>>>(P);
+    } else {
+        if (metric == 1) k_search_batch<1, FX_SEARCH_THREADS, FX_SEARCH_MINB><<<blocks, FX_SEARCH_THREADS, 0, st>>>(P);
+        else k_search_batch<2, FX_SEARCH_THREADS, FX_SEARCH_MINB><<<blocks, FX_SEARCH_THREADS, 0, st>>>(P);
+    }
     FX_LAUNCH_CHECK(ctx);
     return FX_OK;
 }

@@ -31,7 +31,9 @@ def method(matrix, start, goal, hchoice):
     starttime = time.time()
     if hchoice not in (1, 2):
         raise ValueError("hchoice must be 1 or 2")
-    occ = (np.asarray(matrix) == 1).astype(np.uint8)
+    occ = np.asarray(matrix)
+    if occ.dtype != np.float64:        # float64 (what the planners pass) is compared `== 1` inside the library
+        occ = (occ == 1).astype(np.uint8)
     max_path = _MAX_PATH
     while True:
         cost_i, cost_f, path_xy, path_len = api.plan_host(occ, [start], [goal], metric=hchoice, max_path=max_path)

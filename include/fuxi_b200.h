@@ -150,6 +150,13 @@ int fx_plan_host(fx_context *ctx, const uint8_t *h_grid, int W, int H,
                  const int32_t *h_starts_xy, const int32_t *h_goals_xy, int Q, int metric,
                  int32_t *h_cost_i, double *h_cost_f, int32_t *h_path_xy, int32_t *h_path_len, int max_path);
 
+/* Same, taking the matrix as the reference's callers hold it: float64 [W][H] (np.zeros, scripts/global_planner_st.py:248),
+ * obstacle iff matrix[x][y] == 1.0 (scripts/jps1.py:20-29).  The `== 1 -> uint8` conversion runs on a few host threads
+ * straight into the pinned staging buffer, overlapped with the H2D copy. */
+int fx_plan_host_f64(fx_context *ctx, const double *h_matrix, int W, int H,
+                     const int32_t *h_starts_xy, const int32_t *h_goals_xy, int Q, int metric,
+                     int32_t *h_cost_i, double *h_cost_f, int32_t *h_path_xy, int32_t *h_path_len, int max_path);
+
 /* host-buffer map pipeline: project + inflate in one call (HOST in, HOST out), for the ROS-side glue */
 int fx_map_host(fx_context *ctx, const float *h_pts, int64_t n, int stride_floats, const float *h_affine3x4,
                 float zmin, float zmax, float ox, float oy, float reso, int W, int H,

@@ -424,3 +424,30 @@ def test_search_pockets_and_obstacle_start(fx, dev, oracle):
             validate_path(m, res.path(int(i)), tuple(s[i]), tuple(g[i]))
     settled = fx.search_stats()[0]
     assert settled < 8 * 40000, "pocket queries flooded the map (%d cells settled)" % settled
+
+
+def test_plan_host_float64_matrix_and_wide_ctas(fx, oracle):
+    """fx_plan_host_f64 evaluates the reference's `matrix[x][y] == 1` (jps1.py:20-29) on the float64 matrix itself
+    (threaded, chunked into the pinned staging buffer): same answers as the uint8 entry point, values other than
+    exactly 1.0 are free.  Small batches run the wide-CTA (latency) form of the search kernel: checked against the
+    oracle here, and against the throughput form on the same queries."""
+    rng = np.random.default_rng(77)
+    W, H = 2304, 2048                       # > 2^22 cells: exercises the chunked conversion
+    occ = (rng.random((W, H)) < 0.2).astype(np.uint8)
+    mat = occ.astype(np.float64)
+    free = mat == 0
+    mat[free & (rng.random((W, H)) < 0.05)] = 100.0          # "occupied" in the message encoding, free for the search
+    mat[free & (rng.random((W, H)) < 0.01)] = 0.999999
+    mat[free & (rng.random((W, H)) < 0.01)] = np.nan
+    s, g = random_queries(occ, 6, rng)
+    want, status, _ = oracle.jps_batch(occ, s, g, 1)
+    a = fx.plan_host(mat, s, g, metric=1, max_path=64)
+    b = fx.plan_host(occ, s, g, metric=1, max_path=64)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[3])
+    for q in range(6):
+        assert (a[0][q] == int(want[q])) if status[q] == 1 else (a[0][q] == -1)
+    # the same six queries inside a batch large enough for the throughput form
+    S, G = random_queries(occ, 400, rng)
+    S[:6], G[:6] = s, g
+    c = fx.plan_host(occ, S, G, metric=1, max_path=0)
+    assert np.array_equal(c[0][:6], a[0])
