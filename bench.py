@@ -119,6 +119,19 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel, n, Q, hchoice):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture of the same
+    workload (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py from the .ncu-rep), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            for rec in json.load(fh):
+                if rec["kernel"] == kernel and rec["grid"] == n and rec["queries"] == Q and rec["hchoice"] == hchoice:
+                    return float(rec["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------ reference arm
 def cpu_sample(m, s, g, hchoice, target_s, oracle):
     """Times the C restatement of jps1.py over all host threads on the first S queries; S is doubled until
@@ -236,7 +249,28 @@ def map_kernel_rooflines(torch, fx, dev, flush, peak):
         entry("edt_%s" % label, 5 * n * n, lambda: fx.edt(occ, out=d2))
         del occ, o2, d2, grid
         torch.cuda.empty_cache()
-    del rng
+    # upstream cloud conditioning: one depth frame (640 x 480 PointXYZRGB, point_step 32) and a scaled
+    # cloud; algorithmic bytes = the points read once + the kept points written (the kernels read the cloud three times:
+    # bounding box, voxel marking, accumulation -- L2-resident at frame size)
+    for label, N in (("frame_640x480", 640 * 480), ("16Mpts", 16 << 20)):
+        c = torch.zeros((N, 8), dtype=torch.float32, device=dev)
+        c[:, 0].uniform_(-3.0, 3.0)
+        c[:, 1].uniform_(-2.0, 2.0)
+        c[:, 2].uniform_(-0.5, 5.0)
+        c[: N // 2, 2] = 3.0 + 0.03 * torch.randn(N // 2, device=dev)      # a wall: something survives the radius filter
+        state = {}
+
+        def run_cf():
+            state["out"], state["counts"] = fx.cloud.cloud_filter(c, rgb_offset=4)
+        run_cf()
+        kept = int(state["counts"][2].item())
+        entry("cloud_filter_%s" % label, N * 32 + kept * 16, run_cf)
+        out["cloud_filter_%s" % label]["counts"] = [int(v) for v in state["counts"].tolist()]
+        del c
+    d = torch.empty((1 << 20, 3), dtype=torch.float64, device=dev).uniform_(-6.0, 6.0)
+    mkept = int(fx.cloud.distance_filter(d, 4.0)[1].item())
+    entry("distance_filter_1Mpts", (1 << 20) * 24 + mkept * 24, lambda: fx.cloud.distance_filter(d, 4.0))
+    del rng, d
     return out
 
 
@@ -269,6 +303,23 @@ def latency_probe(fx, m4096, s, g, hchoice):
     m4 = m4096.astype(np.float64)
     pairs4 = [(tuple(int(v) for v in s[i]), tuple(int(v) for v in g[i])) for i in range(40)]
     res["grid_%dx%d" % m4096.shape] = run(m4, pairs4, 8)
+    # the whole planner iteration in one call (decode + pad/shift + inflate + goal relocation + search + shortcutting +
+    # world coordinates, fx_replan_host): OccupancyGrid message of the cfg1 map in, world path out
+    from fuxi_planner_b200 import planner
+    msg = planner.array_to_occupancy_grid(z["-16.40-4.80_out.png"])
+    Wm, Hm = m1.shape
+    ts = []
+    for i, (a, b) in enumerate(pairs[:220]):
+        st_xy = (-16.4 + 0.2 * (a[0] + 0.5), -4.8 + 0.2 * (a[1] + 0.5))
+        go_xy = (-16.4 + 0.2 * (b[0] + 0.5), -4.8 + 0.2 * (b[1] + 0.5))
+        t0 = time.perf_counter()
+        planner.replan_fused(msg, Wm, Hm, (-16.4, -4.8), 0.2, st_xy, go_xy, ifa=1, variant="st", hchoice=hchoice)
+        dt = time.perf_counter() - t0
+        if i >= 20:
+            ts.append(dt)
+    ts = np.array(ts) * 1e3
+    res["replan_fused_cfg1"] = {"p50_ms": float(np.percentile(ts, 50)), "p90_ms": float(np.percentile(ts, 90)),
+                                "p99_ms": float(np.percentile(ts, 99)), "n": len(ts)}
     return res
 
 
@@ -324,11 +375,13 @@ def run_b200(args):
     launches0 = ctx.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    kernel_ms = []
     for a, b in ev:
         flush()
         a.record()
         res = step()
         b.record()
+        kernel_ms.append(fx.search_kernel_ms(ctx))      # waits for this step's k_search_batch; the next step starts after it
     barrier()
     launches = ctx.launches - launches0
     t_ms = float(sum(a.elapsed_time(b) for a, b in ev))
@@ -364,7 +417,8 @@ def run_b200(args):
     settled_all = float(st.item())
     ms_step = t_ms_max / args.steps
     alg_bytes = settled / 1.0 * 5.0            # this rank's last step: settled cells x (1 B occupancy + 4 B cost)
-    achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+    k_ms = float(np.mean(kernel_ms))           # k_search_batch alone: CUDA events on its own stream, inside the C library
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -374,9 +428,10 @@ def run_b200(args):
                 "api": "fx_plan_host (fuxi_planner_b200.plan_host), host numpy buffers"},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "k_search_batch", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": ncu_traffic("k_search_batch", n, Q, args.hchoice),
+                     "peak_source": peak_src, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step,
                      "algorithmic_bytes": "settled cells x 5 B (SURVEY §8d early-exit form)",
-                     "full_field_form_gbs": Q * n * n * 5.0 / (ms_step * 1e-3) / 1e9},
+                     "full_field_form_gbs": Q * n * n * 5.0 / (k_ms * 1e-3) / 1e9},
         "search": {"settled_cells_per_step_rank0": int(settled), "nodes_per_s": settled_all / (ms_step * 1e-3),
                    "levels": int(levels), "passes": int(passes), "band_only": int(band_only),
                    "answered_rank0": answered, "queries_rank0": Q},

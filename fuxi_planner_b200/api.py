@@ -131,6 +131,14 @@ def search_stats(ctx=None):
     return tuple(int(v) for v in a)
 
 
+def search_kernel_ms(ctx=None):
+    """Duration (ms) of the last k_search_batch launch alone, from CUDA events on its stream (fx_search_kernel_ms)."""
+    ctx = _ctx(ctx)
+    ms = C.c_float(0.0)
+    ctx.check(ctx.lib.fx_search_kernel_ms(ctx.handle, C.byref(ms)), "fx_search_kernel_ms")
+    return float(ms.value)
+
+
 def field(grid, source, metric=1, out=None, ctx=None, check=True):
     """Cost-from-source field, int32 [W][H], -1 = unreachable (fx_field)."""
     grid = _u8_grid(grid)

@@ -59,6 +59,8 @@ extern "C" int fx_create(int device, fx_context **out)
     if (e == cudaSuccess) e = cudaMemset(ctx->fstate, 0, 32 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->edt_flag, 4 * sizeof(int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_search[0]);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_search[1]);
     if (e != cudaSuccess) {
         fx_set_err(nullptr, FX_ERR_CUDA, "context allocation: %s", cudaGetErrorString(e));
         fx_destroy(ctx);
@@ -82,6 +84,8 @@ extern "C" int fx_destroy(fx_context *ctx)
         if (dev[i]) cudaFree(dev[i]);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->ev_search[0]) cudaEventDestroy(ctx->ev_search[0]);
+    if (ctx->ev_search[1]) cudaEventDestroy(ctx->ev_search[1]);
     free(ctx);
     return FX_OK;
 }

@@ -17,6 +17,7 @@
 #ifndef FX_SEARCH_WIDE
 #define FX_SEARCH_WIDE 512 /* threads per CTA of the latency form (batches of at most sm_count queries) */
 #endif
+#define FX_SMALL_CELLS 20000 /* maps up to this many cells are searched entirely in one SM's shared memory (small.cu) */
 #define FX_DIRTY_SHIFT 5 /* one dirty flag per 32 field cells (one 128 B line) */
 
 struct fx_context {
@@ -85,6 +86,9 @@ struct fx_context {
         cl_acc_bytes, cl_vox_bytes, cl_state_bytes, cl_out_bytes, df_rec_bytes;
     unsigned long long cl_cap_bits;  // voxel index space the bitmap is reserved for (fx_cloud_reserve)
     cudaStream_t own_stream;
+    cudaEvent_t ev_search[2];  // around the last k_search_batch launch (fx_search_kernel_ms)
+    int ev_search_valid;
+    int small_attr_set, cfg_small_off;
 };
 
 int fx_set_err(fx_context *ctx, int code, const char *fmt, ...);
@@ -199,4 +203,7 @@ int fx_search_reserve(fx_context *ctx, int W, int H, int max_path);
 // band.cu: LPT query order + per-query upper bounds from the band pass (one warp per query)
 int fx_band_bounds(fx_context *ctx, const uint8_t *grid, int W, int H, const int32_t *starts_xy, const int32_t *goals_xy, int Q,
                    int metric, cudaStream_t st);
+// small.cu: whole query in shared memory; returns 1 when the map is too large for it
+int fx_search_small(fx_context *ctx, const uint8_t *grid, int W, int H, const int32_t *starts_xy, const int32_t *goals_xy, int Q,
+                    int metric, int32_t *cost_i, double *cost_f, int32_t *path_xy, int32_t *path_len, int max_path, cudaStream_t st);
 int fx_build_moves(fx_context *ctx, const uint8_t *grid, int W, int H, bool tiled, cudaStream_t st);

@@ -18,6 +18,8 @@
 //   128-byte lines a query touched are reset afterwards (dirty flags).
 //   Path: warp-parallel descent from the goal along cost-consistent predecessors, 32 cells of a
 //   straight run per round trip, emitting turning points.
+#include <stdlib.h>
+
 #include "common.cuh"
 #if !FX_TILED
 #error "search.cu relies on the 8x8-tiled scratch layout (step tables)"
@@ -647,6 +649,15 @@ extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int 
     if (Q == 0) return FX_OK;
     cudaStream_t st = (cudaStream_t)stream;
     FX_CUDA(ctx, cudaSetDevice(ctx->device));
+    {
+        // maps that fit one SM's shared memory (every map the reference ships): one launch, no global scratch.
+        // FUXI_B200_SMALL=0 routes them through the batched kernel instead (tests cover both forms on the same maps).
+        const char *e = getenv("FUXI_B200_SMALL");
+        if (!(e && e[0] == '0')) {
+            const int r = fx_search_small(ctx, grid, W, H, starts_xy, goals_xy, Q, metric, cost_i, cost_f, path_xy, path_len, max_path, st);
+            if (r <= 0) return r;
+        }
+    }
     int rc = fx_search_reserve(ctx, W, H, path_xy ? max_path : 1);
     if (rc) return rc;
     rc = fx_build_moves(ctx, grid, W, H, true, st);
@@ -665,6 +676,7 @@ extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int 
     if (rc) return rc;
     P.order = ctx->q_order; P.ubound = ctx->q_ubound;
     int blocks = ctx->slots < Q ? ctx->slots : Q;
+    FX_CUDA(ctx, cudaEventRecord(ctx->ev_search[0], st));
     const int wide = ctx->cfg_wide_below >= 0 ? ctx->cfg_wide_below : ctx->sm_count;  // batches of at most this many queries
     if (Q <= wide) {
         if (metric == 1) k_search_batch<1, FX_SEARCH_WIDE, 1><<<blocks, FX_SEARCH_WIDE, 0, st>>>(P);
@@ -674,6 +686,8 @@ extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int 
         else k_search_batch<2, FX_SEARCH_THREADS, FX_SEARCH_MINB><<<blocks, FX_SEARCH_THREADS, 0, st>>>(P);
     }
     FX_LAUNCH_CHECK(ctx);
+    FX_CUDA(ctx, cudaEventRecord(ctx->ev_search[1], st));
+    ctx->ev_search_valid = 1;
     return FX_OK;
 }
 
@@ -692,6 +706,17 @@ extern "C" int fx_search_phase_clocks(fx_context *ctx, int64_t *h_8)
     FX_CUDA(ctx, cudaDeviceSynchronize());
     FX_CUDA(ctx, cudaMemcpy(c, ctx->counters, sizeof(c), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 8; i++) h_8[i] = (int64_t)c[8 + i];
+    return FX_OK;
+}
+
+/* duration of the last k_search_batch launch alone (CUDA events recorded on the launching stream around it) */
+extern "C" int fx_search_kernel_ms(fx_context *ctx, float *h_ms)
+{
+    if (!ctx || !h_ms) return FX_ERR_ARG;
+    if (!ctx->ev_search_valid) return fx_set_err(ctx, FX_ERR_ARG, "fx_search_kernel_ms: no search has run on this context");
+    FX_CUDA(ctx, cudaSetDevice(ctx->device));
+    FX_CUDA(ctx, cudaEventSynchronize(ctx->ev_search[1]));
+    FX_CUDA(ctx, cudaEventElapsedTime(h_ms, ctx->ev_search[0], ctx->ev_search[1]));
     return FX_OK;
 }
 

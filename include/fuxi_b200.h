@@ -142,6 +142,9 @@ int fx_field_status(fx_context *ctx, int64_t *h_levels, int64_t *h_settled);
  * h_stats[0] = cells settled (popped and expanded), [1] = wavefront levels, [2] = search passes,
  * [3] = queries answered in the band-limited first pass alone. */
 int fx_search_stats(fx_context *ctx, int64_t *h_stats4);
+/* duration in ms of the last k_search_batch launch alone: CUDA events recorded on the launching stream immediately
+ * before and after it (waits for that launch to finish).  bench.py: roofline of the dominant kernel. */
+int fx_search_kernel_ms(fx_context *ctx, float *h_ms);
 
 /* ---- host-buffer convenience = what the Python drop-in `jps1.method` calls ---------------------
  * Same as fx_search_batch but all buffers are HOST memory; copies in, runs, copies out and

@@ -13,9 +13,9 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_r
 # launch list of the same command (cold-cache, serialised: shares only)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-extras > $OUT/ncu_launches.log 2>&1; echo "ncu list rc=$?"
-# full captures: search (one launch on a smaller batch keeps the replay short), projection, inflation, EDT
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_search_batch -s 1 -c 1 -o $OUT/prof_search \
-    python bench.py --steps 1 --warmup 1 --no-extras --queries 1024 > $OUT/ncu_search.log 2>&1; echo "ncu search rc=$?"
+# full captures: search (one launch of the bench's own batch: 8192 queries), projection, inflation, EDT
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_search_batch -s 1 -c 1 -o $OUT/prof_search \
+    python bench.py --steps 1 --warmup 1 --no-extras > $OUT/ncu_search.log 2>&1; echo "ncu search rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_project|k_inflate|k_edt' -c 12 -o $OUT/prof_map \
     python scripts/map_kernels.py > $OUT/ncu_map.log 2>&1; echo "ncu map rc=$?"
 ls -la $OUT

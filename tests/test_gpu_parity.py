@@ -54,6 +54,30 @@ def test_project_bit_exact(fx, dev, oracle, stride, n):
         assert np.array_equal(got.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("stride", [3, 4])
+def test_project_large_grid_bit_form(fx, dev, oracle, stride):
+    """Grids beyond L2 size take the bit form (RED.OR into an L2-resident bit-packed grid + streaming expand): same
+    grid as the oracle bit for bit, with a cell count that is not a multiple of the expand kernel's 16-cell step and a
+    cloud concentrated in a small patch (heavy same-word contention)."""
+    rng = np.random.default_rng(stride)
+    W, H, reso = 6001, 5599, 0.2                      # 33.6 M cells > 32 Mi, odd cell count
+    n = (4 << 20) + 37
+    pts = np.zeros((n, stride), dtype=np.float32)
+    pts[:, 0] = rng.uniform(-5.0, W * reso + 5.0, n)
+    pts[:, 1] = rng.uniform(-5.0, H * reso + 5.0, n)
+    pts[:, 2] = rng.uniform(-0.5, 3.0, n)
+    pts[11] = np.nan
+    want = oracle.hostref.project(pts[:, :3], np.eye(3, 4), 0.3, np.inf, 0.0, 0.0, reso, W, H)
+    got = fx.project(_t(pts, dev), None, 0.3, np.inf, (0.0, 0.0), reso, (W, H))
+    assert np.array_equal(got.cpu().numpy(), want)
+    pts[:, 0] = rng.uniform(600.0, 640.0, n)
+    pts[:, 1] = rng.uniform(500.0, 540.0, n)
+    want = oracle.hostref.project(pts[:, :3], np.eye(3, 4), 0.3, np.inf, 0.0, 0.0, reso, W, H)
+    got = fx.project(_t(pts, dev), None, 0.3, np.inf, (0.0, 0.0), reso, (W, H))
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert 199 * 199 <= int(want.sum()) <= 202 * 202
+
+
 def test_project_unaligned_and_accumulate(fx, dev, oracle):
     import torch
     rng = np.random.default_rng(3)
@@ -192,22 +216,32 @@ def _check_batch(fx, dev, oracle, m, recs, max_path=1024):
                 assert d1 != d2
 
 
-def test_search_all_reference_maps(fx, dev, oracle, golden, maps):
+def test_search_all_reference_maps(fx, dev, oracle, golden, maps, search_form):
     for name, recs in golden["maps"].items():
         _check_batch(fx, dev, oracle, maps[name], recs)
 
 
-def test_search_cfg1_300_pairs(fx, dev, oracle, golden, maps):
+@pytest.fixture(params=["shared-memory", "batched"])
+def search_form(request, monkeypatch):
+    """Maps below FX_SMALL_CELLS (every map the reference ships) are searched by the one-CTA shared-memory kernel
+    (small.cu); FUXI_B200_SMALL=0 sends the same maps through the batched kernel (search.cu): both are checked against
+    the same golden vectors."""
+    if request.param == "batched":
+        monkeypatch.setenv("FUXI_B200_SMALL", "0")
+    return request.param
+
+
+def test_search_cfg1_300_pairs(fx, dev, oracle, golden, maps, search_form):
     _check_batch(fx, dev, oracle, maps["-16.40-4.80_out.png"], golden["cfg1"])
 
 
-def test_search_edge_cases(fx, dev, oracle, golden):
+def test_search_edge_cases(fx, dev, oracle, golden, search_form):
     for rec in golden["edge"]:
         m = (np.array(rec["grid"]) == 1).astype(np.uint8)
         _check_batch(fx, dev, oracle, m, [rec])
 
 
-def test_search_random_small(fx, dev, oracle, golden):
+def test_search_random_small(fx, dev, oracle, golden, search_form):
     for g in golden["random_small"]:
         _check_batch(fx, dev, oracle, unpack_grid(g), g["queries"])
 
@@ -217,7 +251,7 @@ def test_search_large_golden(fx, dev, oracle, golden):
         _check_batch(fx, dev, oracle, large_grid(g), g["queries"], max_path=4096)
 
 
-def test_search_start_oob_and_goal_oob(fx, dev):
+def test_search_start_oob_and_goal_oob(fx, dev, search_form):
     import torch
     m = np.zeros((8, 8), dtype=np.uint8)
     s = np.array([[8, 0], [0, 0], [-1, 3]], dtype=np.int32)
@@ -424,6 +458,25 @@ def test_search_pockets_and_obstacle_start(fx, dev, oracle):
             validate_path(m, res.path(int(i)), tuple(s[i]), tuple(g[i]))
     settled = fx.search_stats()[0]
     assert settled < 8 * 40000, "pocket queries flooded the map (%d cells settled)" % settled
+
+
+@pytest.mark.parametrize("shape,fill", [((120, 140), 0.1), ((141, 141), 0.3), ((199, 100), 0.45), ((3, 5000), 0.2), ((1, 40), 0.0)])
+def test_search_small_maps_vs_oracle(fx, dev, oracle, shape, fill, search_form):
+    """Maps of the reference's own size (< 20 000 cells) against the Dijkstra oracle, through both kernel forms: random
+    queries including starts ON obstacles and goals in sealed pockets, both metrics, paths validated move by move."""
+    rng = np.random.default_rng(shape[0] * 7 + int(fill * 100))
+    m = (rng.random(shape) < fill).astype(np.uint8)
+    Q = 200
+    s = np.c_[rng.integers(shape[0], size=Q), rng.integers(shape[1], size=Q)].astype(np.int32)      # any cell, obstacles too
+    g = np.c_[rng.integers(shape[0], size=Q), rng.integers(shape[1], size=Q)].astype(np.int32)
+    for metric in (1, 2):
+        want = oracle.sssp_batch(m, s, g, metric)
+        res = fx.plan_batch(_t(m, dev), _t(s, dev), _t(g, dev), metric=metric, max_path=4096)
+        got = res.cost_i.cpu().numpy().astype(np.int64)
+        assert np.array_equal(got, want), (metric, np.flatnonzero(got != want)[:5])
+        for i in np.flatnonzero(want > 0)[:60]:
+            a, b = validate_path(m, res.path(int(i)), tuple(s[i]), tuple(g[i]))
+            assert a * (10 if metric == 1 else fx.FX_EUCLID_WS) + b * (14 if metric == 1 else fx.FX_EUCLID_WD) == want[i]
 
 
 def test_plan_host_float64_matrix_and_wide_ctas(fx, oracle):
