@@ -210,6 +210,33 @@ static int plan_host_impl(fx_context *ctx, const uint8_t *h_grid, const double *
     char *pin = (char *)ctx->h_pin;
     memcpy(pin + off_s, h_starts_xy, qb);
     memcpy(pin + off_g, h_goals_xy, qb);
+    {
+        // Maps of the reference's own size, a handful of queries: no copies at all.  The pinned staging buffer is mapped
+        // into the device's address space (unified addressing), so the shared-memory kernel reads the grid and the
+        // queries from it once and writes its few result bytes straight back: one launch, one synchronisation.
+        const char *e = getenv("FUXI_B200_SMALL");
+        if (cells <= FX_SMALL_CELLS && Q <= 64 && !(e && e[0] == '0')) {
+            if (h_matrix) convert_f64_chunk(h_matrix, (uint8_t *)pin + off_grid, cells, 1);
+            else memcpy(pin + off_grid, h_grid, cells);
+            rc = fx_search_small(ctx, (const uint8_t *)pin + off_grid, W, H, (const int32_t *)(pin + off_s), (const int32_t *)(pin + off_g), Q,
+                                 metric, (int32_t *)(pin + off_ci), (double *)(pin + off_cf), want_path ? (int32_t *)(pin + off_p) : nullptr,
+                                 (int32_t *)(pin + off_pl), want_path ? max_path : 0, st);
+            if (rc) return rc < 0 ? rc : fx_set_err(ctx, FX_ERR_ARG, "fx_plan_host: small-map path refused the map");
+            FX_CUDA(ctx, cudaStreamSynchronize(st));
+            memcpy(h_cost_i, pin + off_ci, (size_t)Q * 4);
+            if (h_path_len) memcpy(h_path_len, pin + off_pl, (size_t)Q * 4);
+            if (h_cost_f) memcpy(h_cost_f, pin + off_cf, (size_t)Q * 8);
+            if (want_path) {
+                // only the points each query produced (the buffers are [Q][max_path][2])
+                const int32_t *pl = (const int32_t *)(pin + off_pl);
+                for (int q = 0; q < Q; q++) {
+                    const int np = pl[q] < 0 ? 0 : (pl[q] < max_path ? pl[q] : max_path);
+                    if (np) memcpy(h_path_xy + (size_t)q * max_path * 2, pin + off_p + (size_t)q * max_path * 8, (size_t)np * 8);
+                }
+            }
+            return FX_OK;
+        }
+    }
     if (h_matrix) {
         unsigned hc = std::thread::hardware_concurrency();
         const int nthreads = (int)(hc == 0 ? 1 : (hc > 16 ? 16 : hc));

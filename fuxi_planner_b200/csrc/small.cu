@@ -31,11 +31,12 @@ struct SmallParams {
     unsigned long long *counters;
 };
 
-// shared-memory layout for `cells` cells: field u32[cells] | queues u16[3][cells] | moves u8[cells] | lut u8[9*256]
+// shared-memory layout for `cells` cells: field u32[cells] | queues u16[3][cells] | moves u8[cells] | lut u8[9*256] |
+// occupancy bits u32[cells/32] (the grid itself is read exactly once: it may live in pinned host memory)
 __host__ __device__ inline size_t small_smem_bytes(size_t cells)
 {
     const size_t c4 = (cells + 3) & ~(size_t)3;
-    return c4 * 4 + 3 * c4 * 2 + c4 + 9 * 256;
+    return c4 * 4 + 3 * c4 * 2 + c4 + 9 * 256 + ((cells + 31) / 32) * 4;
 }
 
 template <int METRIC>
@@ -53,13 +54,17 @@ __global__ void __launch_bounds__(SM_THREADS) k_search_small(const SmallParams P
     uint16_t *queue = reinterpret_cast<uint16_t *>(s_raw + (size_t)c4 * 4);
     uint8_t *moves = s_raw + (size_t)c4 * 4 + (size_t)c4 * 6;
     uint8_t *lut = moves + c4;
+    unsigned *occb = reinterpret_cast<unsigned *>(lut + 9 * 256);
     for (int i = tid; i < 9 * 256; i += SM_THREADS) lut[i] = (uint8_t)fx_canon_succ((unsigned)(i >> 8), (unsigned)(i & 255));
     // legal-move masks (k_build_moves of search.cu, scripts/jps1.py:14-31), from a shared-memory copy of the grid parked in
     // the queue area
     {
         uint8_t *g = reinterpret_cast<uint8_t *>(queue);
+        for (int i = tid; i < (cells + 31) / 32; i += SM_THREADS) occb[i] = 0;
         for (int i = tid; i < cells; i += SM_THREADS) g[i] = P.grid[i];
         __syncthreads();
+        for (int i = tid; i < cells; i += SM_THREADS)
+            if (g[i] == 1) atomicOr(&occb[i >> 5], 1u << (i & 31));
         for (int i = tid; i < cells; i += SM_THREADS) {
             const int x = i / H, y = i - x * H;
             unsigned nb = 0;
@@ -95,7 +100,7 @@ __global__ void __launch_bounds__(SM_THREADS) k_search_small(const SmallParams P
         if (!s_in) out_cost = FX_COST_START_OOB;
         else if (!g_in) out_cost = FX_COST_UNREACHABLE;
         else if (sx == gx && sy == gy) out_cost = 0;                              // jps1.py:199-208
-        else if (P.grid[(size_t)gx * H + gy] == 1) out_cost = FX_COST_UNREACHABLE;  // jump() tests the cell first
+        else if ((occb[(gx * H + gy) >> 5] >> ((gx * H + gy) & 31)) & 1u) out_cost = FX_COST_UNREACHABLE;  // jump() tests the cell first
         else if (moves[sx * H + sy] == 0) out_cost = FX_COST_UNREACHABLE;          // the start cannot move
         else trivial = false;
         if (trivial) {
