@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(SM_THREADS) k_search_small(const SmallParams P
     constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ unsigned s_cnt[4];
-    __shared__ unsigned s_goal;
+    __shared__ unsigned s_goal[2];  // cost of the goal when popped, one slot per level parity (written in level k, read after its barrier)
     __shared__ int s_npts;
     __shared__ unsigned s_ab[2];
     const int W = P.W, H = P.H, tid = threadIdx.x, lane = tid & 31;
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(SM_THREADS) k_search_small(const SmallParams P
         for (int i = tid; i < cells; i += SM_THREADS) field[i] = SM_INF;
         if (tid == 0) {
             s_cnt[0] = 1; s_cnt[1] = 0; s_cnt[2] = 0; s_cnt[3] = 0;
-            s_goal = SM_INF;
+            s_goal[0] = SM_INF; s_goal[1] = SM_INF;
             queue[0] = (uint16_t)sidx;
         }
         __syncthreads();
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(SM_THREADS) k_search_small(const SmallParams P
                 if (!(v & 1u) || g < lo || g >= hi) continue;  // settled already, or improved into an earlier bucket
                 field[c] = v & ~1u;  // one entry per cell and bucket: nobody else claims it
                 my_settled++;
-                if (c == gidx) s_goal = g;
+                if (c == gidx) s_goal[k & 1] = g;
                 unsigned succ = lut[(((v >> 1) & 15u) << 8) | moves[c]];
                 while (succ) {
                     const int d = __ffs(succ) - 1;
@@ -166,7 +166,10 @@ __global__ void __launch_bounds__(SM_THREADS) k_search_small(const SmallParams P
             }
             __syncthreads();
             k++;
-            if (s_goal != SM_INF) { best = s_goal; break; }  // the goal was popped in this level: every cell of a popped bucket is final
+            // the goal was popped in the level that just ended (every cell of a popped bucket is final).  Level k writes the
+            // other slot, so a warp that is already inside it does not race with this read.
+            const unsigned gc = s_goal[(k - 1) & 1];
+            if (gc != SM_INF) { best = gc; break; }
         }
         tot_settled += my_settled;
         tot_levels += k;
