@@ -145,7 +145,7 @@ int fx_build_moves(fx_context *ctx, const uint8_t *grid, int W, int H, bool tile
 // ------------------------------------------------------------------------------------------------
 struct __align__(16) CtaState {
     unsigned tailS[4], tailD[4];  // entries per bucket: cells that arrived by a straight / by a diagonal move
-    unsigned goal;   // cost of the goal cell once it has been popped (FX_INF = not yet)
+    unsigned goal[2];  // cost of the goal cell once it has been popped (FX_INF = not yet); slot = parity of the level that popped it
     unsigned ovf_level;  // level + 1 in which a cost left the 28-bit range (0 = never)
     unsigned U;      // prune bound on g + h
     unsigned flags;
@@ -187,7 +187,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
     if (tid == 0) {
         S.tailS[0] = 1; S.tailS[1] = 0; S.tailS[2] = 0; S.tailS[3] = 0;
         S.tailD[0] = 0; S.tailD[1] = 0; S.tailD[2] = 0; S.tailD[3] = 0;
-        S.goal = FX_INF; S.U = U0; S.pruned = 0; S.ovf_level = 0;
+        S.goal[0] = FX_INF; S.goal[1] = FX_INF; S.U = U0; S.pruned = 0; S.ovf_level = 0;
         S.xlo = min(S.xlo, sx - 1); S.xhi = max(S.xhi, sx + 1);
         __stcg(queue, make_uint2(((uint32_t)sx << 16) | (uint32_t)sy, fx_pack(0u, FX_CODE_START)));
         __stcg(field + sidx, fx_pack(0u, FX_CODE_START));
@@ -210,11 +210,11 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
         const unsigned n1 = S.tailS[(k + 1) & 3] + S.tailD[(k + 1) & 3];
         PH_START(n)
         // Shared state read here must look the same to a warp that is still at the top of level k and to one that is
-        // already inside it: S.goal (written when the goal is popped, in the level of its bucket) only counts once
-        // its level is over; S.ovf_level likewise; n is complete since the last barrier; n1 is still growing but
-        // only matters when n == 0, i.e. when nobody pushes in this level.
-        const unsigned goalc = S.goal;
-        if (goalc != FX_INF && goalc / WS < k) { result = goalc; break; }  // the goal was popped in an earlier level: final
+        // already inside it: S.goal is double-buffered by level parity (level k writes slot k & 1, this reads the slot of
+        // level k-1, complete since the last barrier); S.ovf_level only counts once its level is over; n is complete
+        // since the last barrier; n1 is still growing but only matters when n == 0, i.e. when nobody pushes in this level.
+        const unsigned goalc = S.goal[(k + 1) & 1];
+        if (goalc != FX_INF) { result = goalc; break; }  // the goal was popped in the previous level: final
         const unsigned ovl = S.ovf_level;
         if (ovl != 0 && ovl <= k) { if (tid == 0) S.flags |= FLAG_OVERFLOW; break; }
         if ((n == 0 && n1 == 0) || (S.flags & FLAG_OVERFLOW)) break;
@@ -248,7 +248,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
             const uint32_t g = e.y >> 4;
             act = act && v == e.y;  // this entry's relaxation won and nothing improved the cell since
             if (act) {
-                if (idx == gidx) S.goal = g;  // unique winner: plain store
+                if (idx == gidx) S.goal[k & 1] = g;  // unique winner: plain store
                 // prune at POP time: a cell outside the ellipse g + h <= U (or outside the band) keeps its cost but is
                 // not expanded.  Every cell of a path of cost <= U satisfies g*(c) + h(c) <= U (h is consistent), and so
                 // do the cells of the alternative paths the canonical pruning relies on: exactness holds.
