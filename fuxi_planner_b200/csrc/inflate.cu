@@ -100,18 +100,18 @@ __global__ void __launch_bounds__(256, 5) k_inflate_tiled(const uint8_t *__restr
 
 template <int R, int STEP>
 __global__ void __launch_bounds__(256, 3) k_inflate_roll(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int W, int H,
-                                                         int strips_y, int ntasks)
+                                                         int strips_y, int ntasks, int rpt)
 {
     const int lane = threadIdx.x & 31;
     const int task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (task >= ntasks) return;
-    const int y0 = (task % strips_y) * INF_TY, x0 = (task / strips_y) * INF_RPT;
+    const int y0 = (task % strips_y) * INF_TY, x0 = (task / strips_y) * rpt;
     const int yl = y0 + 16 * lane;
     const bool in_y = yl < H;
     // halo: the 4 cells next to the strip (R <= 4), one 4-byte load on lane 0 (left) / lane 31 (right)
     const int ye = lane == 0 ? y0 - 4 : y0 + INF_TY;
     const bool has_e = (lane == 0 || lane == 31) && ye >= 0 && ye < H;
-    const int xo_end = min(x0 + INF_RPT, W);  // output rows [x0, xo_end)
+    const int xo_end = min(x0 + rpt, W);  // output rows [x0, xo_end)
     const int xr_end = xo_end + R;            // input rows fed: [x0 - R, xr_end)
     unsigned ring[2 * R + 1];
 #pragma unroll
@@ -159,11 +159,15 @@ __global__ void __launch_bounds__(256, 3) k_inflate_roll(const uint8_t *__restri
 }
 
 template <int R, int STEP>
-static void launch_roll(const uint8_t *in, uint8_t *out, int W, int H, cudaStream_t st)
+static void launch_roll(const uint8_t *in, uint8_t *out, int W, int H, int sm_count, cudaStream_t st)
 {
     const int strips_y = (H + INF_TY - 1) / INF_TY;
-    const long long ntasks = (long long)strips_y * ((W + INF_RPT - 1) / INF_RPT);
-    k_inflate_roll<R, STEP><<<(unsigned)((ntasks + 7) / 8), 256, 0, st>>>(in, out, W, H, strips_y, (int)ntasks);
+    // rows per warp: 64 on grids that fill the machine anyway (halo re-reads 2R/64); shorter strips on small grids,
+    // where a warp walking 64 rows one after the other is the whole run time (1024^2: 32 warps, 20 us -> 256 warps)
+    int rpt = INF_RPT;
+    while (rpt > 8 && (long long)strips_y * ((W + rpt - 1) / rpt) < 8LL * sm_count) rpt >>= 1;
+    const long long ntasks = (long long)strips_y * ((W + rpt - 1) / rpt);
+    k_inflate_roll<R, STEP><<<(unsigned)((ntasks + 7) / 8), 256, 0, st>>>(in, out, W, H, strips_y, (int)ntasks, rpt);
 }
 
 // any shape / alignment / radius: one thread per output cell, reads the stencil directly
@@ -200,13 +204,13 @@ extern "C" int fx_inflate(fx_context *ctx, const uint8_t *in, uint8_t *out, int 
     if (fast && radius >= 1 && radius <= 4) {
         const bool dense = step == 1;
         switch (radius * 2 + (dense ? 1 : 0)) {
-        case 2: case 3: launch_roll<1, 1>(in, out, W, H, st); break;   // r = 1: the 9-point stencil IS the dense 3x3
-        case 5: launch_roll<2, 1>(in, out, W, H, st); break;
-        case 4: launch_roll<2, 2>(in, out, W, H, st); break;
-        case 7: launch_roll<3, 1>(in, out, W, H, st); break;
-        case 6: launch_roll<3, 3>(in, out, W, H, st); break;
-        case 9: launch_roll<4, 1>(in, out, W, H, st); break;
-        default: launch_roll<4, 4>(in, out, W, H, st); break;
+        case 2: case 3: launch_roll<1, 1>(in, out, W, H, ctx->sm_count, st); break;   // r = 1: the 9-point stencil IS the dense 3x3
+        case 5: launch_roll<2, 1>(in, out, W, H, ctx->sm_count, st); break;
+        case 4: launch_roll<2, 2>(in, out, W, H, ctx->sm_count, st); break;
+        case 7: launch_roll<3, 1>(in, out, W, H, ctx->sm_count, st); break;
+        case 6: launch_roll<3, 3>(in, out, W, H, ctx->sm_count, st); break;
+        case 9: launch_roll<4, 1>(in, out, W, H, ctx->sm_count, st); break;
+        default: launch_roll<4, 4>(in, out, W, H, ctx->sm_count, st); break;
         }
     } else if (fast) {
         // larger radii: shared-memory tile kernel; small grids get shorter tiles so that the grid still covers the SMs
