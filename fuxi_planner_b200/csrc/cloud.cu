@@ -65,14 +65,30 @@ __global__ void __launch_bounds__(256) k_cl_bbox(CloudArgs a, CloudState *s)
             mn[k] = min(mn[k], o), mx[k] = max(mx[k], o);
         }
     }
+    // warp reduce, then one set of atomics per CTA: the seven result words are hot addresses, and same-address atomics
+    // serialise in L2 (one set per warp made this kernel 45 us on a 307 k-point frame)
+    __shared__ unsigned s_mn[3][8], s_mx[3][8], s_c[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
-    if (cnt == 0) return;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        unsigned lo = __reduce_min_sync(0xFFFFFFFFu, mn[k]), hi = __reduce_max_sync(0xFFFFFFFFu, mx[k]);
-        if ((threadIdx.x & 31) == 0) atomicMin(&s->bb[k], lo), atomicMax(&s->bb[3 + k], hi);
+        const unsigned lo = __reduce_min_sync(0xFFFFFFFFu, mn[k]), hi = __reduce_max_sync(0xFFFFFFFFu, mx[k]);
+        if (lane == 0) s_mn[k][warp] = lo, s_mx[k][warp] = hi;
     }
-    if ((threadIdx.x & 31) == 0) atomicAdd(&s->n_pass, cnt);
+    if (lane == 0) s_c[warp] = cnt;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned c = lane < 8 ? s_c[lane] : 0u;
+        const unsigned tot = __reduce_add_sync(0xFFFFFFFFu, c);
+        if (tot == 0) return;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const unsigned lo = __reduce_min_sync(0xFFFFFFFFu, lane < 8 ? s_mn[k][lane] : 0xFFFFFFFFu);
+            const unsigned hi = __reduce_max_sync(0xFFFFFFFFu, lane < 8 ? s_mx[k][lane] : 0u);
+            if (lane == 0) atomicMin(&s->bb[k], lo), atomicMax(&s->bb[3 + k], hi);
+        }
+        if (lane == 0) atomicAdd(&s->n_pass, tot);
+    }
 }
 
 // VoxelGrid<PointT>::applyFilter: min_b = floor(min_p * inverse_leaf), div_b = max_b - min_b + 1
@@ -115,14 +131,35 @@ __global__ void k_cl_zero_bits(unsigned *bits, const unsigned *nbits)
     for (size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; w < words; w += (size_t)gridDim.x * blockDim.x) bits[w] = 0;
 }
 
+#define CL_SMEM_BITS (1u << 18) /* voxel index spaces up to this many bits are marked in shared memory first (32 KB) */
 __global__ void __launch_bounds__(256) k_cl_mark(CloudArgs a, const CloudState *s, unsigned *bits)
 {
-    if (s->total_bits == 0) return;
+    __shared__ unsigned s_bits[CL_SMEM_BITS / 32];
+    const unsigned total = s->total_bits;
+    if (total == 0) return;
+    // A depth frame falls into a few hundred bitmap words; RED.ORs to the same 128-byte line serialise in L2 (52 us for
+    // one frame).  Small index spaces are therefore marked in a per-CTA shared-memory copy whose non-zero words are
+    // OR-ed into the global bitmap once.
+    const bool local = total <= CL_SMEM_BITS;
+    const unsigned words = (total + 31) / 32;
+    if (local) {
+        for (unsigned w = threadIdx.x; w < words; w += blockDim.x) s_bits[w] = 0;
+        __syncthreads();
+    }
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
         float x, y, z;
         if (!cl_load(a, i, x, y, z)) continue;
-        unsigned v = cl_voxel(s, a, x, y, z), m = 1u << (v & 31);
-        if (!(bits[v >> 5] & m)) atomicOr(&bits[v >> 5], m);
+        const unsigned v = cl_voxel(s, a, x, y, z), m = 1u << (v & 31);
+        if (local) {
+            if (!(s_bits[v >> 5] & m)) atomicOr(&s_bits[v >> 5], m);
+        } else if (!(bits[v >> 5] & m)) atomicOr(&bits[v >> 5], m);
+    }
+    if (local) {
+        __syncthreads();
+        for (unsigned w = threadIdx.x; w < words; w += blockDim.x) {
+            const unsigned m = s_bits[w];
+            if (m && (bits[w] & m) != m) atomicOr(&bits[w], m);
+        }
     }
 }
 
@@ -196,28 +233,39 @@ __global__ void __launch_bounds__(1024) k_scan_chunks(unsigned *chunk, const uns
     if (threadIdx.x == 0) *out_total = total;
 }
 
-// MODE 0: vidx[rank] = bit index.  MODE 1: out[rank] = src[bit index] (rank < cap).
+// MODE 0: vidx[rank] = bit index.  MODE 1: out[rank] = src[bit index] (rank < cap).  One thread per bitmap word (eight
+// consecutive lanes share a 256-bit group and take their in-group prefix from each other by shuffles); the first lane of
+// a group also finalises gpref[g].  (One thread per group walked up to 256 bits one after the other: 75 us per frame.)
 template <int MODE>
 __global__ void __launch_bounds__(256) k_scan_emit(const unsigned *bits, const unsigned *nbits, unsigned *gpref, const unsigned *chunk,
                                                    unsigned *vidx, const float4 *src, float4 *out, long long cap)
 {
-    const size_t groups = ((size_t)*nbits + 255) / 256;
-    for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
-        unsigned w[8];
-        popc8(bits, g, w);
-        unsigned r = gpref[g] + chunk[g >> 10];
-        gpref[g] = r;
+    const size_t groups = ((size_t)*nbits + 255) / 256, nwords = groups * 8;
+    const size_t wpad = (nwords + 31) & ~(size_t)31;  // whole warps: the shuffles below need every lane
+    for (size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; w < wpad; w += (size_t)gridDim.x * blockDim.x) {
+        const bool live = w < nwords;
+        const size_t g = w >> 3;
+        unsigned m = live ? bits[w] : 0u;
+        const unsigned c = __popc(m);
+        // exclusive prefix of c inside the 8-lane segment
+        unsigned inc = c;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            unsigned m = w[k];
-            while (m) {
-                const unsigned idx = (unsigned)(g * 256 + k * 32) + (__ffs(m) - 1);
-                m &= m - 1;
-                if (MODE == 0) vidx[r] = idx;
-                else if ((long long)r < cap) out[r] = src[idx];
-                r++;
-            }
+        for (int o = 1; o < 8; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xFFFFFFFFu, inc, o, 8);
+            if ((threadIdx.x & 7) >= o) inc += t;
         }
+        if (!live) continue;
+        const unsigned base = gpref[g] + chunk[g >> 10];
+        unsigned r = base + inc - c;
+        while (m) {
+            const unsigned idx = (unsigned)(w * 32) + (__ffs(m) - 1);
+            m &= m - 1;
+            if (MODE == 0) vidx[r] = idx;
+            else if ((long long)r < cap) out[r] = src[idx];
+            r++;
+        }
+        __syncwarp(__activemask());
+        if ((w & 7) == 0) gpref[g] = base;  // after every lane of the group has read the unfinalised value
     }
 }
 
@@ -282,39 +330,72 @@ __global__ void k_cl_centroid(const unsigned long long *acc, const unsigned *n_v
 
 // RadiusOutlierRemoval<PointT>::applyFilterIndices: k = radiusSearch(p, r) (the point itself included, squared
 // distance < r^2 in float: FLANN L2_Simple + RadiusResultSet); kept iff k > min_neighbors
+// Eight lanes per centroid: the (2wz+1)(2wy+1) bitmap rows of its window are dealt round-robin to the lanes, the
+// partial counts meet in a 3-step shuffle.  A CTA (8 warps x 4 centroids) takes 32 consecutive centroids and writes
+// their keep bits as one word.
 __global__ void __launch_bounds__(256) k_cl_ror(const float4 *vox, const unsigned *vidx, const unsigned *bits, const unsigned *gpref,
                                                 const CloudState *s, int wx, int wy, int wz, float r2, int min_nb, unsigned *keep)
 {
+    __shared__ unsigned s_nib[8];
     const unsigned n = s->n_vox, nr = (n + 255u) & ~255u;
     const int dx = s->div[0], dy = s->div[1], dz = s->div[2];
-    for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < nr; r += gridDim.x * blockDim.x) {
-        bool kp = false;
+    const unsigned lane = threadIdx.x & 31, sub = lane & 7, seg = lane >> 3, warp = threadIdx.x >> 5;
+    const int ny = 2 * wy + 1, nrows = (2 * wz + 1) * ny;
+    for (unsigned r0 = blockIdx.x * 32; r0 < nr; r0 += gridDim.x * 32) {
+        const unsigned r = r0 + 4 * warp + seg;
+        int cnt = 0;
         if (r < n) {
             const float4 c = vox[r];
             const unsigned v = vidx[r];
             const int i = (int)(v % (unsigned)dx), j = (int)((v / (unsigned)dx) % (unsigned)dy), k = (int)(v / ((unsigned)dx * (unsigned)dy));
             const int i0 = max(i - wx, 0), i1 = min(i + wx, dx - 1), len = i1 - i0 + 1;
             const unsigned lmask = len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u);
-            int cnt = 0;
-            for (int kk = max(k - wz, 0); kk <= min(k + wz, dz - 1) && cnt <= min_nb; kk++)
-                for (int jj = max(j - wy, 0); jj <= min(j + wy, dy - 1); jj++) {
-                    const unsigned b0 = ((unsigned)kk * (unsigned)dy + (unsigned)jj) * (unsigned)dx + (unsigned)i0;
-                    const unsigned sh = b0 & 31u;
-                    const unsigned lo = bits[b0 >> 5], hi = (sh + (unsigned)len > 32u) ? bits[(b0 >> 5) + 1] : 0u;
-                    unsigned win = __funnelshift_r(lo, hi, sh) & lmask;
-                    if (!win) continue;
-                    unsigned q = cl_rank(bits, gpref, b0);
-                    for (; win; win &= win - 1, q++) {
-                        const float4 p = vox[q];
-                        const float ex = __fsub_rn(c.x, p.x), ey = __fsub_rn(c.y, p.y), ez = __fsub_rn(c.z, p.z);
-                        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
-                        cnt += d2 < r2;
-                    }
+            for (int t = (int)sub; t < nrows; t += 8) {
+                const int kk = k - wz + t / ny, jj = j - wy + t % ny;
+                if (kk < 0 || kk >= dz || jj < 0 || jj >= dy) continue;
+                const unsigned b0 = ((unsigned)kk * (unsigned)dy + (unsigned)jj) * (unsigned)dx + (unsigned)i0;
+                const unsigned sh = b0 & 31u;
+                const unsigned lo = bits[b0 >> 5], hi = (sh + (unsigned)len > 32u) ? bits[(b0 >> 5) + 1] : 0u;
+                unsigned win = __funnelshift_r(lo, hi, sh) & lmask;
+                if (!win) continue;
+                unsigned q = cl_rank(bits, gpref, b0);
+                for (; win; win &= win - 1, q++) {
+                    const float4 p = vox[q];
+                    const float ex = __fsub_rn(c.x, p.x), ey = __fsub_rn(c.y, p.y), ez = __fsub_rn(c.z, p.z);
+                    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+                    cnt += d2 < r2;
                 }
-            kp = cnt > min_nb;
+            }
         }
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, kp);
-        if ((threadIdx.x & 31) == 0) keep[r >> 5] = m;
+        cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 1);
+        cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 2);
+        cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 4);
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, sub == 0 && cnt > min_nb);  // bits 0, 8, 16, 24
+        if (lane == 0) s_nib[warp] = (m & 1u) | ((m >> 7) & 2u) | ((m >> 14) & 4u) | ((m >> 21) & 8u);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned word = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) word |= s_nib[w] << (4 * w);
+            keep[r0 >> 5] = word;
+        }
+        __syncthreads();
+    }
+}
+
+// order-preserving compaction of the kept centroids: one thread per centroid, its output slot is the (not yet
+// finalised) group prefix of the keep bitmap + the set bits below it inside the group
+__global__ void __launch_bounds__(256) k_cl_compact(const unsigned *keep, const unsigned *n_vox, const unsigned *gpref2, const unsigned *chunk2,
+                                                    const float4 *vox, float4 *out, long long cap)
+{
+    const unsigned n = *n_vox;
+    for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        if (!((keep[r >> 5] >> (r & 31)) & 1u)) continue;
+        const unsigned g = r >> 8;
+        unsigned d = gpref2[g] + chunk2[g >> 10];
+        for (unsigned w = g * 8; w < (r >> 5); w++) d += __popc(keep[w]);
+        d += __popc(keep[r >> 5] & ((1u << (r & 31)) - 1u));
+        if ((long long)d < cap) out[d] = vox[r];
     }
 }
 
@@ -383,7 +464,7 @@ extern "C" int fx_cloud_filter(fx_context *ctx, const float *pts, int64_t n, con
     const int gp = grid_for(ctx, n, 256, 8), gw = ctx->sm_count * 8;
     k_cl_reset<<<1, 32, 0, st>>>(s);
     FX_LAUNCH_CHECK(ctx);
-    k_cl_bbox<<<gp, 256, 0, st>>>(a, s);
+    k_cl_bbox<<<grid_for(ctx, n, 1024, 4), 256, 0, st>>>(a, s);
     FX_LAUNCH_CHECK(ctx);
     k_cl_setup<<<1, 32, 0, st>>>(s, a.inv[0], a.inv[1], a.inv[2], ctx->cl_cap_bits);
     FX_LAUNCH_CHECK(ctx);
@@ -409,7 +490,7 @@ extern "C" int fx_cloud_filter(fx_context *ctx, const float *pts, int64_t n, con
     FX_LAUNCH_CHECK(ctx);
     k_scan_chunks<<<1, 1024, 0, st>>>(ctx->cl_chunk2, &s->n_vox, &s->n_keep);
     FX_LAUNCH_CHECK(ctx);
-    k_scan_emit<1><<<gw, 256, 0, st>>>(ctx->cl_keep, &s->n_vox, ctx->cl_gpref2, ctx->cl_chunk2, nullptr, ctx->cl_vox, (float4 *)out, cap);
+    k_cl_compact<<<gw, 256, 0, st>>>(ctx->cl_keep, &s->n_vox, ctx->cl_gpref2, ctx->cl_chunk2, ctx->cl_vox, (float4 *)out, cap);
     FX_LAUNCH_CHECK(ctx);
     k_cl_counts<<<1, 32, 0, st>>>(s, (long long *)d_counts);
     FX_LAUNCH_CHECK(ctx);

@@ -446,10 +446,26 @@ __global__ void __launch_bounds__(128) k_edt_fix(const unsigned *__restrict__ bi
     const unsigned n = *fix_count;
     if (n > fix_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) *flag = 1; return; }  // too many: the windowed path redoes the grid
     const int H = HW * 32;
-    // one warp per listed cell: lane l looks at the rows x +- d for d = l, l + 32, ...; the warp's best so far bounds
-    // every lane's search after each round (a listed cell is > EDT_R from everything, so the brute force walks tens of
-    // rows: one thread doing that alone was the longest kernel of the whole transform on small grids)
     const unsigned lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    if (n > 8u * nwarps) {
+        // long list (large sparse grids): one thread per cell, the list itself is the parallelism
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const int x = (int)fix_list[2 * (size_t)i], y = (int)fix_list[2 * (size_t)i + 1];
+            long long best = (long long)1 << 40;
+            for (int d = 0; (long long)d * d < best && (x - d >= 0 || x + d < W); d++) {
+                const long long room = best - (long long)d * d;
+                int lim = H;
+                if (room < (long long)H * H) { lim = (int)sqrtf((float)room) + 1; if (lim > H) lim = H; }
+                if (x - d >= 0) { const int g = edt_row_nearest(bits + (size_t)(x - d) * HW, HW, y, lim); if (g >= 0) best = min(best, (long long)d * d + (long long)g * g); }
+                if (d > 0 && x + d < W) { const int g = edt_row_nearest(bits + (size_t)(x + d) * HW, HW, y, lim); if (g >= 0) best = min(best, (long long)d * d + (long long)g * g); }
+            }
+            out[(size_t)x * H + y] = best > 0x7FFFFFFFLL ? 0x7FFFFFFF : (int32_t)best;
+        }
+        return;
+    }
+    // short list (small grids): one warp per cell, lane l looks at the rows x +- d for d = l, l + 32, ...; the warp's
+    // best so far bounds every lane's search after each round (a listed cell is > EDT_R from everything, so the brute
+    // force walks tens of rows: one thread doing that alone was the longest kernel of the whole transform at 1024^2)
     for (unsigned i = warp; i < n; i += nwarps) {
         const int x = (int)fix_list[2 * (size_t)i], y = (int)fix_list[2 * (size_t)i + 1];
         long long best = (long long)1 << 40;
