@@ -274,6 +274,44 @@ def map_kernel_rooflines(torch, fx, dev, flush, peak):
     return out
 
 
+def other_configs(torch, fx, dev, flush, hchoice):
+    """BASELINE.json's other single-GPU configurations as reported numbers (not the bench line): cfg3 = 4096 queries on
+    a 1024^2 grid at 20 % fill (SURVEY §8d: grid default_rng(2), queries default_rng(3)), both metrics, device-resident;
+    plus the host-side baselines SURVEY §8d asks for next to the map kernels (numpy restatements of the reference's
+    inline inflation blocks and of distance_filter, timed on this box's host)."""
+    import oracle
+    out = {}
+    n, Q = 1024, 4096
+    m = (np.random.default_rng(2).random((n, n)) < 0.2).astype(np.uint8)
+    free = np.argwhere(m == 0)
+    rng = np.random.default_rng(3)
+    s = free[rng.integers(len(free), size=Q)].astype(np.int32)
+    g = free[rng.integers(len(free), size=Q)].astype(np.int32)
+    d_m, d_s, d_g = torch.from_numpy(m).to(dev), torch.from_numpy(s).to(dev), torch.from_numpy(g).to(dev)
+    for metric in (1, 2):
+        ms, _ = time_kernel(torch, lambda: fx.plan_batch(d_m, d_s, d_g, metric=metric, max_path=1024), flush)
+        settled = fx.search_stats()[0]
+        res = fx.plan_batch(d_m, d_s, d_g, metric=metric, max_path=1024)
+        S = 256
+        want, status, _ = oracle.jps_batch(m, s[:S], g[:S], metric)
+        ci, cf = res.cost_i[:S].cpu().numpy(), res.cost_f[:S].cpu().numpy()
+        ok = status == 1
+        bad = (ci[ok] != want[ok]) if metric == 1 else (np.abs(cf[ok] - want[ok]) > 1e-5 * np.maximum(want[ok], 1e-12))
+        out["cfg3_1024_4096q_metric%d" % metric] = {"ms": ms, "queries_per_s": Q / (ms * 1e-3), "settled_cells": int(settled),
+                                                    "nodes_per_s": settled / (ms * 1e-3),
+                                                    "parity_mismatches_first_256": int(bad.sum()) + int(((ci >= 0) != ok).sum())}
+    # host baselines (the reference's own numpy code, restated in oracle/hostref.py)
+    occ = (np.random.default_rng(1).random((1024, 1024)) < 0.02).astype(np.float64)
+    occ[:4] = 0; occ[-4:] = 0; occ[:, :4] = 0; occ[:, -4:] = 0      # the reference pads before it inflates (st:230-250)
+    t0 = time.perf_counter(); oracle.hostref.inflate_ccst(occ.copy(), 2); t1 = time.perf_counter()
+    oracle.hostref.inflate_st(occ.copy(), 1); t2 = time.perf_counter()
+    pts = np.random.default_rng(1).uniform(-6, 6, (1 << 20, 3))
+    t3 = time.perf_counter(); oracle.hostref.distance_filter(pts, 4.0); t4 = time.perf_counter()
+    out["host_numpy_baselines_ms"] = {"inflate_ccst_r2_1024": 1e3 * (t1 - t0), "inflate_st_r1_1024": 1e3 * (t2 - t1),
+                                      "distance_filter_1Mpts": 1e3 * (t4 - t3), "cores": 1}
+    return out
+
+
 def latency_probe(fx, m4096, s, g, hchoice):
     """p50 of one drop-in replan: jps1.method(matrix, start, goal, 2) wall clock, host buffers in and out."""
     import contextlib
@@ -440,6 +478,7 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_extras:
         line["kernels"] = map_kernel_rooflines(torch, fx, dev, flush, peak)
         line["latency"] = latency_probe(fx, m, s, g, args.hchoice)
+        line["other_configs"] = other_configs(torch, fx, dev, flush, args.hchoice)
         import oracle
         oracle.build()
         S, dt, used, cost, status = cpu_sample(m, s, g, args.hchoice, args.cpu_seconds, oracle)
