@@ -8,6 +8,8 @@ OccupancyGrid and publishing a path (scripts/global_planner_st.py:15-25,226-298;
 """
 from dataclasses import dataclass
 
+import math
+
 import numpy as np
 import torch
 
@@ -161,3 +163,37 @@ def waypoint_ccst(path_world, global_goal):
     """global_planner_ccst.py:523-526: blend of the second and third path points, or the goal for short paths."""
     p = np.asarray(path_world)
     return (p[1] * 1.4 + p[2] * 0.6) / 2 if len(p) > 2 else np.asarray(global_goal)
+
+
+def waypoint_st(path_cells, map_start, reso, origin, global_goal, pos, end_occu, prev_wp=None,
+                dis_wp_tre=2.0, ang_wp_tre=math.pi / 4):
+    """Next waypoint as the Octomap planner picks it (global_planner_st.py:291-325).
+
+    path_cells: the path `jps1.method` returned (cells of the planning grid); the planner works on ``path2 = path + [1, 1]``.
+    Walk the path until the bearing from the vehicle stops closing in on the bearing of the path's end (and the point
+    is more than 2 cells away): the point before that is the candidate.  It is kept only if the path has more than
+    two points and the candidate is farther than `dis_wp_tre` or the last bearing gap lies in (ang_wp_tre, pi/2);
+    otherwise the goal itself is the waypoint; with `end_occu == 1` the vehicle holds position and that position becomes
+    the goal.  `prev_wp` is the waypoint of the previous iteration (the reference's `wp` survives between iterations and
+    is what `uav2next_wp` measures when no candidate is found).  Returns (wp, global_goal, ang_wp)."""
+    path2 = np.asarray(path_cells, dtype=np.int64) + np.array([1, 1])
+    start = np.asarray(map_start)
+    goal = np.asarray(global_goal, dtype=np.float64)
+    end_bearing = math.atan2(*(path2[-1] - start))          # atan2(dx, dy): the reference's argument order
+    wp, gap = prev_wp, 0.0
+    for k in range(1, len(path2)):
+        rel = path2[k] - start
+        here = abs(end_bearing - math.atan2(rel[0], rel[1]))
+        if here <= gap and np.linalg.norm(rel) > 2:
+            wp = path2[k - 1] * reso + np.asarray(origin, dtype=np.float64)
+            break
+        gap = here
+    if wp is None:
+        wp = goal
+    far = float(np.linalg.norm(np.asarray(wp)[0:2] - np.asarray(pos, dtype=np.float64)[0:2]))
+    if end_occu == 1:
+        wp = np.asarray(pos, dtype=np.float64)
+        goal = wp
+    elif not (len(path2) > 2 and (far > dis_wp_tre or (ang_wp_tre < gap < math.pi * 0.5))):
+        wp = goal
+    return wp, goal, gap

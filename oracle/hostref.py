@@ -350,3 +350,26 @@ def merge_premap(mapu, map_o, map_t, map_pre, ori_pre, reso):
     mapu0[ori_prei[0]:ori_prei[0] + l1_pre, ori_prei[1]:ori_prei[1] + l2_pre] = map_pre
     mapu0[map_oi[0]:map_oi[0] + map_c, map_oi[1]:map_oi[1] + map_r] = mapu
     return mapu0, map_o1
+
+
+def waypoint_st(path1, map_start, map_reso, map_o, global_goal, px, py, pz, end_occu, wp=None, dis_wp_tre=2,
+                ang_wp_tre=math.pi / 4):
+    """scripts/global_planner_st.py:291-325 line by line (`wp` comes in with the previous iteration's value, st:127)."""
+    path2 = np.array(path1) + np.array([1, 1])
+    ang_wp = 0
+    for k in range(1, len(path2)):
+        map_wp = path2[k]
+        if abs(math.atan2((path2[-1] - map_start)[0], (path2[-1] - map_start)[1]) - math.atan2((map_wp - map_start)[0], (map_wp - map_start)[1])) <= ang_wp and np.linalg.norm(map_wp - map_start) > 2:
+            map_wp = path2[k - 1]
+            wp = map_wp * map_reso + map_o
+            break
+        ang_wp = abs(math.atan2((path2[-1] - map_start)[0], (path2[-1] - map_start)[1]) - math.atan2((map_wp - map_start)[0], (map_wp - map_start)[1]))
+    if wp is None:
+        wp = global_goal
+    uav2next_wp = np.linalg.norm(wp[0:2] - np.array([px, py]))
+    if end_occu == 1:
+        wp = np.array([px, py, pz])
+        global_goal = wp
+    elif not (len(path2) > 2 and (uav2next_wp > dis_wp_tre or (ang_wp > ang_wp_tre and ang_wp < math.pi * 0.5))):
+        wp = global_goal
+    return wp, global_goal, ang_wp

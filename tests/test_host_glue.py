@@ -92,3 +92,30 @@ def test_formats_host_side():
     assert msg["header"]["frame_id"] == "map" and len(msg["poses"]) == 2
     assert msg["poses"][1]["pose"]["position"] == {"x": 3.5, "y": 4.5, "z": 0.0}
     assert msg["poses"][0]["header"] == {"frame_id": "map", "stamp": 12.5}
+
+
+def test_waypoint_st_matches_the_restated_block(oracle, golden, maps):
+    """planner.waypoint_st against the line-by-line restatement of global_planner_st.py:291-325 on real paths (the
+    reference's own jump-point paths from the golden file) and on random walks, with and without a previous waypoint."""
+    from fuxi_planner_b200 import planner
+    rng = np.random.default_rng(5)
+    paths = [r["path"] for r in golden["cfg1"] if r.get("path") and len(r["path"]) >= 2][:120]
+    for _ in range(80):
+        n = int(rng.integers(2, 12))
+        paths.append(np.cumsum(rng.integers(-6, 7, size=(n, 2)), axis=0) + 60)
+    kept = 0
+    for i, p in enumerate(paths):
+        p = np.asarray(p)
+        start = p[0] + rng.integers(-1, 2, size=2)
+        origin = np.array([-16.4, -4.8]) + rng.uniform(-1, 1, 2)
+        pos = np.r_[start * 0.2 + origin + rng.uniform(-0.3, 0.3, 2), 1.2]
+        goal = np.r_[p[-1] * 0.2 + origin, 1.0]
+        prev = None if i % 3 else np.r_[rng.uniform(-5, 5, 2), 0.0]
+        for end_occu in (0, 1):
+            want = oracle.hostref.waypoint_st(p, start, 0.2, origin, goal, pos[0], pos[1], pos[2], end_occu, wp=prev)
+            got = planner.waypoint_st(p, start, 0.2, origin, goal, pos, end_occu, prev_wp=prev)
+            assert np.array_equal(np.asarray(got[0], dtype=np.float64), np.asarray(want[0], dtype=np.float64)), i
+            assert np.array_equal(np.asarray(got[1], dtype=np.float64), np.asarray(want[1], dtype=np.float64))
+            assert got[2] == want[2]
+            kept += int(not np.array_equal(np.asarray(got[0]), goal) and end_occu == 0)
+    assert kept > 10          # the interesting branch (an intermediate waypoint) is exercised
