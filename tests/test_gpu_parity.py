@@ -504,3 +504,34 @@ def test_plan_host_float64_matrix_and_wide_ctas(fx, oracle):
     S[:6], G[:6] = s, g
     c = fx.plan_host(occ, S, G, metric=1, max_path=0)
     assert np.array_equal(c[0][:6], a[0])
+
+
+def test_search_extreme_shapes_and_empty_batches(fx, dev, oracle):
+    """The largest extent the packed (x << 16 | y) queue entries allow (32767), one-cell-wide corridors, an empty batch,
+    max_path = 0, and the refusal above the limit."""
+    import torch
+    rng = np.random.default_rng(9)
+    for shape in ((32767, 4), (4, 32767)):
+        m = (rng.random(shape) < 0.15).astype(np.uint8)
+        m[:, 0] = 0 if shape[1] == 4 else m[:, 0]
+        if shape[0] == 4:
+            m[0, :] = 0
+        free = np.argwhere(m == 0)
+        s = free[rng.integers(len(free), size=24)].astype(np.int32)
+        g = free[rng.integers(len(free), size=24)].astype(np.int32)
+        s[0], g[0] = free[0], free[-1]                      # end to end: ~32766 straight steps
+        want = oracle.sssp_batch(m, s, g, 2)
+        res = fx.plan_batch(_t(m, dev), _t(s, dev), _t(g, dev), metric=2, max_path=8192)
+        got = res.cost_i.cpu().numpy().astype(np.int64)
+        assert np.array_equal(got, want), np.flatnonzero(got != want)[:5]
+        assert want[0] > 32000 * fx.FX_EUCLID_WS
+        validate_path(m, res.path(0), tuple(s[0]), tuple(g[0]))
+    m = np.zeros((64, 64), dtype=np.uint8)
+    empty = torch.zeros((0, 2), dtype=torch.int32, device=dev)
+    res = fx.plan_batch(_t(m, dev), empty, empty, metric=1)
+    assert res.cost_i.numel() == 0
+    one = torch.tensor([[1, 1]], dtype=torch.int32, device=dev), torch.tensor([[60, 50]], dtype=torch.int32, device=dev)
+    res = fx.plan_batch(_t(m, dev), one[0], one[1], metric=1, max_path=0)      # costs only
+    assert res.path_xy is None and int(res.cost_i[0]) == 14 * 49 + 10 * 10
+    with pytest.raises(fx.FuxiError):
+        fx.plan_batch(torch.zeros((32768, 2), dtype=torch.uint8, device=dev), one[0], one[1], metric=1)
