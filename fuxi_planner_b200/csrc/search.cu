@@ -228,22 +228,33 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
         uint2 *__restrict__ q2 = queue + (size_t)((k + 2) & 3) * qcap;
         const uint32_t kbase = k * WS;
         auto slot_of = [&](unsigned i) { return i < nS ? i : qhalf + (i - nS); };
-        uint2 e_next = (unsigned)tid < n ? __ldcg(qk + slot_of((unsigned)tid)) : make_uint2(0u, 0u);
+        // Two-deep software pipeline over the rounds of a level: while round r is processed, the cost word and move mask
+        // of round r+1 and the queue entry of round r+2 are already in flight, so only the first round of a level waits
+        // for two dependent L2 round trips.  Loading a cell's word before this level's own reductions are issued is safe:
+        // the cells popped in level k hold costs of bucket k and every reduction of level k carries a cost of bucket
+        // k+1 or later, so their words do not change during the level.
+        uint2 e_cur = (unsigned)tid < n ? __ldcg(qk + slot_of((unsigned)tid)) : make_uint2(0u, 0u);
+        uint2 e_nxt = (unsigned)tid + (unsigned)nthreads < n ? __ldcg(qk + slot_of((unsigned)tid + (unsigned)nthreads)) : make_uint2(0u, 0u);
+        int idx_cur = fx_cidx((int)(e_cur.x >> 16), (int)(e_cur.x & 0xFFFFu), H, TY);
+        uint32_t v_cur = FX_INF;
+        unsigned m_cur = 0;
+        if ((unsigned)tid < n) { v_cur = __ldcg(field + idx_cur); m_cur = (unsigned)__ldg(moves + idx_cur); }
         for (unsigned i0 = (unsigned)(tid - lane); i0 < n; i0 += (unsigned)nthreads) {
             const unsigned i = i0 + lane;
             bool act = i < n;
-            const uint2 e = e_next;
-            if (i + nthreads < n) e_next = __ldcg(qk + slot_of(i + nthreads));  // the next round's entry is already on its way
+            const uint2 e = e_cur;
+            const int idx = idx_cur;  // < 2^30 (W, H <= 32767)
+            const uint32_t v = v_cur;
+            const unsigned m = m_cur;
+            e_cur = e_nxt;
+            idx_cur = fx_cidx((int)(e_cur.x >> 16), (int)(e_cur.x & 0xFFFFu), H, TY);
+            v_cur = FX_INF;
+            m_cur = 0;
+            if (i + nthreads < n) { v_cur = __ldcg(field + idx_cur); m_cur = (unsigned)__ldg(moves + idx_cur); }
+            if (i + 2u * nthreads < n) e_nxt = __ldcg(qk + slot_of(i + 2u * nthreads));
             const int x = (int)(e.x >> 16), y = (int)(e.x & 0xFFFFu);
             PH_MARK(0, e.x)  // queue entry arrived
-            const int idx = fx_cidx(x, y, H, TY);  // < 2^30 (W, H <= 32767)
-            uint32_t v = FX_INF;
-            unsigned m = 0;
-            if (act) {
-                v = __ldcg(field + idx);
-                m = (unsigned)__ldg(moves + idx);
-                dirty[idx >> FX_DIRTY_SHIFT] = 1;  // every relaxed cell has an entry: lines are marked when entries are popped
-            }
+            if (act) dirty[idx >> FX_DIRTY_SHIFT] = 1;  // every relaxed cell has an entry: lines are marked when entries are popped
             PH_MARK(1, v + m)  // cost + move mask arrived
             const uint32_t g = e.y >> 4;
             act = act && v == e.y;  // this entry's relaxation won and nothing improved the cell since
