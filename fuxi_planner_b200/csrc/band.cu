@@ -19,6 +19,9 @@
 #define BAND_M 24                 /* rows allowed before the start / after the goal along the major axis */
 #define BAND_Q 128                /* queue entries (8 bytes) per bucket and warp (shared memory) */
 #define BAND_WARPS 8
+#ifndef BAND_MINB
+#define BAND_MINB 6                 /* resident CTAs per SM the register budget is compiled for (40 registers; 5: 44, 8: 32 + spills, measured slower) */
+#endif
 
 struct BandParams {
     const uint8_t *grid, *moves;
@@ -78,7 +81,7 @@ __device__ __forceinline__ unsigned band_atoms_add(unsigned *p, unsigned v)
 }
 
 template <int METRIC>
-__global__ void __launch_bounds__(BAND_WARPS * 32, 4) k_band_bound(const BandParams P)
+__global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) k_band_bound(const BandParams P)
 {
     constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
     __shared__ uint2 s_queue[BAND_WARPS][3][BAND_Q];
@@ -204,7 +207,7 @@ int fx_band_bounds(fx_context *ctx, const uint8_t *grid, int W, int H, const int
         ctx->q_cap = (size_t)Q;
     }
     const size_t bcap = ((size_t)(W > H ? W : H) + 2 * BAND_M + 1) * 32;
-    const int bslots = ctx->sm_count * 4 * BAND_WARPS;
+    const int bslots = ctx->sm_count * BAND_MINB * BAND_WARPS;
     if (ctx->bcap < bcap || ctx->bslots < bslots) {
         if (ctx->bfields) cudaFree(ctx->bfields);
         ctx->bfields = nullptr; ctx->bcap = 0; ctx->bslots = 0;
@@ -218,7 +221,7 @@ int fx_band_bounds(fx_context *ctx, const uint8_t *grid, int W, int H, const int
     P.grid = grid; P.moves = ctx->moves; P.W = W; P.H = H; P.TY = fx_tiles_y(H); P.starts = starts_xy; P.goals = goals_xy; P.Q = Q;
     P.order = ctx->q_order; P.ubound = ctx->q_ubound; P.bfields = ctx->bfields; P.bcap = ctx->bcap; P.counter = ctx->counters + 6;
     int blocks = (Q + BAND_WARPS - 1) / BAND_WARPS;
-    if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
+    if (blocks > ctx->sm_count * BAND_MINB) blocks = ctx->sm_count * BAND_MINB;
     if (metric == 1) k_band_bound<1><<<blocks, BAND_WARPS * 32, 0, st>>>(P);
     else k_band_bound<2><<<blocks, BAND_WARPS * 32, 0, st>>>(P);
     FX_LAUNCH_CHECK(ctx);
