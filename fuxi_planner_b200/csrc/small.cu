@@ -15,7 +15,9 @@
 // path exists.
 #include "common.cuh"
 
+#ifndef SM_THREADS
 #define SM_THREADS 256
+#endif
 #define SM_INF 0xFFFFFFFFu
 
 struct SmallParams {
@@ -61,7 +63,23 @@ __global__ void __launch_bounds__(SM_THREADS) k_search_small(const SmallParams P
     {
         uint8_t *g = reinterpret_cast<uint8_t *>(queue);
         for (int i = tid; i < (cells + 31) / 32; i += SM_THREADS) occb[i] = 0;
-        for (int i = tid; i < cells; i += SM_THREADS) g[i] = P.grid[i];
+        // the grid may live in mapped pinned host memory (fx_plan_host): 16-byte loads, all in flight at once, so that
+        // the copy costs one PCIe round trip instead of one per loop iteration
+        if ((reinterpret_cast<uintptr_t>(P.grid) & 15u) == 0) {
+            const uint4 *g4 = reinterpret_cast<const uint4 *>(P.grid);
+            const int n16 = cells >> 4;
+            for (int i0 = tid; i0 < n16; i0 += 4 * SM_THREADS) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = i0 + u * SM_THREADS < n16 ? __ldg(g4 + i0 + u * SM_THREADS) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (i0 + u * SM_THREADS < n16) reinterpret_cast<uint4 *>(g)[i0 + u * SM_THREADS] = v[u];
+            }
+            for (int i = (n16 << 4) + tid; i < cells; i += SM_THREADS) g[i] = P.grid[i];
+        } else {
+            for (int i = tid; i < cells; i += SM_THREADS) g[i] = P.grid[i];
+        }
         __syncthreads();
         for (int i = tid; i < cells; i += SM_THREADS)
             if (g[i] == 1) atomicOr(&occb[i >> 5], 1u << (i & 31));
