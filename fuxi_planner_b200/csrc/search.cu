@@ -254,11 +254,13 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
             if (i + 2u * nthreads < n) e_nxt = __ldcg(qk + slot_of(i + 2u * nthreads));
             const int x = (int)(e.x >> 16), y = (int)(e.x & 0xFFFFu);
             PH_MARK(0, e.x)  // queue entry arrived
-            if (act) dirty[idx >> FX_DIRTY_SHIFT] = 1;  // every relaxed cell has an entry: lines are marked when entries are popped
             PH_MARK(1, v + m)  // cost + move mask arrived
             const uint32_t g = e.y >> 4;
             act = act && v == e.y;  // this entry's relaxation won and nothing improved the cell since
             if (act) {
+                // every relaxed cell has an entry that carries its final word (the winner's): marking the line when THAT
+                // entry is popped -- or swept below if it never is -- covers every touched line; stale entries skip the store
+                dirty[idx >> FX_DIRTY_SHIFT] = 1;
                 if (idx == gidx) S.goal[k & 1] = g;  // unique winner: plain store
                 // prune at POP time: a cell outside the ellipse g + h <= U (or outside the band) keeps its cost but is
                 // not expanded.  Every cell of a path of cost <= U satisfies g*(c) + h(c) <= U (h is consistent), and so

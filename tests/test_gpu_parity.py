@@ -535,3 +535,22 @@ def test_search_extreme_shapes_and_empty_batches(fx, dev, oracle):
     assert res.path_xy is None and int(res.cost_i[0]) == 14 * 49 + 10 * 10
     with pytest.raises(fx.FuxiError):
         fx.plan_batch(torch.zeros((32768, 2), dtype=torch.uint8, device=dev), one[0], one[1], metric=1)
+
+
+def test_search_slot_reuse_resets_completely(fx, dev, oracle):
+    """Two search slots, 400 queries: every slot answers ~200 queries one after the other on the same scratch field, so a
+    field line that a query touched and the reset missed would corrupt a later answer.  Costs against the oracle."""
+    import torch
+    rng = np.random.default_rng(31)
+    m = (rng.random((300, 340)) < 0.25).astype(np.uint8)
+    s, g = random_queries(m, 400, rng)
+    ctx = fx.Context(0)
+    ctx.check(ctx.lib.fx_set_search_tuning(ctx.handle, 2, 0), "fx_set_search_tuning")
+    try:
+        for metric in (1, 2):
+            want = oracle.sssp_batch(m, s, g, metric)
+            res = fx.plan_batch(_t(m, dev), _t(s, dev), _t(g, dev), metric=metric, max_path=0, ctx=ctx)
+            torch.cuda.synchronize()
+            assert np.array_equal(res.cost_i.cpu().numpy().astype(np.int64), want), metric
+    finally:
+        ctx.close()
