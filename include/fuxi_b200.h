@@ -52,7 +52,7 @@ const char *fx_last_error(fx_context *ctx);     /* ctx may be NULL: last creatio
 int         fx_version(void);                   /* ABI version, currently 1 */
 /* number of kernels this library launched through ctx since creation (bench.py: gpu_launches) */
 int64_t     fx_launch_count(fx_context *ctx);
-/* tuning: number of concurrent search slots (0 = auto: 4 per SM, bounded by free memory) and the
+/* tuning: number of concurrent search slots (0 = auto: 8 per SM, bounded by half of the free memory) and the
  * half-width in cells of the first (band-limited) search attempt (0 = default 16) */
 int         fx_set_search_tuning(fx_context *ctx, int slots, int band0);
 
@@ -103,6 +103,10 @@ int fx_edt_cols(fx_context *ctx, const uint16_t *g, int32_t *dist2, int W, int H
  * joined by a straight 8-direction run -- same contract as the reference's jump-point list), or NULL;
  * path_len: int32 [Q] number of turning points (may exceed max_path: only max_path were stored;
  * FX_COST_* when there is no path), or NULL.
+ * Three forms behind this one entry point, same results: maps up to 20 000 cells (every map the reference ships)
+ * are searched by one CTA per query entirely in shared memory, one launch per batch; larger maps by the batched
+ * wavefront kernel, with 512-thread CTAs when the batch is smaller than the machine (latency) and 128-thread CTAs,
+ * eight per SM, otherwise (throughput).  W, H <= 32767.
  */
 int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int H,
                     const int32_t *starts_xy, const int32_t *goals_xy, int Q, int metric,
