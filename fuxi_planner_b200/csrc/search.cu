@@ -331,7 +331,11 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
     if (my_xhi >= 0) { atomicMin(&S.xlo, my_xlo - 1); atomicMax(&S.xhi, my_xhi + 1); }
     if (my_pruned) S.pruned = 1;  // S.pruned was zeroed before the first barrier of this pass; nobody reads it until the next one
     __syncthreads();
-    if (my_settled) atomicAdd(&S.settled, (unsigned long long)my_settled);
+    {
+        // one 64-bit shared-memory atomic per warp (it is a CAS loop in SASS: 128 lanes on one address would spin)
+        const unsigned ws = __reduce_add_sync(0xFFFFFFFFu, my_settled);
+        if (lane == 0 && ws) atomicAdd(&S.settled, (unsigned long long)ws);
+    }
     if (tid == 0) S.levels += k;
     return result;
 }
