@@ -49,7 +49,7 @@ def build(force=False, verbose=False, extra_flags=(), out=None):
             failed = True
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.run([nvcc, "-shared", "-o", so] + objs + ["-lcudart"], check=True)
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", so] + objs + ["-lcudart"], check=True)
     return so
 
 
