@@ -300,16 +300,38 @@ def other_configs(torch, fx, dev, flush, hchoice):
         out["cfg3_1024_4096q_metric%d" % metric] = {"ms": ms, "queries_per_s": Q / (ms * 1e-3), "settled_cells": int(settled),
                                                     "nodes_per_s": settled / (ms * 1e-3),
                                                     "parity_mismatches_first_256": int(bad.sum()) + int(((ci >= 0) != ok).sum())}
-    # host baselines (the reference's own numpy code, restated in oracle/hostref.py)
+    try:
+        out["host_numpy_baselines_ms"] = host_baselines()
+    except Exception as exc:          # a reported baseline must never take the bench line down
+        out["host_numpy_baselines_ms"] = {"error": repr(exc)}
+    return out
+
+
+def host_baselines():
+    """The host-side baselines SURVEY §8d lists next to the map kernels, timed on this box's host (one core, no GPU):
+    numpy restatements of the reference's inline inflation blocks (a10, a11) and of distance_filter (a17), and the
+    cloud node's DBSCAN step (a19, scikit-learn as in the reference, plc_point2_st.py:299-300: eps 0.4, min_samples 6)
+    on two synthetic frames of 5 000 points.  Reported as baselines only."""
+    import oracle
     occ = (np.random.default_rng(1).random((1024, 1024)) < 0.02).astype(np.float64)
     occ[:4] = 0; occ[-4:] = 0; occ[:, :4] = 0; occ[:, -4:] = 0      # the reference pads before it inflates (st:230-250)
     t0 = time.perf_counter(); oracle.hostref.inflate_ccst(occ.copy(), 2); t1 = time.perf_counter()
     oracle.hostref.inflate_st(occ.copy(), 1); t2 = time.perf_counter()
     pts = np.random.default_rng(1).uniform(-6, 6, (1 << 20, 3))
     t3 = time.perf_counter(); oracle.hostref.distance_filter(pts, 4.0); t4 = time.perf_counter()
-    out["host_numpy_baselines_ms"] = {"inflate_ccst_r2_1024": 1e3 * (t1 - t0), "inflate_st_r1_1024": 1e3 * (t2 - t1),
-                                      "distance_filter_1Mpts": 1e3 * (t4 - t3), "cores": 1}
-    return out
+    res = {"inflate_ccst_r2_1024": 1e3 * (t1 - t0), "inflate_st_r1_1024": 1e3 * (t2 - t1),
+           "distance_filter_1Mpts": 1e3 * (t4 - t3), "cores": 1}
+    try:
+        from sklearn.cluster import DBSCAN
+        rng = np.random.default_rng(2)
+        frames = [np.concatenate([c + 0.15 * rng.standard_normal((500, 3)) for c in rng.uniform(-4, 4, (10, 3))]) for _ in range(2)]
+        t5 = time.perf_counter()
+        labels = [DBSCAN(eps=0.4, min_samples=6).fit(f).labels_ for f in frames]
+        res["dbscan_2x5000pts"] = 1e3 * (time.perf_counter() - t5)
+        res["dbscan_clusters"] = [int(l.max()) + 1 for l in labels]
+    except ImportError:
+        res["dbscan_2x5000pts"] = None
+    return res
 
 
 def latency_probe(fx, m4096, s, g, hchoice):
@@ -476,9 +498,14 @@ def run_b200(args):
         "clocks": clocks,
     }
     if rank == 0 and world == 1 and not args.no_extras:
-        line["kernels"] = map_kernel_rooflines(torch, fx, dev, flush, peak)
-        line["latency"] = latency_probe(fx, m, s, g, args.hchoice)
-        line["other_configs"] = other_configs(torch, fx, dev, flush, args.hchoice)
+        # reported extras: a failure in one of them is recorded, it must not take the bench line down
+        for key, fn in (("kernels", lambda: map_kernel_rooflines(torch, fx, dev, flush, peak)),
+                        ("latency", lambda: latency_probe(fx, m, s, g, args.hchoice)),
+                        ("other_configs", lambda: other_configs(torch, fx, dev, flush, args.hchoice))):
+            try:
+                line[key] = fn()
+            except Exception as exc:
+                line[key] = {"error": repr(exc)}
         import oracle
         oracle.build()
         S, dt, used, cost, status = cpu_sample(m, s, g, args.hchoice, args.cpu_seconds, oracle)

@@ -28,3 +28,11 @@ def test_gpu_arm_refuses_without_a_device():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True,
                          text=True, timeout=300, cwd=ROOT)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_host_baselines_block_runs_without_a_gpu():
+    sys.path.insert(0, ROOT)
+    import bench
+    res = bench.host_baselines()
+    assert res["cores"] == 1 and res["inflate_ccst_r2_1024"] > 0 and res["distance_filter_1Mpts"] > 0
+    assert res["dbscan_2x5000pts"] is None or (res["dbscan_2x5000pts"] > 0 and min(res["dbscan_clusters"]) >= 1)
