@@ -70,3 +70,30 @@ def test_sass_is_sm100a(built):
         pytest.skip("cuobjdump not on PATH")
     out = subprocess.run(["cuobjdump", "-lelf", built.SO_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out, out
+
+
+def test_header_is_plain_c_and_structs_match_the_ctypes_mirrors(tmp_path):
+    """include/fuxi_b200.h must compile as C99 (it is the FFI surface), and the ctypes mirrors of its structs must have
+    the C compiler's sizes and field offsets."""
+    import ctypes as C
+    import subprocess
+    from fuxi_planner_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "probe.c"
+    src.write_text('''
+#include <stdio.h>
+#include <stddef.h>
+#include "fuxi_b200.h"
+int main(void) {
+    printf("%zu %zu %zu %zu\\n", sizeof(fx_replan_in), sizeof(fx_replan_out), sizeof(fx_cloud_params), offsetof(fx_cloud_params, radius));
+    printf("%zu %zu %zu\\n", offsetof(fx_replan_in, origin_x), offsetof(fx_replan_out, cost_f), offsetof(fx_replan_out, origin_x));
+    return 0;
+}
+''')
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    got = [int(v) for v in out]
+    want = [C.sizeof(_lib.ReplanIn), C.sizeof(_lib.ReplanOut), C.sizeof(_lib.CloudParams), _lib.CloudParams.radius.offset,
+            _lib.ReplanIn.origin_x.offset, _lib.ReplanOut.cost_f.offset, _lib.ReplanOut.origin_x.offset]
+    assert got == want, (got, want)
