@@ -72,6 +72,7 @@ def load():
     lib.fx_launch_count.argtypes = [vp]
     lib.fx_launch_count.restype = i64
     lib.fx_set_search_tuning.argtypes = [vp, i32, i32]
+    lib.fx_canon_successors.argtypes = [i32, i32]
     lib.fx_project.argtypes = [vp, vp, i64, i32, C.POINTER(f32), f32, f32, f32, f32, f32, i32, i32, vp, i32, vp]
     lib.fx_inflate.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     lib.fx_edt.argtypes = [vp, vp, vp, i32, i32, vp]

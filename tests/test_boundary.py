@@ -97,3 +97,35 @@ int main(void) {
     want = [C.sizeof(_lib.ReplanIn), C.sizeof(_lib.ReplanOut), C.sizeof(_lib.CloudParams), _lib.CloudParams.radius.offset,
             _lib.ReplanIn.origin_x.offset, _lib.ReplanOut.cost_f.offset, _lib.ReplanOut.origin_x.offset]
     assert got == want, (got, want)
+
+
+def test_ctypes_argument_counts_match_the_header():
+    """Every prototype in include/fuxi_b200.h has as many parameters as the argtypes list bound to it in _lib.py
+    (ctypes would otherwise mis-call silently), and pointer / integer / floating parameters sit at the same positions."""
+    import ctypes as C
+    import re
+    from fuxi_planner_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "fuxi_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    lib = _lib.load()
+    seen = 0
+    for m in re.finditer(r"\b(?:int|int64_t|const char \*)\s*(fx_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        name, params = m.group(1), m.group(2).strip()
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        argtypes = getattr(lib, name).argtypes
+        assert argtypes is not None, name
+        assert len(argtypes) == len(plist), (name, len(argtypes), plist)
+        for p, t in zip(plist, argtypes):
+            is_ptr = "*" in p
+            if is_ptr:
+                assert t is C.c_void_p or isinstance(t, type) and issubclass(t, (C._Pointer, C.c_char_p.__class__)) or t is C.c_char_p, (name, p, t)
+            elif re.search(r"\b(float|double)\b", p):
+                assert t in (C.c_float, C.c_double), (name, p, t)
+                assert (t is C.c_double) == bool(re.search(r"\bdouble\b", p)), (name, p, t)
+            else:
+                assert t in (C.c_int, C.c_int64, C.c_size_t, C.c_int32), (name, p, t)
+                if re.search(r"\b(int64_t|size_t)\b", p):
+                    assert t in (C.c_int64, C.c_size_t), (name, p, t)
+        seen += 1
+    assert seen == len(_lib.SYMBOLS), (seen, len(_lib.SYMBOLS))
