@@ -314,12 +314,17 @@ def replan_host(map_data, width, height, origin, reso, start_xy, goal_xy, ifa=1,
 
 def plan_host(grid, starts, goals, metric=2, max_path=512, ctx=None, device=0):
     """numpy in / numpy out through fx_plan_host (H2D + search + D2H inside the call).  A float64 grid is taken as the
-    reference's matrix (obstacle iff == 1.0, fx_plan_host_f64); any other dtype is cast to uint8 occupancy.
+    reference's matrix (obstacle iff == 1.0, fx_plan_host_f64); uint8 is passed as is; any other dtype becomes `grid == 1`.
     Returns (cost_i int32[Q], cost_f float64[Q], path_xy int32[Q,max_path,2] or None, path_len int32[Q])."""
     ctx = ctx or default_context(device)
     grid = np.asarray(grid)
     f64 = grid.dtype == np.float64          # the reference's own matrix type: `== 1` is evaluated inside the library
-    g = np.ascontiguousarray(grid) if f64 else np.ascontiguousarray(grid, dtype=np.uint8)
+    if f64 or grid.dtype == np.uint8:
+        g = np.ascontiguousarray(grid)
+    else:
+        # the reference's test is `matrix[x][y] == 1` (jps1.py:20-29): 257 or 1.5 are FREE cells; a plain astype(uint8)
+        # would wrap / truncate them to 1
+        g = np.ascontiguousarray((grid == 1).astype(np.uint8))
     s = np.ascontiguousarray(starts, dtype=np.int32).reshape(-1, 2)
     t = np.ascontiguousarray(goals, dtype=np.int32).reshape(-1, 2)
     Q = len(s)

@@ -61,6 +61,7 @@ extern "C" int fx_create(int device, fx_context **out)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_search[0]);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_search[1]);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();  // the memsets above ran on the legacy stream; own_stream does not wait for it
     if (e != cudaSuccess) {
         fx_set_err(nullptr, FX_ERR_CUDA, "context allocation: %s", cudaGetErrorString(e));
         fx_destroy(ctx);

@@ -199,7 +199,7 @@ __device__ __forceinline__ int fx_cidx(int x, int y, int H, int TY)
 
 int fx_grow_bytes(fx_context *ctx, void **p, size_t *cap, size_t want_bytes);
 int fx_grow_pinned(fx_context *ctx, size_t want);
-int fx_search_reserve(fx_context *ctx, int W, int H, int max_path);
+int fx_search_reserve(fx_context *ctx, int W, int H, int max_path, cudaStream_t st);
 // band.cu: LPT query order + per-query upper bounds from the band pass (one warp per query)
 int fx_band_bounds(fx_context *ctx, const uint8_t *grid, int W, int H, const int32_t *starts_xy, const int32_t *goals_xy, int Q,
                    int metric, cudaStream_t st);

@@ -517,6 +517,9 @@ extern "C" int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W
     if (!ctx) return FX_ERR_ARG;
     if (!occ || !dist2 || W <= 0 || H <= 0) return fx_set_err(ctx, FX_ERR_ARG, "fx_edt: bad argument");
     if (W > 65534 || H > 65534) return fx_set_err(ctx, FX_ERR_UNSUPPORTED, "fx_edt: W,H must be <= 65534");
+    // the output is int32 and INT32_MAX is the "no obstacle" sentinel: the largest possible squared distance must stay below it
+    if ((long long)(W - 1) * (W - 1) + (long long)(H - 1) * (H - 1) >= 0x7FFFFFFFll)
+        return fx_set_err(ctx, FX_ERR_UNSUPPORTED, "fx_edt: (W-1)^2 + (H-1)^2 must be < 2^31 - 1 (int32 squared distances)");
     cudaStream_t st = (cudaStream_t)stream;
     FX_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t cells = (size_t)W * H;
@@ -611,6 +614,9 @@ extern "C" int fx_edt_cols(fx_context *ctx, const uint16_t *g, int32_t *dist2, i
     if (!ctx) return FX_ERR_ARG;
     if (!g || !dist2 || W <= 0 || H <= 0) return fx_set_err(ctx, FX_ERR_ARG, "fx_edt_cols: bad argument");
     if (W > 65534) return fx_set_err(ctx, FX_ERR_UNSUPPORTED, "fx_edt_cols: W must be <= 65534");
+    // int32 output with INT32_MAX as the "no obstacle" sentinel: the caller guarantees (W-1)^2 + (row extent - 1)^2 < 2^31 - 1
+    // (fx_edt checks it for the whole grid; tiled.edt_tiled for the stitched one); here only W itself can be checked
+    if ((long long)(W - 1) * (W - 1) >= 0x7FFFFFFFll) return fx_set_err(ctx, FX_ERR_UNSUPPORTED, "fx_edt_cols: (W-1)^2 must be < 2^31 - 1");
     cudaStream_t st = (cudaStream_t)stream;
     FX_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = edt_reserve(ctx, (size_t)W * H);

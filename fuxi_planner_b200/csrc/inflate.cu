@@ -201,7 +201,9 @@ extern "C" int fx_inflate(fx_context *ctx, const uint8_t *in, uint8_t *out, int 
     cudaStream_t st = (cudaStream_t)stream;
     FX_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool fast = (H % 16 == 0) && (((uintptr_t)in | (uintptr_t)out) & 15u) == 0 && radius <= INF_MAXR;
-    if (fast && radius >= 1 && radius <= 4) {
+    // the rolling-window kernels exist for the two reference stencils only (step == 1 dense, step == radius 9-point);
+    // any other divisor of the radius (e.g. radius 4, step 2) goes to the tile / generic kernels, which honour `step`
+    if (fast && radius >= 1 && radius <= 4 && (step == 1 || step == radius)) {
         const bool dense = step == 1;
         switch (radius * 2 + (dense ? 1 : 0)) {
         case 2: case 3: launch_roll<1, 1>(in, out, W, H, ctx->sm_count, st); break;   // r = 1: the 9-point stencil IS the dense 3x3

@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-int fx_search_reserve(fx_context *ctx, int W, int H, int max_path)
+int fx_search_reserve(fx_context *ctx, int W, int H, int max_path, cudaStream_t st)
 {
     size_t cells = fx_scratch_cells(W, H);
     int path_cap = max_path > 0 ? max_path : 1;
@@ -647,8 +647,10 @@ int fx_search_reserve(fx_context *ctx, int W, int H, int max_path)
     FX_CUDA(ctx, cudaMalloc(&ctx->dirty, (size_t)slots * dirty_n));
     FX_CUDA(ctx, cudaMalloc(&ctx->queues, (size_t)slots * 4 * qcap * sizeof(uint2)));
     FX_CUDA(ctx, cudaMalloc(&ctx->tmp_path, (size_t)slots * path_cap * 8));
-    FX_CUDA(ctx, cudaMemset(ctx->fields, 0xFF, (size_t)slots * cells_al * 4));
-    FX_CUDA(ctx, cudaMemset(ctx->dirty, 0, (size_t)slots * dirty_n));
+    // on the LAUNCH stream: the synchronous-API memset runs on the legacy default stream, which a cudaStreamNonBlocking
+    // stream (the context's own stream of the *_host entry points) does not wait for
+    FX_CUDA(ctx, cudaMemsetAsync(ctx->fields, 0xFF, (size_t)slots * cells_al * 4, st));
+    FX_CUDA(ctx, cudaMemsetAsync(ctx->dirty, 0, (size_t)slots * dirty_n, st));
     ctx->sW = W; ctx->sH = H; ctx->slots = slots; ctx->qcap = qcap; ctx->path_cap = path_cap;
     ctx->cells = cells_al; ctx->dirty_n = dirty_n;
     return FX_OK;
@@ -675,7 +677,7 @@ extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int 
             if (r <= 0) return r;
         }
     }
-    int rc = fx_search_reserve(ctx, W, H, path_xy ? max_path : 1);
+    int rc = fx_search_reserve(ctx, W, H, path_xy ? max_path : 1, st);
     if (rc) return rc;
     rc = fx_build_moves(ctx, grid, W, H, true, st);
     if (rc) return rc;

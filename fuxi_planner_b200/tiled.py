@@ -242,6 +242,8 @@ def edt_tiled(own_rows, W, group=None, ops=None):
     h, H = own_rows.shape
     if h != x1 - x0:
         raise FuxiError("own_rows has %d rows, slab_bounds says %d" % (h, x1 - x0))
+    if (W - 1) ** 2 + (H - 1) ** 2 >= 2 ** 31 - 1:          # int32 squared distances, INT32_MAX = no obstacle (fx_edt's own check)
+        raise FuxiError("edt_tiled: (W-1)^2 + (H-1)^2 must be < 2^31 - 1")
     g = ops.edt_rows(own_rows.contiguous())
     if n == 1:
         return ops.edt_cols(g)

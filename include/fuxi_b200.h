@@ -81,7 +81,8 @@ int fx_inflate(fx_context *ctx, const uint8_t *in, uint8_t *out, int W, int H, i
                void *stream);
 
 /* Exact squared Euclidean distance (in cells^2) to the nearest cell > 0; INT32_MAX if the grid has
- * none.  Not in the reference (north-star addition); oracle = scipy.ndimage.distance_transform_edt. */
+ * none.  Not in the reference (north-star addition); oracle = scipy.ndimage.distance_transform_edt.
+ * W, H <= 65534 and (W-1)^2 + (H-1)^2 < 2^31 - 1 (the output is int32), else FX_ERR_UNSUPPORTED. */
 int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W, int H, void *stream);
 /* The two separable passes of fx_edt on their own (row-tiled multi-GPU mode, tiled.edt_tiled): fx_edt_rows writes
  * g[x][y] = distance along y to the nearest cell > 0 of row x (uint16, 0xFFFF = the row has none) -- local to an x-slab;
@@ -101,8 +102,9 @@ int fx_edt_cols(fx_context *ctx, const uint16_t *g, int32_t *dist2, int W, int H
  * starts_xy / goals_xy: int32 [Q][2].  cost_i: int32 [Q] (or FX_COST_*).  cost_f: double [Q] or NULL.
  * path_xy: int32 [Q][max_path][2] turning points, start first, goal last (consecutive points are
  * joined by a straight 8-direction run -- same contract as the reference's jump-point list), or NULL;
- * path_len: int32 [Q] number of turning points (may exceed max_path: only max_path were stored;
- * FX_COST_* when there is no path), or NULL.
+ * path_len: int32 [Q] number of turning points (FX_COST_* when there is no path), or NULL.  path_len[q] > max_path
+ * means the path did not fit: the contents of that query's path buffer are then unspecified (the forms below
+ * differ in which points they keep) -- call again with max_path >= path_len[q].
  * Three forms behind this one entry point, same results: maps up to 20 000 cells (every map the reference ships)
  * are searched by one CTA per query entirely in shared memory, one launch per batch; larger maps by the batched
  * wavefront kernel, with 512-thread CTAs when the batch is smaller than the machine (latency) and 128-thread CTAs,

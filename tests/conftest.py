@@ -49,3 +49,37 @@ def unpack_grid(rec):
 def large_grid(rec):
     n = rec["n"]
     return (np.random.default_rng(rec["grid_seed"]).random((n, n)) < 0.2).astype(np.uint8)
+
+
+@pytest.fixture(scope="session")
+def inline_golden():
+    """a10/a11/a13/a14: outputs of the reference's own inline source lines (tests/golden/make_inline_golden.py)."""
+    import base64
+    import zlib
+    with open(os.path.join(GOLDEN, "inline_golden.json")) as fh:
+        d = json.load(fh)
+
+    def arr(s, shape):
+        return np.frombuffer(zlib.decompress(base64.b64decode(s)), dtype=np.uint8).reshape(shape).copy()
+
+    cases = []
+    for r in d["cases"]:
+        c = dict(r)
+        c["X"] = arr(r["X"], (r["W"], r["H"]))
+        c["map_o"] = [float(v) for v in r["map_o"]]
+        c["reso"] = float(r["reso"])
+        c["start"] = [float(v) for v in r["start"]]
+        c["goal"] = [float(v) for v in r["goal"]]
+        if r["out"] is not None:
+            o = dict(r["out"])
+            o["grid"] = arr(o["grid"], tuple(o["shape"]))
+            o["map_o"] = [float(v) for v in o["map_o"]]
+            c["out"] = o
+        cases.append(c)
+    return cases
+
+
+@pytest.fixture(scope="session")
+def cfg4_golden():
+    with open(os.path.join(GOLDEN, "cfg4_golden.json")) as fh:
+        return json.load(fh)

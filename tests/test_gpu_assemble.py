@@ -308,3 +308,39 @@ def test_replan_array_layout_equals_message_layout(fx, oracle, maps):
     a = fx.replan_host(msg, m.shape[0], m.shape[1], (0.0, 0.0), 0.2, (0.5, 0.5), (28.0, 9.0), ifa=1, variant="st", want_grid=True)
     b = fx.replan_host(m, m.shape[0], m.shape[1], (0.0, 0.0), 0.2, (0.5, 0.5), (28.0, 9.0), ifa=1, variant="st", layout="array", want_grid=True)
     assert np.array_equal(a[3], b[3]) and a[1].tolist() == b[1].tolist() and a[0].cost_f == b[0].cost_f and a[0].path_len > 1
+
+
+# ------------------------------------------------------------------------------------------ reference-executed goldens
+def test_replan_vs_reference_inline_lines(fx, dev, oracle, inline_golden):
+    """a10/a11/a13/a14 on the device against the outputs of the reference's OWN source lines
+    (global_planner_st.py:226-275 / global_planner_ccst.py:411-464, exec'd by tests/golden/make_inline_golden.py):
+    fx_replan_host's planning grid (pad/shift + inflation) bit-exact, start / goal cells after relocation, map_d,
+    shifted origin bit-exact, end_occu; fx_inflate and fx_relocate_goal alone on the same data."""
+    n = n_moved = 0
+    for c in inline_golden:
+        want = c["out"]
+        X = c["X"]
+        msg = oracle.hostref.encode_occupancy_grid(X.astype(np.int64))
+        out, cells, world, grid = fx.replan_host(msg, c["W"], c["H"], tuple(c["map_o"]), c["reso"], tuple(c["start"]), tuple(c["goal"]),
+                                                 ifa=c["ifa"], variant=c["variant"], hchoice=2, shortcut=False, want_grid=True)
+        assert (out.W, out.H) == tuple(want["shape"])
+        assert np.array_equal(grid, want["grid"])
+        assert [out.paste_x, out.paste_y] == want["map_d"]
+        assert [out.origin_x, out.origin_y] == want["map_o"]
+        assert [out.start_x, out.start_y] == want["map_start"]
+        assert [out.goal_x, out.goal_y] == want["map_goal"]
+        assert out.end_occu == want["end_occu"]
+        # a10 / a11 alone: fx_inflate of the padded grid == the reference's inflated grid
+        pad = np.zeros(tuple(want["shape"]), dtype=np.uint8)
+        d = want["map_d"]
+        pad[d[0]:d[0] + c["W"], d[1]:d[1] + c["H"]] = X
+        step = "st" if c["variant"] == "st" else "ccst"
+        assert np.array_equal(fx.inflate(_t(pad, dev), c["ifa"], step).cpu().numpy(), want["grid"])
+        # a14 alone: fx_relocate_goal from the unrelocated goal cell
+        off = -1 if c["variant"] == "st" else 0
+        g0 = [want["map_goal0"][k] + d[k] + off for k in (0, 1)]
+        rel = fx.relocate_goal(_t(want["grid"], dev), tuple(g0), ifa=c["ifa"], variant=c["variant"]).cpu().numpy().tolist()
+        assert rel[:2] == want["map_goal"] and rel[3] == want["end_occu"]
+        n_moved += int(rel[2] == 1)
+        n += 1
+    assert n >= 150 and n_moved > 20

@@ -554,3 +554,83 @@ def test_search_slot_reuse_resets_completely(fx, dev, oracle):
             assert np.array_equal(res.cost_i.cpu().numpy().astype(np.int64), want), metric
     finally:
         ctx.close()
+
+
+# ------------------------------------------------------------------------------------------ BASELINE configurations
+def _cfg4_workload(n=4096, q=256):
+    """cfg4 of SURVEY §8d exactly as bench.py builds it: grid default_rng(4) at 20 % fill, queries default_rng(5)."""
+    m = (np.random.default_rng(4).random((n, n)) < 0.2).astype(np.uint8)
+    free = np.argwhere(m == 0)
+    rng = np.random.default_rng(5)
+    s = free[rng.integers(len(free), size=8192)].astype(np.int32)[:q]
+    g = free[rng.integers(len(free), size=8192)].astype(np.int32)[:q]
+    return m, s, g
+
+
+def test_search_cfg4_4096(fx, dev, oracle, cfg4_golden):
+    """The headline configuration (cfg4: 4096^2, 20 % fill): the first 256 queries of the benchmark's batch, both
+    metrics, against the C restatement of jps1.py, every path validated move by move; plus the queries whose costs
+    were produced by the UNMODIFIED reference at this size (tests/golden/cfg4_golden.json, minutes per query)."""
+    m, s, g = _cfg4_workload()
+    gm = _t(m, dev)
+    for metric in (1, 2):
+        want, status, _ = oracle.jps_batch(m, s, g, metric)
+        res = fx.plan_batch(gm, _t(s, dev), _t(g, dev), metric=metric, max_path=2048)
+        ci, cf = res.cost_i.cpu().numpy(), res.cost_f.cpu().numpy()
+        assert (status == 1).sum() > 250
+        for q in range(len(s)):
+            if status[q] != 1:
+                assert ci[q] == -1, (metric, q, ci[q])
+            elif metric == 1:
+                assert ci[q] == int(want[q]), (metric, q, ci[q], want[q])
+            else:
+                assert abs(cf[q] - want[q]) <= RTOL * max(want[q], 1e-12), (metric, q, cf[q], want[q])
+        for q in np.flatnonzero(status == 1)[::4]:
+            a, b = validate_path(m, res.path(int(q)), tuple(s[q]), tuple(g[q]))
+            if metric == 1:
+                assert 10 * a + 14 * b == ci[q]
+            else:
+                assert a * fx.FX_EUCLID_WS + b * fx.FX_EUCLID_WD == ci[q] and cf[q] == a + b * SQRT2
+        # the reference's own answers
+        recs = [r for r in cfg4_golden if r["h"] == metric]
+        assert len(recs) >= 3
+        for r in recs:
+            q = r["index"]
+            assert list(s[q]) == r["start"] and list(g[q]) == r["goal"]
+            if metric == 1:
+                assert ci[q] == int(float(r["cost"])), (q, ci[q], r["cost"])
+            else:
+                assert abs(cf[q] - float(r["cost"])) <= RTOL * float(r["cost"]), (q, cf[q], r["cost"])
+    # the small-batch (latency) form on the same grid: same costs
+    res1 = fx.plan_batch(gm, _t(s[:8], dev), _t(g[:8], dev), metric=2, max_path=2048)
+    assert np.array_equal(res1.cost_i.cpu().numpy(), ci[:8])
+
+
+def test_cfg5_field_vs_oracle(fx, dev, oracle):
+    """cfg5 (16384^2, default_rng(6), 20 % fill; query = first free cell -> last free cell): the whole cost field of one
+    GPU against the C oracle's Dijkstra field bit for bit, and the goal's cost against the goal-directed batched search
+    (fx_search_batch) on the same query, both metrics for the query."""
+    import torch
+    n = 16384
+    m = (np.random.default_rng(6).random((n, n)) < 0.2).astype(np.uint8)
+    free_first = np.unravel_index(np.flatnonzero(m.reshape(-1) == 0)[0], m.shape)
+    free_last = np.unravel_index(np.flatnonzero(m.reshape(-1) == 0)[-1], m.shape)
+    s = np.array([free_first], dtype=np.int32)
+    g = np.array([free_last], dtype=np.int32)
+    gm = _t(m, dev)
+    want = oracle.sssp_field(m, tuple(int(v) for v in s[0]), metric=2)          # int64, -1 unreachable
+    field = fx.field(gm, tuple(int(v) for v in s[0]), metric=2)
+    got = field.cpu().numpy()
+    assert got.dtype == np.int32 and got.shape == (n, n)
+    assert np.array_equal(got, want.astype(np.int32))
+    goal_cost = int(want[g[0][0], g[0][1]])
+    assert goal_cost > 16000 * fx.FX_EUCLID_WS
+    del field, got
+    torch.cuda.empty_cache()
+    res = fx.plan_batch(gm, _t(s, dev), _t(g, dev), metric=2, max_path=8192)
+    assert int(res.cost_i[0]) == goal_cost
+    a, b = validate_path(m, res.path(0), tuple(s[0]), tuple(g[0]))
+    assert a * fx.FX_EUCLID_WS + b * fx.FX_EUCLID_WD == goal_cost
+    want1 = oracle.sssp_batch(m, s, g, 1)
+    res1 = fx.plan_batch(gm, _t(s, dev), _t(g, dev), metric=1, max_path=8192)
+    assert int(res1.cost_i[0]) == int(want1[0])

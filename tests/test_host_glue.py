@@ -119,3 +119,40 @@ def test_waypoint_st_matches_the_restated_block(oracle, golden, maps):
             assert got[2] == want[2]
             kept += int(not np.array_equal(np.asarray(got[0]), goal) and end_occu == 0)
     assert kept > 10          # the interesting branch (an intermediate waypoint) is exercised
+
+
+def test_inline_blocks_restatement_matches_reference_lines(oracle, inline_golden):
+    """a10/a11/a13/a14: oracle/hostref.py's restatement of the planner loops' inline blocks against the outputs of the
+    reference's OWN source lines (global_planner_st.py:226-275, global_planner_ccst.py:411-464, exec'd by
+    tests/golden/make_inline_golden.py): padded + inflated grid bit-exact, start / goal cells after relocation, map_d,
+    shifted origin (float64 bit-exact), end_occu."""
+    n = 0
+    for c in inline_golden:
+        want = c["out"]
+        assert want is not None
+        got = oracle.hostref.replan_pipeline(c["X"].astype(np.int64), c["map_o"], c["reso"], c["start"], c["goal"], c["ifa"], c["variant"])
+        assert got["grid"].shape == tuple(want["shape"])
+        assert np.array_equal(got["grid"].astype(np.uint8), want["grid"])
+        assert list(got["start"]) == want["map_start"] and list(got["goal"]) == want["map_goal"]
+        assert list(got["map_d"]) == want["map_d"] and got["origin"] == want["map_o"]
+        assert got["end_occu"] == want["end_occu"]
+        # the inflation restatements on their own (a10 / a11): padded grid before inflation -> grid after
+        pad, _, _, _, _ = oracle.hostref.assemble_grid(c["X"].astype(np.int64), c["map_o"], c["reso"], c["start"], c["goal"], c["ifa"], c["variant"])
+        inf = oracle.hostref.inflate_st(pad, c["ifa"]) if c["variant"] == "st" else oracle.hostref.inflate_ccst(pad, c["ifa"])
+        assert np.array_equal(inf.astype(np.uint8), want["grid"])
+        assert np.array_equal(oracle.inflate((pad > 0).astype(np.uint8), c["ifa"], c["ifa"] if c["variant"] == "st" else 1), want["grid"])
+        n += 1
+    assert n >= 150
+
+
+def test_plan_assembly_matches_reference_lines(inline_golden):
+    """planner.plan_assembly (the product's host arithmetic for a13) against the reference's own lines."""
+    for c in inline_golden:
+        want = c["out"]
+        a = planner.plan_assembly((c["W"], c["H"]), c["map_o"], c["reso"], c["start"], c["goal"], c["ifa"], c["variant"])
+        assert a.shape == tuple(want["shape"]) and a.paste_at == tuple(want["map_d"])
+        assert list(a.origin) == want["map_o"]
+        # a.start / a.goal are the cells BEFORE relocation: goal0 + map_d (- 1 for st)
+        off = -1 if c["variant"] == "st" else 0
+        assert list(a.goal) == [want["map_goal0"][k] + want["map_d"][k] + off for k in (0, 1)]
+        assert list(a.start) == want["map_start"]
