@@ -7,9 +7,10 @@ i.e. 8 192 queries per GPU, "weak" scaling), plus p50 single-replan latency of t
 ``jps1.method``.  One "step" = one fx_search_batch launch over this rank's batch of queries
 (move-mask build + search + path extraction), Euclidean metric (hchoice 2, what the planners use).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]                 # this repo's CUDA path
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # this repo's CUDA path (cfg4, the headline)
     python bench.py --impl reference ...                                # CPU arm (see below)
     torchrun --nproc-per-node N bench.py --gpus N ...                   # N > 1
+    python bench.py --config cfg2|cfg3|cfg5 ...                         # BASELINE.json's other configurations, same JSON contract
 
 `value`   queries/s with grid and queries resident in HBM, CUDA-event timed, max over ranks.
 `e2e`     the same queries through the host-buffer C-ABI call (fx_plan_host): H2D of the grid and the
@@ -18,7 +19,9 @@ i.e. 8 192 queries per GPU, "weak" scaling), plus p50 single-replan latency of t
           inflation, EDT) at the BASELINE sizes and at HBM-exercising scaled sizes.
 `cpu_baseline` / `--impl reference`: the reference itself is Python (scripts/jps1.py) and
           /root/reference does not exist on the GPU box, so the CPU arm is the C restatement of jps1.py in
-          oracle/ (kind "port"), OpenMP over all host threads, on a bounded sample of the same queries.
+          oracle/ (kind "port"), OpenMP over ALL host cores (the thread count is passed explicitly: torchrun exports
+          OMP_NUM_THREADS=1), 16 queries per thread per step, rank 0 only.
+`per_rank`  ms_per_step / k_search_batch ms / k_band_bound ms / median SM clock of every rank (N > 1: names the straggler).
 """
 import argparse
 import json
@@ -49,7 +52,17 @@ def parse_args():
     ap.add_argument("--max-path", type=int, default=1024)
     ap.add_argument("--no-extras", action="store_true", help="skip map-kernel rooflines, latency and cpu_baseline")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work for the cpu_baseline sample")
+    ap.add_argument("--config", default="cfg4", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE.json configuration (cfg4 = the headline metric; the others print the same JSON contract)")
     return ap.parse_args()
+
+
+def host_threads():
+    """Cores this process may use.  OMP_NUM_THREADS is ignored on purpose (torchrun sets it to 1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 # ------------------------------------------------------------------------------------------ workload
@@ -136,11 +149,11 @@ def ncu_traffic(kernel, n, Q, hchoice):
 def cpu_sample(m, s, g, hchoice, target_s, oracle):
     """Times the C restatement of jps1.py over all host threads on the first S queries; S is doubled until
     the sample costs about target_s seconds of wall clock (bounded: S <= 64 x threads)."""
-    threads = oracle.num_threads()
-    S = min(len(s), max(threads, 8))
+    threads = host_threads()
+    S = min(len(s), 16 * threads)
     while True:
         t0 = time.perf_counter()
-        cost, status, used = oracle.jps_batch(m, s[:S], g[:S], hchoice)
+        cost, status, used = oracle.jps_batch(m, s[:S], g[:S], hchoice, threads=threads)
         dt = time.perf_counter() - t0
         if dt >= target_s / 3 or S >= len(s) or S >= 64 * threads:
             return S, dt, used, cost, status
@@ -153,28 +166,33 @@ def run_reference(args):
         return 0
     import oracle
     oracle.build()
+    if args.config != "cfg4":
+        return run_reference_other(args, oracle)
     n, Q = args.grid, args.queries
     m, s, g = make_workload(n, Q * args.gpus)
-    threads = oracle.num_threads()
-    # one step = a bounded sample of the workload: 2 queries per host thread (≈ 1.5 s per query per core at 4096^2)
-    S = min(len(s), 2 * threads)
-    for _ in range(args.warmup):
-        oracle.jps_batch(m, s[:S], g[:S], args.hchoice)
+    threads = host_threads()
+    # one step = a bounded sample of the workload: the first 16 queries per host thread (~0.17 s per query per core at
+    # 4096^2, dynamic schedule), all cores of the box whatever OMP_NUM_THREADS says
+    S = min(len(s), 16 * threads)
+    for _ in range(min(args.warmup, 1)):
+        oracle.jps_batch(m, s[:S], g[:S], args.hchoice, threads=threads)
     times = []
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        oracle.jps_batch(m, s[:S], g[:S], args.hchoice)
+        _, _, used = oracle.jps_batch(m, s[:S], g[:S], args.hchoice, threads=threads)
         times.append(time.perf_counter() - t0)
     total = sum(times)
     value = S * args.steps / total
+    cfg = workload_config(args, args.queries)
+    cfg["cpu_sample_queries_per_step"] = S
     line = {
         "impl": "reference", "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, args.queries),
-        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": threads, "kind": "port",
-                         "sample": "first %d of the workload's queries per step, C restatement of scripts/jps1.py "
-                                   "(oracle/fuxi_oracle.c), OpenMP over %d host threads" % (S, threads)},
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": int(used), "kind": "port",
+                         "sample": "first %d of the workload's queries per step (16 per thread; 1 warm-up step), C restatement of "
+                                   "scripts/jps1.py (oracle/fuxi_oracle.c), OpenMP over %d host threads" % (S, used)},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -360,9 +378,36 @@ def latency_probe(fx, m4096, s, g, hchoice):
                 "p99_ms": float(np.percentile(ts, 99)), "n": len(ts)}
 
     res["cfg1_map_148x52"] = run(m1, pairs, 20)
+    # the same 280 queries through the C restatement of jps1.py on ONE host core of this box (the reference's own
+    # Python is ~2 orders of magnitude slower: BASELINE.md §2 measured p50 10.5 ms on another machine)
+    try:
+        import oracle
+        occ1 = (m1 == 1).astype(np.uint8)
+        ts = []
+        for i, (a, b) in enumerate(pairs):
+            t0 = time.perf_counter()
+            oracle.capi.jps(occ1, a, b, hchoice, max_path=4096)
+            if i >= 20:
+                ts.append(time.perf_counter() - t0)
+        ts = np.array(ts) * 1e3
+        res["cfg1_map_148x52"]["cpu_port_p50_ms"] = float(np.percentile(ts, 50))
+        res["cfg1_map_148x52"]["cpu_port_p99_ms"] = float(np.percentile(ts, 99))
+        res["cfg1_map_148x52"]["cpu_port"] = "oracle/fuxi_oracle.c fxo_jps, 1 core, same box, same 280 queries"
+    except Exception as exc:
+        res["cfg1_map_148x52"]["cpu_port_error"] = repr(exc)
     m4 = m4096.astype(np.float64)
-    pairs4 = [(tuple(int(v) for v in s[i]), tuple(int(v) for v in g[i])) for i in range(40)]
-    res["grid_%dx%d" % m4096.shape] = run(m4, pairs4, 8)
+    pairs4 = [(tuple(int(v) for v in s[i]), tuple(int(v) for v in g[i])) for i in range(220)]
+    res["grid_%dx%d" % m4096.shape] = run(m4, pairs4, 20)
+    # the same through the uint8 host entry point (no float64 -> uint8 conversion of 16 Mi cells on the host)
+    tsu = []
+    for i, (a, b) in enumerate(pairs4):
+        t0 = time.perf_counter()
+        fx.plan_host(m4096, np.array([a], dtype=np.int32), np.array([b], dtype=np.int32), metric=hchoice, max_path=2048)
+        if i >= 20:
+            tsu.append(time.perf_counter() - t0)
+    tsu = np.array(tsu) * 1e3
+    res["grid_%dx%d_uint8_host" % m4096.shape] = {"p50_ms": float(np.percentile(tsu, 50)), "p90_ms": float(np.percentile(tsu, 90)),
+                                                  "p99_ms": float(np.percentile(tsu, 99)), "n": len(tsu)}
     # the whole planner iteration in one call (decode + pad/shift + inflate + goal relocation + search + shortcutting +
     # world coordinates, fx_replan_host): OccupancyGrid message of the cfg1 map in, world path out
     from fuxi_planner_b200 import planner
@@ -407,6 +452,12 @@ def run_b200(args):
     if os.environ.get("FUXI_SLOTS"):  # tuning experiments only: concurrent search slots
         ctx.check(ctx.lib.fx_set_search_tuning(ctx.handle, int(os.environ["FUXI_SLOTS"]), 0), "fx_set_search_tuning")
 
+    if args.config != "cfg4":
+        rc = run_other_config(args, torch, dist, fx, ctx, dev, world, rank, local)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return rc
     n, Q = args.grid, args.queries
     m, s_all, g_all = make_workload(n, Q * world)
     s, g = s_all[rank * Q:(rank + 1) * Q], g_all[rank * Q:(rank + 1) * Q]
@@ -430,19 +481,21 @@ def run_b200(args):
         res = step()
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()                      # every rank samples its own GPU (per_rank names a slow one)
     launches0 = ctx.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    kernel_ms = []
+    kernel_ms, band_ms = [], []
     for a, b in ev:
         flush()
         a.record()
         res = step()
         b.record()
-        kernel_ms.append(fx.search_kernel_ms(ctx))      # waits for this step's k_search_batch; the next step starts after it
+        bm, km = fx.search_timings(ctx)                 # waits for this step's k_search_batch; the next step starts after it
+        kernel_ms.append(km)
+        band_ms.append(bm)
     barrier()
+    clocks_dev = sampler.stop()                         # clocks under the device-timed region only
     launches = ctx.launches - launches0
     t_ms = float(sum(a.elapsed_time(b) for a, b in ev))
     settled, levels, passes, band_only = fx.search_stats(ctx)
@@ -453,6 +506,15 @@ def run_b200(args):
         dist.all_reduce(st, op=dist.ReduceOp.SUM)
     t_ms_max = float(tt.item())
     value = Q * world * args.steps / (t_ms_max * 1e-3)
+    mine = torch.tensor([t_ms / args.steps, float(np.mean(kernel_ms)), float(np.mean(band_ms)), float(clocks_dev.get("sm_mhz") or 0.0),
+                         float(settled)], dtype=torch.float64, device=dev)
+    allr = [torch.zeros_like(mine) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allr, mine)
+    else:
+        allr = [mine]
+    per_rank = [{"rank": r, "ms_per_step": float(v[0]), "search_kernel_ms": float(v[1]), "band_kernel_ms": float(v[2]),
+                 "sm_mhz": float(v[3]), "settled_cells": int(v[4])} for r, v in enumerate(t.cpu() for t in allr)]
     answered = int((res.cost_i >= 0).sum().item())
 
     # ---- e2e: host buffers through fx_plan_host (H2D grid + queries, D2H costs + paths), wall clock, max over ranks
@@ -467,11 +529,16 @@ def run_b200(args):
     e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = clocks_dev if rank == 0 else None
     e2e_value = Q * world * e2e_steps / float(e2e_t.item())
     assert np.array_equal(ci, res.cost_i.cpu().numpy()), "host-buffer path and device path disagree"
     h2d = m.nbytes + s.nbytes + g.nbytes
-    d2h = Q * (4 + 4 + 8) + Q * args.max_path * 8
+    d2h = int(ctx.lib.fx_last_d2h_bytes(ctx.handle))    # costs + lengths + offsets + the points of the paths found (compact form)
+    pl_dev = res.path_len.cpu().numpy()
+    for q in range(0, Q, max(1, Q // 64)):              # the padded rows the host call filled == the device rows
+        k = int(pl_dev[q])
+        if 0 < k <= args.max_path:
+            assert np.array_equal(pxy[q, :k], res.path_xy[q, :k].cpu().numpy()), "host path rows differ from the device rows"
 
     peak, peak_src = measured_peak()
     settled_all = float(st.item())
@@ -485,7 +552,8 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "u32 (cost in 1/2378 cell, packed with the arrival direction)" if args.hchoice == 2 else "u32",
         "data": "synthetic", "config": workload_config(args, Q),
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "api": "fx_plan_host (fuxi_planner_b200.plan_host), host numpy buffers"},
+                "api": "fx_plan_host (fuxi_planner_b200.plan_host), host numpy buffers; paths cross the bus in compact form "
+                       "and are scattered into the caller's padded rows on the host"},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "k_search_batch", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic("k_search_batch", n, Q, args.hchoice),
@@ -496,7 +564,9 @@ def run_b200(args):
                    "levels": int(levels), "passes": int(passes), "band_only": int(band_only),
                    "answered_rank0": answered, "queries_rank0": Q},
         "clocks": clocks,
+        "per_rank": per_rank,
     }
+    line["roofline"]["band_kernel_ms"] = float(np.mean(band_ms))
     if rank == 0 and world == 1 and not args.no_extras:
         # reported extras: a failure in one of them is recorded, it must not take the bench line down
         for key, fn in (("kernels", lambda: map_kernel_rooflines(torch, fx, dev, flush, peak)),
@@ -510,7 +580,7 @@ def run_b200(args):
         oracle.build()
         S, dt, used, cost, status = cpu_sample(m, s, g, args.hchoice, args.cpu_seconds, oracle)
         line["cpu_baseline"] = {"value": S / dt, "unit": "queries/s", "cores": int(used), "kind": "port",
-                                "sample": "first %d queries of the step's batch, C restatement of scripts/jps1.py "
+                                "sample": "first %d queries of the step's batch (16 per thread), C restatement of scripts/jps1.py "
                                           "(oracle/fuxi_oracle.c) over %d OpenMP threads, %.1f s" % (S, used, dt)}
         # the sample doubles as a parity spot-check of the timed batch
         got = cf[:S]
@@ -522,6 +592,315 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ other BASELINE configurations
+CFG_METRIC = {
+    "cfg2": ("cloud -> inflated occupancy grid, 1 Mi points -> 1024^2 cells, dense r=2 inflation: points/s", "points/s", True),
+    "cfg3": ("planning queries/s, 1024^2 grid (20% fill), 4096 batched start/goal queries", "queries/s", True),
+    "cfg5": ("single-query latency, 16384^2 grid (20% fill), first free cell -> last free cell", "ms", False),
+}
+
+
+def cfg2_cloud():
+    """default_rng(1), x,y ~ U(-102.4, 102.4), z ~ U(-0.5, 3.0), float32; origin (-102.4, -102.4), reso 0.2."""
+    rng = np.random.default_rng(1)
+    N = 1 << 20
+    pts = np.empty((N, 4), dtype=np.float32)
+    pts[:, 0:2] = rng.uniform(-102.4, 102.4, (N, 2))
+    pts[:, 2] = rng.uniform(-0.5, 3.0, N)
+    pts[:, 3] = 0
+    return pts
+
+
+def cfg3_workload():
+    m = (np.random.default_rng(2).random((1024, 1024)) < 0.2).astype(np.uint8)
+    free = np.argwhere(m == 0)
+    rng = np.random.default_rng(3)
+    s = free[rng.integers(len(free), size=4096)].astype(np.int32)
+    g = free[rng.integers(len(free), size=4096)].astype(np.int32)
+    return m, s, g
+
+
+def cfg5_workload(n=16384):
+    m = (np.random.default_rng(6).random((n, n)) < 0.2).astype(np.uint8)
+    ff = np.flatnonzero(m.reshape(-1) == 0)
+    s = np.array(np.unravel_index(ff[0], m.shape), dtype=np.int32)
+    g = np.array(np.unravel_index(ff[-1], m.shape), dtype=np.int32)
+    return m, s, g
+
+
+def base_line(args, world, value, ms_step, cfgd, dtype):
+    name, unit, hib = CFG_METRIC[args.config]
+    return {"metric": name, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": hib, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+            "dtype": dtype, "data": "synthetic", "config": cfgd}
+
+
+def run_other_config(args, torch, dist, fx, ctx, dev, world, rank, local):
+    peak, peak_src = measured_peak()
+    flush_buf = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def flush():
+        flush_buf.fill_(1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        l0 = ctx.launches
+        ts = []
+        for _ in range(args.steps):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        barrier()
+        clocks = sampler.stop()
+        t = torch.tensor([float(sum(ts))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / args.steps, clocks, ctx.launches - l0
+
+    if args.config == "cfg3":
+        m, s_all, g_all = cfg3_workload()
+        Q = len(s_all) // world
+        s, g = s_all[rank * Q:(rank + 1) * Q], g_all[rank * Q:(rank + 1) * Q]
+        d_m, d_s, d_g = torch.from_numpy(m).to(dev), torch.from_numpy(s).to(dev), torch.from_numpy(g).to(dev)
+        ms, clocks, launches = timed(lambda: fx.plan_batch(d_m, d_s, d_g, metric=args.hchoice, max_path=args.max_path))
+        band_ms, k_ms = fx.search_timings(ctx)
+        settled = fx.search_stats(ctx)[0]
+        fx.plan_host(m, s, g, metric=args.hchoice, max_path=args.max_path, ctx=ctx)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ci, cf, pxy, pl = fx.plan_host(m, s, g, metric=args.hchoice, max_path=args.max_path, ctx=ctx)
+        e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        line = base_line(args, world, Q * world / (ms * 1e-3), ms,
+                         {"workload": "cfg3: 4096 start/goal queries on a 1024x1024 random-obstacle grid (20% fill, default_rng(2)/(3)), "
+                                      "hchoice %d" % args.hchoice, "l2": "flushed between timed steps"},
+                         "u32 (packed cost | arrival direction)")
+        line["e2e"] = {"value": Q * world * args.steps / float(e2e_t.item()), "unit": "queries/s",
+                       "h2d_bytes_per_step": int(m.nbytes + s.nbytes + g.nbytes), "d2h_bytes_per_step": int(ctx.lib.fx_last_d2h_bytes(ctx.handle)),
+                       "api": "fx_plan_host"}
+        line["gpu_launches"] = int(launches)
+        ach = settled * 5.0 / (k_ms * 1e-3) / 1e9
+        line["roofline"] = {"kernel": "k_search_batch", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                            "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms, "band_kernel_ms": band_ms,
+                            "algorithmic_bytes": "settled cells x 5 B"}
+        line["search"] = {"settled_cells": int(settled), "nodes_per_s": settled / (ms * 1e-3)}
+        line["clocks"] = clocks
+        if rank == 0:
+            import oracle
+            oracle.build()
+            S, dt, used, cost, status = cpu_sample(m, s, g, args.hchoice, args.cpu_seconds, oracle)
+            ok = status == 1
+            bad = np.abs(cf[:S][ok] - cost[ok]) > 1e-5 * np.maximum(cost[ok], 1e-12) if args.hchoice == 2 else ci[:S][ok] != cost[ok]
+            line["cpu_baseline"] = {"value": S / dt, "unit": "queries/s", "cores": int(used), "kind": "port",
+                                    "sample": "first %d queries, C restatement of scripts/jps1.py over %d threads, %.1f s" % (S, used, dt),
+                                    "parity_mismatches": int(bad.sum()) + int(((ci[:S] >= 0) != ok).sum())}
+            print(json.dumps(line), flush=True)
+        return 0
+
+    if args.config == "cfg2":
+        import oracle
+        pts = cfg2_cloud()
+        N, W, H = len(pts), 1024, 1024
+        d_p = torch.from_numpy(pts).to(dev)
+        grid = torch.empty((W, H), dtype=torch.uint8, device=dev)
+        infl = torch.empty_like(grid)
+
+        def step():
+            fx.project(d_p, None, 0.3, float("inf"), (-102.4, -102.4), 0.2, out=grid)
+            fx.inflate(grid, 2, "ccst", out=infl)
+        ms, clocks, launches = timed(step)
+        want = oracle.hostref.project(pts[:, :3], np.eye(3, 4), 0.3, np.inf, -102.4, -102.4, 0.2, W, H)
+        parity = int(np.array_equal(grid.cpu().numpy(), want)) + int(np.array_equal(infl.cpu().numpy(), oracle.inflate(want, 2, 1)))
+        out = fx.map_host(pts, None, 0.3, float("inf"), (-102.4, -102.4), 0.2, (W, H), radius=2, variant="ccst", ctx=ctx)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out = fx.map_host(pts, None, 0.3, float("inf"), (-102.4, -102.4), 0.2, (W, H), radius=2, variant="ccst", ctx=ctx)
+        e2e_s = (time.perf_counter() - t0) / args.steps
+        parity += int(np.array_equal(out, oracle.inflate(want, 2, 1)))
+        alg = N * 16 + W * H + 2 * W * H
+        line = base_line(args, world, N / (ms * 1e-3), ms,
+                         {"workload": "cfg2: 1 Mi float4 points (default_rng(1)) -> 1024x1024 grid (reso 0.2, z > 0.3) + dense r=2 inflation",
+                          "l2": "flushed between timed steps"}, "f32 transform / u8 grid")
+        line["e2e"] = {"value": N / e2e_s, "unit": "points/s", "h2d_bytes_per_step": int(pts.nbytes), "d2h_bytes_per_step": W * H,
+                       "api": "fx_map_host (host cloud in, inflated grid out)", "ms": e2e_s * 1e3}
+        line["gpu_launches"] = int(launches)
+        ach = alg / (ms * 1e-3) / 1e9
+        line["roofline"] = {"kernel": "k_project_f4 + k_inflate_roll", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                            "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                            "algorithmic_bytes": "N*16 + W*H (projection) + 2*W*H (inflation); 20 MB per step: launch-latency-bound at this size, "
+                                                 "see kernels.*_scaled of the cfg4 line for the HBM-exercising sizes"}
+        line["clocks"] = clocks
+        line["parity_checks_passed_of_3"] = parity
+        # host baseline: the reference's numpy transform + height filter (a15/a16), the projection restatement, the a11 block
+        t0 = time.perf_counter()
+        p64 = pts[:, :3].astype(np.float64)
+        e = oracle.hostref.transform_cloud(p64, (0.0, 0.0, 0.0), (0.0, 0.0, 0.0))
+        e = oracle.hostref.height_filter(e, 0.3)
+        t1 = time.perf_counter()
+        gr = oracle.hostref.project(pts[:, :3], np.eye(3, 4), 0.3, np.inf, -102.4, -102.4, 0.2, W, H)
+        t2 = time.perf_counter()
+        pad = np.zeros((W + 8, H + 8)); pad[4:-4, 4:-4] = gr
+        oracle.hostref.inflate_ccst(pad, 2)
+        t3 = time.perf_counter()
+        line["cpu_baseline"] = {"value": N / (t3 - t0), "unit": "points/s", "cores": 1, "kind": "port",
+                                "sample": "whole step once: numpy a15/a16 transform + height filter %.1f ms, projection restatement %.1f ms, "
+                                          "reference inflation block a11 %.1f ms" % (1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2))}
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        return 0
+
+    # ---- cfg5: one query on a 16384^2 grid.  N = 1: goal-directed batched search (bidirectional, ellipse-pruned) and the
+    # whole cost field; N > 1: the row-tiled field over N slabs (halo exchange), with rank 0's one-GPU numbers beside it.
+    from fuxi_planner_b200 import tiled
+    n = 16384
+    m, s, g = cfg5_workload(n)
+    one = {}
+    if rank == 0:
+        d_m = torch.from_numpy(m).to(dev)
+        d_s, d_g = torch.from_numpy(s[None]).to(dev), torch.from_numpy(g[None]).to(dev)
+        res = fx.plan_batch(d_m, d_s, d_g, metric=args.hchoice, max_path=8192)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(max(args.steps, 1)):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); res = fx.plan_batch(d_m, d_s, d_g, metric=args.hchoice, max_path=8192); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        st = fx.search_stats(ctx)
+        one["goal_directed_ms"] = float(np.mean(ts))
+        one["goal_directed_settled_cells"] = int(st[0])
+        one["goal_directed_levels"] = int(st[1])
+        one["cost_i"] = int(res.cost_i[0])
+        one["launches"] = 0
+        fld = torch.empty((n, n), dtype=torch.int32, device=dev)
+        fx.field(d_m, tuple(int(v) for v in s), metric=args.hchoice, out=fld)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(max(min(args.steps, 3), 1)):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fx.field(d_m, tuple(int(v) for v in s), metric=args.hchoice, out=fld, check=False); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        one["full_field_ms"] = float(np.mean(ts))
+        one["full_field_goal_cost"] = int(fld[int(g[0]), int(g[1])])
+        one["full_field_cells_reached"] = int((fld >= 0).sum())
+        del fld
+        if world > 1:
+            del d_m
+        torch.cuda.empty_cache()
+    cfgd = {"workload": "cfg5: one query on a 16384x16384 random-obstacle grid (20% fill, default_rng(6)), first free cell -> last free "
+                        "cell, hchoice %d" % args.hchoice, "l2": "flushed between timed steps"}
+    if world == 1:
+        ms = one["goal_directed_ms"]
+        line = base_line(args, world, ms, ms, cfgd, "u32 (packed cost | arrival direction)")
+        line["scaling"] = "replicas only (a single query does not shard profitably; see DESIGN.md §5)"
+        launches = 3
+    else:
+        x0, x1 = tiled.slab_bounds(n, world, rank)
+        own = torch.from_numpy(m[x0:x1]).to(dev)
+        fld, rounds = tiled.field_tiled(own, n, tuple(int(v) for v in s), metric=args.hchoice)      # warm-up (allocations, NCCL)
+        barrier()
+        ts = []
+        for _ in range(max(min(args.steps, 3), 1)):
+            t0 = time.perf_counter()
+            fld, rounds = tiled.field_tiled(own, n, tuple(int(v) for v in s), metric=args.hchoice)
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        t = torch.tensor([float(np.mean(ts))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        goal_cost = torch.tensor([int(fld[int(g[0]) - x0, int(g[1])]) if x0 <= int(g[0]) < x1 else -1], dtype=torch.int64, device=dev)
+        dist.all_reduce(goal_cost, op=dist.ReduceOp.MAX)
+        ms = float(t.item()) * 1e3
+        line = base_line(args, world, ms, ms, cfgd, "i32 field")
+        line["row_tiled"] = {"field_ms": ms, "exchange_rounds": int(rounds), "goal_cost": int(goal_cost.item()),
+                             "slab_rows": n // world, "timing": "wall clock around the whole exchange loop, warm, max over ranks"}
+        launches = 0
+    line["one_gpu"] = one
+    line["e2e"] = {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "note": "device-resident grid (256 MiB); the host-buffer form adds one 256 MiB H2D copy (~5 ms)"}
+    line["gpu_launches"] = launches
+    settled = one.get("goal_directed_settled_cells", 0)
+    ach = settled * 5.0 / (one.get("goal_directed_ms", 1.0) * 1e-3) / 1e9 if settled else 0.0
+    line["roofline"] = {"kernel": "k_search_batch (one CTA)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes": "settled cells x 5 B"}
+    line["clocks"] = None
+    if rank == 0:
+        # bounded CPU sample: the same grid, a query 1/8 of the way along the diagonal (the whole query costs > 1 min on one core)
+        import oracle
+        oracle.build()
+        ff = np.argwhere(m[2040:2056, 2040:2056] == 0)[0] + 2040
+        gs = np.array([ff], dtype=np.int32)
+        t0 = time.perf_counter()
+        cost, status, used = oracle.jps_batch(m, s[None], gs, args.hchoice, threads=1)
+        dt = time.perf_counter() - t0
+        r2 = fx.plan_batch(torch.from_numpy(m).to(dev), torch.from_numpy(s[None]).to(dev), torch.from_numpy(gs).to(dev), metric=args.hchoice, max_path=8192)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); r2 = fx.plan_batch(torch.from_numpy(m).to(dev), torch.from_numpy(s[None]).to(dev), torch.from_numpy(gs).to(dev), metric=args.hchoice, max_path=8192); b.record()
+        torch.cuda.synchronize()
+        got = float(r2.cost_f[0]) if args.hchoice == 2 else float(r2.cost_i[0])
+        line["cpu_baseline"] = {"value": dt * 1e3, "unit": "ms", "cores": 1, "kind": "port",
+                                "sample": "same grid, first free cell -> (%d, %d) (1/8 of the diagonal): C restatement of jps1.py %.0f ms; "
+                                          "this library on the same sub-query (incl. H2D of the grid) %.1f ms; costs agree: %s"
+                                          % (int(gs[0][0]), int(gs[0][1]), dt * 1e3, a.elapsed_time(b), abs(got - float(cost[0])) <= 1e-5 * float(cost[0]))}
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_reference_other(args, oracle):
+    """CPU arm of the other configurations: the C restatement (or the numpy restatements for cfg2) on a bounded sample."""
+    name, unit, hib = CFG_METRIC[args.config]
+    threads = host_threads()
+    if args.config == "cfg3":
+        m, s, g = cfg3_workload()
+        S = min(len(s), 16 * threads)
+        fn = lambda: oracle.jps_batch(m, s[:S], g[:S], args.hchoice, threads=threads)
+        units, sample = S, "first %d of the 4096 queries per step, C restatement of jps1.py over %d threads" % (S, threads)
+    elif args.config == "cfg2":
+        pts = cfg2_cloud()
+        def fn():
+            e = oracle.hostref.height_filter(oracle.hostref.transform_cloud(pts[:, :3].astype(np.float64), (0.0, 0.0, 0.0), (0.0, 0.0, 0.0)), 0.3)
+            gr = oracle.hostref.project(pts[:, :3], np.eye(3, 4), 0.3, np.inf, -102.4, -102.4, 0.2, 1024, 1024)
+            pad = np.zeros((1032, 1032)); pad[4:-4, 4:-4] = gr
+            oracle.hostref.inflate_ccst(pad, 2)
+        units, sample, threads = len(pts), "the whole step: numpy a15/a16 + projection restatement + reference inflation block a11, 1 core", 1
+    else:
+        m, s, g = cfg5_workload()
+        ff = np.argwhere(m[2040:2056, 2040:2056] == 0)[0] + 2040
+        fn = lambda: oracle.jps_batch(m, s[None], np.array([ff], dtype=np.int32), args.hchoice, threads=1)
+        units, sample, threads = 1, "same grid, first free cell -> (%d, %d) (1/8 of the diagonal), C restatement of jps1.py, 1 core" % (ff[0], ff[1]), 1
+    for _ in range(min(args.warmup, 1)):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = dt * 1e3 if unit == "ms" else units / dt
+    line = {"impl": "reference", "metric": name, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": hib, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.config},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
     return 0
 
 

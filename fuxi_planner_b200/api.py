@@ -139,6 +139,14 @@ def search_kernel_ms(ctx=None):
     return float(ms.value)
 
 
+def search_timings(ctx=None):
+    """(k_band_bound ms, k_search_batch ms) of the last batch (fx_search_timings)."""
+    ctx = _ctx(ctx)
+    ms = (C.c_float * 2)()
+    ctx.check(ctx.lib.fx_search_timings(ctx.handle, ms), "fx_search_timings")
+    return float(ms[0]), float(ms[1])
+
+
 def field(grid, source, metric=1, out=None, ctx=None, check=True):
     """Cost-from-source field, int32 [W][H], -1 = unreachable (fx_field)."""
     grid = _u8_grid(grid)
@@ -310,6 +318,46 @@ def replan_host(map_data, width, height, origin, reso, start_xy, goal_xy, ifa=1,
         ctx.check(ctx.lib.fx_replan_grid_host(ctx.handle, vp(grid), grid.size, None, None), "fx_replan_grid_host")
     return rout, pxy[:n].copy(), pw[:n].copy(), grid
 
+
+
+def paths_compact(path_xy, path_len, ctx=None):
+    """Padded path rows -> (offsets int64 [Q+1], xy int32 [total, 2]) on the device (fx_paths_compact)."""
+    ctx = _ctx(ctx, path_xy)
+    Q, max_path = int(path_xy.shape[0]), int(path_xy.shape[1])
+    offsets = torch.empty(Q + 1, dtype=torch.int64, device=path_xy.device)
+    n = path_len.clamp(min=0)
+    cap = int(torch.where(n <= max_path, n, torch.zeros_like(n)).sum().item())
+    out = torch.empty((max(cap, 1), 2), dtype=torch.int32, device=path_xy.device)
+    ctx.check(ctx.lib.fx_paths_compact(ctx.handle, _ptr(path_xy), _ptr(path_len), Q, max_path, _ptr(offsets), _ptr(out), cap,
+                                       _stream()), "fx_paths_compact")
+    return offsets, out[:cap]
+
+
+def plan_host_csr(grid, starts, goals, metric=2, max_path=512, cap=None, ctx=None, device=0):
+    """plan_host with the paths in compact form (fx_plan_host_csr): returns (cost_i, cost_f, path_len, offsets int64 [Q+1],
+    xy int32 [total, 2]).  cap = room for the points (default 64 per query; retried once with the exact total if it is short)."""
+    ctx = ctx or default_context(device)
+    grid = np.asarray(grid)
+    g = np.ascontiguousarray(grid) if grid.dtype == np.uint8 else np.ascontiguousarray((grid == 1).astype(np.uint8))
+    s = np.ascontiguousarray(starts, dtype=np.int32).reshape(-1, 2)
+    t = np.ascontiguousarray(goals, dtype=np.int32).reshape(-1, 2)
+    Q = len(s)
+    W, H = g.shape
+    cost_i = np.empty(Q, dtype=np.int32)
+    cost_f = np.empty(Q, dtype=np.float64)
+    path_len = np.empty(Q, dtype=np.int32)
+    offsets = np.zeros(Q + 1, dtype=np.int64)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    cap = int(cap) if cap is not None else 64 * max(Q, 1)
+    while True:
+        xy = np.empty((max(cap, 1), 2), dtype=np.int32)
+        total = C.c_int64(0)
+        rc = ctx.lib.fx_plan_host_csr(ctx.handle, vp(g), W, H, vp(s), vp(t), Q, int(metric), vp(cost_i), vp(cost_f), vp(path_len),
+                                      int(max_path), vp(offsets), vp(xy), cap, C.byref(total))
+        ctx.check(rc, "fx_plan_host_csr")
+        if total.value <= cap:
+            return cost_i, cost_f, path_len, offsets, xy[:total.value]
+        cap = int(total.value)
 
 
 def plan_host(grid, starts, goals, metric=2, max_path=512, ctx=None, device=0):

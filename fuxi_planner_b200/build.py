@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libfuxi_b200.so")
-SOURCES = ["api.cu", "project.cu", "inflate.cu", "edt.cu", "search.cu", "band.cu", "small.cu", "field.cu", "assemble.cu", "post.cu", "replan.cu", "cloud.cu"]
+SOURCES = ["api.cu", "project.cu", "inflate.cu", "edt.cu", "search.cu", "paths.cu", "band.cu", "small.cu", "field.cu", "assemble.cu", "post.cu", "replan.cu", "cloud.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"]
 

@@ -24,6 +24,8 @@ extern "C" const char *fx_last_error(fx_context *ctx) { return ctx ? ctx->err : 
 
 extern "C" int64_t fx_launch_count(fx_context *ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int64_t fx_last_d2h_bytes(fx_context *ctx) { return ctx ? ctx->last_d2h_bytes : 0; }
+
 extern "C" int fx_create(int device, fx_context **out)
 {
     if (!out) return FX_ERR_ARG;
@@ -52,6 +54,7 @@ extern "C" int fx_create(int device, fx_context **out)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->cfg_wide_below = -1;
     if (const char *e = getenv("FUXI_B200_WIDE_BELOW")) ctx->cfg_wide_below = atoi(e);  // tuning experiments only
+    if (const char *e = getenv("FUXI_B200_BIDIR")) ctx->cfg_unidir = e[0] == '0';          // tuning experiments only
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
     e = cudaMalloc(&ctx->counters, 16 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(ctx->counters, 0, 16 * sizeof(unsigned long long));
@@ -61,6 +64,8 @@ extern "C" int fx_create(int device, fx_context **out)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_search[0]);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_search[1]);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_band[0]);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_band[1]);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();  // the memsets above ran on the legacy stream; own_stream does not wait for it
     if (e != cudaSuccess) {
         fx_set_err(nullptr, FX_ERR_CUDA, "context allocation: %s", cudaGetErrorString(e));
@@ -79,7 +84,7 @@ extern "C" int fx_destroy(fx_context *ctx)
     void *dev[] = {ctx->fields, ctx->dirty, ctx->queues, ctx->tmp_path, ctx->moves, ctx->counters, ctx->fq, ctx->fstate,
                    ctx->seeds, ctx->seeds_sorted, ctx->seed_hist, ctx->edt_g, ctx->edt_s, ctx->edt_t, ctx->edt_flag,
                    ctx->d_grid, ctx->d_grid2, ctx->d_q, ctx->d_out_i, ctx->d_out_f, ctx->d_path, ctx->d_pts, ctx->proj_bits, ctx->q_order, ctx->q_ubound, ctx->bfields,
-                   ctx->d_msg, ctx->d_rp, ctx->cl_bits, ctx->cl_gpref, ctx->cl_chunk, ctx->cl_vidx, ctx->cl_keep, ctx->cl_gpref2,
+                   ctx->d_msg, ctx->d_rp, ctx->d_cpath, ctx->d_coff, ctx->cl_bits, ctx->cl_gpref, ctx->cl_chunk, ctx->cl_vidx, ctx->cl_keep, ctx->cl_gpref2,
                    ctx->cl_chunk2, ctx->cl_acc, ctx->cl_vox, ctx->cl_state, ctx->cl_out, ctx->df_rec};
     for (size_t i = 0; i < sizeof(dev) / sizeof(dev[0]); i++)
         if (dev[i]) cudaFree(dev[i]);
@@ -87,6 +92,8 @@ extern "C" int fx_destroy(fx_context *ctx)
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->ev_search[0]) cudaEventDestroy(ctx->ev_search[0]);
     if (ctx->ev_search[1]) cudaEventDestroy(ctx->ev_search[1]);
+    if (ctx->ev_band[0]) cudaEventDestroy(ctx->ev_band[0]);
+    if (ctx->ev_band[1]) cudaEventDestroy(ctx->ev_band[1]);
     free(ctx);
     return FX_OK;
 }
@@ -175,9 +182,11 @@ static void par_memcpy(void *dst, const void *src, size_t bytes)
     for (auto &t : th) t.join();
 }
 
+// csr != NULL: paths are returned packed (offsets[Q+1] + xy[total][2]) instead of in padded rows
+struct CsrOut { int64_t *h_offsets; int32_t *h_xy; int64_t cap; int64_t *h_total; };
 static int plan_host_impl(fx_context *ctx, const uint8_t *h_grid, const double *h_matrix, int W, int H, const int32_t *h_starts_xy,
                           const int32_t *h_goals_xy, int Q, int metric, int32_t *h_cost_i, double *h_cost_f,
-                          int32_t *h_path_xy, int32_t *h_path_len, int max_path);
+                          int32_t *h_path_xy, int32_t *h_path_len, int max_path, const CsrOut *csr);
 
 extern "C" int fx_plan_host(fx_context *ctx, const uint8_t *h_grid, int W, int H, const int32_t *h_starts_xy,
                             const int32_t *h_goals_xy, int Q, int metric, int32_t *h_cost_i, double *h_cost_f,
@@ -185,7 +194,7 @@ extern "C" int fx_plan_host(fx_context *ctx, const uint8_t *h_grid, int W, int H
 {
     if (!ctx) return FX_ERR_ARG;
     if (!h_grid) return fx_set_err(ctx, FX_ERR_ARG, "fx_plan_host: bad argument");
-    return plan_host_impl(ctx, h_grid, nullptr, W, H, h_starts_xy, h_goals_xy, Q, metric, h_cost_i, h_cost_f, h_path_xy, h_path_len, max_path);
+    return plan_host_impl(ctx, h_grid, nullptr, W, H, h_starts_xy, h_goals_xy, Q, metric, h_cost_i, h_cost_f, h_path_xy, h_path_len, max_path, nullptr);
 }
 
 extern "C" int fx_plan_host_f64(fx_context *ctx, const double *h_matrix, int W, int H, const int32_t *h_starts_xy,
@@ -194,20 +203,31 @@ extern "C" int fx_plan_host_f64(fx_context *ctx, const double *h_matrix, int W, 
 {
     if (!ctx) return FX_ERR_ARG;
     if (!h_matrix) return fx_set_err(ctx, FX_ERR_ARG, "fx_plan_host_f64: bad argument");
-    return plan_host_impl(ctx, nullptr, h_matrix, W, H, h_starts_xy, h_goals_xy, Q, metric, h_cost_i, h_cost_f, h_path_xy, h_path_len, max_path);
+    return plan_host_impl(ctx, nullptr, h_matrix, W, H, h_starts_xy, h_goals_xy, Q, metric, h_cost_i, h_cost_f, h_path_xy, h_path_len, max_path, nullptr);
+}
+
+extern "C" int fx_plan_host_csr(fx_context *ctx, const uint8_t *h_grid, int W, int H, const int32_t *h_starts_xy,
+                                const int32_t *h_goals_xy, int Q, int metric, int32_t *h_cost_i, double *h_cost_f,
+                                int32_t *h_path_len, int max_path, int64_t *h_offsets, int32_t *h_xy, int64_t cap, int64_t *h_total)
+{
+    if (!ctx) return FX_ERR_ARG;
+    if (!h_grid || !h_offsets || cap < 0 || (cap > 0 && !h_xy) || max_path <= 0) return fx_set_err(ctx, FX_ERR_ARG, "fx_plan_host_csr: bad argument");
+    CsrOut csr = {h_offsets, h_xy, cap, h_total};
+    return plan_host_impl(ctx, h_grid, nullptr, W, H, h_starts_xy, h_goals_xy, Q, metric, h_cost_i, h_cost_f, nullptr, h_path_len, max_path, &csr);
 }
 
 static int plan_host_impl(fx_context *ctx, const uint8_t *h_grid, const double *h_matrix, int W, int H, const int32_t *h_starts_xy,
                           const int32_t *h_goals_xy, int Q, int metric, int32_t *h_cost_i, double *h_cost_f,
-                          int32_t *h_path_xy, int32_t *h_path_len, int max_path)
+                          int32_t *h_path_xy, int32_t *h_path_len, int max_path, const CsrOut *csr)
 {
+    if (csr && Q == 0) { csr->h_offsets[0] = 0; if (csr->h_total) *csr->h_total = 0; }
     if (W <= 0 || H <= 0 || Q < 0 || (Q > 0 && (!h_starts_xy || !h_goals_xy || !h_cost_i)) || max_path < 0)
         return fx_set_err(ctx, FX_ERR_ARG, "fx_plan_host: bad argument");
     if (Q == 0) return FX_OK;
     FX_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->own_stream;
     const size_t cells = (size_t)W * H;
-    const bool want_path = h_path_xy && max_path > 0;
+    const bool want_path = (h_path_xy || csr) && max_path > 0;
     int rc;
     if ((rc = grow(ctx, &ctx->d_grid, &ctx->d_grid_cap, cells))) return rc;
     if ((rc = grow(ctx, &ctx->d_q, &ctx->d_q_cap, (size_t)Q * 4 * sizeof(int32_t)))) return rc;
@@ -222,10 +242,14 @@ static int plan_host_impl(fx_context *ctx, const uint8_t *h_grid, const double *
     }
     const size_t path_bytes = want_path ? (size_t)Q * max_path * 2 * sizeof(int32_t) : 0;
     if (want_path && (rc = grow(ctx, &ctx->d_path, &ctx->d_path_cap, path_bytes))) return rc;
-    // pinned staging: [grid | starts | goals | cost_i | path_len | cost_f | paths]
+    // compact form of the paths on the device: offsets[Q+1] + packed points (paths.cu)
+    if (want_path && (rc = grow(ctx, &ctx->d_cpath, &ctx->d_cpath_cap, path_bytes))) return rc;
+    if (want_path && (rc = grow(ctx, &ctx->d_coff, &ctx->d_coff_cap, ((size_t)Q + 1) * sizeof(int64_t)))) return rc;
+    // pinned staging: [grid | starts | goals | cost_i | path_len | cost_f | offsets | paths]
     const size_t qb = (size_t)Q * 2 * sizeof(int32_t);
     size_t off_grid = 0, off_s = (cells + 15) / 16 * 16, off_g = off_s + qb, off_ci = off_g + qb,
-           off_pl = off_ci + (size_t)Q * 4, off_cf = (off_pl + (size_t)Q * 4 + 7) / 8 * 8, off_p = off_cf + (size_t)Q * 8;
+           off_pl = off_ci + (size_t)Q * 4, off_cf = (off_pl + (size_t)Q * 4 + 7) / 8 * 8, off_o = off_cf + (size_t)Q * 8,
+           off_p = off_o + ((size_t)Q + 1) * 8;
     if ((rc = grow_pinned(ctx, off_p + path_bytes))) return rc;
     char *pin = (char *)ctx->h_pin;
     memcpy(pin + off_s, h_starts_xy, qb);
@@ -249,10 +273,19 @@ static int plan_host_impl(fx_context *ctx, const uint8_t *h_grid, const double *
             if (want_path) {
                 // only the points each query produced (the buffers are [Q][max_path][2])
                 const int32_t *pl = (const int32_t *)(pin + off_pl);
+                int64_t run = 0;
                 for (int q = 0; q < Q; q++) {
-                    const int np = pl[q] < 0 ? 0 : (pl[q] < max_path ? pl[q] : max_path);
-                    if (np) memcpy(h_path_xy + (size_t)q * max_path * 2, pin + off_p + (size_t)q * max_path * 8, (size_t)np * 8);
+                    const int np = (pl[q] <= 0 || pl[q] > max_path) ? 0 : pl[q];
+                    if (csr) {
+                        csr->h_offsets[q] = run;
+                        for (int i = 0; i < np; i++)
+                            if (run + i < csr->cap) memcpy(csr->h_xy + (run + i) * 2, pin + off_p + ((size_t)q * max_path + i) * 8, 8);
+                        run += np;
+                    } else if (np) {
+                        memcpy(h_path_xy + (size_t)q * max_path * 2, pin + off_p + (size_t)q * max_path * 8, (size_t)np * 8);
+                    }
                 }
+                if (csr) { csr->h_offsets[Q] = run; if (csr->h_total) *csr->h_total = run; }
             }
             return FX_OK;
         }
@@ -276,14 +309,39 @@ static int plan_host_impl(fx_context *ctx, const uint8_t *h_grid, const double *
     rc = fx_search_batch(ctx, ctx->d_grid, W, H, d_s, d_g, Q, metric, d_ci, ctx->d_out_f, want_path ? ctx->d_path : nullptr,
                          d_pl, want_path ? max_path : 0, (void *)st);
     if (rc) return rc;
+    if (want_path) {
+        rc = fx_paths_compact(ctx, ctx->d_path, d_pl, Q, max_path, ctx->d_coff, ctx->d_cpath, (int64_t)Q * max_path, (void *)st);
+        if (rc) return rc;
+        FX_CUDA(ctx, cudaMemcpyAsync(pin + off_o, ctx->d_coff, ((size_t)Q + 1) * 8, cudaMemcpyDeviceToHost, st));
+    }
     FX_CUDA(ctx, cudaMemcpyAsync(pin + off_ci, d_ci, (size_t)Q * 8, cudaMemcpyDeviceToHost, st));  // cost_i + path_len
     FX_CUDA(ctx, cudaMemcpyAsync(pin + off_cf, ctx->d_out_f, (size_t)Q * 8, cudaMemcpyDeviceToHost, st));
-    if (want_path) FX_CUDA(ctx, cudaMemcpyAsync(pin + off_p, ctx->d_path, path_bytes, cudaMemcpyDeviceToHost, st));
     FX_CUDA(ctx, cudaStreamSynchronize(st));
     memcpy(h_cost_i, pin + off_ci, (size_t)Q * 4);
     if (h_path_len) memcpy(h_path_len, pin + off_pl, (size_t)Q * 4);
     if (h_cost_f) memcpy(h_cost_f, pin + off_cf, (size_t)Q * 8);
-    if (want_path) par_memcpy(h_path_xy, pin + off_p, path_bytes);
+    ctx->last_d2h_bytes = (int64_t)Q * 16;
+    if (want_path) {
+        // only the points the batch produced cross the bus: `total` is known after the first (small) copy
+        const int64_t *offs = (const int64_t *)(pin + off_o);
+        const int64_t total = offs[Q];
+        if (total > 0) {
+            FX_CUDA(ctx, cudaMemcpyAsync(pin + off_p, ctx->d_cpath, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
+            FX_CUDA(ctx, cudaStreamSynchronize(st));
+        }
+        ctx->last_d2h_bytes += ((int64_t)Q + 1) * 8 + total * 8;
+        if (csr) {
+            memcpy(csr->h_offsets, offs, ((size_t)Q + 1) * 8);
+            if (csr->h_total) *csr->h_total = total;
+            const int64_t ncopy = total < csr->cap ? total : csr->cap;
+            if (ncopy > 0) memcpy(csr->h_xy, pin + off_p, (size_t)ncopy * 8);
+        } else {
+            for (int q = 0; q < Q; q++) {
+                const int64_t n = offs[q + 1] - offs[q];
+                if (n > 0) memcpy(h_path_xy + (size_t)q * max_path * 2, pin + off_p + (size_t)offs[q] * 8, (size_t)n * 8);
+            }
+        }
+    }
     return FX_OK;
 }
 

@@ -9,10 +9,10 @@
 
 #define FX_INF 0xFFFFFFFFu
 #ifndef FX_SEARCH_THREADS
-#define FX_SEARCH_THREADS 128
+#define FX_SEARCH_THREADS 256
 #endif
 #ifndef FX_SEARCH_MINB
-#define FX_SEARCH_MINB 8 /* resident search CTAs per SM the register budget is compiled for (64 registers) */
+#define FX_SEARCH_MINB 4 /* resident search CTAs per SM the register budget is compiled for (64 registers) */
 #endif
 #ifndef FX_SEARCH_WIDE
 #define FX_SEARCH_WIDE 512 /* threads per CTA of the latency form (batches of at most sm_count queries) */
@@ -31,14 +31,15 @@ struct fx_context {
     int cfg_slots;
     int cfg_band0;
     int cfg_wide_below;  // batches of at most this many queries use the wide (latency) CTA form; -1 = sm_count
+    int cfg_unidir;      // tuning experiments: exact pass from the start only (FUXI_B200_BIDIR=0)
 
     // search scratch (sized for sW x sH, reallocated when the grid shape grows)
     int sW, sH, slots, qcap, path_cap;
     size_t cells, dirty_n;
-    uint32_t *fields;   // [slots][cells]   cost-from-start, FX_INF = unreached
-    uint8_t *dirty;     // [slots][dirty_n] one flag per 32 cells
+    uint32_t *fields;   // [slots][2][cells] packed cost | arrival direction from the start / from the goal, FX_INF = unreached
+    uint8_t *dirty;     // [slots][dirty_n] one flag per 32 words of the slot's two fields
     uint32_t *queues;   // [slots][4][qcap] rotating Dial buckets of packed (x<<16|y)
-    int32_t *tmp_path;  // [slots][path_cap][2] goal->start turning points before reversal
+    int32_t *tmp_path;  // [slots][2][path_cap][2] turning points of the two walks of the path extraction
     uint8_t *moves;     // [cells] legal-move mask per cell
     size_t moves_cap;
     unsigned long long *counters;  // [8]: 0 work counter, 1 settled, 2 levels, 3 passes, 4 band-only, 5 flags
@@ -71,6 +72,9 @@ struct fx_context {
     int32_t *d_out_i;           size_t d_out_cap;    // cost_i + path_len
     double *d_out_f;
     int32_t *d_path;            size_t d_path_cap;
+    int32_t *d_cpath;           size_t d_cpath_cap;  // compact paths (paths.cu)
+    int64_t *d_coff;            size_t d_coff_cap;   // offsets[Q+1]
+    int64_t last_d2h_bytes;                          // device->host bytes of the last fx_plan_host* call
     float *d_pts;               size_t d_pts_cap;
     void *h_pin;                size_t h_pin_cap;
     // fused replan (assemble.cu): raw OccupancyGrid message, small device block {bbox4, goal4, start2, path_len, cost_i, ...}
@@ -87,6 +91,7 @@ struct fx_context {
     unsigned long long cl_cap_bits;  // voxel index space the bitmap is reserved for (fx_cloud_reserve)
     cudaStream_t own_stream;
     cudaEvent_t ev_search[2];  // around the last k_search_batch launch (fx_search_kernel_ms)
+    cudaEvent_t ev_band[2];    // around the last k_band_bound launch (fx_search_timings)
     int ev_search_valid;
     int small_attr_set, cfg_small_off;
 };

@@ -14,6 +14,12 @@
 //   reaches the goal with cost <= U is exact, because every path of cost <= U lies inside the ellipse.
 //   U comes from a first pass restricted to a narrow band around the start-goal line (any path it
 //   finds is a valid upper bound); if that cost already equals the octile lower bound it is final.
+//   The exact pass is BIDIRECTIONAL: one wavefront from the start and one from the goal advance in the
+//   same levels (same bucket index, same queues, one bit of the queue entry says which side it belongs
+//   to), each into its own cost field, each pruned by its own ellipse; a cell popped by one side looks
+//   at the other side's field and proposes mu = g_s + g_t; once 2*k*WS > mu + WD the proposal is the
+//   optimum (see run_pass).  Both halves of the ellipse are settled once, but the chain of dependent
+//   levels is half as long and a level carries twice the cells.
 //   The cost field lives in a per-slot scratch array in HBM (L2-resident working set); only the
 //   128-byte lines a query touched are reset afterwards (dirty flags).
 //   Path: warp-parallel descent from the goal along cost-consistent predecessors, 32 cells of a
@@ -84,6 +90,7 @@ struct SearchParams {
     int band0;
     const uint32_t *order;   // LPT query order (band.cu) or NULL
     const uint32_t *ubound;  // per-query upper bound from the band pass or NULL
+    int bidir;               // exact pass runs from both ends (0: from the start only)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -145,7 +152,9 @@ int fx_build_moves(fx_context *ctx, const uint8_t *grid, int W, int H, bool tile
 // ------------------------------------------------------------------------------------------------
 struct __align__(16) CtaState {
     unsigned tailS[4], tailD[4];  // entries per bucket: cells that arrived by a straight / by a diagonal move
+    unsigned long long mu[3];  // bidirectional pass: min over cells seen by both sides of (g_s + g_t) << 32 | packed xy; slot = level % 3
     unsigned goal[2];  // cost of the goal cell once it has been popped (FX_INF = not yet); slot = parity of the level that popped it
+    unsigned meet;     // bidirectional pass: packed xy of the cell the two sides met at
     unsigned ovf_level;  // level + 1 in which a cost left the 28-bit range (0 = never)
     unsigned U;      // prune bound on g + h
     unsigned flags;
@@ -170,7 +179,21 @@ struct __align__(16) CtaState {
 // cost.  Whether the relaxation won is decided when the entry is POPPED: it is expanded iff the field still holds
 // exactly the entry's value (the writer of the final minimum is unique), so losers and superseded entries drop out
 // there.  A level is therefore: queue load -> field + move-mask load -> ALU -> stores, then one block barrier.
-template <int METRIC>
+//
+// BIDIR: a second wavefront starts at the goal and advances in the same levels.  Bit 31 of a queue entry's packed
+// xy says which side it belongs to; side 1 uses the second cost field of the slot (field + P.cells) and prunes with
+// the ellipse around the START.  Among free cells the move graph is symmetric (a diagonal tests the same two
+// orthogonal cells both ways; the goal is free, and the search never enters an obstacle), so the wavefront from the
+// goal settles exact cost-TO-goal values.  Every valid pop in the late levels (k >= h0/(2 WS) - 2: two labels of one
+// cell sum to at least h0) also reads the other side's word of the same cell and proposes mu = g + g_other, always
+// the cost of a real path.  Termination: at the top of level k both sides have settled every cell of cost < k*WS.  Walk
+// the optimal path P from the start and let c be its last cell with g_s(c) < k*WS: g_s(c) >= k*WS - WD, so
+// g_t(c) = U* - g_s(c) < k*WS as soon as 2*k*WS > U* + WD, i.e. c was popped by both sides with exact values and
+// proposed mu = U*.  The loop tests 2*k*WS > mu + WD with the smallest proposal so far; mu >= U* makes the test
+// imply the condition above, so whatever it returns is the optimum, and it fires at the first level the condition
+// holds.  A start on an obstacle can leave it but cannot be entered: the goal side never labels it, and c != start
+// because the test needs k >= 2.  The cell that proposed the minimum is returned in S.meet.
+template <int METRIC, bool BIDIR>
 __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *__restrict__ s_lut, const int *__restrict__ s_step,
                              uint32_t *__restrict__ field, uint8_t *__restrict__ dirty, uint2 *__restrict__ queue,
                              int sx, int sy, int gx, int gy, uint32_t U0, float bandL, unsigned budget, bool *budget_hit)
@@ -180,26 +203,42 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
     const int tid = threadIdx.x, lane = tid & 31, nthreads = blockDim.x;
     const unsigned qcap = (unsigned)P.qcap, qhalf = qcap >> 1;
     const int TY = P.TY;
-    const int sidx = fx_cidx(sx, sy, H, TY), gidx = fx_cidx(gx, gy, H, TY);
+    const unsigned side_cells = (unsigned)P.cells;  // word offset of the goal side's field (2 * cells <= 2^31: W, H <= 32767)
+    const unsigned sidx = (unsigned)fx_cidx(sx, sy, H, TY), gidx = (unsigned)fx_cidx(gx, gy, H, TY);
     const float qdx = (float)(gx - sx), qdy = (float)(gy - sy);
     const uint8_t *__restrict__ moves = P.moves;
+    // cell index (move masks) and field index (cost word: + side_cells for the goal side) of a queue entry's packed xy
+    auto cell_of = [&](uint32_t exy) { return (unsigned)fx_cidx((int)((exy >> 16) & 0x7FFFu), (int)(exy & 0xFFFFu), H, TY); };
+    auto foff_of = [&](uint32_t exy) { return BIDIR ? (exy >> 31) * side_cells : 0u; };
 
     if (tid == 0) {
-        S.tailS[0] = 1; S.tailS[1] = 0; S.tailS[2] = 0; S.tailS[3] = 0;
+        S.tailS[0] = BIDIR ? 2 : 1; S.tailS[1] = 0; S.tailS[2] = 0; S.tailS[3] = 0;
         S.tailD[0] = 0; S.tailD[1] = 0; S.tailD[2] = 0; S.tailD[3] = 0;
         S.goal[0] = FX_INF; S.goal[1] = FX_INF; S.U = U0; S.pruned = 0; S.ovf_level = 0;
+        S.mu[0] = ~0ull; S.mu[1] = ~0ull; S.mu[2] = ~0ull; S.meet = 0;
         S.xlo = min(S.xlo, sx - 1); S.xhi = max(S.xhi, sx + 1);
         __stcg(queue, make_uint2(((uint32_t)sx << 16) | (uint32_t)sy, fx_pack(0u, FX_CODE_START)));
         __stcg(field + sidx, fx_pack(0u, FX_CODE_START));
         dirty[sidx >> FX_DIRTY_SHIFT] = 1;
+        if (BIDIR) {
+            S.xlo = min(S.xlo, gx - 1); S.xhi = max(S.xhi, gx + 1);
+            __stcg(queue + 1, make_uint2(0x80000000u | ((uint32_t)gx << 16) | (uint32_t)gy, fx_pack(0u, FX_CODE_START)));
+            __stcg(field + (side_cells + gidx), fx_pack(0u, FX_CODE_START));
+            dirty[(side_cells + gidx) >> FX_DIRTY_SHIFT] = 1;
+        }
     }
     __syncthreads();
 
     unsigned my_settled = 0;
     int my_xlo = 0x7FFFFFFF, my_xhi = -1;
     unsigned k = 0, popped = 0;
+    unsigned k3 = 0;  // k % 3
     bool my_pruned = false;
     uint32_t result = FX_INF;
+    unsigned long long mu = ~0ull;
+    // the first level in which a cell can carry labels of both sides
+    const uint32_t h0 = octile(abs(sx - gx), abs(sy - gy), WS, WD - WS);
+    const unsigned k_meet = h0 / (2u * WS) > 2u ? h0 / (2u * WS) - 2u : 0u;
     *budget_hit = false;
     PH_DECL
     for (;;) {
@@ -211,13 +250,27 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
         PH_START(n)
         // Shared state read here must look the same to a warp that is still at the top of level k and to one that is
         // already inside it: S.goal is double-buffered by level parity (level k writes slot k & 1, this reads the slot of
-        // level k-1, complete since the last barrier); S.ovf_level only counts once its level is over; n is complete
-        // since the last barrier; n1 is still growing but only matters when n == 0, i.e. when nobody pushes in this level.
-        const unsigned goalc = S.goal[(k + 1) & 1];
-        if (goalc != FX_INF) { result = goalc; break; }  // the goal was popped in the previous level: final
+        // level k-1, complete since the last barrier); S.mu rotates over three slots the same way (level k writes slot
+        // k % 3, this reads the slot of level k-1 and clears the slot of level k+1, last read at the top of level k-1);
+        // S.ovf_level only counts once its level is over; n is complete since the last barrier; n1 is still growing but
+        // only matters when n == 0, i.e. when nobody pushes in this level.
+        if (BIDIR) {
+            const unsigned long long m_prev = S.mu[k3 == 0 ? 2 : k3 - 1];
+            mu = m_prev < mu ? m_prev : mu;
+            const uint32_t mc = (uint32_t)(mu >> 32);
+            if (mc != FX_INF && 2ull * k * WS > (unsigned long long)mc + WD) { result = mc; break; }  // see the proof above
+            if (tid == 0) S.mu[k3 == 2 ? 0 : k3 + 1] = ~0ull;
+        } else {
+            const unsigned goalc = S.goal[(k + 1) & 1];
+            if (goalc != FX_INF) { result = goalc; break; }  // the goal was popped in the previous level: final
+        }
         const unsigned ovl = S.ovf_level;
         if (ovl != 0 && ovl <= k) { if (tid == 0) S.flags |= FLAG_OVERFLOW; break; }
-        if ((n == 0 && n1 == 0) || (S.flags & FLAG_OVERFLOW)) break;
+        if ((n == 0 && n1 == 0) || (S.flags & FLAG_OVERFLOW)) {
+            // drained: every cell inside the pruning region is settled (by both sides), so the smallest proposal is exact
+            if (BIDIR) result = (uint32_t)(mu >> 32);
+            break;
+        }
         popped += n;
         if (budget && popped > budget) { *budget_hit = true; break; }
         if (nS > qhalf || nD > qhalf) { if (tid == 0) S.flags |= FLAG_OVERFLOW; break; }  // entries beyond a half were dropped at push time
@@ -227,6 +280,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
         uint2 *__restrict__ q1 = queue + (size_t)((k + 1) & 3) * qcap;
         uint2 *__restrict__ q2 = queue + (size_t)((k + 2) & 3) * qcap;
         const uint32_t kbase = k * WS;
+        const bool meet_level = BIDIR && k >= k_meet;
         auto slot_of = [&](unsigned i) { return i < nS ? i : qhalf + (i - nS); };
         // Two-deep software pipeline over the rounds of a level: while round r is processed, the cost word and move mask
         // of round r+1 and the queue entry of round r+2 are already in flight, so only the first round of a level waits
@@ -235,37 +289,41 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
         // k+1 or later, so their words do not change during the level.
         uint2 e_cur = (unsigned)tid < n ? __ldcg(qk + slot_of((unsigned)tid)) : make_uint2(0u, 0u);
         uint2 e_nxt = (unsigned)tid + (unsigned)nthreads < n ? __ldcg(qk + slot_of((unsigned)tid + (unsigned)nthreads)) : make_uint2(0u, 0u);
-        int idx_cur = fx_cidx((int)(e_cur.x >> 16), (int)(e_cur.x & 0xFFFFu), H, TY);
+        unsigned idx_cur = cell_of(e_cur.x), fo_cur = foff_of(e_cur.x);
         uint32_t v_cur = FX_INF;
         unsigned m_cur = 0;
-        if ((unsigned)tid < n) { v_cur = __ldcg(field + idx_cur); m_cur = (unsigned)__ldg(moves + idx_cur); }
+        if ((unsigned)tid < n) { v_cur = __ldcg(field + (idx_cur + fo_cur)); m_cur = (unsigned)__ldg(moves + idx_cur); }
         for (unsigned i0 = (unsigned)(tid - lane); i0 < n; i0 += (unsigned)nthreads) {
             const unsigned i = i0 + lane;
             bool act = i < n;
             const uint2 e = e_cur;
-            const int idx = idx_cur;  // < 2^30 (W, H <= 32767)
+            const unsigned idx = idx_cur, fo = fo_cur;  // idx < 2^30 (W, H <= 32767)
             const uint32_t v = v_cur;
             const unsigned m = m_cur;
             e_cur = e_nxt;
-            idx_cur = fx_cidx((int)(e_cur.x >> 16), (int)(e_cur.x & 0xFFFFu), H, TY);
+            idx_cur = cell_of(e_cur.x); fo_cur = foff_of(e_cur.x);
             v_cur = FX_INF;
             m_cur = 0;
-            if (i + nthreads < n) { v_cur = __ldcg(field + idx_cur); m_cur = (unsigned)__ldg(moves + idx_cur); }
+            if (i + nthreads < n) { v_cur = __ldcg(field + (idx_cur + fo_cur)); m_cur = (unsigned)__ldg(moves + idx_cur); }
             if (i + 2u * nthreads < n) e_nxt = __ldcg(qk + slot_of(i + 2u * nthreads));
-            const int x = (int)(e.x >> 16), y = (int)(e.x & 0xFFFFu);
+            const int x = (int)((e.x >> 16) & 0x7FFFu), y = (int)(e.x & 0xFFFFu);
+            const bool side = BIDIR && (e.x >> 31) != 0u;
             PH_MARK(0, e.x)  // queue entry arrived
             PH_MARK(1, v + m)  // cost + move mask arrived
             const uint32_t g = e.y >> 4;
             act = act && v == e.y;  // this entry's relaxation won and nothing improved the cell since
+            uint32_t other = FX_INF;
+            if (meet_level && act) other = __ldcg(field + (idx + (side ? 0u : side_cells)));
             if (act) {
                 // every relaxed cell has an entry that carries its final word (the winner's): marking the line when THAT
                 // entry is popped -- or swept below if it never is -- covers every touched line; stale entries skip the store
-                dirty[idx >> FX_DIRTY_SHIFT] = 1;
-                if (idx == gidx) S.goal[k & 1] = g;  // unique winner: plain store
+                dirty[(idx + fo) >> FX_DIRTY_SHIFT] = 1;
+                if (!BIDIR && idx == gidx) S.goal[k & 1] = g;  // unique winner: plain store
                 // prune at POP time: a cell outside the ellipse g + h <= U (or outside the band) keeps its cost but is
                 // not expanded.  Every cell of a path of cost <= U satisfies g*(c) + h(c) <= U (h is consistent), and so
                 // do the cells of the alternative paths the canonical pruning relies on: exactness holds.
-                const uint32_t h = octile(abs(x - gx), abs(y - gy), WS, WD - WS);
+                const int tx = side ? sx : gx, ty = side ? sy : gy;
+                const uint32_t h = octile(abs(x - tx), abs(y - ty), WS, WD - WS);
                 bool keep = ((uint64_t)g + h) <= (uint64_t)U;
                 if (bandL >= 0.f) {
                     const float lat = (float)(x - sx) * qdy - (float)(y - sy) * qdx;
@@ -273,6 +331,8 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
                 }
                 if (!keep) { my_pruned = true; act = false; }
             }
+            if (BIDIR && other != FX_INF)  // both sides have labelled this cell: a real start-goal path through it
+                atomicMin(&S.mu[k3], ((unsigned long long)(g + (other >> 4)) << 32) | (unsigned long long)(e.x & 0x7FFFFFFFu));
             unsigned succ = 0;
             if (act) {
                 my_settled++; my_xlo = min(my_xlo, x); my_xhi = max(my_xhi, x);
@@ -298,13 +358,14 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
             uint2 *__restrict__ qD = (diag2 ? q2 : q1) + posD;
             const uint32_t nvS = fx_pack(g + WS, 0u), nvD = fx_pack(g + WD, 0u);
             const int *__restrict__ stp = s_step + 2 * (idx & 63);  // tile-local position (x & 7) << 3 | (y & 7)
+            uint32_t *__restrict__ fbase = field + (idx + fo);
             while (succ) {
                 const int d = __ffs(succ) - 1;
                 succ &= succ - 1;
                 const int2 st = *reinterpret_cast<const int2 *>(stp + 2 * 64 * d);  // (packed xy step, tiled index step)
                 const uint32_t nv = (d < 4 ? nvS : nvD) | (unsigned)d;
-                fx_red_min(field + (idx + st.y), nv);
-                const uint2 child = make_uint2(e.x + (uint32_t)st.x, nv);
+                fx_red_min(fbase + st.y, nv);
+                const uint2 child = make_uint2(e.x + (uint32_t)st.x, nv);  // keeps the side bit
                 if (d < 4) __stcg(qS++, child);
                 else __stcg(qD++, child);
             }
@@ -315,6 +376,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
         PH_MARK(5, k)  // barrier (includes waiting for the other warps' rounds)
         PH_COUNT(7, 1)  // levels
         k++;
+        k3 = k3 == 2 ? 0 : k3 + 1;
     }
     PH_FLUSH
     // entries that were never popped (buckets k and k+1; k+2 is still empty at the top of a level): mark their lines too
@@ -323,13 +385,14 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
         const unsigned mS = min(S.tailS[b & 3], qhalf), mD = min(S.tailD[b & 3], qhalf);
         for (unsigned i = (unsigned)tid; i < mS + mD; i += (unsigned)nthreads) {
             const uint32_t xy = __ldcg(qb + (i < mS ? i : qhalf + (i - mS))).x;
-            dirty[fx_cidx((int)(xy >> 16), (int)(xy & 0xFFFFu), H, TY) >> FX_DIRTY_SHIFT] = 1;
+            dirty[(cell_of(xy) + foff_of(xy)) >> FX_DIRTY_SHIFT] = 1;
         }
     }
     // every thread leaves the loop at the same k with the same decision (all read the same shared state
     // after the same barrier); one more barrier so that nobody is still reading S when it is re-initialised
     if (my_xhi >= 0) { atomicMin(&S.xlo, my_xlo - 1); atomicMax(&S.xhi, my_xhi + 1); }
     if (my_pruned) S.pruned = 1;  // S.pruned was zeroed before the first barrier of this pass; nobody reads it until the next one
+    if (BIDIR && tid == 0) S.meet = (unsigned)(mu & 0x7FFFFFFFull);
     __syncthreads();
     {
         // one 64-bit shared-memory atomic per warp (it is a CAS loop in SASS: 128 lanes on one address would spin)
@@ -341,7 +404,8 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
 }
 
 // reset every 128-byte field line this query touched: only the dirty flags of the x-rows [xlo, xhi] are scanned
-__device__ void reset_slot(CtaState &S, uint32_t *__restrict__ field, uint8_t *__restrict__ dirty, size_t dirty_n, size_t cells, int H)
+// (`both`: in the goal side's field as well -- after a bidirectional pass)
+__device__ void reset_slot(CtaState &S, uint32_t *__restrict__ field, uint8_t *__restrict__ dirty, size_t dirty_n, size_t cells, int H, bool both)
 {
     __syncthreads();
     const int xlo = max(S.xlo, 0), xhi = S.xhi;
@@ -350,55 +414,56 @@ __device__ void reset_slot(CtaState &S, uint32_t *__restrict__ field, uint8_t *_
     __syncthreads();
     if (threadIdx.x == 0) { S.xlo = 0x7FFFFFFF; S.xhi = -1; }
     if (xhi < xlo) { __syncthreads(); return; }
-#if FX_TILED
-    const size_t c_lo = (size_t)(xlo >> 3) * fx_tiles_y(H) * 64, c_hi = (size_t)((xhi >> 3) + 1) * fx_tiles_y(H) * 64;
-#else
-    const size_t c_lo = (size_t)xlo * H, c_hi = (size_t)(xhi + 1) * H;
-#endif
-    size_t i0 = (c_lo >> FX_DIRTY_SHIFT) / 16, i1 = ((c_hi >> FX_DIRTY_SHIFT) + 16) / 16;
-    const size_t n16 = dirty_n / 16;  // dirty_n is padded to a multiple of 16
-    if (i1 > n16) i1 = n16;
+    const size_t c_lo = (size_t)(xlo >> 3) * fx_tiles_y(H) * 64;
+    size_t c_hi = (size_t)((xhi >> 3) + 1) * fx_tiles_y(H) * 64;
+    if (c_hi > cells) c_hi = cells;
+    const size_t n16 = dirty_n / 16;  // dirty_n is padded to a multiple of 16 and covers both fields (2 * cells words)
     uint4 *d4 = reinterpret_cast<uint4 *>(dirty);
     const uint4 inf4 = make_uint4(FX_INF, FX_INF, FX_INF, FX_INF);
-    for (size_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-        uint4 v = __ldcg(d4 + i);
-        if (force) v = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
-        if ((v.x | v.y | v.z | v.w) == 0u) continue;
-        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    for (int f = 0; f < (both ? 2 : 1); f++) {
+        const size_t base = (size_t)f * cells;  // cells is a multiple of 512: the second field's flags start on a uint4
+        size_t i0 = ((base + c_lo) >> FX_DIRTY_SHIFT) / 16, i1 = (((base + c_hi) >> FX_DIRTY_SHIFT) + 15) / 16;
+        if (i1 > n16) i1 = n16;
+        for (size_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+            uint4 v = __ldcg(d4 + i);
+            if (force) v = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+            if ((v.x | v.y | v.z | v.w) == 0u) continue;
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int a = 0; a < 4; a++) {
-            if (!w[a]) continue;
+            for (int a = 0; a < 4; a++) {
+                if (!w[a]) continue;
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-                if (!((w[a] >> (8 * b)) & 0xFFu)) continue;
-                size_t chunk = i * 16 + a * 4 + b;
-                size_t c0 = chunk << FX_DIRTY_SHIFT;
-                if (c0 + 32 <= cells) {
-                    uint4 *f4 = reinterpret_cast<uint4 *>(field + c0);
+                for (int b = 0; b < 4; b++) {
+                    if (!((w[a] >> (8 * b)) & 0xFFu)) continue;
+                    const size_t chunk = i * 16 + a * 4 + b;
+                    const size_t c0 = chunk << FX_DIRTY_SHIFT;
+                    if (c0 + 32 <= 2 * cells) {
+                        uint4 *f4 = reinterpret_cast<uint4 *>(field + c0);
 #pragma unroll
-                    for (int t = 0; t < 8; t++) __stcg(f4 + t, inf4);
-                } else {
-                    for (size_t c = c0; c < cells; c++) __stcg(field + c, FX_INF);
+                        for (int t = 0; t < 8; t++) __stcg(f4 + t, inf4);
+                    }
                 }
             }
+            __stcg(d4 + i, make_uint4(0, 0, 0, 0));
         }
-        __stcg(d4 + i, make_uint4(0, 0, 0, 0));
     }
     __syncthreads();
 }
 
-// Warp 0 walks goal -> start along the arrival directions stored in the packed field and records turning points
-// into tmp (goal first).  Returns the number of points (may exceed cap: only cap are stored), -1 if the field is
-// inconsistent (cannot happen after a successful pass); straight/diagonal step counts in *na, *nb.
+// Warp 0 walks from (vx0, vy0) back to the source (sx, sy) of `field` along the arrival directions stored in the packed
+// words and records turning points into tmp ((vx0, vy0) first, the source last).  Returns the number of points (may
+// exceed cap: only cap are stored), -1 if the field is inconsistent (cannot happen after a successful pass);
+// straight/diagonal step counts are ADDED to *na, *nb; *first_dir = arrival direction of (vx0, vy0) (8 for the source).
 template <int METRIC>
-__device__ int extract_path(const SearchParams &P, const uint32_t *__restrict__ field, int sx, int sy, int gx, int gy,
-                            int32_t *__restrict__ tmp, int cap, unsigned *na, unsigned *nb)
+__device__ int extract_path(const SearchParams &P, const uint32_t *__restrict__ field, int sx, int sy, int vx0, int vy0,
+                            int32_t *__restrict__ tmp, int cap, unsigned *na, unsigned *nb, int *first_dir)
 {
     const int H = P.H, W = P.W, TY = P.TY, lane = threadIdx.x & 31;
-    int vx = gx, vy = gy;
+    int vx = vx0, vy = vy0;
     uint32_t v = __ldcg(field + fx_cidx(vx, vy, H, TY));
     int npts = 1, prev_d = -1;
     unsigned a = 0, b = 0;
+    *first_dir = (int)(v & 15u);
     if (lane == 0 && cap > 0) { tmp[0] = vx; tmp[1] = vy; }
     const unsigned long long max_steps = (unsigned long long)W * H;
     unsigned long long steps = 0;
@@ -425,9 +490,11 @@ __device__ int extract_path(const SearchParams &P, const uint32_t *__restrict__ 
         steps += (unsigned)run;
         if (d < 4) a += run; else b += run;
     }
-    if (lane == 0 && npts < cap) { tmp[2 * npts] = sx; tmp[2 * npts + 1] = sy; }
-    npts++;
-    *na = a; *nb = b;
+    if (!(vx0 == sx && vy0 == sy)) {
+        if (lane == 0 && npts < cap) { tmp[2 * npts] = sx; tmp[2 * npts + 1] = sy; }
+        npts++;
+    }
+    *na += a; *nb += b;
     return npts;
 }
 
@@ -441,14 +508,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
     __shared__ CtaState S;
     __shared__ uint8_t s_lut[9 * 256];
     __shared__ __align__(8) int s_step[8 * 64 * 2];  // [direction][x&7][y&7] -> (step of the packed xy, step of the tiled index)
-    __shared__ int s_npts;
+    __shared__ int s_npts, s_seg[3];
     __shared__ unsigned s_ab[2];
     const int tid = threadIdx.x;
     const int slot = blockIdx.x;
-    uint32_t *field = P.fields + (size_t)slot * P.cells;
+    uint32_t *field = P.fields + (size_t)slot * P.cells * 2;  // [start side | goal side]
     uint8_t *dirty = P.dirty + (size_t)slot * P.dirty_n;
     uint2 *queue = P.queues + (size_t)slot * 4 * P.qcap;
-    int32_t *tmp = P.tmp_path + (size_t)slot * P.path_cap * 2;
+    int32_t *tmp = P.tmp_path + (size_t)slot * P.path_cap * 4;  // two runs of path_cap points
     const int W = P.W, H = P.H;
     if (tid == 0) { S.settled = 0; S.levels = 0; S.flags = 0; S.xlo = 0x7FFFFFFF; S.xhi = -1; }
     for (int i = tid; i < 9 * 256; i += blockDim.x) s_lut[i] = (uint8_t)fx_canon_succ((unsigned)(i >> 8), (unsigned)(i & 255));
@@ -508,7 +575,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
         // step into) the query is unreachable and the forward search need not flood the start's whole component.
         // If the flood reaches the start its cost is the exact answer and pass A is skipped.
         {
-            uint32_t back = run_pass<METRIC>(P, S, s_lut, s_step, field, dirty, queue, gx, gy, sx, sy, 0x7FFFFFFFu, -1.f, FX_POCKET_BUDGET, &hit);
+            uint32_t back = run_pass<METRIC, false>(P, S, s_lut, s_step, field, dirty, queue, gx, gy, sx, sy, 0x7FFFFFFFu, -1.f, FX_POCKET_BUDGET, &hit);
             passes++;
             overflow = (S.flags & FLAG_OVERFLOW) != 0;
             const bool start_free = P.grid[(size_t)sx * H + sy] != 1;
@@ -525,7 +592,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
                 }
             }
             __syncthreads();
-            reset_slot(S, field, dirty, P.dirty_n, P.cells, H);
+            reset_slot(S, field, dirty, P.dirty_n, P.cells, H, false);
         }
         // upper bound from the warp-per-query band pass (band.cu).  If it equals the octile lower bound it is the
         // answer and only the path is still needed: one pass inside the same band with U = h0 recovers it (the band
@@ -533,11 +600,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
         const uint32_t hint = P.ubound ? P.ubound[q] : FX_INF;
         if (!overflow && !unreachable && best == FX_INF && hint != FX_INF) {
             if (hint == h0) {
-                best = run_pass<METRIC>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, h0, (float)P.band0 * L, 0u, &hit);
+                best = run_pass<METRIC, false>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, h0, (float)P.band0 * L, 0u, &hit);
                 passes++;
                 overflow = (S.flags & FLAG_OVERFLOW) != 0;
                 if (best != FX_INF) { exact = true; band_only++; }
-                else if (!overflow) reset_slot(S, field, dirty, P.dirty_n, P.cells, H);
+                else if (!overflow) reset_slot(S, field, dirty, P.dirty_n, P.cells, H, false);
             } else {
                 best = hint;
             }
@@ -550,21 +617,28 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
             uint64_t U64 = (uint64_t)h0 + slack;
             uint32_t U0 = (last || U64 > 0x7FFFFFFFull) ? 0x7FFFFFFFu : (uint32_t)U64;
             float bandL = last ? -1.f : band * L;
-            best = run_pass<METRIC>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, U0, bandL, 0u, &hit);
+            best = run_pass<METRIC, false>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, U0, bandL, 0u, &hit);
             passes++;
             overflow = (S.flags & FLAG_OVERFLOW) != 0;
             if (overflow) break;
             if (best != FX_INF) { exact = last || best == h0; if (attempt == 0 && exact) band_only++; break; }
             if (last || !S.pruned) break;  // nothing was pruned and the queue drained: the start's component is exhausted
             __syncthreads();
-            reset_slot(S, field, dirty, P.dirty_n, P.cells, H);
+            reset_slot(S, field, dirty, P.dirty_n, P.cells, H, false);
             band *= 8.f; slack = slack * 4;
         }
-        // pass B: no band, U = the upper bound -> exact
+        // pass B: no band, U = the upper bound -> exact.  Bidirectional (see run_pass): two half-length level chains
+        // instead of one, the optimum and the meeting cell come out of the termination test.
+        bool bidir = false;
         if (!overflow && !unreachable && best != FX_INF && !exact) {
             __syncthreads();
-            reset_slot(S, field, dirty, P.dirty_n, P.cells, H);
-            best = run_pass<METRIC>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, best, -1.f, 0u, &hit);
+            reset_slot(S, field, dirty, P.dirty_n, P.cells, H, false);
+            if (P.bidir) {
+                best = run_pass<METRIC, true>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, best, -1.f, 0u, &hit);
+                bidir = true;
+            } else {
+                best = run_pass<METRIC, false>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, best, -1.f, 0u, &hit);
+            }
             passes++;
             overflow = (S.flags & FLAG_OVERFLOW) != 0;
         }
@@ -581,10 +655,28 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
                 if (P.path_len) P.path_len[q] = FX_COST_UNREACHABLE;
             }
         } else {
+            // tmp holds two runs of turning points: [0, cap) the walk from the meeting cell (or the goal) back to the
+            // start, [cap, 2 cap) the walk from the meeting cell back to the goal through the goal side's field
+            const int cap = P.path_cap;
             if (tid < 32) {
                 unsigned a = 0, b = 0;
-                int npts = extract_path<METRIC>(P, field, sx, sy, gx, gy, tmp, P.path_cap, &a, &b);
-                if (tid == 0) { s_npts = npts; s_ab[0] = a; s_ab[1] = b; }
+                int n1, n2 = 1, d1 = 8, d2 = 8;
+                if (bidir) {
+                    const int mx = (int)(S.meet >> 16), my = (int)(S.meet & 0xFFFFu);
+                    n1 = extract_path<METRIC>(P, field, sx, sy, mx, my, tmp, cap, &a, &b, &d1);
+                    n2 = extract_path<METRIC>(P, field + P.cells, gx, gy, mx, my, tmp + 2 * (size_t)cap, cap, &a, &b, &d2);
+                } else {
+                    n1 = extract_path<METRIC>(P, field, sx, sy, gx, gy, tmp, cap, &a, &b, &d1);
+                }
+                if (tid == 0) {
+                    // the meeting cell is a turning point unless the travel direction into it (d1) equals the travel
+                    // direction out of it (the opposite of the goal side's arrival direction d2)
+                    const int opp2 = d2 < 4 ? (d2 ^ 1) : (d2 < 8 ? 11 - d2 : 8);
+                    s_seg[0] = n1; s_seg[1] = n2;
+                    s_seg[2] = (bidir && n1 > 1 && n2 > 1 && d1 == opp2) ? 1 : 0;
+                    s_npts = (n1 < 0 || n2 < 0) ? -1 : n1 + n2 - 1 - s_seg[2];
+                    s_ab[0] = a; s_ab[1] = b;
+                }
             }
             __syncthreads();
             const int npts = s_npts;
@@ -594,20 +686,19 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
                     P.cost_f[q] = METRIC == 1 ? (double)best : __dadd_rn((double)s_ab[0], __dmul_rn((double)s_ab[1], 1.4142135623730951));
                 if (P.path_len) P.path_len[q] = npts < 0 ? FX_COST_OVERFLOW : npts;
             }
-            if (P.path_xy && npts > 0) {
-                const int stored = min(npts, P.path_cap);
-                const int nout = min(stored, P.max_path);
-                // tmp holds goal..start; output start..goal.  If npts > stored the points nearest the start were
-                // dropped: path_len > max_path tells the caller to retry with a larger max_path.
+            if (P.path_xy && npts > 0 && npts <= P.max_path && s_seg[0] <= cap && s_seg[1] <= cap) {
+                // output start..goal: the first run reversed (minus the meeting cell when it is collinear), then the second
+                // run without its first point.  A path that does not fit (path_len > max_path) is not written at all.
+                const int n1 = s_seg[0], drop = s_seg[2], nfirst = n1 - drop;
                 int32_t *out = P.path_xy + (size_t)q * P.max_path * 2;
-                for (int i = tid; i < nout; i += blockDim.x) {
-                    int src = stored - 1 - i;
-                    out[2 * i] = __ldcg(tmp + 2 * src); out[2 * i + 1] = __ldcg(tmp + 2 * src + 1);
+                for (int i = tid; i < npts; i += blockDim.x) {
+                    const int32_t *src = i < nfirst ? tmp + 2 * (size_t)(n1 - 1 - i) : tmp + 2 * (size_t)cap + 2 * (size_t)(i - nfirst + 1);
+                    out[2 * i] = __ldcg(src); out[2 * i + 1] = __ldcg(src + 1);
                 }
             }
         }
         __syncthreads();
-        reset_slot(S, field, dirty, P.dirty_n, P.cells, H);
+        reset_slot(S, field, dirty, P.dirty_n, P.cells, H, bidir);
     }
     if (tid == 0) {
         atomicAdd(P.counters + 1, S.settled);
@@ -632,24 +723,25 @@ int fx_search_reserve(fx_context *ctx, int W, int H, int max_path, cudaStream_t 
     ctx->fields = nullptr; ctx->dirty = nullptr; ctx->queues = nullptr; ctx->tmp_path = nullptr;
     ctx->sW = ctx->sH = 0;
 
-    size_t dirty_n = ((cells >> FX_DIRTY_SHIFT) + 1 + 15) / 16 * 16;
+    // two cost fields per slot (start side, goal side of the bidirectional pass); cells padded to a multiple of 512 so that
+    // field rows are 16-byte aligned for the uint4 reset and the second field's dirty flags start on a uint4
+    const size_t cells_al = (cells + 511) / 512 * 512;
+    size_t dirty_n = (2 * cells_al) >> FX_DIRTY_SHIFT;  // a multiple of 32
     int qcap = 8 * (W + H) + 1024;
-    size_t per_slot = cells * 4 + dirty_n + (size_t)qcap * 32 + (size_t)path_cap * 8;
+    size_t per_slot = 2 * cells_al * 4 + dirty_n + (size_t)qcap * 32 + (size_t)path_cap * 16;
     size_t free_b = 0, total_b = 0;
     FX_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
     int slots = ctx->cfg_slots > 0 ? ctx->cfg_slots : ctx->sm_count * FX_SEARCH_MINB;
     size_t budget = free_b / 2;  // leave half of what is free to the caller
     if ((size_t)slots * per_slot > budget) slots = (int)(budget / per_slot);
     if (slots < 1) return fx_set_err(ctx, FX_ERR_NOMEM, "search scratch for a %dx%d grid does not fit (%zu B per slot, %zu free)", W, H, per_slot, free_b);
-    // field rows must start 16-byte aligned for the uint4 reset
-    size_t cells_al = (cells + 31) / 32 * 32;
-    FX_CUDA(ctx, cudaMalloc(&ctx->fields, (size_t)slots * cells_al * 4));
+    FX_CUDA(ctx, cudaMalloc(&ctx->fields, (size_t)slots * 2 * cells_al * 4));
     FX_CUDA(ctx, cudaMalloc(&ctx->dirty, (size_t)slots * dirty_n));
     FX_CUDA(ctx, cudaMalloc(&ctx->queues, (size_t)slots * 4 * qcap * sizeof(uint2)));
-    FX_CUDA(ctx, cudaMalloc(&ctx->tmp_path, (size_t)slots * path_cap * 8));
+    FX_CUDA(ctx, cudaMalloc(&ctx->tmp_path, (size_t)slots * path_cap * 16));
     // on the LAUNCH stream: the synchronous-API memset runs on the legacy default stream, which a cudaStreamNonBlocking
     // stream (the context's own stream of the *_host entry points) does not wait for
-    FX_CUDA(ctx, cudaMemsetAsync(ctx->fields, 0xFF, (size_t)slots * cells_al * 4, st));
+    FX_CUDA(ctx, cudaMemsetAsync(ctx->fields, 0xFF, (size_t)slots * 2 * cells_al * 4, st));
     FX_CUDA(ctx, cudaMemsetAsync(ctx->dirty, 0, (size_t)slots * dirty_n, st));
     ctx->sW = W; ctx->sH = H; ctx->slots = slots; ctx->qcap = qcap; ctx->path_cap = path_cap;
     ctx->cells = cells_al; ctx->dirty_n = dirty_n;
@@ -694,6 +786,7 @@ extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int 
     rc = fx_band_bounds(ctx, grid, W, H, starts_xy, goals_xy, Q, metric, st);
     if (rc) return rc;
     P.order = ctx->q_order; P.ubound = ctx->q_ubound;
+    P.bidir = ctx->cfg_unidir ? 0 : 1;
     int blocks = ctx->slots < Q ? ctx->slots : Q;
     FX_CUDA(ctx, cudaEventRecord(ctx->ev_search[0], st));
     const int wide = ctx->cfg_wide_below >= 0 ? ctx->cfg_wide_below : ctx->sm_count;  // batches of at most this many queries
@@ -736,6 +829,18 @@ extern "C" int fx_search_kernel_ms(fx_context *ctx, float *h_ms)
     FX_CUDA(ctx, cudaSetDevice(ctx->device));
     FX_CUDA(ctx, cudaEventSynchronize(ctx->ev_search[1]));
     FX_CUDA(ctx, cudaEventElapsedTime(h_ms, ctx->ev_search[0], ctx->ev_search[1]));
+    return FX_OK;
+}
+
+/* {k_band_bound, k_search_batch} durations of the last batch that ran the batched kernel */
+extern "C" int fx_search_timings(fx_context *ctx, float *h_ms2)
+{
+    if (!ctx || !h_ms2) return FX_ERR_ARG;
+    if (!ctx->ev_search_valid) return fx_set_err(ctx, FX_ERR_ARG, "fx_search_timings: no search has run on this context");
+    FX_CUDA(ctx, cudaSetDevice(ctx->device));
+    FX_CUDA(ctx, cudaEventSynchronize(ctx->ev_search[1]));
+    FX_CUDA(ctx, cudaEventElapsedTime(h_ms2 + 0, ctx->ev_band[0], ctx->ev_band[1]));
+    FX_CUDA(ctx, cudaEventElapsedTime(h_ms2 + 1, ctx->ev_search[0], ctx->ev_search[1]));
     return FX_OK;
 }
 

@@ -115,6 +115,14 @@ int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int H,
                     int32_t *cost_i, double *cost_f, int32_t *path_xy, int32_t *path_len, int max_path,
                     void *stream);
 
+/* Compact (CSR) form of the path output: offsets[q] = number of points of the paths before q (int64 [Q+1], offsets[Q] =
+ * total), out_xy = the points of all paths back to back (int32 [cap][2]; points beyond cap are dropped -- compare
+ * offsets[Q] with cap).  A query without a path (path_len <= 0) or whose path did not fit max_path contributes no point.
+ * path_xy / path_len: exactly what fx_search_batch wrote.  The reference returns one Python list per call
+ * (scripts/jps1.py:199-208); this is the batched equivalent without the padding. */
+int fx_paths_compact(fx_context *ctx, const int32_t *path_xy, const int32_t *path_len, int Q, int max_path,
+                     int64_t *offsets, int32_t *out_xy, int64_t cap, void *stream);
+
 /* Successor rule of the batched search, exposed for parity tests (pure host function, no GPU needed).
  * Replaces: scripts/jps1.py:49-93 `nodeNeighbours` (natural + forced neighbours of a cell given the direction it
  * was reached by), in single-step form.  code: 0..7 = arrival direction in the order (-1,0) (+1,0) (0,-1) (0,+1)
@@ -151,6 +159,8 @@ int fx_search_stats(fx_context *ctx, int64_t *h_stats4);
 /* duration in ms of the last k_search_batch launch alone: CUDA events recorded on the launching stream immediately
  * before and after it (waits for that launch to finish).  bench.py: roofline of the dominant kernel. */
 int fx_search_kernel_ms(fx_context *ctx, float *h_ms);
+/* the same for both kernels of the batched search: h_ms2 = {k_band_bound (upper bounds), k_search_batch} */
+int fx_search_timings(fx_context *ctx, float *h_ms2);
 
 /* ---- host-buffer convenience = what the Python drop-in `jps1.method` calls ---------------------
  * Same as fx_search_batch but all buffers are HOST memory; copies in, runs, copies out and
@@ -158,6 +168,17 @@ int fx_search_kernel_ms(fx_context *ctx, float *h_ms);
 int fx_plan_host(fx_context *ctx, const uint8_t *h_grid, int W, int H,
                  const int32_t *h_starts_xy, const int32_t *h_goals_xy, int Q, int metric,
                  int32_t *h_cost_i, double *h_cost_f, int32_t *h_path_xy, int32_t *h_path_len, int max_path);
+
+/* Same with the paths in compact form: h_offsets int64 [Q+1], h_xy int32 [cap][2] (the first min(total, cap) points),
+ * *h_total = offsets[Q] (may be NULL).  Only `total` points cross the bus (fx_plan_host does the same internally and
+ * scatters them into the padded rows).  max_path still bounds a single path (longer ones report path_len > max_path
+ * and contribute no point). */
+int fx_plan_host_csr(fx_context *ctx, const uint8_t *h_grid, int W, int H,
+                     const int32_t *h_starts_xy, const int32_t *h_goals_xy, int Q, int metric,
+                     int32_t *h_cost_i, double *h_cost_f, int32_t *h_path_len, int max_path,
+                     int64_t *h_offsets, int32_t *h_xy, int64_t cap, int64_t *h_total);
+/* device->host bytes the last fx_plan_host / fx_plan_host_f64 / fx_plan_host_csr on ctx copied (bench.py: e2e) */
+int64_t fx_last_d2h_bytes(fx_context *ctx);
 
 /* Same, taking the matrix as the reference's callers hold it: float64 [W][H] (np.zeros, scripts/global_planner_st.py:248),
  * obstacle iff matrix[x][y] == 1.0 (scripts/jps1.py:20-29).  The `== 1 -> uint8` conversion runs on a few host threads

@@ -36,3 +36,24 @@ def test_host_baselines_block_runs_without_a_gpu():
     res = bench.host_baselines()
     assert res["cores"] == 1 and res["inflate_ccst_r2_1024"] > 0 and res["distance_filter_1Mpts"] > 0
     assert res["dbscan_2x5000pts"] is None or (res["dbscan_2x5000pts"] > 0 and min(res["dbscan_clusters"]) >= 1)
+
+
+def test_reference_arm_ignores_omp_num_threads_and_says_its_sample():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must still use every core it may run on and report the true
+    number of queries it timed per step (round-1 verdict: the N > 1 ratios were void because of both)."""
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--grid", "256", "--queries", "4096",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    cores = len(os.sched_getaffinity(0))
+    assert line["cpu_baseline"]["cores"] == cores
+    assert line["config"]["cpu_sample_queries_per_step"] == min(4096, 16 * cores)
+
+
+def test_reference_arm_other_config_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "cfg2", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "points/s" and line["value"] > 0 and line["cpu_baseline"]["cores"] == 1

@@ -609,7 +609,7 @@ def test_search_cfg4_4096(fx, dev, oracle, cfg4_golden):
 def test_cfg5_field_vs_oracle(fx, dev, oracle):
     """cfg5 (16384^2, default_rng(6), 20 % fill; query = first free cell -> last free cell): the whole cost field of one
     GPU against the C oracle's Dijkstra field bit for bit, and the goal's cost against the goal-directed batched search
-    (fx_search_batch) on the same query, both metrics for the query."""
+    (fx_search_batch) on the same query.  The oracle's field costs ~75 s of host time."""
     import torch
     n = 16384
     m = (np.random.default_rng(6).random((n, n)) < 0.2).astype(np.uint8)
@@ -631,6 +631,44 @@ def test_cfg5_field_vs_oracle(fx, dev, oracle):
     assert int(res.cost_i[0]) == goal_cost
     a, b = validate_path(m, res.path(0), tuple(s[0]), tuple(g[0]))
     assert a * fx.FX_EUCLID_WS + b * fx.FX_EUCLID_WD == goal_cost
-    want1 = oracle.sssp_batch(m, s, g, 1)
-    res1 = fx.plan_batch(gm, _t(s, dev), _t(g, dev), metric=1, max_path=8192)
-    assert int(res1.cost_i[0]) == int(want1[0])
+
+
+def test_paths_compact_and_host_csr(fx, dev, oracle):
+    """Compact (CSR) path output: fx_paths_compact of the padded rows and fx_plan_host_csr against the padded forms,
+    including unreachable queries, start == goal, and paths that do not fit max_path (they contribute no point)."""
+    rng = np.random.default_rng(41)
+    m = (rng.random((700, 650)) < 0.3).astype(np.uint8)
+    s, g = random_queries(m, 300, rng)
+    s[5] = g[5]
+    m2 = m.copy()
+    m2[200:260, 300] = 1; m2[200:260, 360] = 1; m2[200, 300:361] = 1; m2[259, 300:361] = 1   # a sealed room
+    m2[220:240, 320:340] = 0
+    g[7] = (230, 330)
+    for max_path in (256, 12):
+        res = fx.plan_batch(_t(m2, dev), _t(s, dev), _t(g, dev), metric=2, max_path=max_path)
+        pl = res.path_len.cpu().numpy()
+        pxy = res.path_xy.cpu().numpy()
+        off, xy = fx.paths_compact(res.path_xy, res.path_len)
+        off, xy = off.cpu().numpy(), xy.cpu().numpy()
+        n = np.where((pl > 0) & (pl <= max_path), pl, 0)
+        assert np.array_equal(off, np.concatenate([[0], np.cumsum(n)]))
+        for q in range(len(s)):
+            assert np.array_equal(xy[off[q]:off[q + 1]], pxy[q, :n[q]])
+        assert pl[5] == 1 and pl[7] == -1
+        if max_path == 12:
+            assert (pl > max_path).any()
+        ci, cf, hxy, hpl = fx.plan_host(m2, s, g, metric=2, max_path=max_path)
+        ci2, cf2, hpl2, hoff, hx = fx.plan_host_csr(m2, s, g, metric=2, max_path=max_path, cap=16)   # forces the retry
+        assert np.array_equal(ci, res.cost_i.cpu().numpy()) and np.array_equal(ci, ci2) and np.array_equal(cf, cf2)
+        assert np.array_equal(hpl, pl) and np.array_equal(hpl2, pl) and np.array_equal(hoff, off) and np.array_equal(hx, xy)
+        for q in range(len(s)):
+            assert np.array_equal(hxy[q, :n[q]], pxy[q, :n[q]])
+    # a map of the reference's own size goes through the shared-memory kernel: same contract
+    ms = (rng.random((120, 90)) < 0.2).astype(np.uint8)
+    ss, gs = random_queries(ms, 40, rng)
+    a = fx.plan_host(ms, ss, gs, metric=1, max_path=64)
+    b = fx.plan_host_csr(ms, ss, gs, metric=1, max_path=64)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[2])
+    for q in range(40):
+        k = max(int(a[3][q]), 0)
+        assert np.array_equal(b[4][b[3][q]:b[3][q + 1]], a[2][q, :k])
