@@ -54,7 +54,6 @@ extern "C" int fx_create(int device, fx_context **out)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->cfg_wide_below = -1;
     if (const char *e = getenv("FUXI_B200_WIDE_BELOW")) ctx->cfg_wide_below = atoi(e);  // tuning experiments only
-    if (const char *e = getenv("FUXI_B200_BIDIR")) ctx->cfg_unidir = e[0] == '0';          // tuning experiments only
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
     e = cudaMalloc(&ctx->counters, 16 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(ctx->counters, 0, 16 * sizeof(unsigned long long));
@@ -81,7 +80,9 @@ extern "C" int fx_destroy(fx_context *ctx)
     if (!ctx) return FX_OK;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    void *dev[] = {ctx->fields, ctx->dirty, ctx->queues, ctx->tmp_path, ctx->moves, ctx->counters, ctx->fq, ctx->fstate,
+    fx_search_release(ctx, 0);
+    fx_search_release(ctx, 1);
+    void *dev[] = {ctx->moves, ctx->counters, ctx->fq, ctx->fstate,
                    ctx->seeds, ctx->seeds_sorted, ctx->seed_hist, ctx->edt_g, ctx->edt_s, ctx->edt_t, ctx->edt_flag,
                    ctx->d_grid, ctx->d_grid2, ctx->d_q, ctx->d_out_i, ctx->d_out_f, ctx->d_path, ctx->d_pts, ctx->proj_bits, ctx->q_order, ctx->q_ubound, ctx->bfields,
                    ctx->d_msg, ctx->d_rp, ctx->d_cpath, ctx->d_coff, ctx->cl_bits, ctx->cl_gpref, ctx->cl_chunk, ctx->cl_vidx, ctx->cl_keep, ctx->cl_gpref2,
@@ -104,12 +105,8 @@ extern "C" int fx_set_search_tuning(fx_context *ctx, int slots, int band0)
     if (slots != ctx->cfg_slots) {  // force re-allocation of the per-slot scratch
         cudaSetDevice(ctx->device);
         cudaDeviceSynchronize();
-        if (ctx->fields) cudaFree(ctx->fields);
-        if (ctx->dirty) cudaFree(ctx->dirty);
-        if (ctx->queues) cudaFree(ctx->queues);
-        if (ctx->tmp_path) cudaFree(ctx->tmp_path);
-        ctx->fields = nullptr; ctx->dirty = nullptr; ctx->queues = nullptr; ctx->tmp_path = nullptr;
-        ctx->sW = ctx->sH = 0;
+        fx_search_release(ctx, 0);
+        fx_search_release(ctx, 1);
     }
     ctx->cfg_slots = slots;
     ctx->cfg_band0 = band0;

@@ -222,7 +222,6 @@ int fx_band_bounds(fx_context *ctx, const uint8_t *grid, int W, int H, const int
     P.order = ctx->q_order; P.ubound = ctx->q_ubound; P.bfields = ctx->bfields; P.bcap = ctx->bcap; P.counter = ctx->counters + 6;
     int blocks = (Q + BAND_WARPS - 1) / BAND_WARPS;
     if (blocks > ctx->sm_count * BAND_MINB) blocks = ctx->sm_count * BAND_MINB;
-    FX_CUDA(ctx, cudaEventRecord(ctx->ev_band[0], st));
     if (metric == 1) k_band_bound<1><<<blocks, BAND_WARPS * 32, 0, st>>>(P);
     else k_band_bound<2><<<blocks, BAND_WARPS * 32, 0, st>>>(P);
     FX_LAUNCH_CHECK(ctx);

@@ -9,10 +9,10 @@
 
 #define FX_INF 0xFFFFFFFFu
 #ifndef FX_SEARCH_THREADS
-#define FX_SEARCH_THREADS 256
+#define FX_SEARCH_THREADS 128
 #endif
 #ifndef FX_SEARCH_MINB
-#define FX_SEARCH_MINB 4 /* resident search CTAs per SM the register budget is compiled for (64 registers) */
+#define FX_SEARCH_MINB 8 /* resident search CTAs per SM the register budget is compiled for (64 registers) */
 #endif
 #ifndef FX_SEARCH_WIDE
 #define FX_SEARCH_WIDE 512 /* threads per CTA of the latency form (batches of at most sm_count queries) */
@@ -31,15 +31,18 @@ struct fx_context {
     int cfg_slots;
     int cfg_band0;
     int cfg_wide_below;  // batches of at most this many queries use the wide (latency) CTA form; -1 = sm_count
-    int cfg_unidir;      // tuning experiments: exact pass from the start only (FUXI_B200_BIDIR=0)
 
-    // search scratch (sized for sW x sH, reallocated when the grid shape grows)
-    int sW, sH, slots, qcap, path_cap;
-    size_t cells, dirty_n;
-    uint32_t *fields;   // [slots][2][cells] packed cost | arrival direction from the start / from the goal, FX_INF = unreached
-    uint8_t *dirty;     // [slots][dirty_n] one flag per 32 words of the slot's two fields
-    uint32_t *queues;   // [slots][4][qcap] rotating Dial buckets of packed (x<<16|y)
-    int32_t *tmp_path;  // [slots][2][path_cap][2] turning points of the two walks of the path extraction
+    // search scratch, one set per kernel form (each sized for its sW x sH, reallocated when the shape changes):
+    //   scr[0] throughput form: one cost field per slot, sm_count * FX_SEARCH_MINB slots
+    //   scr[1] latency form (batches of at most sm_count queries): two fields per slot (bidirectional pass), sm_count slots
+    struct SearchScratch {
+        int sW, sH, slots, qcap, path_cap, nfields;
+        size_t cells, dirty_n;
+        uint32_t *fields;   // [slots][nfields][cells] packed cost | arrival direction, FX_INF = unreached
+        uint8_t *dirty;     // [slots][dirty_n] one flag per 32 words of the slot's fields
+        uint32_t *queues;   // [slots][4][qcap] rotating Dial buckets of (packed xy, packed word)
+        int32_t *tmp_path;  // [slots][2][path_cap][2] turning points of the two walks of the path extraction
+    } scr[2];
     uint8_t *moves;     // [cells] legal-move mask per cell
     size_t moves_cap;
     unsigned long long *counters;  // [8]: 0 work counter, 1 settled, 2 levels, 3 passes, 4 band-only, 5 flags
@@ -204,7 +207,8 @@ __device__ __forceinline__ int fx_cidx(int x, int y, int H, int TY)
 
 int fx_grow_bytes(fx_context *ctx, void **p, size_t *cap, size_t want_bytes);
 int fx_grow_pinned(fx_context *ctx, size_t want);
-int fx_search_reserve(fx_context *ctx, int W, int H, int max_path, cudaStream_t st);
+int fx_search_reserve(fx_context *ctx, int which, int W, int H, int max_path, cudaStream_t st);
+void fx_search_release(fx_context *ctx, int which);
 // band.cu: LPT query order + per-query upper bounds from the band pass (one warp per query)
 int fx_band_bounds(fx_context *ctx, const uint8_t *grid, int W, int H, const int32_t *starts_xy, const int32_t *goals_xy, int Q,
                    int metric, cudaStream_t st);

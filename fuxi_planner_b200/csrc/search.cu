@@ -32,6 +32,7 @@
 #endif
 
 #define FLAG_OVERFLOW 1u
+#define FLAG_UNREACH 2u /* bidirectional pass: one side exhausted its component unpruned without meeting the other */
 #define FX_POCKET_BUDGET 4096u /* queue pops of the bounded flood from the goal */
 
 // -DFX_PHASE_CLOCKS: tuning build that accumulates, for warp 0 of every CTA, the cycles spent in each dependent step of
@@ -90,7 +91,6 @@ struct SearchParams {
     int band0;
     const uint32_t *order;   // LPT query order (band.cu) or NULL
     const uint32_t *ubound;  // per-query upper bound from the band pass or NULL
-    int bidir;               // exact pass runs from both ends (0: from the start only)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -160,6 +160,8 @@ struct __align__(16) CtaState {
     unsigned flags;
     int xlo, xhi;     // x-rows this query has touched since the last reset (bounds the dirty-flag scan)
     unsigned pruned;  // this pass rejected a legal move by the ellipse or the band (so a drained queue proves nothing)
+    unsigned prl[2];   // bidirectional pass: side s has pruned a cell (written as it happens)
+    unsigned alive[2][4];  // bidirectional pass: side s has pushed an entry into bucket slot b
     int q;
     unsigned long long settled, levels;
 };
@@ -216,6 +218,9 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
         S.tailD[0] = 0; S.tailD[1] = 0; S.tailD[2] = 0; S.tailD[3] = 0;
         S.goal[0] = FX_INF; S.goal[1] = FX_INF; S.U = U0; S.pruned = 0; S.ovf_level = 0;
         S.mu[0] = ~0ull; S.mu[1] = ~0ull; S.mu[2] = ~0ull; S.meet = 0;
+        S.prl[0] = 0; S.prl[1] = 0;
+        for (int a = 0; a < 8; a++) S.alive[a >> 2][a & 3] = 0;
+        S.alive[0][0] = 1; S.alive[1][0] = 1;
         S.xlo = min(S.xlo, sx - 1); S.xhi = max(S.xhi, sx + 1);
         __stcg(queue, make_uint2(((uint32_t)sx << 16) | (uint32_t)sy, fx_pack(0u, FX_CODE_START)));
         __stcg(field + sidx, fx_pack(0u, FX_CODE_START));
@@ -239,6 +244,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
     // the first level in which a cell can carry labels of both sides
     const uint32_t h0 = octile(abs(sx - gx), abs(sy - gy), WS, WD - WS);
     const unsigned k_meet = h0 / (2u * WS) > 2u ? h0 / (2u * WS) - 2u : 0u;
+    const bool start_free = BIDIR && P.grid[(size_t)sx * H + sy] != 1;
     *budget_hit = false;
     PH_DECL
     for (;;) {
@@ -259,7 +265,19 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
             mu = m_prev < mu ? m_prev : mu;
             const uint32_t mc = (uint32_t)(mu >> 32);
             if (mc != FX_INF && 2ull * k * WS > (unsigned long long)mc + WD) { result = mc; break; }  // see the proof above
-            if (tid == 0) S.mu[k3 == 2 ? 0 : k3 + 1] = ~0ull;
+            // A side with nothing in buckets k and k+1 is finished (bucket k+2 is only filled by this level's own pops).  If
+            // it never pruned, it has labelled its whole component: no proposal by now means the other end is not in it
+            // (the start side pops the goal -- labelled by the goal side from level 0 -- before it can run dry; the goal side
+            // pops the start likewise if the start is a free cell.  A start on an obstacle can be left but never entered: there
+            // the goal side instead pops a free cell n the start can step into, after level 0 -- n carries the start side's
+            // label from level 0 on -- unless n is the goal itself, which the start side pops in level 1: so from level 2 on
+            // the goal side's exhaustion counts for obstacle starts as well).
+            // All four words are stable here: nobody pushes or prunes for a side that has no entry in bucket k.
+            if (mc == FX_INF) {
+                const bool dead0 = !S.alive[0][k & 3] && !S.alive[0][(k + 1) & 3], dead1 = !S.alive[1][k & 3] && !S.alive[1][(k + 1) & 3];
+                if ((dead0 && !S.prl[0]) || (dead1 && !S.prl[1] && (start_free || k >= 2u))) { if (tid == 0) S.flags |= FLAG_UNREACH; break; }
+            }
+            if (tid == 0) { S.mu[k3 == 2 ? 0 : k3 + 1] = ~0ull; S.alive[0][(k + 3) & 3] = 0; S.alive[1][(k + 3) & 3] = 0; }
         } else {
             const unsigned goalc = S.goal[(k + 1) & 1];
             if (goalc != FX_INF) { result = goalc; break; }  // the goal was popped in the previous level: final
@@ -329,7 +347,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
                     const float lat = (float)(x - sx) * qdy - (float)(y - sy) * qdx;
                     keep = keep && fabsf(lat) <= bandL;
                 }
-                if (!keep) { my_pruned = true; act = false; }
+                if (!keep) { my_pruned = true; act = false; if (BIDIR) S.prl[side ? 1 : 0] = 1; }
             }
             if (BIDIR && other != FX_INF)  // both sides have labelled this cell: a real start-goal path through it
                 atomicMin(&S.mu[k3], ((unsigned long long)(g + (other >> 4)) << 32) | (unsigned long long)(e.x & 0x7FFFFFFFu));
@@ -350,6 +368,10 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
                 if (ns) posS = fx_atoms_add(&S.tailS[(k + 1) & 3], ns);
                 if (nd) posD = qhalf + fx_atoms_add(&S.tailD[(k + (diag2 ? 2 : 1)) & 3], nd);
                 if (posS + ns > qhalf || posD + nd > qcap) succ = 0;  // no room: the tail counts flag the overflow at the next level
+                if (BIDIR) {
+                    if (ns) S.alive[side ? 1 : 0][(k + 1) & 3] = 1;
+                    if (nd) S.alive[side ? 1 : 0][(k + (diag2 ? 2 : 1)) & 3] = 1;
+                }
             }
             PH_MARK(3, posS + posD)  // queue space reserved
             // the loop below runs as often as the busiest lane of the warp has successors, so it is kept short: the
@@ -501,7 +523,14 @@ __device__ int extract_path(const SearchParams &P, const uint32_t *__restrict__ 
 // THREADS / MINB: the throughput form (128 threads, 8 CTAs per SM hide each other's L2 round trips) and the latency
 // form for batches smaller than the machine (FX_SEARCH_WIDE threads: a whole level of a single query -- a few hundred
 // frontier cells -- is one round of loads instead of three).
-template <int METRIC, int THREADS, int MINB>
+// LAT (latency form): no band kernel, no pocket pre-pass.  The exact pass is bidirectional and its prune bound is a
+// GUESS that is widened until it holds: a pass pruned with U0 is accepted iff it returns mu <= U0 -- then U0 was a real
+// upper bound on the optimum, the pruning was sound and the termination proof of run_pass applies.  mu > U0 is still
+// the cost of a real path, so the next pass with U0 = mu is final; no proposal at all widens the guess fourfold (about
+// half of the queries of the headline workload are within 0.8 % of the octile lower bound, nearly all within 7 %).
+// A pass in which one side exhausts its component without pruning and without meeting the other proves "unreachable"
+// at the cost of the SMALLER component.
+template <int METRIC, int THREADS, int MINB, bool LAT>
 __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchParams P)
 {
     constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
@@ -512,7 +541,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
     __shared__ unsigned s_ab[2];
     const int tid = threadIdx.x;
     const int slot = blockIdx.x;
-    uint32_t *field = P.fields + (size_t)slot * P.cells * 2;  // [start side | goal side]
+    uint32_t *field = P.fields + (size_t)slot * P.cells * (LAT ? 2 : 1);  // LAT: [start side | goal side]
     uint8_t *dirty = P.dirty + (size_t)slot * P.dirty_n;
     uint2 *queue = P.queues + (size_t)slot * 4 * P.qcap;
     int32_t *tmp = P.tmp_path + (size_t)slot * P.path_cap * 4;  // two runs of path_cap points
@@ -569,78 +598,90 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
         uint32_t best = FX_INF;
         bool exact = false, overflow = false;
         bool hit = false, unreachable = false;
-        // pocket check: a bounded flood FROM THE GOAL.  Among free cells the move graph is symmetric (a diagonal
-        // tests the same two orthogonal cells both ways), so if the flood drains below the budget the goal sits in a
-        // small sealed component: unless it met the start (or, for a start on an obstacle, a cell the start can
-        // step into) the query is unreachable and the forward search need not flood the start's whole component.
-        // If the flood reaches the start its cost is the exact answer and pass A is skipped.
-        {
-            uint32_t back = run_pass<METRIC, false>(P, S, s_lut, s_step, field, dirty, queue, gx, gy, sx, sy, 0x7FFFFFFFu, -1.f, FX_POCKET_BUDGET, &hit);
-            passes++;
-            overflow = (S.flags & FLAG_OVERFLOW) != 0;
-            const bool start_free = P.grid[(size_t)sx * H + sy] != 1;
-            if (!overflow && !hit) {
-                if (back != FX_INF && start_free) { best = back; }        // symmetric cost; pass B with U = best proves it
-                else if (back == FX_INF) {
-                    bool touch = false;
-                    if (!start_free) {
-                        const unsigned ms = P.moves[fx_cidx(sx, sy, H, P.TY)];
-                        for (int d = 0; d < 8; d++)
-                            if (((ms >> d) & 1u) && __ldcg(field + fx_cidx(sx + fx_dx(d), sy + fx_dy(d), H, P.TY)) != FX_INF) touch = true;
-                    }
-                    unreachable = !touch;
-                }
+        bool bidir = false;
+        if constexpr (LAT) {
+            uint64_t U_try = (uint64_t)h0 + h0 / 128 + 4 * WD;
+            for (int attempt = 0; attempt < 6; attempt++) {
+                const bool last = attempt == 5 || U_try >= 0x7FFFFFFFull;
+                const uint32_t U0 = last ? 0x7FFFFFFFu : (uint32_t)U_try;
+                const uint32_t r = run_pass<METRIC, true>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, U0, -1.f, 0u, &hit);
+                passes++;
+                bidir = true;
+                overflow = (S.flags & FLAG_OVERFLOW) != 0;
+                if (overflow) break;
+                if (r != FX_INF && r <= U0) { best = r; break; }           // the bound held: exact
+                if ((S.flags & FLAG_UNREACH) || last || (r == FX_INF && !S.pruned)) { unreachable = true; break; }
+                U_try = r != FX_INF ? (uint64_t)r : (uint64_t)h0 + (U_try - h0) * 4;  // a real path's cost / a wider guess
+                __syncthreads();
+                reset_slot(S, field, dirty, P.dirty_n, P.cells, H, true);
             }
-            __syncthreads();
-            reset_slot(S, field, dirty, P.dirty_n, P.cells, H, false);
-        }
-        // upper bound from the warp-per-query band pass (band.cu).  If it equals the octile lower bound it is the
-        // answer and only the path is still needed: one pass inside the same band with U = h0 recovers it (the band
-        // of band.cu is a subset of this one, so the pass finds a path of that cost).  Otherwise it seeds pass B.
-        const uint32_t hint = P.ubound ? P.ubound[q] : FX_INF;
-        if (!overflow && !unreachable && best == FX_INF && hint != FX_INF) {
-            if (hint == h0) {
-                best = run_pass<METRIC, false>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, h0, (float)P.band0 * L, 0u, &hit);
+        } else {
+            // pocket check: a bounded flood FROM THE GOAL.  Among free cells the move graph is symmetric (a diagonal
+            // tests the same two orthogonal cells both ways), so if the flood drains below the budget the goal sits in a
+            // small sealed component: unless it met the start (or, for a start on an obstacle, a cell the start can
+            // step into) the query is unreachable and the forward search need not flood the start's whole component.
+            // If the flood reaches the start its cost is the exact answer and pass A is skipped.
+            {
+                uint32_t back = run_pass<METRIC, false>(P, S, s_lut, s_step, field, dirty, queue, gx, gy, sx, sy, 0x7FFFFFFFu, -1.f, FX_POCKET_BUDGET, &hit);
                 passes++;
                 overflow = (S.flags & FLAG_OVERFLOW) != 0;
-                if (best != FX_INF) { exact = true; band_only++; }
-                else if (!overflow) reset_slot(S, field, dirty, P.dirty_n, P.cells, H, false);
-            } else {
-                best = hint;
+                const bool start_free = P.grid[(size_t)sx * H + sy] != 1;
+                if (!overflow && !hit) {
+                    if (back != FX_INF && start_free) { best = back; }        // symmetric cost; pass B with U = best proves it
+                    else if (back == FX_INF) {
+                        bool touch = false;
+                        if (!start_free) {
+                            const unsigned ms = P.moves[fx_cidx(sx, sy, H, P.TY)];
+                            for (int d = 0; d < 8; d++)
+                                if (((ms >> d) & 1u) && __ldcg(field + fx_cidx(sx + fx_dx(d), sy + fx_dy(d), H, P.TY)) != FX_INF) touch = true;
+                        }
+                        unreachable = !touch;
+                    }
+                }
+                __syncthreads();
+                reset_slot(S, field, dirty, P.dirty_n, P.cells, H, false);
             }
-        }
-        // pass A (only without a usable hint): narrow band, generous bound; escalate if the band is sealed
-        float band = (float)P.band0;
-        uint32_t slack = h0 / 16 + 64 * WS;
-        for (int attempt = 0; attempt < 3 && !overflow && !unreachable && best == FX_INF; attempt++) {
-            const bool last = attempt == 2;
-            uint64_t U64 = (uint64_t)h0 + slack;
-            uint32_t U0 = (last || U64 > 0x7FFFFFFFull) ? 0x7FFFFFFFu : (uint32_t)U64;
-            float bandL = last ? -1.f : band * L;
-            best = run_pass<METRIC, false>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, U0, bandL, 0u, &hit);
-            passes++;
-            overflow = (S.flags & FLAG_OVERFLOW) != 0;
-            if (overflow) break;
-            if (best != FX_INF) { exact = last || best == h0; if (attempt == 0 && exact) band_only++; break; }
-            if (last || !S.pruned) break;  // nothing was pruned and the queue drained: the start's component is exhausted
-            __syncthreads();
-            reset_slot(S, field, dirty, P.dirty_n, P.cells, H, false);
-            band *= 8.f; slack = slack * 4;
-        }
-        // pass B: no band, U = the upper bound -> exact.  Bidirectional (see run_pass): two half-length level chains
-        // instead of one, the optimum and the meeting cell come out of the termination test.
-        bool bidir = false;
-        if (!overflow && !unreachable && best != FX_INF && !exact) {
-            __syncthreads();
-            reset_slot(S, field, dirty, P.dirty_n, P.cells, H, false);
-            if (P.bidir) {
-                best = run_pass<METRIC, true>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, best, -1.f, 0u, &hit);
-                bidir = true;
-            } else {
+            // upper bound from the warp-per-query band pass (band.cu).  If it equals the octile lower bound it is the
+            // answer and only the path is still needed: one pass inside the same band with U = h0 recovers it (the band
+            // of band.cu is a subset of this one, so the pass finds a path of that cost).  Otherwise it seeds pass B.
+            const uint32_t hint = P.ubound ? P.ubound[q] : FX_INF;
+            if (!overflow && !unreachable && best == FX_INF && hint != FX_INF) {
+                if (hint == h0) {
+                    best = run_pass<METRIC, false>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, h0, (float)P.band0 * L, 0u, &hit);
+                    passes++;
+                    overflow = (S.flags & FLAG_OVERFLOW) != 0;
+                    if (best != FX_INF) { exact = true; band_only++; }
+                    else if (!overflow) reset_slot(S, field, dirty, P.dirty_n, P.cells, H, false);
+                } else {
+                    best = hint;
+                }
+            }
+            // pass A (only without a usable hint): narrow band, generous bound; escalate if the band is sealed
+            float band = (float)P.band0;
+            uint32_t slack = h0 / 16 + 64 * WS;
+            for (int attempt = 0; attempt < 3 && !overflow && !unreachable && best == FX_INF; attempt++) {
+                const bool last = attempt == 2;
+                uint64_t U64 = (uint64_t)h0 + slack;
+                uint32_t U0 = (last || U64 > 0x7FFFFFFFull) ? 0x7FFFFFFFu : (uint32_t)U64;
+                float bandL = last ? -1.f : band * L;
+                best = run_pass<METRIC, false>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, U0, bandL, 0u, &hit);
+                passes++;
+                overflow = (S.flags & FLAG_OVERFLOW) != 0;
+                if (overflow) break;
+                if (best != FX_INF) { exact = last || best == h0; if (attempt == 0 && exact) band_only++; break; }
+                if (last || !S.pruned) break;  // nothing was pruned and the queue drained: the start's component is exhausted
+                __syncthreads();
+                reset_slot(S, field, dirty, P.dirty_n, P.cells, H, false);
+                band *= 8.f; slack = slack * 4;
+            }
+            // pass B: no band, U = the upper bound -> exact
+            if (!overflow && !unreachable && best != FX_INF && !exact) {
+                __syncthreads();
+                reset_slot(S, field, dirty, P.dirty_n, P.cells, H, false);
                 best = run_pass<METRIC, false>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, best, -1.f, 0u, &hit);
+                passes++;
+                overflow = (S.flags & FLAG_OVERFLOW) != 0;
             }
-            passes++;
-            overflow = (S.flags & FLAG_OVERFLOW) != 0;
         }
         if (overflow || (best != FX_INF && best > 0x7FFFFFFFu)) {
             if (tid == 0) {
@@ -711,40 +752,47 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-int fx_search_reserve(fx_context *ctx, int W, int H, int max_path, cudaStream_t st)
+void fx_search_release(fx_context *ctx, int which)
 {
+    fx_context::SearchScratch &S = ctx->scr[which];
+    if (S.fields) cudaFree(S.fields);
+    if (S.dirty) cudaFree(S.dirty);
+    if (S.queues) cudaFree(S.queues);
+    if (S.tmp_path) cudaFree(S.tmp_path);
+    memset(&S, 0, sizeof(S));
+}
+
+int fx_search_reserve(fx_context *ctx, int which, int W, int H, int max_path, cudaStream_t st)
+{
+    fx_context::SearchScratch &S = ctx->scr[which];
     size_t cells = fx_scratch_cells(W, H);
     int path_cap = max_path > 0 ? max_path : 1;
-    if (ctx->fields && ctx->sW == W && ctx->sH == H && ctx->path_cap >= path_cap) return FX_OK;
-    if (ctx->fields) cudaFree(ctx->fields);
-    if (ctx->dirty) cudaFree(ctx->dirty);
-    if (ctx->queues) cudaFree(ctx->queues);
-    if (ctx->tmp_path) cudaFree(ctx->tmp_path);
-    ctx->fields = nullptr; ctx->dirty = nullptr; ctx->queues = nullptr; ctx->tmp_path = nullptr;
-    ctx->sW = ctx->sH = 0;
+    if (S.fields && S.sW == W && S.sH == H && S.path_cap >= path_cap) return FX_OK;
+    fx_search_release(ctx, which);
 
-    // two cost fields per slot (start side, goal side of the bidirectional pass); cells padded to a multiple of 512 so that
-    // field rows are 16-byte aligned for the uint4 reset and the second field's dirty flags start on a uint4
+    // cells padded to a multiple of 512: field rows stay 16-byte aligned for the uint4 reset and a second field's dirty
+    // flags start on a uint4
+    const int nfields = which == 1 ? 2 : 1;
     const size_t cells_al = (cells + 511) / 512 * 512;
-    size_t dirty_n = (2 * cells_al) >> FX_DIRTY_SHIFT;  // a multiple of 32
+    size_t dirty_n = (nfields * cells_al) >> FX_DIRTY_SHIFT;  // a multiple of 16
     int qcap = 8 * (W + H) + 1024;
-    size_t per_slot = 2 * cells_al * 4 + dirty_n + (size_t)qcap * 32 + (size_t)path_cap * 16;
+    size_t per_slot = nfields * cells_al * 4 + dirty_n + (size_t)qcap * 32 + (size_t)path_cap * 16;
     size_t free_b = 0, total_b = 0;
     FX_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-    int slots = ctx->cfg_slots > 0 ? ctx->cfg_slots : ctx->sm_count * FX_SEARCH_MINB;
+    int slots = which == 1 ? ctx->sm_count : (ctx->cfg_slots > 0 ? ctx->cfg_slots : ctx->sm_count * FX_SEARCH_MINB);
     size_t budget = free_b / 2;  // leave half of what is free to the caller
     if ((size_t)slots * per_slot > budget) slots = (int)(budget / per_slot);
     if (slots < 1) return fx_set_err(ctx, FX_ERR_NOMEM, "search scratch for a %dx%d grid does not fit (%zu B per slot, %zu free)", W, H, per_slot, free_b);
-    FX_CUDA(ctx, cudaMalloc(&ctx->fields, (size_t)slots * 2 * cells_al * 4));
-    FX_CUDA(ctx, cudaMalloc(&ctx->dirty, (size_t)slots * dirty_n));
-    FX_CUDA(ctx, cudaMalloc(&ctx->queues, (size_t)slots * 4 * qcap * sizeof(uint2)));
-    FX_CUDA(ctx, cudaMalloc(&ctx->tmp_path, (size_t)slots * path_cap * 16));
+    FX_CUDA(ctx, cudaMalloc(&S.fields, (size_t)slots * nfields * cells_al * 4));
+    FX_CUDA(ctx, cudaMalloc(&S.dirty, (size_t)slots * dirty_n));
+    FX_CUDA(ctx, cudaMalloc(&S.queues, (size_t)slots * 4 * qcap * sizeof(uint2)));
+    FX_CUDA(ctx, cudaMalloc(&S.tmp_path, (size_t)slots * path_cap * 16));
     // on the LAUNCH stream: the synchronous-API memset runs on the legacy default stream, which a cudaStreamNonBlocking
     // stream (the context's own stream of the *_host entry points) does not wait for
-    FX_CUDA(ctx, cudaMemsetAsync(ctx->fields, 0xFF, (size_t)slots * 2 * cells_al * 4, st));
-    FX_CUDA(ctx, cudaMemsetAsync(ctx->dirty, 0, (size_t)slots * dirty_n, st));
-    ctx->sW = W; ctx->sH = H; ctx->slots = slots; ctx->qcap = qcap; ctx->path_cap = path_cap;
-    ctx->cells = cells_al; ctx->dirty_n = dirty_n;
+    FX_CUDA(ctx, cudaMemsetAsync(S.fields, 0xFF, (size_t)slots * nfields * cells_al * 4, st));
+    FX_CUDA(ctx, cudaMemsetAsync(S.dirty, 0, (size_t)slots * dirty_n, st));
+    S.sW = W; S.sH = H; S.slots = slots; S.qcap = qcap; S.path_cap = path_cap; S.nfields = nfields;
+    S.cells = cells_al; S.dirty_n = dirty_n;
     return FX_OK;
 }
 
@@ -769,33 +817,41 @@ extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int 
             if (r <= 0) return r;
         }
     }
-    int rc = fx_search_reserve(ctx, W, H, path_xy ? max_path : 1, st);
+    // batches of at most this many queries run the latency form (one wide CTA per query, bidirectional, no band kernel)
+    const int wide = ctx->cfg_wide_below >= 0 ? ctx->cfg_wide_below : ctx->sm_count;
+    const int which = Q <= wide ? 1 : 0;
+    int rc = fx_search_reserve(ctx, which, W, H, path_xy ? max_path : 1, st);
     if (rc) return rc;
     rc = fx_build_moves(ctx, grid, W, H, true, st);
     if (rc) return rc;
     FX_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, 16 * sizeof(unsigned long long), st));
+    const fx_context::SearchScratch &X = ctx->scr[which];
     SearchParams P;
     P.grid = grid; P.moves = ctx->moves; P.W = W; P.H = H; P.TY = fx_tiles_y(H);
     P.starts = starts_xy; P.goals = goals_xy; P.Q = Q;
     P.cost_i = cost_i; P.cost_f = cost_f; P.path_xy = path_xy; P.path_len = path_len;
     P.max_path = path_xy ? max_path : 0;
-    P.fields = ctx->fields; P.dirty = ctx->dirty; P.queues = reinterpret_cast<uint2 *>(ctx->queues); P.tmp_path = ctx->tmp_path;
-    P.cells = ctx->cells; P.dirty_n = ctx->dirty_n; P.qcap = ctx->qcap; P.path_cap = ctx->path_cap;
+    P.fields = X.fields; P.dirty = X.dirty; P.queues = reinterpret_cast<uint2 *>(X.queues); P.tmp_path = X.tmp_path;
+    P.cells = X.cells; P.dirty_n = X.dirty_n; P.qcap = X.qcap; P.path_cap = X.path_cap;
     P.counters = ctx->counters;
     P.band0 = ctx->cfg_band0 > 0 ? ctx->cfg_band0 : 16;
-    rc = fx_band_bounds(ctx, grid, W, H, starts_xy, goals_xy, Q, metric, st);
-    if (rc) return rc;
-    P.order = ctx->q_order; P.ubound = ctx->q_ubound;
-    P.bidir = ctx->cfg_unidir ? 0 : 1;
-    int blocks = ctx->slots < Q ? ctx->slots : Q;
-    FX_CUDA(ctx, cudaEventRecord(ctx->ev_search[0], st));
-    const int wide = ctx->cfg_wide_below >= 0 ? ctx->cfg_wide_below : ctx->sm_count;  // batches of at most this many queries
-    if (Q <= wide) {
-        if (metric == 1) k_search_batch<1, FX_SEARCH_WIDE, 1><<<blocks, FX_SEARCH_WIDE, 0, st>>>(P);
-        else k_search_batch<2, FX_SEARCH_WIDE, 1><<<blocks, FX_SEARCH_WIDE, 0, st>>>(P);
+    P.order = nullptr; P.ubound = nullptr;
+    FX_CUDA(ctx, cudaEventRecord(ctx->ev_band[0], st));
+    if (which == 0) {
+        rc = fx_band_bounds(ctx, grid, W, H, starts_xy, goals_xy, Q, metric, st);
+        if (rc) return rc;
+        P.order = ctx->q_order; P.ubound = ctx->q_ubound;
     } else {
-        if (metric == 1) k_search_batch<1, FX_SEARCH_THREADS, FX_SEARCH_MINB><<<blocks, FX_SEARCH_THREADS, 0, st>>>(P);
-        else k_search_batch<2, FX_SEARCH_THREADS, FX_SEARCH_MINB><<<blocks, FX_SEARCH_THREADS, 0, st>>>(P);
+        FX_CUDA(ctx, cudaEventRecord(ctx->ev_band[1], st));
+    }
+    int blocks = X.slots < Q ? X.slots : Q;
+    FX_CUDA(ctx, cudaEventRecord(ctx->ev_search[0], st));
+    if (which == 1) {
+        if (metric == 1) k_search_batch<1, FX_SEARCH_WIDE, 1, true><<<blocks, FX_SEARCH_WIDE, 0, st>>>(P);
+        else k_search_batch<2, FX_SEARCH_WIDE, 1, true><<<blocks, FX_SEARCH_WIDE, 0, st>>>(P);
+    } else {
+        if (metric == 1) k_search_batch<1, FX_SEARCH_THREADS, FX_SEARCH_MINB, false><<<blocks, FX_SEARCH_THREADS, 0, st>>>(P);
+        else k_search_batch<2, FX_SEARCH_THREADS, FX_SEARCH_MINB, false><<<blocks, FX_SEARCH_THREADS, 0, st>>>(P);
     }
     FX_LAUNCH_CHECK(ctx);
     FX_CUDA(ctx, cudaEventRecord(ctx->ev_search[1], st));
