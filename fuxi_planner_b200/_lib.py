@@ -18,10 +18,11 @@ FX_EUCLID_WD = 3363
 SYMBOLS = ["fx_create", "fx_destroy", "fx_last_error", "fx_version", "fx_launch_count", "fx_set_search_tuning", "fx_canon_successors",
            "fx_project", "fx_inflate", "fx_edt", "fx_edt_rows", "fx_edt_cols", "fx_search_batch", "fx_field", "fx_field_relax", "fx_field_status",
            "fx_search_stats", "fx_search_kernel_ms", "fx_search_timings", "fx_plan_host", "fx_plan_host_f64", "fx_plan_host_csr", "fx_last_d2h_bytes",
-           "fx_paths_compact", "fx_map_host", "fx_halo_merge",
+           "fx_paths_compact", "fx_paths_jump_points", "fx_jump_points_host", "fx_map_host", "fx_halo_merge",
            "fx_grid_decode", "fx_grid_encode", "fx_grid_paste", "fx_grid_bbox", "fx_relocate_goal", "fx_path_post",
            "fx_replan_host", "fx_replan_grid_host", "fx_grid_to_image", "fx_image_to_grid",
-           "fx_cloud_reserve", "fx_cloud_filter", "fx_cloud_filter_host", "fx_distance_filter", "fx_distance_filter_host"]
+           "fx_cloud_reserve", "fx_cloud_filter", "fx_cloud_filter_host", "fx_distance_filter", "fx_distance_filter_host",
+           "fx_transform_filter", "fx_transform_filter_host"]
 
 
 class ReplanIn(C.Structure):
@@ -93,6 +94,8 @@ def load():
     lib.fx_last_d2h_bytes.argtypes = [vp]
     lib.fx_last_d2h_bytes.restype = i64
     lib.fx_paths_compact.argtypes = [vp, vp, vp, i32, i32, vp, vp, i64, vp]
+    lib.fx_paths_jump_points.argtypes = [vp, vp, i32, i32, vp, vp, i32, i32, vp, vp, i32, vp]
+    lib.fx_jump_points_host.argtypes = [vp, vp, i32, i32, vp, i32, vp, i32, C.POINTER(i32)]
     lib.fx_map_host.argtypes = [vp, vp, i64, i32, C.POINTER(f32), f32, f32, f32, f32, f32, i32, i32, i32, i32, vp]
     f64p = C.POINTER(C.c_double)
     lib.fx_grid_decode.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp]
@@ -110,6 +113,8 @@ def load():
     lib.fx_cloud_filter_host.argtypes = [vp, vp, i64, C.POINTER(CloudParams), vp, i64, C.POINTER(i64)]
     lib.fx_distance_filter.argtypes = [vp, vp, i64, C.c_double, vp, vp, vp]
     lib.fx_distance_filter_host.argtypes = [vp, vp, i64, C.c_double, vp, C.POINTER(i64)]
+    lib.fx_transform_filter.argtypes = [vp, vp, i64, i32, i32, f64p, f64p, f64p, C.c_double, C.c_double, C.c_double, vp, vp, vp]
+    lib.fx_transform_filter_host.argtypes = [vp, vp, i64, i32, i32, f64p, f64p, f64p, C.c_double, C.c_double, C.c_double, vp, C.POINTER(i64)]
     for s in SYMBOLS:
         if s not in ("fx_last_error", "fx_launch_count", "fx_last_d2h_bytes"):
             getattr(lib, s).restype = i32

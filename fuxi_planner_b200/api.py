@@ -333,6 +333,39 @@ def paths_compact(path_xy, path_len, ctx=None):
     return offsets, out[:cap]
 
 
+def paths_jump_points(grid, path_xy, path_len, max_out=None, ctx=None):
+    """Jump-point form of the padded path rows (fx_paths_jump_points): returns (out_xy int32 [Q, max_out, 2], out_len int32 [Q])."""
+    grid = _u8_grid(grid)
+    ctx = _ctx(ctx, grid)
+    Q, max_path = int(path_xy.shape[0]), int(path_xy.shape[1])
+    W, H = grid.shape
+    max_out = int(max_out) if max_out is not None else min(4 * max_path, W + H + 2)
+    out = torch.empty((Q, max_out, 2), dtype=torch.int32, device=grid.device)
+    out_len = torch.empty(Q, dtype=torch.int32, device=grid.device)
+    ctx.check(ctx.lib.fx_paths_jump_points(ctx.handle, _ptr(grid), W, H, _ptr(path_xy.contiguous()), _ptr(path_len.contiguous()), Q, max_path,
+                                           _ptr(out), _ptr(out_len), max_out, _stream()), "fx_paths_jump_points")
+    return out, out_len
+
+
+def jump_points_host(grid, path, ctx=None, device=0):
+    """One path (sequence of (x, y) turning points, start first) -> the list of (x, y) jump points the reference would
+    return for the same cell path (fx_jump_points_host).  grid: host array, obstacle iff == 1."""
+    ctx = ctx or default_context(device)
+    g = np.asarray(grid)
+    g = np.ascontiguousarray(g) if g.dtype == np.uint8 else np.ascontiguousarray((g == 1).astype(np.uint8))
+    p = np.ascontiguousarray(np.asarray(path, dtype=np.int32).reshape(-1, 2))
+    W, H = g.shape
+    cap = max(16, 4 * len(p))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    while True:
+        out = np.empty((cap, 2), dtype=np.int32)
+        n = C.c_int32(0)
+        ctx.check(ctx.lib.fx_jump_points_host(ctx.handle, vp(g), W, H, vp(p), len(p), vp(out), cap, C.byref(n)), "fx_jump_points_host")
+        if n.value <= cap:
+            return [(int(a), int(b)) for a, b in out[:n.value]]
+        cap = n.value
+
+
 def plan_host_csr(grid, starts, goals, metric=2, max_path=512, cap=None, ctx=None, device=0):
     """plan_host with the paths in compact form (fx_plan_host_csr): returns (cost_i, cost_f, path_len, offsets int64 [Q+1],
     xy int32 [total, 2]).  cap = room for the points (default 64 per query; retried once with the exact total if it is short)."""

@@ -141,3 +141,58 @@ def distance_filter_host(plc, dis, ctx=None, device=0):
     ctx.check(ctx.lib.fx_distance_filter_host(ctx.handle, p.ctypes.data_as(C.c_void_p), p.shape[0], float(dis),
                                               out.ctypes.data_as(C.c_void_p), C.byref(cnt)), "fx_distance_filter_host")
     return out[:cnt.value].copy()
+
+
+def rotation_elementwise(roll, pitch, yaw):
+    """The body->earth matrix with the products grouped the way utils.body_to_earth_frame evaluates them
+    (scripts/utils.py:21-28: each entry left to right, e.g. (cos y * sin p) * sin r - sin y * cos r), so that the float64
+    entries -- and with them every transformed coordinate -- carry the same bits as the reference's.  rotation_zyx above
+    multiplies three matrices instead and differs in the last place."""
+    sr, cr = math.sin(roll), math.cos(roll)
+    sp, cp = math.sin(pitch), math.cos(pitch)
+    sy, cy = math.sin(yaw), math.cos(yaw)
+    m = np.empty((3, 3), dtype=np.float64)
+    m[0] = (cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr)
+    m[1] = (sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr)
+    m[2] = (-sp, cp * sr, cp * cr)
+    return m
+
+
+def node_cloud_host(points, rpy, pos, dt=0.0, ang_vel=(0.0, 0.0, 0.0), line_vel=(0.0, 0.0, 0.0), local_pos=None, zmin=0.3, dis=4.0,
+                    ctx=None, device=0):
+    """The cloud `plc_point2_st.py` publishes on /points_global_all (lines 243-256 + 336-339): camera-frame points (host
+    array [n, >= 3], float32 PointCloud2 data or float64) -> transformed to the earth frame with the time-compensated
+    attitude / position, height filter, range filter around `local_pos` (default: pos) sorted by distance.  float64 [m, 3].
+    One call of fx_transform_filter_host; the [n_dyn, 0, 0] row the node appends (:341) is the caller's."""
+    p = np.asarray(points)
+    is64 = p.dtype == np.float64
+    p = np.ascontiguousarray(p, dtype=np.float64 if is64 else np.float32)
+    if p.ndim != 2 or p.shape[1] < 3:
+        raise FuxiError("points must be [n, >= 3]")
+    r, pp, y = np.array(rpy, dtype=np.float64) + float(dt) * np.array(ang_vel, dtype=np.float64)        # :248
+    R = np.ascontiguousarray(rotation_elementwise(r, pp, y))
+    t = np.ascontiguousarray(float(dt) * np.array(line_vel, dtype=np.float64) + np.array(pos, dtype=np.float64))   # :250
+    c = np.ascontiguousarray(np.array(pos if local_pos is None else local_pos, dtype=np.float64))
+    return _tf_host(p, is64, R, t, c, zmin, 0.0, dis, ctx, device)
+
+
+def octomap_local_host(centres, local_pos, box=4.0, dis=4.0, ctx=None, device=0):
+    """/octomap_point_cloud_centers_local (plc_point2_st.py:351-362): voxel centres within `box` of the vehicle on every
+    axis and within `dis` of it, sorted by distance.  float64 [m, 3]."""
+    p = np.asarray(centres)
+    is64 = p.dtype == np.float64
+    p = np.ascontiguousarray(p, dtype=np.float64 if is64 else np.float32)
+    c = np.ascontiguousarray(np.array(local_pos, dtype=np.float64))
+    return _tf_host(p, is64, None, None, c, -math.inf, box, dis, ctx, device)
+
+
+def _tf_host(p, is64, R, t, c, zmin, box, dis, ctx, device):
+    ctx = ctx or default_context(device)
+    n, stride = p.shape
+    out = np.empty((max(n, 1), 3), dtype=np.float64)
+    cnt = C.c_int64(0)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+    ctx.check(ctx.lib.fx_transform_filter_host(ctx.handle, p.ctypes.data_as(C.c_void_p), n, stride, int(is64), dp(R), dp(t), dp(c),
+                                               float(zmin), float(box), float(dis), out.ctypes.data_as(C.c_void_p), C.byref(cnt)),
+              "fx_transform_filter_host")
+    return out[:cnt.value].copy()

@@ -671,3 +671,104 @@ extern "C" int fx_distance_filter_host(fx_context *ctx, const double *h_pts, int
     }
     return FX_OK;
 }
+
+// ---- the cloud node's product: transformed + filtered + sorted cloud (scripts/plc_point2_st.py:243-256, 336-339; 351-362) --------
+// camera branch (h_R9 != NULL):  b = (z_c + 0.12, -x_c, -y_c);  e_k = ((R_k0*b0 + R_k1*b1) + R_k2*b2) + t_k  (float64, one
+//   rounding per operation; numpy hands the same product to BLAS, whose summation order is not specified: parity with the
+//   reference's own lines is to a few ulps, with the restatement in oracle/hostref.py bit for bit);  keep e_z > zmin (:255-256)
+// octomap-centres branch (h_R9 == NULL):  e = p  (:351-359)
+// then q = e - c;  [box > 0: keep |q_k| < box on every axis (:361)];  distance_filter(q, dis) (:139-148);  out = q + c (:339, :362)
+struct TfArgs {
+    double R[9], t[3], c[3];
+    double zmin, box;
+    int camera, stride, is_f64;
+};
+
+__global__ void k_tf_points(const void *__restrict__ pts, long long n, TfArgs a, double *__restrict__ q)
+{
+    const double nan = __longlong_as_double(0x7FF8000000000000ll);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double x, y, z;
+        if (a.is_f64) {
+            const double *p = reinterpret_cast<const double *>(pts) + i * a.stride;
+            x = p[0], y = p[1], z = p[2];
+        } else {
+            const float *p = reinterpret_cast<const float *>(pts) + i * a.stride;
+            x = (double)p[0], y = (double)p[1], z = (double)p[2];
+        }
+        double e0 = x, e1 = y, e2 = z;
+        bool keep = true;
+        if (a.camera) {
+            const double b0 = __dadd_rn(z, 0.12), b1 = -x, b2 = -y;
+            e0 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(a.R[0], b0), __dmul_rn(a.R[1], b1)), __dmul_rn(a.R[2], b2)), a.t[0]);
+            e1 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(a.R[3], b0), __dmul_rn(a.R[4], b1)), __dmul_rn(a.R[5], b2)), a.t[1]);
+            e2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(a.R[6], b0), __dmul_rn(a.R[7], b1)), __dmul_rn(a.R[8], b2)), a.t[2]);
+            keep = e2 > a.zmin;
+        }
+        const double q0 = __dsub_rn(e0, a.c[0]), q1 = __dsub_rn(e1, a.c[1]), q2 = __dsub_rn(e2, a.c[2]);
+        if (a.box > 0.0) keep = keep && fabs(q0) < a.box && fabs(q1) < a.box && fabs(q2) < a.box;
+        // a rejected point becomes NaN: its norm is NaN, `d < dis` is false, distance_filter drops it
+        q[i * 3] = keep ? q0 : nan; q[i * 3 + 1] = keep ? q1 : nan; q[i * 3 + 2] = keep ? q2 : nan;
+    }
+}
+
+__global__ void k_tf_add(double *__restrict__ out, const int *__restrict__ count, double c0, double c1, double c2)
+{
+    const long long n = *count;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        out[i * 3] = __dadd_rn(out[i * 3], c0);
+        out[i * 3 + 1] = __dadd_rn(out[i * 3 + 1], c1);
+        out[i * 3 + 2] = __dadd_rn(out[i * 3 + 2], c2);
+    }
+}
+
+extern "C" int fx_transform_filter(fx_context *ctx, const void *pts, int64_t n, int stride, int is_f64, const double *h_R9,
+                                   const double *h_t3, const double *h_c3, double zmin, double box, double dis, double *out,
+                                   int32_t *d_count, void *stream)
+{
+    if (!ctx || n < 0 || (n > 0 && (!pts || !out)) || !d_count || stride < 3 || !h_c3 || (h_R9 && !h_t3))
+        return fx_set_err(ctx, FX_ERR_ARG, "fx_transform_filter: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    FX_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = fx_grow_bytes(ctx, (void **)&ctx->tf_q, &ctx->tf_q_bytes, (size_t)(n > 0 ? n : 1) * 24);
+    if (rc) return rc;
+    TfArgs a;
+    memset(&a, 0, sizeof(a));
+    a.camera = h_R9 != nullptr; a.stride = stride; a.is_f64 = is_f64 != 0; a.zmin = zmin; a.box = box;
+    if (h_R9) { memcpy(a.R, h_R9, sizeof(a.R)); memcpy(a.t, h_t3, sizeof(a.t)); }
+    memcpy(a.c, h_c3, sizeof(a.c));
+    if (n > 0) {
+        k_tf_points<<<grid_for(ctx, n, 256, 8), 256, 0, st>>>(pts, n, a, (double *)ctx->tf_q);
+        FX_LAUNCH_CHECK(ctx);
+    }
+    rc = fx_distance_filter(ctx, (const double *)ctx->tf_q, n, dis, out, d_count, stream);
+    if (rc) return rc;
+    k_tf_add<<<grid_for(ctx, n > 0 ? n : 1, 256, 8), 256, 0, st>>>(out, d_count, a.c[0], a.c[1], a.c[2]);
+    FX_LAUNCH_CHECK(ctx);
+    return FX_OK;
+}
+
+extern "C" int fx_transform_filter_host(fx_context *ctx, const void *h_pts, int64_t n, int stride, int is_f64, const double *h_R9,
+                                        const double *h_t3, const double *h_c3, double zmin, double box, double dis, double *h_out,
+                                        int64_t *h_count)
+{
+    if (!ctx || n < 0 || (n > 0 && (!h_pts || !h_out)) || !h_count) return fx_set_err(ctx, FX_ERR_ARG, "fx_transform_filter_host: bad argument");
+    FX_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->own_stream;
+    const size_t in_bytes = (size_t)n * stride * (is_f64 ? 8 : 4), out_bytes = (size_t)n * 24;
+    int rc;
+    if ((rc = fx_grow_bytes(ctx, (void **)&ctx->d_pts, &ctx->d_pts_cap, in_bytes + 16))) return rc;
+    if ((rc = fx_grow_bytes(ctx, (void **)&ctx->cl_out, &ctx->cl_out_bytes, out_bytes + 64))) return rc;
+    int *d_count = (int *)((char *)ctx->cl_out + ((out_bytes + 15) & ~(size_t)15));
+    FX_CUDA(ctx, cudaMemcpyAsync(ctx->d_pts, h_pts, in_bytes, cudaMemcpyHostToDevice, st));
+    if ((rc = fx_transform_filter(ctx, ctx->d_pts, n, stride, is_f64, h_R9, h_t3, h_c3, zmin, box, dis, (double *)ctx->cl_out, d_count, st))) return rc;
+    int cnt = 0;
+    FX_CUDA(ctx, cudaMemcpyAsync(&cnt, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FX_CUDA(ctx, cudaStreamSynchronize(st));
+    *h_count = cnt;
+    if (cnt) {
+        FX_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->cl_out, (size_t)cnt * 24, cudaMemcpyDeviceToHost, st));
+        FX_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return FX_OK;
+}

@@ -89,6 +89,7 @@ struct fx_context {
     unsigned long long *cl_acc;
     float4 *cl_vox;
     void *cl_state, *cl_out, *df_rec;
+    void *tf_q; size_t tf_q_bytes;  // fx_transform_filter: UAV-relative float64 points
     size_t cl_bits_bytes, cl_gpref_bytes, cl_chunk_bytes, cl_vidx_bytes, cl_keep_bytes, cl_gpref2_bytes, cl_chunk2_bytes,
         cl_acc_bytes, cl_vox_bytes, cl_state_bytes, cl_out_bytes, df_rec_bytes;
     unsigned long long cl_cap_bits;  // voxel index space the bitmap is reserved for (fx_cloud_reserve)

@@ -14,8 +14,10 @@ Contract kept from scripts/jps1.py:183-230:
     on stdout like the reference's ``print(gscore[goal])`` (:207).
   * no path  -> ``(0, secs)`` with the int literal 0 (callers test ``path1[0] is 0``, global_planner_st.py:287).
   * start outside the array -> IndexError (numpy raises it in the reference).
-Difference (documented in DESIGN.md): interior points are turning points of an optimal path, not the
-reference's jump points; the cost is identical.
+Interior points: by default the turning points of an optimal path (all the callers need: they index path[1], path[2]
+and convert to an ndarray).  ``jps1.POINTS = "jump"`` returns the jump points instead -- every cell of the path at which
+the reference's ``jump`` (:95-164) would have stopped, i.e. the list the reference itself returns for that cell path
+(when several optimal paths exist the reference's heap order picks one of them, the wavefront another: same cost).
 """
 import time
 
@@ -25,6 +27,7 @@ from . import api
 from ._lib import FX_COST_OVERFLOW, FX_COST_START_OOB, FuxiError
 
 _MAX_PATH = 1024
+POINTS = "turning"      # or "jump": the reference's jump-point list (fx_jump_points_host)
 
 
 class _Fast:
@@ -94,6 +97,8 @@ def method(matrix, start, goal, hchoice):
     endtime = time.time()
     if cost_i < 0:
         return (0, round(endtime - starttime, 6))
+    if POINTS == "jump" and n > 1:
+        rows = api.jump_points_host(occ, rows)
     data = [(p[0], p[1]) for p in rows]
     data[0] = start
     if n == 1:

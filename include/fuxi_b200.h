@@ -123,6 +123,19 @@ int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int H,
 int fx_paths_compact(fx_context *ctx, const int32_t *path_xy, const int32_t *path_len, int Q, int max_path,
                      int64_t *offsets, int32_t *out_xy, int64_t cap, void *stream);
 
+/* Jump-point form of the paths (opt-in): the reference returns the jump points of its path (scripts/jps1.py:199-208), the
+ * search the turning points.  For each path this keeps, besides the turning points, every cell of its straight runs at
+ * which jps1.jump (:95-164) would have stopped -- the goal, a cell with a forced neighbour for the travel direction, on a
+ * diagonal run a cell whose straight sub-jump finds a jump point -- i.e. the list the reference would return for the same
+ * cell path.  path_xy / path_len as fx_search_batch wrote them; out_xy int32 [Q][max_out][2], out_len int32 [Q] (may exceed
+ * max_out: only max_out were stored; FX_COST_* is passed through). */
+int fx_paths_jump_points(fx_context *ctx, const uint8_t *grid, int W, int H, const int32_t *path_xy, const int32_t *path_len,
+                         int Q, int max_path, int32_t *out_xy, int32_t *out_len, int max_out, void *stream);
+/* host-buffer form for one path (the drop-in jps1.method with POINTS = "jump"); h_grid == NULL reuses the grid the last
+ * fx_plan_host* call on ctx uploaded */
+int fx_jump_points_host(fx_context *ctx, const uint8_t *h_grid, int W, int H, const int32_t *h_path_xy, int n,
+                        int32_t *h_out_xy, int max_out, int32_t *h_out_len);
+
 /* Successor rule of the batched search, exposed for parity tests (pure host function, no GPU needed).
  * Replaces: scripts/jps1.py:49-93 `nodeNeighbours` (natural + forced neighbours of a cell given the direction it
  * was reached by), in single-step form.  code: 0..7 = arrival direction in the order (-1,0) (+1,0) (0,-1) (0,+1)
@@ -306,6 +319,23 @@ int fx_cloud_filter_host(fx_context *ctx, const float *h_pts, int64_t n, const f
  * pts / out: double [n][3]; d_count: device int32 = rows written.  Bit-exact against the reference function. */
 int fx_distance_filter(fx_context *ctx, const double *pts, int64_t n, double dis, double *out, int32_t *d_count, void *stream);
 int fx_distance_filter_host(fx_context *ctx, const double *h_pts, int64_t n, double dis, double *h_out, int64_t *h_count);
+
+/* fx_transform_filter: the cloud the node publishes, scripts/plc_point2_st.py:243-256 + 336-339 (= plc_point2_ccst.py:310-326,
+ * 405-408), float64 like the reference:
+ *   camera branch (h_R9 != NULL): b = (z_c + 0.12, -x_c, -y_c); e = R b + t with R = utils.body_to_earth_frame(r, p, y)
+ *     (row major, utils.py:21-28) and t = local_pos1, each component ((R_k0 b0 + R_k1 b1) + R_k2 b2) + t_k with one rounding per
+ *     operation; keep e_z > zmin (0.3 in the reference);
+ *   octomap-centres branch (h_R9 == NULL, plc_point2_st.py:351-362): e = p;
+ *   then q = e - c (c = local_pos); box > 0: keep |q_k| < box on every axis (:361, 4 in the reference); distance_filter(q, dis):
+ *     keep ||q|| < dis, order by (||q||, z, y, x) like np.lexsort; out = q + c.
+ * pts: n points of `stride` elements each (x y z first), float32 (is_f64 == 0: PointCloud2 data) or float64.  out: double [n][3];
+ * d_count: device int32 = rows written.  The appended [n_dyn, 0, 0] row (:341) and the float32 packing (a18) stay on the host. */
+int fx_transform_filter(fx_context *ctx, const void *pts, int64_t n, int stride, int is_f64, const double *h_R9,
+                        const double *h_t3, const double *h_c3, double zmin, double box, double dis, double *out,
+                        int32_t *d_count, void *stream);
+int fx_transform_filter_host(fx_context *ctx, const void *h_pts, int64_t n, int stride, int is_f64, const double *h_R9,
+                             const double *h_t3, const double *h_c3, double zmin, double box, double dis, double *h_out,
+                             int64_t *h_count);
 
 #ifdef __cplusplus
 }

@@ -19,8 +19,8 @@ Projection (octomap_server / ccmapping, un-vendored, unpinned) and EDT (not in t
 are "parity unpinned": their semantics are defined in DESIGN.md and checked against numpy/scipy.
 """
 from .capi import (build, lib_path, jps, jps_batch, sssp_field, sssp_cost, sssp_batch,
-                   inflate, edt, num_threads, cloud_filter)
+                   inflate, edt, num_threads, cloud_filter, jump)
 from . import hostref
 
 __all__ = ["build", "lib_path", "jps", "jps_batch", "sssp_field", "sssp_cost", "sssp_batch",
-           "inflate", "edt", "num_threads", "cloud_filter", "hostref"]
+           "inflate", "edt", "num_threads", "cloud_filter", "jump", "hostref"]

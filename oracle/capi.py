@@ -49,6 +49,8 @@ def _load():
     lib.fxo_cloud_filter.argtypes = [f32p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                      C.c_double, C.c_int, f32p, C.c_int64, i64p]
     lib.fxo_cloud_filter.restype = C.c_int
+    lib.fxo_jump.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
+    lib.fxo_jump.restype = C.c_int
     for f in ("fxo_jps", "fxo_jps_batch", "fxo_sssp", "fxo_sssp_batch", "fxo_inflate", "fxo_edt", "fxo_num_threads"):
         getattr(lib, f).restype = C.c_int
     _lib = lib
@@ -87,6 +89,16 @@ def jps(matrix, start, goal, hchoice, max_path=1 << 16):
         return 0, None, exp.value
     n = min(plen.value, max_path)
     return [tuple(int(v) for v in p) for p in path[:n]], cost.value, exp.value
+
+
+def jump(matrix, cell, direction, goal):
+    """Restated jps1.jump(cX, cY, dX, dY, matrix, goal): the jump point as a tuple, or None."""
+    occ = _occ(matrix)
+    W, H = occ.shape
+    out = np.zeros(2, dtype=np.int32)
+    r = _load().fxo_jump(_p(occ, C.c_uint8), W, H, int(cell[0]), int(cell[1]), int(direction[0]), int(direction[1]),
+                         int(goal[0]), int(goal[1]), _p(out, C.c_int32))
+    return (int(out[0]), int(out[1])) if r else None
 
 
 def jps_batch(matrix, starts, goals, hchoice, threads=0):

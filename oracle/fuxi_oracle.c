@@ -652,6 +652,16 @@ int fxo_cloud_filter(const float *pts, int64_t n, int stride, int rgb_off, float
     return 0;
 }
 
+/* scripts/jps1.py:95-164 on its own (tests of the jump-point path form): returns 1 and the jump point, or 0 for None */
+int fxo_jump(const uint8_t *occ, int W, int H, int cX, int cY, int dX, int dY, int gx, int gy, int32_t *rxy)
+{
+    grid_t g = {occ, W, H};
+    int rx = 0, ry = 0;
+    if (!jump(&g, cX, cY, dX, dY, gx, gy, &rx, &ry)) return 0;
+    rxy[0] = rx; rxy[1] = ry;
+    return 1;
+}
+
 int fxo_num_threads(void)
 {
 #ifdef _OPENMP

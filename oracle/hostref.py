@@ -266,6 +266,30 @@ def height_filter(plc_c, zmin=0.3):
     return plc_c[plc_c[:, 2] > zmin]
 
 
+def node_cloud(plc, rpy, pos, dt=0.0, ang_vel=(0.0, 0.0, 0.0), line_vel=(0.0, 0.0, 0.0), local_pos=None, zmin=0.3, dis=4.0):
+    """What the cloud node publishes on /points_global_all, scripts/plc_point2_st.py:243-256 + 336-339: transform, height
+    filter, `plc1 - local_pos`, distance_filter(.., 4), `+ local_pos`.  The rotation is applied with an explicit summation
+    order, ((R_k0*b0 + R_k1*b1) + R_k2*b2) + t_k (the reference hands the product to BLAS through np.matmul, whose order is
+    not specified: tests/golden/make_cloud_golden.py records how far the two are apart -- a few ulps)."""
+    plc = np.asarray(plc, dtype=np.float64)
+    b0, b1, b2 = plc[:, 2] + 0.12, -plc[:, 0], -plc[:, 1]
+    r, p, y = np.array(rpy, dtype=float) + dt * np.array(ang_vel, dtype=float)
+    R = body_to_earth_frame(r, p, y)
+    t = dt * np.array(line_vel, dtype=float) + np.array(pos, dtype=float)
+    e = np.stack([((R[k, 0] * b0 + R[k, 1] * b1) + R[k, 2] * b2) + t[k] for k in range(3)], axis=1)
+    e = e[e[:, 2] > zmin]
+    c = np.array(pos if local_pos is None else local_pos, dtype=float)
+    return distance_filter(e - c, dis) + c
+
+
+def octomap_local(centres, local_pos, box=4.0, dis=4.0):
+    """/octomap_point_cloud_centers_local, scripts/plc_point2_st.py:357-362."""
+    c = np.array(local_pos, dtype=float)
+    q = np.asarray(centres, dtype=np.float64) - c
+    q = q[(abs(q) < box).all(axis=1)]
+    return distance_filter(q, dis) + c
+
+
 # --------------------------------------------------------------------------- a17 / a18
 def distance_filter(plc, dis):
     """scripts/plc_point2_st.py:139-148: keep |p| < dis, sort by (d, z, y, x) (np.lexsort: last key primary)."""

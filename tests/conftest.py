@@ -83,3 +83,15 @@ def inline_golden():
 def cfg4_golden():
     with open(os.path.join(GOLDEN, "cfg4_golden.json")) as fh:
         return json.load(fh)
+
+
+@pytest.fixture(scope="session")
+def cloud_golden():
+    """Outputs of the reference's own cloud-node lines (tests/golden/make_cloud_golden.py)."""
+    z = np.load(os.path.join(GOLDEN, "cloud_golden.npz"))
+    cases = []
+    for i in range(int(z["ncase"][0])):
+        par = z["par_%d" % i]
+        cases.append(dict(cam=z["cam_%d" % i], rpy=par[0:3], pos=par[3:6], local_pos=par[6:9], ang_vel=par[9:12], line_vel=par[12:15],
+                          dt=float(par[15]), out=z["out_%d" % i], cen=z["cen_%d" % i], octo=z["octo_%d" % i]))
+    return cases

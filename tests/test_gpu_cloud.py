@@ -163,3 +163,30 @@ def test_distance_filter_device_entry(fx, oracle):
     m = int(count.item())
     assert m == len(want)
     assert np.array_equal(out[:m].cpu().numpy().view(np.uint64), want.view(np.uint64))
+
+
+def test_node_cloud_vs_restatement_and_reference_lines(fx, oracle, cloud_golden):
+    """fx_transform_filter (the cloud the node publishes: transform + height filter + range filter + distance sort in
+    float64) bit for bit against the restatement, and against the reference's own lines to 4 ulps (np.matmul's order);
+    the octomap-centres branch bit-exact against the reference's own output."""
+    n_rows = 0
+    for c in cloud_golden:
+        got = fx.cloud.node_cloud_host(c["cam"], c["rpy"], c["pos"], c["dt"], c["ang_vel"], c["line_vel"], local_pos=c["local_pos"])
+        want = oracle.hostref.node_cloud(c["cam"], c["rpy"], c["pos"], c["dt"], c["ang_vel"], c["line_vel"], c["local_pos"])
+        assert np.array_equal(got, want)
+        assert got.shape == c["out"].shape
+        assert (np.abs(got - c["out"]) <= 4 * np.finfo(np.float64).eps * np.maximum(np.abs(c["out"]), 1.0)).all()
+        # float64 input (np.array of read_points tuples) gives the same as the float32 PointCloud2 data
+        got64 = fx.cloud.node_cloud_host(c["cam"].astype(np.float64), c["rpy"], c["pos"], c["dt"], c["ang_vel"], c["line_vel"], local_pos=c["local_pos"])
+        assert np.array_equal(got64, got)
+        assert np.array_equal(fx.cloud.octomap_local_host(c["cen"], c["local_pos"]), c["octo"])
+        n_rows += len(got)
+    assert n_rows > 3000
+    # edge cases: empty cloud, nothing in range, NaN points
+    z = np.zeros((0, 3), dtype=np.float32)
+    assert fx.cloud.node_cloud_host(z, (0, 0, 0), (0, 0, 1)).shape == (0, 3)
+    far = np.full((10, 3), 50.0, dtype=np.float32)
+    assert fx.cloud.node_cloud_host(far, (0, 0, 0), (0, 0, 1)).shape == (0, 3)
+    p = np.array([[0.1, -0.2, 1.0], [np.nan, 0.0, 1.0], [0.0, 0.0, 2.0]], dtype=np.float32)
+    got = fx.cloud.node_cloud_host(p, (0, 0, 0), (0, 0, 1))
+    assert np.array_equal(got, oracle.hostref.node_cloud(p, (0, 0, 0), (0, 0, 1))) and len(got) == 2

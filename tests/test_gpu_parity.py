@@ -672,3 +672,67 @@ def test_paths_compact_and_host_csr(fx, dev, oracle):
     for q in range(40):
         k = max(int(a[3][q]), 0)
         assert np.array_equal(b[4][b[3][q]:b[3][q + 1]], a[2][q, :k])
+
+
+def _check_jump_list(oracle, m, jp, tp, s, g, want_cost, ws, wd):
+    """jp: jump-point list of the path whose turning points are tp."""
+    a, b = validate_path(m, jp, s, g)
+    assert a * ws + b * wd == want_cost
+    it = iter(jp)
+    assert all(any(tuple(p) == tuple(q) for q in it) for p in tp), "turning points must be a subsequence of the jump points"
+    for p, q in zip(jp[:-1], jp[1:]):
+        d = (int(np.sign(q[0] - p[0])), int(np.sign(q[1] - p[1])))
+        assert oracle.jump(m, p, d, g) == tuple(q), ("not what jps1.jump returns", p, d, q)
+
+
+def test_jump_point_path_form(fx, dev, oracle, maps, golden):
+    """Opt-in jump-point output (fx_paths_jump_points / jps1.POINTS = "jump"): every consecutive pair of the returned list
+    is exactly what the reference's jump() returns from the first point in that direction (checked with the restated
+    jump, itself pinned on the reference in tests/test_oracle.py), the list contains the turning points, costs unchanged.
+    Where the reference's own path (jps1_golden.json) runs through the same cells the two lists are identical."""
+    import contextlib
+    import io
+    rng = np.random.default_rng(12)
+    same = total = 0
+    for name in sorted(maps)[::4]:
+        m = maps[name]
+        recs = [r for r in golden["maps"][name] if r["h"] == 1 and r["cost"] is not None and "path" in r]
+        s = np.array([r["start"] for r in recs], dtype=np.int32)
+        g = np.array([r["goal"] for r in recs], dtype=np.int32)
+        res = fx.plan_batch(_t(m, dev), _t(s, dev), _t(g, dev), metric=1, max_path=512)
+        jxy, jl = fx.paths_jump_points(_t(m, dev), res.path_xy, res.path_len)
+        jxy, jl = jxy.cpu().numpy(), jl.cpu().numpy()
+        for q, r in enumerate(recs):
+            if s[q].tolist() == g[q].tolist():
+                continue
+            tp = res.path(q)
+            jp = [tuple(int(v) for v in p) for p in jxy[q, :jl[q]]]
+            _check_jump_list(oracle, m, jp, tp, tuple(s[q]), tuple(g[q]), int(float(r["cost"])), 10, 14)
+            total += 1
+            same += jp == [tuple(p) for p in r["path"]]
+    assert total > 100 and same >= 1, (same, total)
+    print("jump-point lists identical to the reference's own:", same, "of", total)
+    # a large random grid, both metrics
+    m = (rng.random((1024, 1024)) < 0.2).astype(np.uint8)
+    s, g = random_queries(m, 64, rng)
+    for metric, ws, wd in ((1, 10, 14), (2, fx.FX_EUCLID_WS, fx.FX_EUCLID_WD)):
+        res = fx.plan_batch(_t(m, dev), _t(s, dev), _t(g, dev), metric=metric, max_path=2048)
+        jxy, jl = fx.paths_jump_points(_t(m, dev), res.path_xy, res.path_len, max_out=4096)
+        jxy, jl, ci = jxy.cpu().numpy(), jl.cpu().numpy(), res.cost_i.cpu().numpy()
+        for q in range(0, 64, 4):
+            if ci[q] > 0:
+                _check_jump_list(oracle, m, [tuple(int(v) for v in p) for p in jxy[q, :jl[q]]], res.path(q), tuple(s[q]), tuple(g[q]), int(ci[q]), ws, wd)
+    # the drop-in
+    name = "-16.40-4.80_out.png"
+    mf = maps[name].astype(np.float64)
+    old = fx.jps1.POINTS
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            fx.jps1.POINTS = "turning"
+            tp, _ = fx.jps1.method(mf, (0, 0), (147, 51), 1)
+            fx.jps1.POINTS = "jump"
+            jp, _ = fx.jps1.method(mf, (0, 0), (147, 51), 1)
+    finally:
+        fx.jps1.POINTS = old
+    assert len(jp) >= len(tp) and jp[0] == (0, 0) and jp[-1] == (147, 51)
+    _check_jump_list(oracle, maps[name], jp, tp, (0, 0), (147, 51), 1674, 10, 14)

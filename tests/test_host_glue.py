@@ -156,3 +156,24 @@ def test_plan_assembly_matches_reference_lines(inline_golden):
         off = -1 if c["variant"] == "st" else 0
         assert list(a.goal) == [want["map_goal0"][k] + want["map_d"][k] + off for k in (0, 1)]
         assert list(a.start) == want["map_start"]
+
+
+def test_node_cloud_restatement_vs_reference_lines(oracle, cloud_golden):
+    """a15 -> a16 -> a17 as the node runs them (plc_point2_st.py:244-256, 336-339, 360-362): the restatement in
+    oracle/hostref.py against the outputs of the reference's own lines.  The reference multiplies through np.matmul (BLAS:
+    summation order unspecified), the restatement with an explicit order: same points, same order, coordinates to 4 ulps;
+    the octomap-centres branch has no product in it and is bit-exact."""
+    worst = 0.0
+    for c in cloud_golden:
+        got = oracle.hostref.node_cloud(c["cam"], c["rpy"], c["pos"], c["dt"], c["ang_vel"], c["line_vel"], c["local_pos"])
+        assert got.shape == c["out"].shape
+        err = np.abs(got - c["out"]) / np.maximum(np.abs(c["out"]), 1.0)
+        worst = max(worst, float(err.max()) if err.size else 0.0)
+        assert np.array_equal(oracle.hostref.octomap_local(c["cen"], c["local_pos"]), c["octo"])
+    assert worst <= 4 * np.finfo(np.float64).eps, worst
+
+
+def test_rotation_elementwise_has_the_reference_bits(hostfn_golden):
+    from fuxi_planner_b200 import cloud
+    for a, R in zip(hostfn_golden["rpy"], hostfn_golden["R"]):
+        assert np.array_equal(cloud.rotation_elementwise(*a), R)

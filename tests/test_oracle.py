@@ -276,3 +276,24 @@ def test_cloud_filter_oracle_against_numpy(oracle):
     assert dist.max() < 1e-5
     assert abs(int(c[2]) - int(keep.sum())) <= int(borderline.sum())
     assert c[2] > 50
+
+
+def test_oracle_jump_matches_reference_golden(oracle, maps):
+    """oracle.jump (the restated jps1.jump, scripts/jps1.py:95-164) against probes answered by the unmodified reference
+    (tests/golden/make_jump_golden.py): the checker of the GPU jump-point tests is itself pinned."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jump_golden.json")) as fh:
+        recs = json.load(fh)
+    n = hits = 0
+    for rec in recs:
+        if "grid" in rec:
+            m = np.unpackbits(np.array(rec["grid"], dtype=np.uint8))[: rec["W"] * rec["H"]].reshape(rec["W"], rec["H"])
+        else:
+            m = maps[rec["name"]]
+        for cx, cy, dx, dy, gx, gy, rx, ry in rec["probes"]:
+            got = oracle.jump(m, (cx, cy), (dx, dy), (gx, gy))
+            assert got == ((rx, ry) if rx >= 0 else None), (rec["name"], cx, cy, dx, dy, gx, gy, got, rx, ry)
+            n += 1
+            hits += rx >= 0
+    assert n > 4000 and hits > 1500
