@@ -64,6 +64,8 @@ struct fx_context {
     unsigned *proj_bits;
     int inflate_attr_set;
     size_t proj_bits_cap;
+    unsigned *proj_part; size_t proj_part_bytes;  // partition form: region buffers + counters + overflow flag
+    int proj_attr_set;
     // EDT scratch
     uint16_t *edt_g;
     uint16_t *edt_s, *edt_t;

@@ -258,11 +258,11 @@ __global__ void __launch_bounds__(128) k_edt_cols_exact(const uint16_t *__restri
 //               (built from three-word windows with funnel shifts), the per-cell level index, and the output is
 //               written with 16-byte streaming stores.  Traffic: bits in, int32 out -- the algorithmic 5 B/cell.
 //   k_edt_fix:  brute-force search on the bit grid for the listed cells.
-#define EDT_R 10
+#define EDT_R 12 /* 10 left 0.18 % of the cells of a 2 %-filled grid to the fix-up kernel (22 % of the time); 12 leaves 0.011 % */
 #define EDT_BT_ROWS 64
 #define EDT_BT_WORDS 8
-#define EDT_MAX_PAIRS 128
-#define EDT_MAX_LEVELS 80
+#define EDT_MAX_PAIRS 256
+#define EDT_MAX_LEVELS 128
 #define EDT_BITS_SMEM (4 * (EDT_R + 1) * (EDT_BT_ROWS + 2 * EDT_R) * EDT_BT_WORDS + 4 * (EDT_BT_ROWS + 2 * EDT_R) * (EDT_BT_WORDS + 2))
 // distinct D = d^2 + r^2 (0 <= d, r <= EDT_R) in increasing order, limited to D <= EDT_R^2 (beyond that a pair with a
 // larger d or r, which the tile does not hold, could win); built at compile time so that the level walk is straight-line
@@ -310,16 +310,16 @@ __device__ __forceinline__ unsigned edt_pairs(const unsigned *__restrict__ base)
 // level LV settles the cells in `nw`; their squared distance D (a compile-time constant) is recorded bit-sliced:
 // plane k collects the cells whose D has bit k set -- no per-cell work, no divergence
 template <int LV>
-__device__ __forceinline__ void edt_levels(const unsigned *__restrict__ base, unsigned &done, unsigned (&pl)[7])
+__device__ __forceinline__ void edt_levels(const unsigned *__restrict__ base, unsigned &done, unsigned (&pl)[8])
 {
     constexpr EdtLevels tab = edt_make_levels();
     if constexpr (LV < tab.nlevels) {
         const unsigned nw = edt_pairs<tab.start[LV], tab.start[LV + 1]>(base) & ~done;
         done |= nw;
         constexpr int D = tab.D[LV];
-        static_assert(D < 128, "seven bit planes");
+        static_assert(D < 256, "eight bit planes");
 #pragma unroll
-        for (int k = 0; k < 7; k++)
+        for (int k = 0; k < 8; k++)
             if ((D >> k) & 1) pl[k] |= nw;
         if (done != 0xFFFFFFFFu) edt_levels<LV + 1>(base, done, pl);
     }
@@ -344,9 +344,7 @@ __global__ void __launch_bounds__(EDT_BT_ROWS * EDT_BT_WORDS) k_edt_bits(const u
                                                                          unsigned *__restrict__ fix_list, unsigned *__restrict__ fix_count, unsigned fix_cap,
                                                                          int *__restrict__ flag)
 {
-    __shared__ unsigned s_cnt, s_base;
-    __shared__ unsigned s_list[1024];  // unresolved cells of this tile, (row << 8 | column); more than that: give up (flag)
-    if (threadIdx.x == 0) s_cnt = 0;
+    (void)flag;
     constexpr int ROWS = EDT_BT_ROWS + 2 * EDT_R, TW = EDT_BT_WORDS;
     extern __shared__ __align__(16) unsigned char edt_smem[];
     unsigned(*T)[ROWS][TW] = reinterpret_cast<unsigned(*)[ROWS][TW]>(edt_smem);                                   // [EDT_R + 1]
@@ -379,16 +377,17 @@ __global__ void __launch_bounds__(EDT_BT_ROWS * EDT_BT_WORDS) k_edt_bits(const u
     {
         const int row = tid / TW, ww = tid - row * TW, tr = row + EDT_R;
         const int x = x0 + row, w = w0 + ww;
+        unsigned um = 0;
         if (x < W && w < HW) {
             unsigned done = 0;
-            unsigned pl[7] = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            unsigned pl[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
             edt_levels<0>(&T[0][tr][ww], done, pl);
             int4 *dst = reinterpret_cast<int4 *>(out + ((size_t)x * HW + w) * 32);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 unsigned acc = 0;  // four cells, one byte each
 #pragma unroll
-                for (int k = 0; k < 7; k++) acc |= ((((pl[k] >> (4 * j)) & 0xFu) * 0x00204081u) & 0x01010101u) << k;
+                for (int k = 0; k < 8; k++) acc |= ((((pl[k] >> (4 * j)) & 0xFu) * 0x00204081u) & 0x01010101u) << k;
                 const unsigned dn = done >> (4 * j);
                 int4 v;
                 v.x = (dn & 1u) ? (int)(acc & 0xFFu) : 0x7FFFFFFF;
@@ -397,26 +396,29 @@ __global__ void __launch_bounds__(EDT_BT_ROWS * EDT_BT_WORDS) k_edt_bits(const u
                 v.w = (dn & 8u) ? (int)(acc >> 24) : 0x7FFFFFFF;
                 __stcs(dst + j, v);
             }
-            unsigned um = ~done;  // farther than EDT_R from every obstacle: fix-up list
+            um = ~done;  // farther than EDT_R from every obstacle: fix-up list
+        }
+        // The unresolved cells go straight to the global list, one reservation per warp: no block barrier after the walk (its
+        // length differs from word to word -- the barrier that used to collect a per-tile list was the top stall of this
+        // kernel, r01: 8.2 per issue), warps retire as they finish.  A list longer than fix_cap makes k_edt_fix raise the
+        // flag and the windowed path redoes the grid.
+        const unsigned lane = (unsigned)tid & 31u;
+        const unsigned mine = (unsigned)__popc(um);
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (unsigned)o) incl += t; }
+        const unsigned total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (total) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(fix_count, total);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            size_t pos = (size_t)base + (incl - mine);
             while (um) {
                 const int b = __ffs(um) - 1;
                 um &= um - 1;
-                const unsigned pos = atomicAdd(&s_cnt, 1u);
-                if (pos < 1024u) s_list[pos] = ((unsigned)row << 8) | (unsigned)(ww * 32 + b);
+                if (pos < fix_cap) { fix_list[2 * pos] = (unsigned)x; fix_list[2 * pos + 1] = (unsigned)(w * 32 + b); }
+                pos++;
             }
-        }
-    }
-    __syncthreads();
-    const unsigned cnt = s_cnt;
-    if (cnt == 0) return;
-    if (cnt > 1024u) { if (tid == 0) *flag = 1; return; }  // a sparse tile: the windowed path redoes the grid
-    if (tid == 0) s_base = atomicAdd(fix_count, cnt);
-    __syncthreads();
-    for (unsigned i = tid; i < cnt; i += blockDim.x) {
-        const size_t pos = (size_t)s_base + i;
-        if (pos < fix_cap) {
-            fix_list[2 * pos] = (unsigned)(x0 + (int)(s_list[i] >> 8));
-            fix_list[2 * pos + 1] = (unsigned)(w0 * 32 + (int)(s_list[i] & 0xFFu));
         }
     }
 }
