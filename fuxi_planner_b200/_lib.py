@@ -15,7 +15,7 @@ FX_EUCLID_WS = 2378
 FX_EUCLID_WD = 3363
 
 # every symbol include/fuxi_b200.h declares (tests/test_boundary.py checks the .so exports all of them)
-SYMBOLS = ["fx_create", "fx_destroy", "fx_last_error", "fx_version", "fx_launch_count", "fx_set_search_tuning", "fx_canon_successors",
+SYMBOLS = ["fx_create", "fx_destroy", "fx_last_error", "fx_version", "fx_launch_count", "fx_set_search_tuning", "fx_set_search_form", "fx_canon_successors",
            "fx_project", "fx_inflate", "fx_edt", "fx_edt_rows", "fx_edt_cols", "fx_search_batch", "fx_field", "fx_field_relax", "fx_field_status",
            "fx_search_stats", "fx_search_kernel_ms", "fx_search_timings", "fx_plan_host", "fx_plan_host_f64", "fx_plan_host_csr", "fx_last_d2h_bytes",
            "fx_paths_compact", "fx_paths_jump_points", "fx_jump_points_host", "fx_map_host", "fx_halo_merge",
@@ -74,6 +74,7 @@ def load():
     lib.fx_launch_count.argtypes = [vp]
     lib.fx_launch_count.restype = i64
     lib.fx_set_search_tuning.argtypes = [vp, i32, i32]
+    lib.fx_set_search_form.argtypes = [vp, i32]
     lib.fx_canon_successors.argtypes = [i32, i32]
     lib.fx_project.argtypes = [vp, vp, i64, i32, C.POINTER(f32), f32, f32, f32, f32, f32, i32, i32, vp, i32, vp]
     lib.fx_inflate.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
@@ -148,6 +149,10 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def set_search_form(self, form):
+        """"auto" (by batch size), "throughput" (forward searches only: forward-canonical paths) or "latency" (bidirectional)."""
+        self.check(self.lib.fx_set_search_form(self.handle, {"auto": 0, "throughput": 1, "latency": 2}[form]), "fx_set_search_form")
 
     @property
     def launches(self):

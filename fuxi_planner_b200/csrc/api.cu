@@ -86,7 +86,7 @@ extern "C" int fx_destroy(fx_context *ctx)
                    ctx->seeds, ctx->seeds_sorted, ctx->seed_hist, ctx->edt_g, ctx->edt_s, ctx->edt_t, ctx->edt_flag,
                    ctx->d_grid, ctx->d_grid2, ctx->d_q, ctx->d_out_i, ctx->d_out_f, ctx->d_path, ctx->d_pts, ctx->proj_bits, ctx->q_order, ctx->q_ubound, ctx->bfields,
                    ctx->d_msg, ctx->d_rp, ctx->d_cpath, ctx->d_coff, ctx->cl_bits, ctx->cl_gpref, ctx->cl_chunk, ctx->cl_vidx, ctx->cl_keep, ctx->cl_gpref2,
-                   ctx->cl_chunk2, ctx->cl_acc, ctx->cl_vox, ctx->cl_state, ctx->cl_out, ctx->df_rec, ctx->tf_q, ctx->proj_part};
+                   ctx->cl_chunk2, ctx->cl_acc, ctx->cl_vox, ctx->cl_state, ctx->cl_out, ctx->df_rec, ctx->tf_q};
     for (size_t i = 0; i < sizeof(dev) / sizeof(dev[0]); i++)
         if (dev[i]) cudaFree(dev[i]);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -110,6 +110,13 @@ extern "C" int fx_set_search_tuning(fx_context *ctx, int slots, int band0)
     }
     ctx->cfg_slots = slots;
     ctx->cfg_band0 = band0;
+    return FX_OK;
+}
+
+extern "C" int fx_set_search_form(fx_context *ctx, int form)
+{
+    if (!ctx || form < 0 || form > 2) return FX_ERR_ARG;
+    ctx->cfg_wide_below = form == 0 ? -1 : (form == 1 ? 0 : 0x7FFFFFFF);
     return FX_OK;
 }
 
@@ -331,11 +338,26 @@ static int plan_host_impl(fx_context *ctx, const uint8_t *h_grid, const double *
             memcpy(csr->h_offsets, offs, ((size_t)Q + 1) * 8);
             if (csr->h_total) *csr->h_total = total;
             const int64_t ncopy = total < csr->cap ? total : csr->cap;
-            if (ncopy > 0) memcpy(csr->h_xy, pin + off_p, (size_t)ncopy * 8);
+            if (ncopy > 0) par_memcpy(csr->h_xy, pin + off_p, (size_t)ncopy * 8);
         } else {
-            for (int q = 0; q < Q; q++) {
-                const int64_t n = offs[q + 1] - offs[q];
-                if (n > 0) memcpy(h_path_xy + (size_t)q * max_path * 2, pin + off_p + (size_t)offs[q] * 8, (size_t)n * 8);
+            // scatter into the caller's padded rows: a few host threads when the batch is large (the rows of a fresh
+            // numpy array are untouched pages: the page faults, not the copies, dominate a single thread)
+            auto rows = [=](int a, int b) {
+                for (int q = a; q < b; q++) {
+                    const int64_t n = offs[q + 1] - offs[q];
+                    if (n > 0) memcpy(h_path_xy + (size_t)q * max_path * 2, pin + off_p + (size_t)offs[q] * 8, (size_t)n * 8);
+                }
+            };
+            unsigned hc = std::thread::hardware_concurrency();
+            const int nthreads = total < (1 << 18) ? 1 : (int)(hc == 0 ? 1 : (hc > 8 ? 8 : hc));
+            if (nthreads <= 1) rows(0, Q);
+            else {
+                std::vector<std::thread> th;
+                const int per = (Q + nthreads - 1) / nthreads;
+                for (int t = 1; t < nthreads; t++)
+                    if (t * per < Q) th.emplace_back(rows, t * per, (t + 1) * per < Q ? (t + 1) * per : Q);
+                rows(0, per < Q ? per : Q);
+                for (auto &t : th) t.join();
             }
         }
     }

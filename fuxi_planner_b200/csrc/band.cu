@@ -115,9 +115,11 @@ __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) k_band_bound(const
         const int L = xmajor ? abs(ddx) : abs(ddy);
         const int sgn = (xmajor ? ddx : ddy) >= 0 ? 1 : -1;
         const int as = xmajor ? sx : sy, bs = xmajor ? sy : sx;
-        const long long slope = ((long long)(xmajor ? ddy : ddx) * 65536) / L;  // minor offset per major step, 2^-16
+        // minor offset per major step in 2^-15 fixed point: |slope| <= 2^15 and |tt| < 2^15 + 48, so tt * slope fits 32 bits
+        // (a third of this kernel's instructions were the 64-bit form of this product: r02b profile)
+        const int slope = (int)(((long long)(xmajor ? ddy : ddx) * 32768) / L);
         const int tmax = L + 2 * BAND_M;
-        auto off = [&](int tt) { return (int)(((long long)tt * slope + 32768) >> 16); };
+        auto off = [&](int tt) { return (tt * slope + 16384) >> 15; };
         // field slot of cell (x, y), or -1 outside the band
         auto slot_of = [&](int x, int y) {
             const int tt = ((xmajor ? x : y) - as) * sgn;

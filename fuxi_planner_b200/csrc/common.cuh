@@ -64,8 +64,6 @@ struct fx_context {
     unsigned *proj_bits;
     int inflate_attr_set;
     size_t proj_bits_cap;
-    unsigned *proj_part; size_t proj_part_bytes;  // partition form: region buffers + counters + overflow flag
-    int proj_attr_set;
     // EDT scratch
     uint16_t *edt_g;
     uint16_t *edt_s, *edt_t;
@@ -99,7 +97,7 @@ struct fx_context {
     cudaEvent_t ev_search[2];  // around the last k_search_batch launch (fx_search_kernel_ms)
     cudaEvent_t ev_band[2];    // around the last k_band_bound launch (fx_search_timings)
     int ev_search_valid;
-    int small_attr_set, cfg_small_off;
+    int small_attr_set, cfg_small_off, lat_attr_set;
 };
 
 int fx_set_err(fx_context *ctx, int code, const char *fmt, ...);

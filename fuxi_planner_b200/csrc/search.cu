@@ -33,6 +33,7 @@
 
 #define FLAG_OVERFLOW 1u
 #define FLAG_UNREACH 2u /* bidirectional pass: one side exhausted its component unpruned without meeting the other */
+#define FX_LAT_SQ 2048 /* latency form: entries per bucket half kept in shared memory (4 x 2 x 2048 x 8 B = 128 KiB) */
 #define FX_POCKET_BUDGET 4096u /* queue pops of the bounded flood from the goal */
 
 // -DFX_PHASE_CLOCKS: tuning build that accumulates, for warp 0 of every CTA, the cycles spent in each dependent step of
@@ -195,9 +196,14 @@ struct __align__(16) CtaState {
 // imply the condition above, so whatever it returns is the optimum, and it fires at the first level the condition
 // holds.  A start on an obstacle can leave it but cannot be entered: the goal side never labels it, and c != start
 // because the test needs k >= 2.  The cell that proposed the minimum is returned in S.meet.
-template <int METRIC, bool BIDIR>
+//
+// SQ > 0 (latency form, one CTA per SM): the first SQ entries of each half of each bucket live in shared memory
+// (sq[4][2][SQ], 64 * SQ bytes), the rest spills to the global queue.  A level of a 4096^2 query holds a few hundred
+// entries per half, so the pop of a level no longer waits for an L2 round trip on the queue before it can issue the
+// field load: one dependent L2 access per level instead of two.
+template <int METRIC, bool BIDIR, int SQ>
 __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *__restrict__ s_lut, const int *__restrict__ s_step,
-                             uint32_t *__restrict__ field, uint8_t *__restrict__ dirty, uint2 *__restrict__ queue,
+                             uint32_t *__restrict__ field, uint8_t *__restrict__ dirty, uint2 *__restrict__ queue, uint2 *__restrict__ sq,
                              int sx, int sy, int gx, int gy, uint32_t U0, float bandL, unsigned budget, bool *budget_hit)
 {
     constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
@@ -212,6 +218,15 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
     // cell index (move masks) and field index (cost word: + side_cells for the goal side) of a queue entry's packed xy
     auto cell_of = [&](uint32_t exy) { return (unsigned)fx_cidx((int)((exy >> 16) & 0x7FFFu), (int)(exy & 0xFFFFu), H, TY); };
     auto foff_of = [&](uint32_t exy) { return BIDIR ? (exy >> 31) * side_cells : 0u; };
+    // entry j of class c (0: straight arrivals, 1: diagonal arrivals) of bucket slot b
+    auto q_load = [&](unsigned b, unsigned c, unsigned j) -> uint2 {
+        if (SQ > 0 && j < (unsigned)SQ) return sq[(b * 2u + c) * (unsigned)SQ + j];
+        return __ldcg(queue + (size_t)b * qcap + (c ? qhalf : 0u) + j);
+    };
+    auto q_store = [&](unsigned b, unsigned c, unsigned j, uint2 v) {
+        if (SQ > 0 && j < (unsigned)SQ) sq[(b * 2u + c) * (unsigned)SQ + j] = v;
+        else __stcg(queue + (size_t)b * qcap + (c ? qhalf : 0u) + j, v);
+    };
 
     if (tid == 0) {
         S.tailS[0] = BIDIR ? 2 : 1; S.tailS[1] = 0; S.tailS[2] = 0; S.tailS[3] = 0;
@@ -222,12 +237,12 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
         for (int a = 0; a < 8; a++) S.alive[a >> 2][a & 3] = 0;
         S.alive[0][0] = 1; S.alive[1][0] = 1;
         S.xlo = min(S.xlo, sx - 1); S.xhi = max(S.xhi, sx + 1);
-        __stcg(queue, make_uint2(((uint32_t)sx << 16) | (uint32_t)sy, fx_pack(0u, FX_CODE_START)));
+        q_store(0u, 0u, 0u, make_uint2(((uint32_t)sx << 16) | (uint32_t)sy, fx_pack(0u, FX_CODE_START)));
         __stcg(field + sidx, fx_pack(0u, FX_CODE_START));
         dirty[sidx >> FX_DIRTY_SHIFT] = 1;
         if (BIDIR) {
             S.xlo = min(S.xlo, gx - 1); S.xhi = max(S.xhi, gx + 1);
-            __stcg(queue + 1, make_uint2(0x80000000u | ((uint32_t)gx << 16) | (uint32_t)gy, fx_pack(0u, FX_CODE_START)));
+            q_store(0u, 0u, 1u, make_uint2(0x80000000u | ((uint32_t)gx << 16) | (uint32_t)gy, fx_pack(0u, FX_CODE_START)));
             __stcg(field + (side_cells + gidx), fx_pack(0u, FX_CODE_START));
             dirty[(side_cells + gidx) >> FX_DIRTY_SHIFT] = 1;
         }
@@ -294,19 +309,17 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
         if (nS > qhalf || nD > qhalf) { if (tid == 0) S.flags |= FLAG_OVERFLOW; break; }  // entries beyond a half were dropped at push time
         if (tid == 0) { S.tailS[(k + 3) & 3] = 0; S.tailD[(k + 3) & 3] = 0; }  // bucket k-1 is done; levels k+1.. will refill this slot
         const uint32_t U = S.U;
-        const uint2 *__restrict__ qk = queue + (size_t)(k & 3) * qcap;
-        uint2 *__restrict__ q1 = queue + (size_t)((k + 1) & 3) * qcap;
-        uint2 *__restrict__ q2 = queue + (size_t)((k + 2) & 3) * qcap;
+        const unsigned bk = k & 3u, b1 = (k + 1u) & 3u, b2 = (k + 2u) & 3u;
         const uint32_t kbase = k * WS;
         const bool meet_level = BIDIR && k >= k_meet;
-        auto slot_of = [&](unsigned i) { return i < nS ? i : qhalf + (i - nS); };
+        auto pop = [&](unsigned i) { return i < nS ? q_load(bk, 0u, i) : q_load(bk, 1u, i - nS); };
         // Two-deep software pipeline over the rounds of a level: while round r is processed, the cost word and move mask
         // of round r+1 and the queue entry of round r+2 are already in flight, so only the first round of a level waits
         // for two dependent L2 round trips.  Loading a cell's word before this level's own reductions are issued is safe:
         // the cells popped in level k hold costs of bucket k and every reduction of level k carries a cost of bucket
         // k+1 or later, so their words do not change during the level.
-        uint2 e_cur = (unsigned)tid < n ? __ldcg(qk + slot_of((unsigned)tid)) : make_uint2(0u, 0u);
-        uint2 e_nxt = (unsigned)tid + (unsigned)nthreads < n ? __ldcg(qk + slot_of((unsigned)tid + (unsigned)nthreads)) : make_uint2(0u, 0u);
+        uint2 e_cur = (unsigned)tid < n ? pop((unsigned)tid) : make_uint2(0u, 0u);
+        uint2 e_nxt = (unsigned)tid + (unsigned)nthreads < n ? pop((unsigned)tid + (unsigned)nthreads) : make_uint2(0u, 0u);
         unsigned idx_cur = cell_of(e_cur.x), fo_cur = foff_of(e_cur.x);
         uint32_t v_cur = FX_INF;
         unsigned m_cur = 0;
@@ -323,7 +336,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
             v_cur = FX_INF;
             m_cur = 0;
             if (i + nthreads < n) { v_cur = __ldcg(field + (idx_cur + fo_cur)); m_cur = (unsigned)__ldg(moves + idx_cur); }
-            if (i + 2u * nthreads < n) e_nxt = __ldcg(qk + slot_of(i + 2u * nthreads));
+            if (i + 2u * nthreads < n) e_nxt = pop(i + 2u * nthreads);
             const int x = (int)((e.x >> 16) & 0x7FFFu), y = (int)(e.x & 0xFFFFu);
             const bool side = BIDIR && (e.x >> 31) != 0u;
             PH_MARK(0, e.x)  // queue entry arrived
@@ -366,8 +379,8 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
                 // ~1-2 cycles each; cheaper than a warp scan + broadcast, and no warp-collective in the loop body)
                 const unsigned ns = (unsigned)__popc(succ & 0x0Fu), nd = (unsigned)__popc(succ & 0xF0u);
                 if (ns) posS = fx_atoms_add(&S.tailS[(k + 1) & 3], ns);
-                if (nd) posD = qhalf + fx_atoms_add(&S.tailD[(k + (diag2 ? 2 : 1)) & 3], nd);
-                if (posS + ns > qhalf || posD + nd > qcap) succ = 0;  // no room: the tail counts flag the overflow at the next level
+                if (nd) posD = fx_atoms_add(&S.tailD[(k + (diag2 ? 2 : 1)) & 3], nd);
+                if (posS + ns > qhalf || posD + nd > qhalf) succ = 0;  // no room: the tail counts flag the overflow at the next level
                 if (BIDIR) {
                     if (ns) S.alive[side ? 1 : 0][(k + 1) & 3] = 1;
                     if (nd) S.alive[side ? 1 : 0][(k + (diag2 ? 2 : 1)) & 3] = 1;
@@ -376,8 +389,13 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
             PH_MARK(3, posS + posD)  // queue space reserved
             // the loop below runs as often as the busiest lane of the warp has successors, so it is kept short: the
             // child's packed xy, its tiled index and its packed value are one table lookup + one add each
-            uint2 *__restrict__ qS = q1 + posS;
-            uint2 *__restrict__ qD = (diag2 ? q2 : q1) + posD;
+            const unsigned bD = diag2 ? b2 : b1;
+            // global slots (pointer bumps in the loop below: the throughput form's inner loop is exactly the r01 one) and,
+            // with SQ, the shared-memory heads of the same bucket halves
+            uint2 *__restrict__ gS = queue + (size_t)b1 * qcap + posS;
+            uint2 *__restrict__ gD = queue + (size_t)bD * qcap + qhalf + posD;
+            uint2 *__restrict__ sS = SQ > 0 ? sq + (b1 * 2u) * (unsigned)SQ : nullptr;
+            uint2 *__restrict__ sD = SQ > 0 ? sq + (bD * 2u + 1u) * (unsigned)SQ : nullptr;
             const uint32_t nvS = fx_pack(g + WS, 0u), nvD = fx_pack(g + WD, 0u);
             const int *__restrict__ stp = s_step + 2 * (idx & 63);  // tile-local position (x & 7) << 3 | (y & 7)
             uint32_t *__restrict__ fbase = field + (idx + fo);
@@ -388,8 +406,13 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
                 const uint32_t nv = (d < 4 ? nvS : nvD) | (unsigned)d;
                 fx_red_min(fbase + st.y, nv);
                 const uint2 child = make_uint2(e.x + (uint32_t)st.x, nv);  // keeps the side bit
-                if (d < 4) __stcg(qS++, child);
-                else __stcg(qD++, child);
+                if (d < 4) {
+                    if (SQ > 0 && posS < (unsigned)SQ) sS[posS] = child; else __stcg(gS, child);
+                    gS++; posS++;
+                } else {
+                    if (SQ > 0 && posD < (unsigned)SQ) sD[posD] = child; else __stcg(gD, child);
+                    gD++; posD++;
+                }
             }
             PH_MARK(4, posS)  // children relaxed and appended
             PH_COUNT(6, 1)    // rounds (warp 0)
@@ -403,10 +426,9 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
     PH_FLUSH
     // entries that were never popped (buckets k and k+1; k+2 is still empty at the top of a level): mark their lines too
     for (unsigned b = k; b <= k + 1; b++) {
-        const uint2 *__restrict__ qb = queue + (size_t)(b & 3) * qcap;
         const unsigned mS = min(S.tailS[b & 3], qhalf), mD = min(S.tailD[b & 3], qhalf);
         for (unsigned i = (unsigned)tid; i < mS + mD; i += (unsigned)nthreads) {
-            const uint32_t xy = __ldcg(qb + (i < mS ? i : qhalf + (i - mS))).x;
+            const uint32_t xy = (i < mS ? q_load(b & 3u, 0u, i) : q_load(b & 3u, 1u, i - mS)).x;
             dirty[(cell_of(xy) + foff_of(xy)) >> FX_DIRTY_SHIFT] = 1;
         }
     }
@@ -539,6 +561,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
     __shared__ __align__(8) int s_step[8 * 64 * 2];  // [direction][x&7][y&7] -> (step of the packed xy, step of the tiled index)
     __shared__ int s_npts, s_seg[3];
     __shared__ unsigned s_ab[2];
+    extern __shared__ __align__(16) unsigned char fx_dyn_smem[];
+    uint2 *sq = reinterpret_cast<uint2 *>(fx_dyn_smem);  // latency form: heads of the bucket queues (run_pass, SQ)
+    (void)sq;
     const int tid = threadIdx.x;
     const int slot = blockIdx.x;
     uint32_t *field = P.fields + (size_t)slot * P.cells * (LAT ? 2 : 1);  // LAT: [start side | goal side]
@@ -604,7 +629,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
             for (int attempt = 0; attempt < 6; attempt++) {
                 const bool last = attempt == 5 || U_try >= 0x7FFFFFFFull;
                 const uint32_t U0 = last ? 0x7FFFFFFFu : (uint32_t)U_try;
-                const uint32_t r = run_pass<METRIC, true>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, U0, -1.f, 0u, &hit);
+                const uint32_t r = run_pass<METRIC, true, FX_LAT_SQ>(P, S, s_lut, s_step, field, dirty, queue, sq, sx, sy, gx, gy, U0, -1.f, 0u, &hit);
                 passes++;
                 bidir = true;
                 overflow = (S.flags & FLAG_OVERFLOW) != 0;
@@ -622,7 +647,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
             // step into) the query is unreachable and the forward search need not flood the start's whole component.
             // If the flood reaches the start its cost is the exact answer and pass A is skipped.
             {
-                uint32_t back = run_pass<METRIC, false>(P, S, s_lut, s_step, field, dirty, queue, gx, gy, sx, sy, 0x7FFFFFFFu, -1.f, FX_POCKET_BUDGET, &hit);
+                uint32_t back = run_pass<METRIC, false, 0>(P, S, s_lut, s_step, field, dirty, queue, nullptr, gx, gy, sx, sy, 0x7FFFFFFFu, -1.f, FX_POCKET_BUDGET, &hit);
                 passes++;
                 overflow = (S.flags & FLAG_OVERFLOW) != 0;
                 const bool start_free = P.grid[(size_t)sx * H + sy] != 1;
@@ -647,7 +672,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
             const uint32_t hint = P.ubound ? P.ubound[q] : FX_INF;
             if (!overflow && !unreachable && best == FX_INF && hint != FX_INF) {
                 if (hint == h0) {
-                    best = run_pass<METRIC, false>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, h0, (float)P.band0 * L, 0u, &hit);
+                    best = run_pass<METRIC, false, 0>(P, S, s_lut, s_step, field, dirty, queue, nullptr, sx, sy, gx, gy, h0, (float)P.band0 * L, 0u, &hit);
                     passes++;
                     overflow = (S.flags & FLAG_OVERFLOW) != 0;
                     if (best != FX_INF) { exact = true; band_only++; }
@@ -664,7 +689,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
                 uint64_t U64 = (uint64_t)h0 + slack;
                 uint32_t U0 = (last || U64 > 0x7FFFFFFFull) ? 0x7FFFFFFFu : (uint32_t)U64;
                 float bandL = last ? -1.f : band * L;
-                best = run_pass<METRIC, false>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, U0, bandL, 0u, &hit);
+                best = run_pass<METRIC, false, 0>(P, S, s_lut, s_step, field, dirty, queue, nullptr, sx, sy, gx, gy, U0, bandL, 0u, &hit);
                 passes++;
                 overflow = (S.flags & FLAG_OVERFLOW) != 0;
                 if (overflow) break;
@@ -678,7 +703,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
             if (!overflow && !unreachable && best != FX_INF && !exact) {
                 __syncthreads();
                 reset_slot(S, field, dirty, P.dirty_n, P.cells, H, false);
-                best = run_pass<METRIC, false>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, best, -1.f, 0u, &hit);
+                best = run_pass<METRIC, false, 0>(P, S, s_lut, s_step, field, dirty, queue, nullptr, sx, sy, gx, gy, best, -1.f, 0u, &hit);
                 passes++;
                 overflow = (S.flags & FLAG_OVERFLOW) != 0;
             }
@@ -834,7 +859,9 @@ extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int 
     P.fields = X.fields; P.dirty = X.dirty; P.queues = reinterpret_cast<uint2 *>(X.queues); P.tmp_path = X.tmp_path;
     P.cells = X.cells; P.dirty_n = X.dirty_n; P.qcap = X.qcap; P.path_cap = X.path_cap;
     P.counters = ctx->counters;
-    P.band0 = ctx->cfg_band0 > 0 ? ctx->cfg_band0 : 16;
+    // half-width (cells along the minor axis) of the band-limited passes of the search kernel; one more than the band kernel's
+    // 15 + rounding of its fixed-point centre line, so that a path the band kernel found lies inside it
+    P.band0 = ctx->cfg_band0 > 0 ? ctx->cfg_band0 : 17;
     P.order = nullptr; P.ubound = nullptr;
     FX_CUDA(ctx, cudaEventRecord(ctx->ev_band[0], st));
     if (which == 0) {
@@ -847,8 +874,14 @@ extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int 
     int blocks = X.slots < Q ? X.slots : Q;
     FX_CUDA(ctx, cudaEventRecord(ctx->ev_search[0], st));
     if (which == 1) {
-        if (metric == 1) k_search_batch<1, FX_SEARCH_WIDE, 1, true><<<blocks, FX_SEARCH_WIDE, 0, st>>>(P);
-        else k_search_batch<2, FX_SEARCH_WIDE, 1, true><<<blocks, FX_SEARCH_WIDE, 0, st>>>(P);
+        const size_t sm = (size_t)4 * 2 * FX_LAT_SQ * sizeof(uint2);
+        if (!ctx->lat_attr_set) {
+            FX_CUDA(ctx, cudaFuncSetAttribute(k_search_batch<1, FX_SEARCH_WIDE, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            FX_CUDA(ctx, cudaFuncSetAttribute(k_search_batch<2, FX_SEARCH_WIDE, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            ctx->lat_attr_set = 1;
+        }
+        if (metric == 1) k_search_batch<1, FX_SEARCH_WIDE, 1, true><<<blocks, FX_SEARCH_WIDE, sm, st>>>(P);
+        else k_search_batch<2, FX_SEARCH_WIDE, 1, true><<<blocks, FX_SEARCH_WIDE, sm, st>>>(P);
     } else {
         if (metric == 1) k_search_batch<1, FX_SEARCH_THREADS, FX_SEARCH_MINB, false><<<blocks, FX_SEARCH_THREADS, 0, st>>>(P);
         else k_search_batch<2, FX_SEARCH_THREADS, FX_SEARCH_MINB, false><<<blocks, FX_SEARCH_THREADS, 0, st>>>(P);

@@ -89,7 +89,16 @@ def method(matrix, start, goal, hchoice):
     if hchoice not in (1, 2):
         raise ValueError("hchoice must be 1 or 2")
     occ = np.asarray(matrix)
-    cost_i, cost_f, n, rows = _plan_one(occ, start, goal, hchoice)
+    if POINTS == "jump":
+        # the jump-point list needs a forward-canonical path: forward searches only (fx_set_search_form)
+        ctx = api.default_context(0)
+        ctx.set_search_form("throughput")
+        try:
+            cost_i, cost_f, n, rows = _plan_one(occ, start, goal, hchoice)
+        finally:
+            ctx.set_search_form("auto")
+    else:
+        cost_i, cost_f, n, rows = _plan_one(occ, start, goal, hchoice)
     if cost_i == FX_COST_START_OOB:
         raise IndexError("index %r is out of bounds for the %dx%d map" % (tuple(start), occ.shape[0], occ.shape[1]))
     if cost_i == FX_COST_OVERFLOW:

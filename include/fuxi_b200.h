@@ -53,8 +53,14 @@ int         fx_version(void);                   /* ABI version, currently 1 */
 /* number of kernels this library launched through ctx since creation (bench.py: gpu_launches) */
 int64_t     fx_launch_count(fx_context *ctx);
 /* tuning: number of concurrent search slots (0 = auto: 8 per SM, bounded by half of the free memory) and the
- * half-width in cells of the first (band-limited) search attempt (0 = default 16) */
+ * half-width in cells of the band-limited passes of the search kernel (0 = default 17) */
 int         fx_set_search_tuning(fx_context *ctx, int slots, int band0);
+/* which form of the batched kernel fx_search_batch uses on maps too large for the shared-memory kernel: 0 = by batch size
+ * (default: at most one query per SM -> latency form, else throughput form), 1 = always the throughput form (band kernel +
+ * one forward search per query: every path is forward-canonical, which fx_paths_jump_points needs to reproduce the
+ * reference's jump-point list), 2 = always the latency form (bidirectional: the goal side's half of a path is canonical
+ * for the REVERSE direction).  Costs are identical in all forms. */
+int         fx_set_search_form(fx_context *ctx, int form);
 
 /* ---- (1) point cloud -> 2D occupancy grid ---------------------------------------------------
  * Replaces: the camera->earth transform + height filter of scripts/plc_point2_st.py:244-256
@@ -128,7 +134,10 @@ int fx_paths_compact(fx_context *ctx, const int32_t *path_xy, const int32_t *pat
  * which jps1.jump (:95-164) would have stopped -- the goal, a cell with a forced neighbour for the travel direction, on a
  * diagonal run a cell whose straight sub-jump finds a jump point -- i.e. the list the reference would return for the same
  * cell path.  path_xy / path_len as fx_search_batch wrote them; out_xy int32 [Q][max_out][2], out_len int32 [Q] (may exceed
- * max_out: only max_out were stored; FX_COST_* is passed through). */
+ * max_out: only max_out were stored; FX_COST_* is passed through).  The result is a list jps1.method could return (every
+ * consecutive pair is what jps1.jump yields) when the path is forward-canonical: the shared-memory kernel and the
+ * throughput form produce such paths, the bidirectional latency form does not (fx_set_search_form(ctx, 1) selects the
+ * throughput form for any batch size). */
 int fx_paths_jump_points(fx_context *ctx, const uint8_t *grid, int W, int H, const int32_t *path_xy, const int32_t *path_len,
                          int Q, int max_path, int32_t *out_xy, int32_t *out_len, int max_out, void *stream);
 /* host-buffer form for one path (the drop-in jps1.method with POINTS = "jump"); h_grid == NULL reuses the grid the last

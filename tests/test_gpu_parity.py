@@ -715,13 +715,30 @@ def test_jump_point_path_form(fx, dev, oracle, maps, golden):
     # a large random grid, both metrics
     m = (rng.random((1024, 1024)) < 0.2).astype(np.uint8)
     s, g = random_queries(m, 64, rng)
-    for metric, ws, wd in ((1, 10, 14), (2, fx.FX_EUCLID_WS, fx.FX_EUCLID_WD)):
-        res = fx.plan_batch(_t(m, dev), _t(s, dev), _t(g, dev), metric=metric, max_path=2048)
-        jxy, jl = fx.paths_jump_points(_t(m, dev), res.path_xy, res.path_len, max_out=4096)
-        jxy, jl, ci = jxy.cpu().numpy(), jl.cpu().numpy(), res.cost_i.cpu().numpy()
-        for q in range(0, 64, 4):
-            if ci[q] > 0:
-                _check_jump_list(oracle, m, [tuple(int(v) for v in p) for p in jxy[q, :jl[q]]], res.path(q), tuple(s[q]), tuple(g[q]), int(ci[q]), ws, wd)
+    ctx = fx.Context(0)
+    ctx.set_search_form("throughput")      # forward searches only: forward-canonical paths (a batch this small would be bidirectional)
+    try:
+        for metric, ws, wd in ((1, 10, 14), (2, fx.FX_EUCLID_WS, fx.FX_EUCLID_WD)):
+            res = fx.plan_batch(_t(m, dev), _t(s, dev), _t(g, dev), metric=metric, max_path=2048, ctx=ctx)
+            jxy, jl = fx.paths_jump_points(_t(m, dev), res.path_xy, res.path_len, max_out=4096, ctx=ctx)
+            jxy, jl, ci = jxy.cpu().numpy(), jl.cpu().numpy(), res.cost_i.cpu().numpy()
+            for q in range(0, 64, 4):
+                if ci[q] > 0:
+                    _check_jump_list(oracle, m, [tuple(int(v) for v in p) for p in jxy[q, :jl[q]]], res.path(q), tuple(s[q]), tuple(g[q]), int(ci[q]), ws, wd)
+    finally:
+        ctx.close()
+    # the drop-in on a map beyond the shared-memory kernel: jump mode switches to forward searches by itself
+    mf = m.astype(np.float64)
+    old = fx.jps1.POINTS
+    try:
+        fx.jps1.POINTS = "jump"
+        with contextlib.redirect_stdout(io.StringIO()):
+            jp, _ = fx.jps1.method(mf, tuple(int(v) for v in s[1]), tuple(int(v) for v in g[1]), 1)
+    finally:
+        fx.jps1.POINTS = old
+    for p, q in zip(jp[:-1], jp[1:]):
+        d = (int(np.sign(q[0] - p[0])), int(np.sign(q[1] - p[1])))
+        assert oracle.jump(m, p, d, tuple(int(v) for v in g[1])) == tuple(q)
     # the drop-in
     name = "-16.40-4.80_out.png"
     mf = maps[name].astype(np.float64)
