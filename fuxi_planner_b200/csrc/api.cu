@@ -53,6 +53,8 @@ extern "C" int fx_create(int device, fx_context **out)
     }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->cfg_wide_below = -1;
+    ctx->cfg_cluster = 1;
+    if (const char *e = getenv("FUXI_B200_CLUSTER")) ctx->cfg_cluster = e[0] != '0';  // tests run the latency form both ways
     if (const char *e = getenv("FUXI_B200_WIDE_BELOW")) ctx->cfg_wide_below = atoi(e);  // tuning experiments only
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
     e = cudaMalloc(&ctx->counters, 16 * sizeof(unsigned long long));

@@ -30,6 +30,7 @@ struct fx_context {
     // tuning
     int cfg_slots;
     int cfg_band0;
+    int cfg_cluster;     // latency form: batches of at most sm_count / 8 queries run one query per thread-block cluster (FUXI_B200_CLUSTER=0: off)
     int cfg_wide_below;  // batches of at most this many queries use the wide (latency) CTA form; -1 = sm_count
 
     // search scratch, one set per kernel form (each sized for its sW x sH, reallocated when the shape changes):

@@ -26,6 +26,8 @@
 //   straight run per round trip, emitting turning points.
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #if !FX_TILED
 #error "search.cu relies on the 8x8-tiled scratch layout (step tables)"
@@ -775,6 +777,379 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
 }
 
 // ------------------------------------------------------------------------------------------------
+// cluster form of the latency kernel: one query per THREAD-BLOCK CLUSTER (FX_CL CTAs on FX_CL SMs)
+// ------------------------------------------------------------------------------------------------
+// A level of a single query is bound by what ONE SM can issue (r02 phase clocks: ~5900 cycles per level at ~700
+// entries, the uncoalesced loads / reductions of the entries fill the SM's LSU pipe), not by memory latency.  Here the
+// entries of a level are dealt over the CTAs of a cluster.  The wavefront state (CtaState) lives in the shared memory of
+// the cluster's rank-0 CTA and is read and updated by the others through distributed shared memory; queue space is
+// reserved once per warp and round (packed prefix scan of the three per-lane counts, then at most three remote atomics
+// by one lane) so that the remote counters see ~100 atomics per level instead of one per lane; one cluster barrier
+// (barrier.cluster arrive/wait) per level replaces the block barrier.  Same algorithm and same results as
+// run_pass<METRIC, true, *> (bidirectional, proof there).
+#define FX_CL 8
+#define FX_CL_THREADS 256
+
+template <int METRIC>
+__device__ uint32_t run_pass_cluster(const SearchParams &P, CtaState *S, const uint8_t *__restrict__ s_lut, const int *__restrict__ s_step,
+                                     uint32_t *__restrict__ field, uint8_t *__restrict__ dirty, uint2 *__restrict__ queue,
+                                     int sx, int sy, int gx, int gy, uint32_t U0)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
+    const int H = P.H, TY = P.TY;
+    const unsigned rank = cluster.block_rank();
+    const unsigned ctid = rank * blockDim.x + threadIdx.x, NT = FX_CL * blockDim.x, lane = threadIdx.x & 31u;
+    const unsigned qcap = (unsigned)P.qcap, qhalf = qcap >> 1;
+    const unsigned side_cells = (unsigned)P.cells;
+    const unsigned sidx = (unsigned)fx_cidx(sx, sy, H, TY), gidx = (unsigned)fx_cidx(gx, gy, H, TY);
+    const uint8_t *__restrict__ moves = P.moves;
+    auto cell_of = [&](uint32_t exy) { return (unsigned)fx_cidx((int)((exy >> 16) & 0x7FFFu), (int)(exy & 0xFFFFu), H, TY); };
+    auto foff_of = [&](uint32_t exy) { return (exy >> 31) * side_cells; };
+
+    if (ctid == 0) {
+        S->tailS[0] = 2; S->tailS[1] = 0; S->tailS[2] = 0; S->tailS[3] = 0;
+        S->tailD[0] = 0; S->tailD[1] = 0; S->tailD[2] = 0; S->tailD[3] = 0;
+        S->U = U0; S->pruned = 0; S->ovf_level = 0;
+        S->mu[0] = ~0ull; S->mu[1] = ~0ull; S->mu[2] = ~0ull; S->meet = 0;
+        S->prl[0] = 0; S->prl[1] = 0;
+        for (int a = 0; a < 8; a++) S->alive[a >> 2][a & 3] = 0;
+        S->alive[0][0] = 1; S->alive[1][0] = 1;
+        S->xlo = min(S->xlo, min(sx, gx) - 1); S->xhi = max(S->xhi, max(sx, gx) + 1);
+        __stcg(queue, make_uint2(((uint32_t)sx << 16) | (uint32_t)sy, fx_pack(0u, FX_CODE_START)));
+        __stcg(queue + 1, make_uint2(0x80000000u | ((uint32_t)gx << 16) | (uint32_t)gy, fx_pack(0u, FX_CODE_START)));
+        __stcg(field + sidx, fx_pack(0u, FX_CODE_START));
+        __stcg(field + (side_cells + gidx), fx_pack(0u, FX_CODE_START));
+        dirty[sidx >> FX_DIRTY_SHIFT] = 1;
+        dirty[(side_cells + gidx) >> FX_DIRTY_SHIFT] = 1;
+    }
+    cluster.sync();
+
+    unsigned my_settled = 0;
+    int my_xlo = 0x7FFFFFFF, my_xhi = -1;
+    unsigned k = 0, k3 = 0;
+    uint32_t result = FX_INF;
+    unsigned long long mu = ~0ull;
+    const uint32_t h0 = octile(abs(sx - gx), abs(sy - gy), WS, WD - WS);
+    const unsigned k_meet = h0 / (2u * WS) > 2u ? h0 / (2u * WS) - 2u : 0u;
+    const bool start_free = P.grid[(size_t)sx * H + sy] != 1;
+    for (;;) {
+        // all of this is rank 0's shared memory: complete since the last cluster barrier (see run_pass for why each word is
+        // stable while the CTAs pass this point at different times)
+        const unsigned nS = S->tailS[k & 3], nD = S->tailD[k & 3], n = nS + nD;
+        const unsigned n1 = S->tailS[(k + 1) & 3] + S->tailD[(k + 1) & 3];
+        const unsigned long long m_prev = S->mu[k3 == 0 ? 2 : k3 - 1];
+        mu = m_prev < mu ? m_prev : mu;
+        const uint32_t mc = (uint32_t)(mu >> 32);
+        if (mc != FX_INF && 2ull * k * WS > (unsigned long long)mc + WD) { result = mc; break; }
+        if (mc == FX_INF) {
+            const bool dead0 = !S->alive[0][k & 3] && !S->alive[0][(k + 1) & 3], dead1 = !S->alive[1][k & 3] && !S->alive[1][(k + 1) & 3];
+            if ((dead0 && !S->prl[0]) || (dead1 && !S->prl[1] && (start_free || k >= 2u))) { if (ctid == 0) S->flags |= FLAG_UNREACH; break; }
+        }
+        const unsigned ovl = S->ovf_level;
+        if (ovl != 0 && ovl <= k) { if (ctid == 0) S->flags |= FLAG_OVERFLOW; break; }
+        if ((n == 0 && n1 == 0) || (S->flags & FLAG_OVERFLOW)) { result = mc; break; }
+        if (nS > qhalf || nD > qhalf) { if (ctid == 0) S->flags |= FLAG_OVERFLOW; break; }
+        if (ctid == 0) {
+            S->tailS[(k + 3) & 3] = 0; S->tailD[(k + 3) & 3] = 0;
+            S->mu[k3 == 2 ? 0 : k3 + 1] = ~0ull; S->alive[0][(k + 3) & 3] = 0; S->alive[1][(k + 3) & 3] = 0;
+        }
+        const uint32_t U = S->U;
+        const uint2 *__restrict__ qk = queue + (size_t)(k & 3) * qcap;
+        uint2 *__restrict__ q1 = queue + (size_t)((k + 1) & 3) * qcap;
+        uint2 *__restrict__ q2 = queue + (size_t)((k + 2) & 3) * qcap;
+        const uint32_t kbase = k * WS;
+        const bool meet_level = k >= k_meet;
+        for (unsigned i0 = ctid - lane; i0 < n; i0 += NT) {
+            const unsigned i = i0 + lane;
+            bool act = i < n;
+            const uint2 e = act ? __ldcg(qk + (i < nS ? i : qhalf + (i - nS))) : make_uint2(0u, 0u);
+            const unsigned idx = cell_of(e.x), fo = foff_of(e.x);
+            uint32_t v = FX_INF;
+            unsigned m = 0;
+            if (act) { v = __ldcg(field + (idx + fo)); m = (unsigned)__ldg(moves + idx); }
+            const int x = (int)((e.x >> 16) & 0x7FFFu), y = (int)(e.x & 0xFFFFu);
+            const bool side = (e.x >> 31) != 0u;
+            const uint32_t g = e.y >> 4;
+            act = act && v == e.y;
+            uint32_t other = FX_INF;
+            if (meet_level && act) other = __ldcg(field + (idx + (side ? 0u : side_cells)));
+            unsigned flagbits = 0;  // bit 0/1: side 0/1 pruned; bits 2..5: alive[side][bucket k+1 / k+2]
+            if (act) {
+                dirty[(idx + fo) >> FX_DIRTY_SHIFT] = 1;
+                const int tx = side ? sx : gx, ty = side ? sy : gy;
+                const uint32_t h = octile(abs(x - tx), abs(y - ty), WS, WD - WS);
+                if (((uint64_t)g + h) > (uint64_t)U) { act = false; flagbits |= side ? 2u : 1u; }
+            }
+            if (other != FX_INF)
+                atomicMin(&S->mu[k3], ((unsigned long long)(g + (other >> 4)) << 32) | (unsigned long long)(e.x & 0x7FFFFFFFu));
+            unsigned succ = 0;
+            if (act) {
+                my_settled++; my_xlo = min(my_xlo, x); my_xhi = max(my_xhi, x);
+                succ = s_lut[((e.y & 15u) << 8) | m];
+                if (g + WD > FX_COST_MAX28) { S->ovf_level = k + 1; succ = 0; }
+            }
+            const bool diag2 = (g - kbase) + WD >= 2u * WS;
+            // queue space, once per warp: the three counts (straight -> k+1, diagonal -> k+1, diagonal -> k+2) ride one
+            // 32-bit word (10 bits each: at most 32 * 4 per warp) through one inclusive scan
+            const unsigned ns = (unsigned)__popc(succ & 0x0Fu), nd = (unsigned)__popc(succ & 0xF0u);
+            const unsigned mine = ns | ((diag2 ? 0u : nd) << 10) | ((diag2 ? nd : 0u) << 20);
+            unsigned incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (unsigned)o) incl += t; }
+            const unsigned tot = __shfl_sync(0xFFFFFFFFu, incl, 31), excl = incl - mine;
+            unsigned base = 0;
+            if (lane < 3u) {
+                const unsigned cnt = (tot >> (10u * lane)) & 1023u;
+                if (cnt) base = atomicAdd(lane == 0u ? &S->tailS[(k + 1) & 3] : &S->tailD[(k + (lane == 2u ? 2 : 1)) & 3], cnt);
+            }
+            const unsigned baseS = __shfl_sync(0xFFFFFFFFu, base, 0), baseA = __shfl_sync(0xFFFFFFFFu, base, 1), baseB = __shfl_sync(0xFFFFFFFFu, base, 2);
+            unsigned posS = baseS + (excl & 1023u);
+            unsigned posD = diag2 ? baseB + ((excl >> 20) & 1023u) : baseA + ((excl >> 10) & 1023u);
+            if (posS + ns > qhalf || posD + nd > qhalf) succ = 0;  // the tail counts flag the overflow at the next level
+            if (succ) {
+                if (ns || (nd && !diag2)) flagbits |= side ? 16u : 4u;
+                if (nd && diag2) flagbits |= side ? 32u : 8u;
+            }
+            const unsigned fb = __reduce_or_sync(0xFFFFFFFFu, flagbits);
+            if (lane == 0 && fb) {
+                if (fb & 1u) S->prl[0] = 1;
+                if (fb & 2u) S->prl[1] = 1;
+                if (fb & 4u) S->alive[0][(k + 1) & 3] = 1;
+                if (fb & 8u) S->alive[0][(k + 2) & 3] = 1;
+                if (fb & 16u) S->alive[1][(k + 1) & 3] = 1;
+                if (fb & 32u) S->alive[1][(k + 2) & 3] = 1;
+            }
+            uint2 *__restrict__ gS = q1 + posS;
+            uint2 *__restrict__ gD = (diag2 ? q2 : q1) + qhalf + posD;
+            const uint32_t nvS = fx_pack(g + WS, 0u), nvD = fx_pack(g + WD, 0u);
+            const int *__restrict__ stp = s_step + 2 * (idx & 63);
+            uint32_t *__restrict__ fbase = field + (idx + fo);
+            while (succ) {
+                const int d = __ffs(succ) - 1;
+                succ &= succ - 1;
+                const int2 st = *reinterpret_cast<const int2 *>(stp + 2 * 64 * d);
+                const uint32_t nv = (d < 4 ? nvS : nvD) | (unsigned)d;
+                fx_red_min(fbase + st.y, nv);
+                const uint2 child = make_uint2(e.x + (uint32_t)st.x, nv);
+                if (d < 4) __stcg(gS++, child);
+                else __stcg(gD++, child);
+            }
+        }
+        cluster.sync();
+        k++;
+        k3 = k3 == 2 ? 0 : k3 + 1;
+    }
+    // entries that were never popped: mark their lines too
+    for (unsigned b = k; b <= k + 1; b++) {
+        const uint2 *__restrict__ qb = queue + (size_t)(b & 3) * qcap;
+        const unsigned mS = min(S->tailS[b & 3], qhalf), mD = min(S->tailD[b & 3], qhalf);
+        for (unsigned i = ctid; i < mS + mD; i += NT) {
+            const uint32_t xy = __ldcg(qb + (i < mS ? i : qhalf + (i - mS))).x;
+            dirty[(cell_of(xy) + foff_of(xy)) >> FX_DIRTY_SHIFT] = 1;
+        }
+    }
+    {
+        const int wlo = __reduce_min_sync(0xFFFFFFFFu, my_xlo), whi = __reduce_max_sync(0xFFFFFFFFu, my_xhi);
+        const unsigned ws = __reduce_add_sync(0xFFFFFFFFu, my_settled);
+        if (lane == 0) {
+            if (whi >= 0) { atomicMin(&S->xlo, wlo - 1); atomicMax(&S->xhi, whi + 1); }
+            if (ws) atomicAdd(&S->settled, (unsigned long long)ws);
+        }
+    }
+    if (ctid == 0) { S->meet = (unsigned)(mu & 0x7FFFFFFFull); S->levels += k; }
+    cluster.sync();
+    if (ctid == 0) S->pruned = S->prl[0] | S->prl[1];
+    return result;
+}
+
+// reset of the lines the query touched, by all threads of the cluster (see reset_slot)
+__device__ void reset_slot_cluster(CtaState *S, uint32_t *__restrict__ field, uint8_t *__restrict__ dirty, size_t dirty_n, size_t cells, int H)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned ctid = cluster.block_rank() * blockDim.x + threadIdx.x, NT = FX_CL * blockDim.x;
+    cluster.sync();
+    const int xlo = max(S->xlo, 0), xhi = S->xhi;
+    const bool force = (S->flags & FLAG_OVERFLOW) != 0;
+    cluster.sync();
+    if (ctid == 0) { S->xlo = 0x7FFFFFFF; S->xhi = -1; }
+    if (xhi >= xlo) {
+        const size_t c_lo = (size_t)(xlo >> 3) * fx_tiles_y(H) * 64;
+        size_t c_hi = (size_t)((xhi >> 3) + 1) * fx_tiles_y(H) * 64;
+        if (c_hi > cells) c_hi = cells;
+        const size_t n16 = dirty_n / 16;
+        uint4 *d4 = reinterpret_cast<uint4 *>(dirty);
+        const uint4 inf4 = make_uint4(FX_INF, FX_INF, FX_INF, FX_INF);
+        for (int f = 0; f < 2; f++) {
+            const size_t base = (size_t)f * cells;
+            size_t i0 = ((base + c_lo) >> FX_DIRTY_SHIFT) / 16, i1 = (((base + c_hi) >> FX_DIRTY_SHIFT) + 15) / 16;
+            if (i1 > n16) i1 = n16;
+            for (size_t i = i0 + ctid; i < i1; i += NT) {
+                uint4 v = __ldcg(d4 + i);
+                if (force) v = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+                if ((v.x | v.y | v.z | v.w) == 0u) continue;
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    if (!w[a]) continue;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        if (!((w[a] >> (8 * b)) & 0xFFu)) continue;
+                        const size_t c0 = (i * 16 + a * 4 + b) << FX_DIRTY_SHIFT;
+                        if (c0 + 32 <= 2 * cells) {
+                            uint4 *f4 = reinterpret_cast<uint4 *>(field + c0);
+#pragma unroll
+                            for (int t = 0; t < 8; t++) __stcg(f4 + t, inf4);
+                        }
+                    }
+                }
+                __stcg(d4 + i, make_uint4(0, 0, 0, 0));
+            }
+        }
+    }
+    cluster.sync();
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(FX_CL_THREADS, 1) k_search_cluster(const SearchParams P)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
+    __shared__ CtaState S_local;
+    __shared__ uint8_t s_lut[9 * 256];
+    __shared__ __align__(8) int s_step[8 * 64 * 2];
+    __shared__ int s_out[6];  // rank 0: npts, n1, n2, drop, a, b of the extracted path
+    CtaState *S = cluster.map_shared_rank(&S_local, 0);
+    int *r_out = cluster.map_shared_rank(s_out, 0);
+    const unsigned rank = cluster.block_rank();
+    const int tid = threadIdx.x;
+    const unsigned ctid = rank * blockDim.x + tid, NT = FX_CL * blockDim.x;
+    const int slot = blockIdx.x / FX_CL;
+    uint32_t *field = P.fields + (size_t)slot * P.cells * 2;
+    uint8_t *dirty = P.dirty + (size_t)slot * P.dirty_n;
+    uint2 *queue = P.queues + (size_t)slot * 4 * P.qcap;
+    int32_t *tmp = P.tmp_path + (size_t)slot * P.path_cap * 4;
+    const int W = P.W, H = P.H;
+    if (ctid == 0) { S->settled = 0; S->levels = 0; S->flags = 0; S->xlo = 0x7FFFFFFF; S->xhi = -1; }
+    for (int i = tid; i < 9 * 256; i += blockDim.x) s_lut[i] = (uint8_t)fx_canon_succ((unsigned)(i >> 8), (unsigned)(i & 255));
+    for (int i = tid; i < 8 * 64; i += blockDim.x) {
+        const int d = i >> 6, xi = (i >> 3) & 7, yi = i & 7, dx = fx_dx(d), dy = fx_dy(d);
+        const int tx = (xi + dx) >> 3, ty = (yi + dy) >> 3;
+        s_step[2 * i] = dx * 65536 + dy;
+        s_step[2 * i + 1] = (tx * P.TY + ty) * 64 + ((((xi + dx) & 7) - xi) << 3) + (((yi + dy) & 7) - yi);
+    }
+    __syncthreads();
+    unsigned long long passes = 0;
+    for (;;) {
+        cluster.sync();
+        if (ctid == 0) { S->q = (int)atomicAdd(P.counters + 0, 1ull); S->flags = 0; }
+        cluster.sync();
+        const int q = S->q;
+        if (q >= P.Q) break;
+        const int sx = P.starts[2 * q], sy = P.starts[2 * q + 1], gx = P.goals[2 * q], gy = P.goals[2 * q + 1];
+        int32_t out_cost = FX_COST_UNREACHABLE;
+        bool trivial = true;
+        const bool s_in = sx >= 0 && sx < W && sy >= 0 && sy < H, g_in = gx >= 0 && gx < W && gy >= 0 && gy < H;
+        if (!s_in) out_cost = FX_COST_START_OOB;
+        else if (!g_in) out_cost = FX_COST_UNREACHABLE;
+        else if (sx == gx && sy == gy) out_cost = 0;
+        else if (P.grid[(size_t)gx * H + gy] == 1) out_cost = FX_COST_UNREACHABLE;
+        else if (P.moves[fx_cidx(sx, sy, H, P.TY)] == 0) out_cost = FX_COST_UNREACHABLE;
+        else {
+            bool any = false;
+            for (int d = 0; d < 8; d++) {
+                const int ux = gx - fx_dx(d), uy = gy - fx_dy(d);
+                if (ux >= 0 && ux < W && uy >= 0 && uy < H && ((P.moves[fx_cidx(ux, uy, H, P.TY)] >> d) & 1)) any = true;
+            }
+            if (any) trivial = false;
+        }
+        if (trivial) {
+            if (ctid == 0) {
+                P.cost_i[q] = out_cost;
+                if (P.cost_f) P.cost_f[q] = out_cost == 0 ? 0.0 : -1.0;
+                if (P.path_len) P.path_len[q] = out_cost == 0 ? 1 : out_cost;
+                if (out_cost == 0 && P.path_xy && P.max_path > 0) {
+                    P.path_xy[(size_t)q * P.max_path * 2] = sx; P.path_xy[(size_t)q * P.max_path * 2 + 1] = sy;
+                }
+            }
+            continue;
+        }
+        const uint32_t h0 = octile(abs(sx - gx), abs(sy - gy), WS, WD - WS);
+        uint32_t best = FX_INF;
+        bool overflow = false;
+        uint64_t U_try = (uint64_t)h0 + h0 / 128 + 4 * WD;
+        for (int attempt = 0; attempt < 6; attempt++) {
+            const bool last = attempt == 5 || U_try >= 0x7FFFFFFFull;
+            const uint32_t U0 = last ? 0x7FFFFFFFu : (uint32_t)U_try;
+            const uint32_t r = run_pass_cluster<METRIC>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, U0);
+            passes++;
+            cluster.sync();
+            const unsigned fl = S->flags, pruned = S->pruned;
+            overflow = (fl & FLAG_OVERFLOW) != 0;
+            if (overflow) break;
+            if (r != FX_INF && r <= U0) { best = r; break; }
+            if ((fl & FLAG_UNREACH) || last || (r == FX_INF && !pruned)) break;
+            U_try = r != FX_INF ? (uint64_t)r : (uint64_t)h0 + (U_try - h0) * 4;
+            reset_slot_cluster(S, field, dirty, P.dirty_n, P.cells, H);
+        }
+        if (overflow || (best != FX_INF && best > 0x7FFFFFFFu)) {
+            if (ctid == 0) {
+                P.cost_i[q] = FX_COST_OVERFLOW;
+                if (P.cost_f) P.cost_f[q] = -3.0;
+                if (P.path_len) P.path_len[q] = FX_COST_OVERFLOW;
+            }
+        } else if (best == FX_INF) {
+            if (ctid == 0) {
+                P.cost_i[q] = FX_COST_UNREACHABLE;
+                if (P.cost_f) P.cost_f[q] = -1.0;
+                if (P.path_len) P.path_len[q] = FX_COST_UNREACHABLE;
+            }
+        } else {
+            const int cap = P.path_cap;
+            if (rank == 0 && tid < 32) {
+                unsigned a = 0, b = 0;
+                int d1 = 8, d2 = 8;
+                const int mx = (int)(S->meet >> 16), my = (int)(S->meet & 0xFFFFu);
+                const int n1 = extract_path<METRIC>(P, field, sx, sy, mx, my, tmp, cap, &a, &b, &d1);
+                const int n2 = extract_path<METRIC>(P, field + P.cells, gx, gy, mx, my, tmp + 2 * (size_t)cap, cap, &a, &b, &d2);
+                if (tid == 0) {
+                    const int opp2 = d2 < 4 ? (d2 ^ 1) : (d2 < 8 ? 11 - d2 : 8);
+                    const int drop = (n1 > 1 && n2 > 1 && d1 == opp2) ? 1 : 0;
+                    s_out[0] = (n1 < 0 || n2 < 0) ? -1 : n1 + n2 - 1 - drop;
+                    s_out[1] = n1; s_out[2] = n2; s_out[3] = drop; s_out[4] = (int)a; s_out[5] = (int)b;
+                }
+            }
+            cluster.sync();
+            const int npts = r_out[0], n1 = r_out[1], n2 = r_out[2], drop = r_out[3];
+            if (ctid == 0) {
+                P.cost_i[q] = npts < 0 ? FX_COST_OVERFLOW : (int32_t)best;
+                if (P.cost_f)
+                    P.cost_f[q] = METRIC == 1 ? (double)best : __dadd_rn((double)(unsigned)r_out[4], __dmul_rn((double)(unsigned)r_out[5], 1.4142135623730951));
+                if (P.path_len) P.path_len[q] = npts < 0 ? FX_COST_OVERFLOW : npts;
+            }
+            if (P.path_xy && npts > 0 && npts <= P.max_path && n1 <= cap && n2 <= cap) {
+                const int nfirst = n1 - drop;
+                int32_t *out = P.path_xy + (size_t)q * P.max_path * 2;
+                for (int i = (int)ctid; i < npts; i += (int)NT) {
+                    const int32_t *src = i < nfirst ? tmp + 2 * (size_t)(n1 - 1 - i) : tmp + 2 * (size_t)cap + 2 * (size_t)(i - nfirst + 1);
+                    out[2 * i] = __ldcg(src); out[2 * i + 1] = __ldcg(src + 1);
+                }
+            }
+        }
+        reset_slot_cluster(S, field, dirty, P.dirty_n, P.cells, H);
+    }
+    cluster.sync();  // nobody leaves while rank 0's shared memory may still be read
+    if (ctid == 0) {
+        atomicAdd(P.counters + 1, S->settled);
+        atomicAdd(P.counters + 2, S->levels);
+        atomicAdd(P.counters + 3, passes);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 void fx_search_release(fx_context *ctx, int which)
@@ -873,7 +1248,23 @@ extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int 
     }
     int blocks = X.slots < Q ? X.slots : Q;
     FX_CUDA(ctx, cudaEventRecord(ctx->ev_search[0], st));
-    if (which == 1) {
+    const bool use_cluster = which == 1 && ctx->cfg_cluster && Q <= ctx->sm_count / FX_CL;
+    if (use_cluster) {
+        // at most one query per cluster of FX_CL SMs: the entries of a level are dealt over FX_CL SMs
+        cudaLaunchConfig_t cfg = {};
+        const int nclusters = Q < X.slots ? Q : X.slots;
+        cfg.gridDim = dim3((unsigned)(nclusters * FX_CL), 1, 1);
+        cfg.blockDim = dim3(FX_CL_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = FX_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (metric == 1) FX_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_search_cluster<1>, P));
+        else FX_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_search_cluster<2>, P));
+    } else if (which == 1) {
         const size_t sm = (size_t)4 * 2 * FX_LAT_SQ * sizeof(uint2);
         if (!ctx->lat_attr_set) {
             FX_CUDA(ctx, cudaFuncSetAttribute(k_search_batch<1, FX_SEARCH_WIDE, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

@@ -601,9 +601,30 @@ def test_search_cfg4_4096(fx, dev, oracle, cfg4_golden):
                 assert ci[q] == int(float(r["cost"])), (q, ci[q], r["cost"])
             else:
                 assert abs(cf[q] - float(r["cost"])) <= RTOL * float(r["cost"]), (q, cf[q], r["cost"])
-    # the small-batch (latency) form on the same grid: same costs
-    res1 = fx.plan_batch(gm, _t(s[:8], dev), _t(g[:8], dev), metric=2, max_path=2048)
-    assert np.array_equal(res1.cost_i.cpu().numpy(), ci[:8])
+    # the latency forms on the same grid: one query per thread-block cluster (at most sm_count / 8 queries), one query per
+    # CTA (at most sm_count queries; also what FUXI_B200_CLUSTER=0 selects for the smallest batches): same costs, valid paths
+    import os
+    for nq, env in ((8, None), (8, "0"), (40, None)):
+        old = os.environ.get("FUXI_B200_CLUSTER")
+        if env is not None:
+            os.environ["FUXI_B200_CLUSTER"] = env
+        try:
+            ctx = fx.Context(0)
+        finally:
+            if env is not None:
+                if old is None:
+                    del os.environ["FUXI_B200_CLUSTER"]
+                else:
+                    os.environ["FUXI_B200_CLUSTER"] = old
+        try:
+            res1 = fx.plan_batch(gm, _t(s[:nq], dev), _t(g[:nq], dev), metric=2, max_path=2048, ctx=ctx)
+            assert np.array_equal(res1.cost_i.cpu().numpy(), ci[:nq]), (nq, env)
+            for q in range(0, nq, 3):
+                if ci[q] > 0:
+                    a, b = validate_path(m, res1.path(q), tuple(s[q]), tuple(g[q]))
+                    assert a * fx.FX_EUCLID_WS + b * fx.FX_EUCLID_WD == ci[q]
+        finally:
+            ctx.close()
 
 
 def test_cfg5_field_vs_oracle(fx, dev, oracle):
