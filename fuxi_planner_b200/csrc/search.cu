@@ -779,92 +779,152 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
 // ------------------------------------------------------------------------------------------------
 // cluster form of the latency kernel: one query per THREAD-BLOCK CLUSTER (FX_CL CTAs on FX_CL SMs)
 // ------------------------------------------------------------------------------------------------
-// A level of a single query is bound by what ONE SM can issue (r02 phase clocks: ~5900 cycles per level at ~700
-// entries, the uncoalesced loads / reductions of the entries fill the SM's LSU pipe), not by memory latency.  Here the
-// entries of a level are dealt over the CTAs of a cluster.  The wavefront state (CtaState) lives in the shared memory of
-// the cluster's rank-0 CTA and is read and updated by the others through distributed shared memory; queue space is
-// reserved once per warp and round (packed prefix scan of the three per-lane counts, then at most three remote atomics
-// by one lane) so that the remote counters see ~100 atomics per level instead of one per lane; one cluster barrier
-// (barrier.cluster arrive/wait) per level replaces the block barrier.  Same algorithm and same results as
-// run_pass<METRIC, true, *> (bidirectional, proof there).
+// One SM issues ~19 instructions per settled cell whatever the form (r02f: 18.7 M warp instructions, 5.4 ms, for one
+// 983 k-cell query on one SM at 42 % issue utilisation), so a single query is bound by what ONE SM can issue.  Here the
+// entries of a level are dealt over the FX_CL CTAs of a cluster.  A first version kept the wavefront state in rank 0's
+// shared memory and let the other CTAs read it and reserve queue space through distributed shared memory: ~7 dependent
+// remote round trips per level, no faster than one CTA (r02e: 3.3 us per level either way; r02f: 92 % of the issue slots
+// idle, barrier + long-scoreboard stalls).  This version has NO remote read and NO remote atomic on the critical path:
+//   * every CTA appends the children it creates to its OWN queue segment (local shared-memory tails, one atomic per lane
+//     exactly like the one-CTA kernel);
+//   * at the end of a level every CTA broadcasts, with fire-and-forget stores into the shared memory of all CTAs of the
+//     cluster, the few words the others need: its segment's entry counts for the next two buckets, its best meeting
+//     proposal, its alive / pruned / overflow bits; one cluster barrier (barrier.cluster arrive.release / wait.acquire)
+//     publishes them, double-buffered by level parity;
+//   * at the top of a level every thread derives the same decisions from its CTA's local copy, and the level's entries
+//     -- the concatenation of the 2 * FX_CL (owner, class) runs -- are dealt out by global index: thread t of CTA r takes
+//     index r * blockDim + t (+ rounds), found in the runs by a 4-step binary search over a per-warp prefix table.
+// Same algorithm and results as run_pass<METRIC, true, *> (bidirectional; proof there).
 #define FX_CL 8
 #define FX_CL_THREADS 256
 
+struct ClState {
+    // local to this CTA
+    unsigned tailS[4], tailD[4];    // entries this CTA appended to its segment of bucket slot b (straight / diagonal arrivals)
+    unsigned alive[2][4];           // this CTA pushed an entry of side s into bucket slot b
+    unsigned prl[2];                // this CTA pruned a cell of side s
+    unsigned ovf;                   // this CTA saw a cost leave the 28-bit range / ran out of segment room
+    unsigned long long mu[2];       // this CTA's best proposal of the level (slot = level parity)
+    int xlo, xhi;                   // x-rows this CTA touched since the last reset
+    unsigned long long settled, levels;
+    // written by every CTA of the cluster (index = source rank), buffer = parity of the level that wrote it
+    uint4 r_cnt[2][FX_CL];          // {nS, nD of the next bucket, nS, nD of the one after}
+    unsigned long long r_mu[2][FX_CL];
+    unsigned r_flags[2][FX_CL];     // bits 0..7 alive[s][b] (s * 4 + b), 8..9 prl, 10 overflow
+    int r_x[2][FX_CL];              // pass end: xlo / xhi of every CTA
+    int r_q;                        // the query index rank 0 fetched
+    unsigned flags;                 // FLAG_* of the pass (every CTA derives the same value)
+    unsigned pruned, meet;
+};
+
 template <int METRIC>
-__device__ uint32_t run_pass_cluster(const SearchParams &P, CtaState *S, const uint8_t *__restrict__ s_lut, const int *__restrict__ s_step,
-                                     uint32_t *__restrict__ field, uint8_t *__restrict__ dirty, uint2 *__restrict__ queue,
-                                     int sx, int sy, int gx, int gy, uint32_t U0)
+__device__ uint32_t run_pass_cluster(const SearchParams &P, ClState &L, ClState *const *peers, const uint8_t *__restrict__ s_lut,
+                                     const int *__restrict__ s_step, uint32_t *__restrict__ field, uint8_t *__restrict__ dirty,
+                                     uint2 *__restrict__ queue, int sx, int sy, int gx, int gy, uint32_t U)
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
     const int H = P.H, TY = P.TY;
     const unsigned rank = cluster.block_rank();
-    const unsigned ctid = rank * blockDim.x + threadIdx.x, NT = FX_CL * blockDim.x, lane = threadIdx.x & 31u;
-    const unsigned qcap = (unsigned)P.qcap, qhalf = qcap >> 1;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, NTC = blockDim.x, NT = FX_CL * blockDim.x;
+    const unsigned segcap = ((unsigned)P.qcap / (2u * FX_CL)) & ~1u;   // entries per (owner, class) run of a bucket
     const unsigned side_cells = (unsigned)P.cells;
     const unsigned sidx = (unsigned)fx_cidx(sx, sy, H, TY), gidx = (unsigned)fx_cidx(gx, gy, H, TY);
     const uint8_t *__restrict__ moves = P.moves;
     auto cell_of = [&](uint32_t exy) { return (unsigned)fx_cidx((int)((exy >> 16) & 0x7FFFu), (int)(exy & 0xFFFFu), H, TY); };
     auto foff_of = [&](uint32_t exy) { return (exy >> 31) * side_cells; };
+    // run (owner o, class c) of bucket slot b starts here
+    auto run_base = [&](unsigned b, unsigned o, unsigned c) { return queue + ((size_t)(b * FX_CL + o) * 2u + c) * segcap; };
 
-    if (ctid == 0) {
-        S->tailS[0] = 2; S->tailS[1] = 0; S->tailS[2] = 0; S->tailS[3] = 0;
-        S->tailD[0] = 0; S->tailD[1] = 0; S->tailD[2] = 0; S->tailD[3] = 0;
-        S->U = U0; S->pruned = 0; S->ovf_level = 0;
-        S->mu[0] = ~0ull; S->mu[1] = ~0ull; S->mu[2] = ~0ull; S->meet = 0;
-        S->prl[0] = 0; S->prl[1] = 0;
-        for (int a = 0; a < 8; a++) S->alive[a >> 2][a & 3] = 0;
-        S->alive[0][0] = 1; S->alive[1][0] = 1;
-        S->xlo = min(S->xlo, min(sx, gx) - 1); S->xhi = max(S->xhi, max(sx, gx) + 1);
-        __stcg(queue, make_uint2(((uint32_t)sx << 16) | (uint32_t)sy, fx_pack(0u, FX_CODE_START)));
-        __stcg(queue + 1, make_uint2(0x80000000u | ((uint32_t)gx << 16) | (uint32_t)gy, fx_pack(0u, FX_CODE_START)));
-        __stcg(field + sidx, fx_pack(0u, FX_CODE_START));
-        __stcg(field + (side_cells + gidx), fx_pack(0u, FX_CODE_START));
-        dirty[sidx >> FX_DIRTY_SHIFT] = 1;
-        dirty[(side_cells + gidx) >> FX_DIRTY_SHIFT] = 1;
+    if (tid == 0) {
+        for (int b = 0; b < 4; b++) { L.tailS[b] = 0; L.tailD[b] = 0; L.alive[0][b] = 0; L.alive[1][b] = 0; }
+        L.prl[0] = 0; L.prl[1] = 0; L.ovf = 0; L.mu[0] = ~0ull; L.mu[1] = ~0ull;
+        L.flags &= ~(FLAG_UNREACH);
+        L.pruned = 0; L.meet = 0;
+        // "level -1" (parity 1): the two seeds sit in rank 0's straight run of bucket 0, both sides alive in slot 0
+        for (int r = 0; r < FX_CL; r++) {
+            L.r_cnt[1][r] = r == 0 ? make_uint4(2u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+            L.r_mu[1][r] = ~0ull;
+            L.r_flags[1][r] = r == 0 ? ((1u << 0) | (1u << 4)) : 0u;
+        }
+        if (rank == 0) {
+            L.tailS[0] = 2; L.alive[0][0] = 1; L.alive[1][0] = 1;
+            L.xlo = min(L.xlo, min(sx, gx) - 1); L.xhi = max(L.xhi, max(sx, gx) + 1);
+            uint2 *q0 = run_base(0u, 0u, 0u);
+            __stcg(q0, make_uint2(((uint32_t)sx << 16) | (uint32_t)sy, fx_pack(0u, FX_CODE_START)));
+            __stcg(q0 + 1, make_uint2(0x80000000u | ((uint32_t)gx << 16) | (uint32_t)gy, fx_pack(0u, FX_CODE_START)));
+            __stcg(field + sidx, fx_pack(0u, FX_CODE_START));
+            __stcg(field + (side_cells + gidx), fx_pack(0u, FX_CODE_START));
+            dirty[sidx >> FX_DIRTY_SHIFT] = 1;
+            dirty[(side_cells + gidx) >> FX_DIRTY_SHIFT] = 1;
+        }
     }
     cluster.sync();
 
     unsigned my_settled = 0;
     int my_xlo = 0x7FFFFFFF, my_xhi = -1;
-    unsigned k = 0, k3 = 0;
+    unsigned k = 0;
     uint32_t result = FX_INF;
     unsigned long long mu = ~0ull;
+    unsigned prl_all = 0;
     const uint32_t h0 = octile(abs(sx - gx), abs(sy - gy), WS, WD - WS);
     const unsigned k_meet = h0 / (2u * WS) > 2u ? h0 / (2u * WS) - 2u : 0u;
     const bool start_free = P.grid[(size_t)sx * H + sy] != 1;
+    unsigned exit_flags = 0;
     for (;;) {
-        // all of this is rank 0's shared memory: complete since the last cluster barrier (see run_pass for why each word is
-        // stable while the CTAs pass this point at different times)
-        const unsigned nS = S->tailS[k & 3], nD = S->tailD[k & 3], n = nS + nD;
-        const unsigned n1 = S->tailS[(k + 1) & 3] + S->tailD[(k + 1) & 3];
-        const unsigned long long m_prev = S->mu[k3 == 0 ? 2 : k3 - 1];
-        mu = m_prev < mu ? m_prev : mu;
+        const unsigned pb = (k + 1u) & 1u;  // buffer written by level k-1
+        // ---- the replicated words of level k-1: every thread of every CTA computes the same values from its local copy
+        unsigned n = 0, n1 = 0, fl = 0;
+        // per-warp prefix table of the 2 * FX_CL runs of bucket k (lane rho = owner * 2 + class holds the exclusive prefix)
+        unsigned mylen = 0;
+        if (lane < 2u * FX_CL) {
+            const uint4 c = L.r_cnt[pb][lane >> 1];
+            mylen = (lane & 1u) ? c.y : c.x;
+        }
+        unsigned incl = mylen;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (unsigned)o) incl += t; }
+        const unsigned pre = incl - mylen;  // exclusive prefix (lanes >= 2 * FX_CL: the total)
+        n = __shfl_sync(0xFFFFFFFFu, incl, 31);
+#pragma unroll
+        for (int r = 0; r < FX_CL; r++) {
+            const uint4 c = L.r_cnt[pb][r];
+            n1 += c.z + c.w;
+            fl |= L.r_flags[pb][r];
+            const unsigned long long m = L.r_mu[pb][r];
+            mu = m < mu ? m : mu;
+        }
+        prl_all |= (fl >> 8) & 3u;
         const uint32_t mc = (uint32_t)(mu >> 32);
         if (mc != FX_INF && 2ull * k * WS > (unsigned long long)mc + WD) { result = mc; break; }
+        if (fl & (1u << 10)) { exit_flags = FLAG_OVERFLOW; break; }
         if (mc == FX_INF) {
-            const bool dead0 = !S->alive[0][k & 3] && !S->alive[0][(k + 1) & 3], dead1 = !S->alive[1][k & 3] && !S->alive[1][(k + 1) & 3];
-            if ((dead0 && !S->prl[0]) || (dead1 && !S->prl[1] && (start_free || k >= 2u))) { if (ctid == 0) S->flags |= FLAG_UNREACH; break; }
+            // (see run_pass: a side with nothing in buckets k and k+1 that never pruned has exhausted its component)
+            const unsigned a0 = (k & 3u), a1 = ((k + 1u) & 3u);
+            const bool dead0 = !((fl >> a0) & 1u) && !((fl >> a1) & 1u), dead1 = !((fl >> (4u + a0)) & 1u) && !((fl >> (4u + a1)) & 1u);
+            if ((dead0 && !(prl_all & 1u)) || (dead1 && !(prl_all & 2u) && (start_free || k >= 2u))) { exit_flags = FLAG_UNREACH; break; }
         }
-        const unsigned ovl = S->ovf_level;
-        if (ovl != 0 && ovl <= k) { if (ctid == 0) S->flags |= FLAG_OVERFLOW; break; }
-        if ((n == 0 && n1 == 0) || (S->flags & FLAG_OVERFLOW)) { result = mc; break; }
-        if (nS > qhalf || nD > qhalf) { if (ctid == 0) S->flags |= FLAG_OVERFLOW; break; }
-        if (ctid == 0) {
-            S->tailS[(k + 3) & 3] = 0; S->tailD[(k + 3) & 3] = 0;
-            S->mu[k3 == 2 ? 0 : k3 + 1] = ~0ull; S->alive[0][(k + 3) & 3] = 0; S->alive[1][(k + 3) & 3] = 0;
+        if (n == 0 && n1 == 0) { result = mc; break; }  // drained: the smallest proposal is exact (see run_pass)
+        if (tid == 0) {
+            // this CTA's slot of bucket k-1 will be bucket k+3: its local words start empty
+            L.tailS[(k + 3) & 3] = 0; L.tailD[(k + 3) & 3] = 0; L.alive[0][(k + 3) & 3] = 0; L.alive[1][(k + 3) & 3] = 0;
         }
-        const uint32_t U = S->U;
-        const uint2 *__restrict__ qk = queue + (size_t)(k & 3) * qcap;
-        uint2 *__restrict__ q1 = queue + (size_t)((k + 1) & 3) * qcap;
-        uint2 *__restrict__ q2 = queue + (size_t)((k + 2) & 3) * qcap;
+        const unsigned bk = k & 3u, b1 = (k + 1u) & 3u, b2 = (k + 2u) & 3u;
         const uint32_t kbase = k * WS;
         const bool meet_level = k >= k_meet;
-        for (unsigned i0 = ctid - lane; i0 < n; i0 += NT) {
+        for (unsigned i0 = rank * NTC + (tid - lane); i0 < n; i0 += NT) {
             const unsigned i = i0 + lane;
             bool act = i < n;
-            const uint2 e = act ? __ldcg(qk + (i < nS ? i : qhalf + (i - nS))) : make_uint2(0u, 0u);
+            // which run holds global index i: 4-step binary search over the prefix table held by lanes 0 .. 2 FX_CL - 1
+            unsigned rho = 0;
+#pragma unroll
+            for (unsigned step = FX_CL; step >= 1u; step >>= 1) {
+                const unsigned p = __shfl_sync(0xFFFFFFFFu, pre, rho + step);
+                if (i >= p) rho += step;
+            }
+            const unsigned rstart = __shfl_sync(0xFFFFFFFFu, pre, rho);
+            const uint2 e = act ? __ldcg(run_base(bk, rho >> 1, rho & 1u) + (i - rstart)) : make_uint2(0u, 0u);
             const unsigned idx = cell_of(e.x), fo = foff_of(e.x);
             uint32_t v = FX_INF;
             unsigned m = 0;
@@ -875,54 +935,34 @@ __device__ uint32_t run_pass_cluster(const SearchParams &P, CtaState *S, const u
             act = act && v == e.y;
             uint32_t other = FX_INF;
             if (meet_level && act) other = __ldcg(field + (idx + (side ? 0u : side_cells)));
-            unsigned flagbits = 0;  // bit 0/1: side 0/1 pruned; bits 2..5: alive[side][bucket k+1 / k+2]
             if (act) {
                 dirty[(idx + fo) >> FX_DIRTY_SHIFT] = 1;
                 const int tx = side ? sx : gx, ty = side ? sy : gy;
                 const uint32_t h = octile(abs(x - tx), abs(y - ty), WS, WD - WS);
-                if (((uint64_t)g + h) > (uint64_t)U) { act = false; flagbits |= side ? 2u : 1u; }
+                if (((uint64_t)g + h) > (uint64_t)U) { act = false; L.prl[side ? 1 : 0] = 1; }
             }
             if (other != FX_INF)
-                atomicMin(&S->mu[k3], ((unsigned long long)(g + (other >> 4)) << 32) | (unsigned long long)(e.x & 0x7FFFFFFFu));
+                atomicMin(&L.mu[k & 1u], ((unsigned long long)(g + (other >> 4)) << 32) | (unsigned long long)(e.x & 0x7FFFFFFFu));
             unsigned succ = 0;
             if (act) {
                 my_settled++; my_xlo = min(my_xlo, x); my_xhi = max(my_xhi, x);
                 succ = s_lut[((e.y & 15u) << 8) | m];
-                if (g + WD > FX_COST_MAX28) { S->ovf_level = k + 1; succ = 0; }
+                if (g + WD > FX_COST_MAX28) { L.ovf = 1; succ = 0; }
             }
             const bool diag2 = (g - kbase) + WD >= 2u * WS;
-            // queue space, once per warp: the three counts (straight -> k+1, diagonal -> k+1, diagonal -> k+2) ride one
-            // 32-bit word (10 bits each: at most 32 * 4 per warp) through one inclusive scan
-            const unsigned ns = (unsigned)__popc(succ & 0x0Fu), nd = (unsigned)__popc(succ & 0xF0u);
-            const unsigned mine = ns | ((diag2 ? 0u : nd) << 10) | ((diag2 ? nd : 0u) << 20);
-            unsigned incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (unsigned)o) incl += t; }
-            const unsigned tot = __shfl_sync(0xFFFFFFFFu, incl, 31), excl = incl - mine;
-            unsigned base = 0;
-            if (lane < 3u) {
-                const unsigned cnt = (tot >> (10u * lane)) & 1023u;
-                if (cnt) base = atomicAdd(lane == 0u ? &S->tailS[(k + 1) & 3] : &S->tailD[(k + (lane == 2u ? 2 : 1)) & 3], cnt);
-            }
-            const unsigned baseS = __shfl_sync(0xFFFFFFFFu, base, 0), baseA = __shfl_sync(0xFFFFFFFFu, base, 1), baseB = __shfl_sync(0xFFFFFFFFu, base, 2);
-            unsigned posS = baseS + (excl & 1023u);
-            unsigned posD = diag2 ? baseB + ((excl >> 20) & 1023u) : baseA + ((excl >> 10) & 1023u);
-            if (posS + ns > qhalf || posD + nd > qhalf) succ = 0;  // the tail counts flag the overflow at the next level
+            unsigned posS = 0, posD = 0;
             if (succ) {
-                if (ns || (nd && !diag2)) flagbits |= side ? 16u : 4u;
-                if (nd && diag2) flagbits |= side ? 32u : 8u;
+                const unsigned ns = (unsigned)__popc(succ & 0x0Fu), nd = (unsigned)__popc(succ & 0xF0u);
+                if (ns) posS = fx_atoms_add(&L.tailS[b1], ns);
+                if (nd) posD = fx_atoms_add(&L.tailD[diag2 ? b2 : b1], nd);
+                if (posS + ns > segcap || posD + nd > segcap) { L.ovf = 1; succ = 0; }
+                else {
+                    if (ns) L.alive[side ? 1 : 0][b1] = 1;
+                    if (nd) L.alive[side ? 1 : 0][diag2 ? b2 : b1] = 1;
+                }
             }
-            const unsigned fb = __reduce_or_sync(0xFFFFFFFFu, flagbits);
-            if (lane == 0 && fb) {
-                if (fb & 1u) S->prl[0] = 1;
-                if (fb & 2u) S->prl[1] = 1;
-                if (fb & 4u) S->alive[0][(k + 1) & 3] = 1;
-                if (fb & 8u) S->alive[0][(k + 2) & 3] = 1;
-                if (fb & 16u) S->alive[1][(k + 1) & 3] = 1;
-                if (fb & 32u) S->alive[1][(k + 2) & 3] = 1;
-            }
-            uint2 *__restrict__ gS = q1 + posS;
-            uint2 *__restrict__ gD = (diag2 ? q2 : q1) + qhalf + posD;
+            uint2 *__restrict__ gS = run_base(b1, rank, 0u) + posS;
+            uint2 *__restrict__ gD = run_base(diag2 ? b2 : b1, rank, 1u) + posD;
             const uint32_t nvS = fx_pack(g + WS, 0u), nvD = fx_pack(g + WD, 0u);
             const int *__restrict__ stp = s_step + 2 * (idx & 63);
             uint32_t *__restrict__ fbase = field + (idx + fo);
@@ -937,16 +977,28 @@ __device__ uint32_t run_pass_cluster(const SearchParams &P, CtaState *S, const u
                 else __stcg(gD++, child);
             }
         }
+        __syncthreads();  // this CTA's tails, flags and proposal of level k are complete
+        // ---- broadcast: lane r of warp 0 writes this CTA's words into CTA r's copy (fire and forget)
+        if (tid < FX_CL) {
+            ClState *dst = peers[tid];
+            const unsigned wb = k & 1u;
+            dst->r_cnt[wb][rank] = make_uint4(L.tailS[b1], L.tailD[b1], L.tailS[b2], L.tailD[b2]);
+            dst->r_mu[wb][rank] = L.mu[k & 1u];
+            unsigned f = (L.prl[0] ? 1u << 8 : 0u) | (L.prl[1] ? 1u << 9 : 0u) | (L.ovf ? 1u << 10 : 0u);
+#pragma unroll
+            for (int b = 0; b < 4; b++) f |= (L.alive[0][b] ? 1u << b : 0u) | (L.alive[1][b] ? 1u << (4 + b) : 0u);
+            dst->r_flags[wb][rank] = f;
+        }
+        if (tid == FX_CL) L.mu[(k + 1u) & 1u] = ~0ull;  // the other slot is free again: level k-1's proposal went out one level ago
         cluster.sync();
         k++;
-        k3 = k3 == 2 ? 0 : k3 + 1;
     }
-    // entries that were never popped: mark their lines too
+    // entries that were never popped (buckets k and k+1 of this CTA's own segment): mark their lines too
     for (unsigned b = k; b <= k + 1; b++) {
-        const uint2 *__restrict__ qb = queue + (size_t)(b & 3) * qcap;
-        const unsigned mS = min(S->tailS[b & 3], qhalf), mD = min(S->tailD[b & 3], qhalf);
-        for (unsigned i = ctid; i < mS + mD; i += NT) {
-            const uint32_t xy = __ldcg(qb + (i < mS ? i : qhalf + (i - mS))).x;
+        const unsigned mS = min(L.tailS[b & 3], segcap), mD = min(L.tailD[b & 3], segcap);
+        const uint2 *__restrict__ rS = run_base(b & 3u, rank, 0u), *__restrict__ rD = run_base(b & 3u, rank, 1u);
+        for (unsigned i = tid; i < mS + mD; i += NTC) {
+            const uint32_t xy = __ldcg(i < mS ? rS + i : rD + (i - mS)).x;
             dirty[(cell_of(xy) + foff_of(xy)) >> FX_DIRTY_SHIFT] = 1;
         }
     }
@@ -954,27 +1006,39 @@ __device__ uint32_t run_pass_cluster(const SearchParams &P, CtaState *S, const u
         const int wlo = __reduce_min_sync(0xFFFFFFFFu, my_xlo), whi = __reduce_max_sync(0xFFFFFFFFu, my_xhi);
         const unsigned ws = __reduce_add_sync(0xFFFFFFFFu, my_settled);
         if (lane == 0) {
-            if (whi >= 0) { atomicMin(&S->xlo, wlo - 1); atomicMax(&S->xhi, whi + 1); }
-            if (ws) atomicAdd(&S->settled, (unsigned long long)ws);
+            if (whi >= 0) { atomicMin(&L.xlo, wlo - 1); atomicMax(&L.xhi, whi + 1); }
+            if (ws) atomicAdd(&L.settled, (unsigned long long)ws);
         }
     }
-    if (ctid == 0) { S->meet = (unsigned)(mu & 0x7FFFFFFFull); S->levels += k; }
+    if (tid == 0) {
+        L.flags |= exit_flags;
+        L.pruned = prl_all;
+        L.meet = (unsigned)(mu & 0x7FFFFFFFull);
+        if (rank == 0) L.levels += k;
+    }
     cluster.sync();
-    if (ctid == 0) S->pruned = S->prl[0] | S->prl[1];
     return result;
 }
 
-// reset of the lines the query touched, by all threads of the cluster (see reset_slot)
-__device__ void reset_slot_cluster(CtaState *S, uint32_t *__restrict__ field, uint8_t *__restrict__ dirty, size_t dirty_n, size_t cells, int H)
+// reset of the lines the query touched, by all threads of the cluster (see reset_slot); the x-range is the union of the
+// CTAs' ranges, exchanged through each other's shared memory
+__device__ void reset_slot_cluster(ClState &L, ClState *const *peers, uint32_t *__restrict__ field, uint8_t *__restrict__ dirty,
+                                   size_t dirty_n, size_t cells, int H)
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
-    const unsigned ctid = cluster.block_rank() * blockDim.x + threadIdx.x, NT = FX_CL * blockDim.x;
+    const unsigned rank = cluster.block_rank();
+    const unsigned ctid = rank * blockDim.x + threadIdx.x, NT = FX_CL * blockDim.x;
+    __syncthreads();
+    if (threadIdx.x < FX_CL) { peers[threadIdx.x]->r_x[0][rank] = L.xlo; peers[threadIdx.x]->r_x[1][rank] = L.xhi; }
     cluster.sync();
-    const int xlo = max(S->xlo, 0), xhi = S->xhi;
-    const bool force = (S->flags & FLAG_OVERFLOW) != 0;
-    cluster.sync();
-    if (ctid == 0) { S->xlo = 0x7FFFFFFF; S->xhi = -1; }
+    int xlo = 0x7FFFFFFF, xhi = -1;
+#pragma unroll
+    for (int r = 0; r < FX_CL; r++) { xlo = min(xlo, L.r_x[0][r]); xhi = max(xhi, L.r_x[1][r]); }
+    xlo = max(xlo, 0);
+    const bool force = (L.flags & FLAG_OVERFLOW) != 0;
+    __syncthreads();
+    if (threadIdx.x == 0) { L.xlo = 0x7FFFFFFF; L.xhi = -1; }
     if (xhi >= xlo) {
         const size_t c_lo = (size_t)(xlo >> 3) * fx_tiles_y(H) * 64;
         size_t c_hi = (size_t)((xhi >> 3) + 1) * fx_tiles_y(H) * 64;
@@ -1018,12 +1082,11 @@ __global__ void __launch_bounds__(FX_CL_THREADS, 1) k_search_cluster(const Searc
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     constexpr uint32_t WS = Wt<METRIC>::WS, WD = Wt<METRIC>::WD;
-    __shared__ CtaState S_local;
+    __shared__ ClState L;
+    __shared__ ClState *peers[FX_CL];
     __shared__ uint8_t s_lut[9 * 256];
     __shared__ __align__(8) int s_step[8 * 64 * 2];
     __shared__ int s_out[6];  // rank 0: npts, n1, n2, drop, a, b of the extracted path
-    CtaState *S = cluster.map_shared_rank(&S_local, 0);
-    int *r_out = cluster.map_shared_rank(s_out, 0);
     const unsigned rank = cluster.block_rank();
     const int tid = threadIdx.x;
     const unsigned ctid = rank * blockDim.x + tid, NT = FX_CL * blockDim.x;
@@ -1033,7 +1096,8 @@ __global__ void __launch_bounds__(FX_CL_THREADS, 1) k_search_cluster(const Searc
     uint2 *queue = P.queues + (size_t)slot * 4 * P.qcap;
     int32_t *tmp = P.tmp_path + (size_t)slot * P.path_cap * 4;
     const int W = P.W, H = P.H;
-    if (ctid == 0) { S->settled = 0; S->levels = 0; S->flags = 0; S->xlo = 0x7FFFFFFF; S->xhi = -1; }
+    if (tid < FX_CL) peers[tid] = cluster.map_shared_rank(&L, tid);
+    if (tid == 0) { L.settled = 0; L.levels = 0; L.flags = 0; L.xlo = 0x7FFFFFFF; L.xhi = -1; }
     for (int i = tid; i < 9 * 256; i += blockDim.x) s_lut[i] = (uint8_t)fx_canon_succ((unsigned)(i >> 8), (unsigned)(i & 255));
     for (int i = tid; i < 8 * 64; i += blockDim.x) {
         const int d = i >> 6, xi = (i >> 3) & 7, yi = i & 7, dx = fx_dx(d), dy = fx_dy(d);
@@ -1042,12 +1106,19 @@ __global__ void __launch_bounds__(FX_CL_THREADS, 1) k_search_cluster(const Searc
         s_step[2 * i + 1] = (tx * P.TY + ty) * 64 + ((((xi + dx) & 7) - xi) << 3) + (((yi + dy) & 7) - yi);
     }
     __syncthreads();
+    int *r_out = cluster.map_shared_rank(s_out, 0);
     unsigned long long passes = 0;
     for (;;) {
         cluster.sync();
-        if (ctid == 0) { S->q = (int)atomicAdd(P.counters + 0, 1ull); S->flags = 0; }
+        if (rank == 0 && tid < FX_CL) {
+            int q = 0;
+            if (tid == 0) q = (int)atomicAdd(P.counters + 0, 1ull);
+            q = __shfl_sync((1u << FX_CL) - 1u, q, 0);
+            peers[tid]->r_q = q;
+        }
+        if (tid == 0) L.flags = 0;
         cluster.sync();
-        const int q = S->q;
+        const int q = L.r_q;
         if (q >= P.Q) break;
         const int sx = P.starts[2 * q], sy = P.starts[2 * q + 1], gx = P.goals[2 * q], gy = P.goals[2 * q + 1];
         int32_t out_cost = FX_COST_UNREACHABLE;
@@ -1084,16 +1155,15 @@ __global__ void __launch_bounds__(FX_CL_THREADS, 1) k_search_cluster(const Searc
         for (int attempt = 0; attempt < 6; attempt++) {
             const bool last = attempt == 5 || U_try >= 0x7FFFFFFFull;
             const uint32_t U0 = last ? 0x7FFFFFFFu : (uint32_t)U_try;
-            const uint32_t r = run_pass_cluster<METRIC>(P, S, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, U0);
+            const uint32_t r = run_pass_cluster<METRIC>(P, L, peers, s_lut, s_step, field, dirty, queue, sx, sy, gx, gy, U0);
             passes++;
-            cluster.sync();
-            const unsigned fl = S->flags, pruned = S->pruned;
+            const unsigned fl = L.flags, pruned = L.pruned;  // identical in every CTA (derived from the replicated words)
             overflow = (fl & FLAG_OVERFLOW) != 0;
             if (overflow) break;
             if (r != FX_INF && r <= U0) { best = r; break; }
             if ((fl & FLAG_UNREACH) || last || (r == FX_INF && !pruned)) break;
             U_try = r != FX_INF ? (uint64_t)r : (uint64_t)h0 + (U_try - h0) * 4;
-            reset_slot_cluster(S, field, dirty, P.dirty_n, P.cells, H);
+            reset_slot_cluster(L, peers, field, dirty, P.dirty_n, P.cells, H);
         }
         if (overflow || (best != FX_INF && best > 0x7FFFFFFFu)) {
             if (ctid == 0) {
@@ -1112,7 +1182,7 @@ __global__ void __launch_bounds__(FX_CL_THREADS, 1) k_search_cluster(const Searc
             if (rank == 0 && tid < 32) {
                 unsigned a = 0, b = 0;
                 int d1 = 8, d2 = 8;
-                const int mx = (int)(S->meet >> 16), my = (int)(S->meet & 0xFFFFu);
+                const int mx = (int)(L.meet >> 16), my = (int)(L.meet & 0xFFFFu);
                 const int n1 = extract_path<METRIC>(P, field, sx, sy, mx, my, tmp, cap, &a, &b, &d1);
                 const int n2 = extract_path<METRIC>(P, field + P.cells, gx, gy, mx, my, tmp + 2 * (size_t)cap, cap, &a, &b, &d2);
                 if (tid == 0) {
@@ -1139,13 +1209,12 @@ __global__ void __launch_bounds__(FX_CL_THREADS, 1) k_search_cluster(const Searc
                 }
             }
         }
-        reset_slot_cluster(S, field, dirty, P.dirty_n, P.cells, H);
+        reset_slot_cluster(L, peers, field, dirty, P.dirty_n, P.cells, H);
     }
-    cluster.sync();  // nobody leaves while rank 0's shared memory may still be read
-    if (ctid == 0) {
-        atomicAdd(P.counters + 1, S->settled);
-        atomicAdd(P.counters + 2, S->levels);
-        atomicAdd(P.counters + 3, passes);
+    cluster.sync();  // nobody leaves while its shared memory may still be written or read by a peer
+    if (tid == 0) {
+        atomicAdd(P.counters + 1, L.settled);
+        if (rank == 0) { atomicAdd(P.counters + 2, L.levels); atomicAdd(P.counters + 3, passes); }
     }
 }
 

@@ -496,9 +496,13 @@ def test_plan_host_float64_matrix_and_wide_ctas(fx, oracle):
     want, status, _ = oracle.jps_batch(occ, s, g, 1)
     a = fx.plan_host(mat, s, g, metric=1, max_path=64)
     b = fx.plan_host(occ, s, g, metric=1, max_path=64)
-    assert np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[3])
+    assert np.array_equal(a[0], b[0])           # (equal-cost paths may differ between two runs: compare costs, validate paths)
     for q in range(6):
         assert (a[0][q] == int(want[q])) if status[q] == 1 else (a[0][q] == -1)
+        for r in (a, b):
+            if status[q] == 1 and r[3][q] <= 64:
+                na, nb = validate_path(occ, [tuple(p) for p in r[2][q, :r[3][q]]], tuple(s[q]), tuple(g[q]))
+                assert 10 * na + 14 * nb == r[0][q]
     # the same six queries inside a batch large enough for the throughput form
     S, G = random_queries(occ, 400, rng)
     S[:6], G[:6] = s, g
