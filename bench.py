@@ -428,6 +428,58 @@ def latency_probe(fx, m4096, s, g, hchoice):
     return res
 
 
+def multi_gpu_checks(torch, dist, fx, dev, world, rank, m):
+    """N > 1 only: the sharded modes of SURVEY §8e beside the query-parallel headline, each compared BIT FOR BIT with the
+    single-GPU kernel on the cfg4 grid (every rank checks its own slab, all-reduced MIN), warm wall-clock times, max over
+    ranks: row-tiled inflation (one halo exchange), row-tiled EDT (two transposes), point-sharded projection (one
+    all-reduce), row-tiled cost field (iterated halo exchange).  These are capacity modes, not the metric."""
+    from fuxi_planner_b200 import tiled
+    n = m.shape[0]
+    x0, x1 = tiled.slab_bounds(n, world, rank)
+    gm = torch.from_numpy(m).to(dev)
+    own = gm[x0:x1].contiguous()
+    out = {}
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize(); dist.barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return r, float(t.item()) * 1e3
+
+    def same(a, b):
+        ok = torch.tensor([int(torch.equal(a, b))], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        return bool(ok.item())
+
+    for radius, variant in ((2, "ccst"), (3, "st")):
+        r, ms = timed(lambda: tiled.inflate_tiled(own, radius, variant))
+        out["inflate_tiled_r%d_%s" % (radius, variant)] = {"ms": ms, "bit_exact_vs_single_gpu": same(r, fx.inflate(gm, radius, variant)[x0:x1])}
+    r, ms = timed(lambda: tiled.edt_tiled(own, n))
+    out["edt_tiled"] = {"ms": ms, "bit_exact_vs_single_gpu": same(r, fx.edt(gm)[x0:x1])}
+    npts = 1 << 22
+    prng = np.random.default_rng(9)
+    pts = torch.from_numpy(np.c_[prng.uniform(0, n * 0.2, (npts, 2)), prng.uniform(-0.5, 3.0, npts)].astype(np.float32)).to(dev)
+    p0, p1 = tiled.shard_queries(npts, world, rank)
+    mine = pts[p0:p1].contiguous()
+    r, ms = timed(lambda: tiled.project_sharded(mine, None, 0.3, float("inf"), (0.0, 0.0), 0.2, (n, n)))
+    out["project_sharded_4Mpts"] = {"ms": ms, "bit_exact_vs_single_gpu": same(r, fx.project(pts, None, 0.3, float("inf"), (0.0, 0.0), 0.2, (n, n)))}
+    free = np.argwhere(m == 0)
+    src = tuple(int(v) for v in free[0])
+    (fld, rounds), ms = timed(lambda: tiled.field_tiled(own, n, src, 2))
+    t0 = time.perf_counter()
+    full = fx.field(gm, src, 2)
+    torch.cuda.synchronize()
+    out["field_tiled"] = {"ms": ms, "exchange_rounds": int(rounds), "bit_exact_vs_single_gpu": same(fld, full[x0:x1]),
+                          "single_gpu_ms_rank0": 1e3 * (time.perf_counter() - t0)}
+    out["grid"] = [n, n]
+    out["world"] = world
+    return out
+
+
 # ------------------------------------------------------------------------------------------ main arm
 def run_b200(args):
     import torch
@@ -598,6 +650,11 @@ def run_b200(args):
         ok = status == 1
         bad = np.abs(got[ok] - cost[ok]) > 1e-5 * np.maximum(cost[ok], 1e-12) if args.hchoice == 2 else ci[:S][ok] != cost[ok]
         line["cpu_baseline"]["parity_mismatches"] = int(bad.sum()) + int(((ci[:S] >= 0) != ok).sum())
+    if world > 1 and not args.no_extras:
+        try:
+            line["multi_gpu_checks"] = multi_gpu_checks(torch, dist, fx, dev, world, rank, m)
+        except Exception as exc:          # a reported extra never takes the bench line down
+            line["multi_gpu_checks"] = {"error": repr(exc)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
