@@ -163,7 +163,7 @@ struct __align__(16) CtaState {
     unsigned flags;
     int xlo, xhi;     // x-rows this query has touched since the last reset (bounds the dirty-flag scan)
     unsigned pruned;  // this pass rejected a legal move by the ellipse or the band (so a drained queue proves nothing)
-    unsigned prl[2];   // bidirectional pass: side s has pruned a cell (written as it happens)
+    unsigned prl[3][2];  // bidirectional pass: side s pruned a cell in the level whose index % 3 is the slot (rotates like mu)
     unsigned alive[2][4];  // bidirectional pass: side s has pushed an entry into bucket slot b
     int q;
     unsigned long long settled, levels;
@@ -235,7 +235,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
         S.tailD[0] = 0; S.tailD[1] = 0; S.tailD[2] = 0; S.tailD[3] = 0;
         S.goal[0] = FX_INF; S.goal[1] = FX_INF; S.U = U0; S.pruned = 0; S.ovf_level = 0;
         S.mu[0] = ~0ull; S.mu[1] = ~0ull; S.mu[2] = ~0ull; S.meet = 0;
-        S.prl[0] = 0; S.prl[1] = 0;
+        for (int a = 0; a < 6; a++) S.prl[a >> 1][a & 1] = 0;
         for (int a = 0; a < 8; a++) S.alive[a >> 2][a & 3] = 0;
         S.alive[0][0] = 1; S.alive[1][0] = 1;
         S.xlo = min(S.xlo, sx - 1); S.xhi = max(S.xhi, sx + 1);
@@ -258,6 +258,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
     bool my_pruned = false;
     uint32_t result = FX_INF;
     unsigned long long mu = ~0ull;
+    unsigned prl0 = 0, prl1 = 0;
     // the first level in which a cell can carry labels of both sides
     const uint32_t h0 = octile(abs(sx - gx), abs(sy - gy), WS, WD - WS);
     const unsigned k_meet = h0 / (2u * WS) > 2u ? h0 / (2u * WS) - 2u : 0u;
@@ -278,8 +279,10 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
         // S.ovf_level only counts once its level is over; n is complete since the last barrier; n1 is still growing but
         // only matters when n == 0, i.e. when nobody pushes in this level.
         if (BIDIR) {
-            const unsigned long long m_prev = S.mu[k3 == 0 ? 2 : k3 - 1];
+            const unsigned kp = k3 == 0 ? 2 : k3 - 1, kn = k3 == 2 ? 0 : k3 + 1;
+            const unsigned long long m_prev = S.mu[kp];
             mu = m_prev < mu ? m_prev : mu;
+            prl0 |= S.prl[kp][0]; prl1 |= S.prl[kp][1];  // what level k-1 pruned (complete); every thread keeps the running OR
             const uint32_t mc = (uint32_t)(mu >> 32);
             if (mc != FX_INF && 2ull * k * WS > (unsigned long long)mc + WD) { result = mc; break; }  // see the proof above
             // A side with nothing in buckets k and k+1 is finished (bucket k+2 is only filled by this level's own pops).  If
@@ -289,12 +292,12 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
             // the goal side instead pops a free cell n the start can step into, after level 0 -- n carries the start side's
             // label from level 0 on -- unless n is the goal itself, which the start side pops in level 1: so from level 2 on
             // the goal side's exhaustion counts for obstacle starts as well).
-            // All four words are stable here: nobody pushes or prunes for a side that has no entry in bucket k.
+            // The alive words are stable here: nobody pushes for a side that has no entry in bucket k.
             if (mc == FX_INF) {
                 const bool dead0 = !S.alive[0][k & 3] && !S.alive[0][(k + 1) & 3], dead1 = !S.alive[1][k & 3] && !S.alive[1][(k + 1) & 3];
-                if ((dead0 && !S.prl[0]) || (dead1 && !S.prl[1] && (start_free || k >= 2u))) { if (tid == 0) S.flags |= FLAG_UNREACH; break; }
+                if ((dead0 && !prl0) || (dead1 && !prl1 && (start_free || k >= 2u))) { if (tid == 0) S.flags |= FLAG_UNREACH; break; }
             }
-            if (tid == 0) { S.mu[k3 == 2 ? 0 : k3 + 1] = ~0ull; S.alive[0][(k + 3) & 3] = 0; S.alive[1][(k + 3) & 3] = 0; }
+            if (tid == 0) { S.mu[kn] = ~0ull; S.prl[kn][0] = 0; S.prl[kn][1] = 0; S.alive[0][(k + 3) & 3] = 0; S.alive[1][(k + 3) & 3] = 0; }
         } else {
             const unsigned goalc = S.goal[(k + 1) & 1];
             if (goalc != FX_INF) { result = goalc; break; }  // the goal was popped in the previous level: final
@@ -362,7 +365,7 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
                     const float lat = (float)(x - sx) * qdy - (float)(y - sy) * qdx;
                     keep = keep && fabsf(lat) <= bandL;
                 }
-                if (!keep) { my_pruned = true; act = false; if (BIDIR) S.prl[side ? 1 : 0] = 1; }
+                if (!keep) { my_pruned = true; act = false; if (BIDIR) S.prl[k3][side ? 1 : 0] = 1; }
             }
             if (BIDIR && other != FX_INF)  // both sides have labelled this cell: a real start-goal path through it
                 atomicMin(&S.mu[k3], ((unsigned long long)(g + (other >> 4)) << 32) | (unsigned long long)(e.x & 0x7FFFFFFFu));
