@@ -161,40 +161,46 @@ __global__ void __launch_bounds__(256) k_edt_cols_tile(const uint16_t *__restric
 {
     if (run_flag && *run_flag == 0) return;
     __shared__ __align__(16) uint16_t tile[EDT_TX + 2 * EDT_WIN][EDT_TYC];
-    const int x0 = blockIdx.y * EDT_TX, y0 = blockIdx.x * EDT_TYC;
     constexpr int ROWS = EDT_TX + 2 * EDT_WIN;
-    // stage: 16 threads x 16 bytes per row, 16 rows per step
-    {
-        const int cchunk = (threadIdx.x & 15) * 8, r0 = threadIdx.x >> 4;
-        for (int rr = r0; rr < ROWS; rr += 16) {
-            const int x = x0 - EDT_WIN + rr;
-            uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-            if (x >= 0 && x < W && y0 + cchunk < H) v = __ldcs(reinterpret_cast<const uint4 *>(g + (size_t)x * H + y0 + cchunk));
-            *reinterpret_cast<uint4 *>(&tile[rr][cchunk]) = v;
-        }
-    }
-    __syncthreads();
-    const int c = threadIdx.x & (EDT_TYC - 1);
+    const int ntx = (H + EDT_TYC - 1) / EDT_TYC, nty = (W + EDT_TX - 1) / EDT_TX;
     bool open = false;
-    if (y0 + c < H) {
-        for (int r = threadIdx.x >> 7; r < EDT_TX; r += 2) {
-            const int x = x0 + r;
-            if (x >= W) break;
-            const int tr = r + EDT_WIN;
-            const unsigned g0 = tile[tr][c];
-            unsigned best = g0 == EDT_NONE ? 0xFFFFFFFFu : g0 * g0;
-            int d = 1;
-            for (; d <= EDT_WIN; d++) {
-                const unsigned dd = (unsigned)(d * d);
-                if (dd >= best) break;
-                if (x - d < 0 && x + d >= W) break;  // nothing left on either side
-                const unsigned ga = tile[tr - d][c], gb = tile[tr + d][c];  // rows outside the grid were staged as NONE
-                if (ga != EDT_NONE) best = min(best, dd + ga * ga);
-                if (gb != EDT_NONE) best = min(best, dd + gb * gb);
+    // the grid is capped (as the conditional fallback of the bit-parallel path this kernel usually returns at once: tens
+    // of thousands of CTAs doing that cost 20 us at 16384^2), a CTA walks over tiles
+    for (int t = blockIdx.x; t < ntx * nty; t += gridDim.x) {
+        const int x0 = (t / ntx) * EDT_TX, y0 = (t % ntx) * EDT_TYC;
+        // stage: 16 threads x 16 bytes per row, 16 rows per step
+        {
+            const int cchunk = (threadIdx.x & 15) * 8, r0 = threadIdx.x >> 4;
+            for (int rr = r0; rr < ROWS; rr += 16) {
+                const int x = x0 - EDT_WIN + rr;
+                uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                if (x >= 0 && x < W && y0 + cchunk < H) v = __ldcs(reinterpret_cast<const uint4 *>(g + (size_t)x * H + y0 + cchunk));
+                *reinterpret_cast<uint4 *>(&tile[rr][cchunk]) = v;
             }
-            if (d > EDT_WIN && (unsigned)(d * d) < best && !(x - d < 0 && x + d >= W)) open = true;
-            __stcs(out + (size_t)x * H + y0 + c, best > 0x7FFFFFFFu ? 0x7FFFFFFF : (int32_t)best);
         }
+        __syncthreads();
+        const int c = threadIdx.x & (EDT_TYC - 1);
+        if (y0 + c < H) {
+            for (int r = threadIdx.x >> 7; r < EDT_TX; r += 2) {
+                const int x = x0 + r;
+                if (x >= W) break;
+                const int tr = r + EDT_WIN;
+                const unsigned g0 = tile[tr][c];
+                unsigned best = g0 == EDT_NONE ? 0xFFFFFFFFu : g0 * g0;
+                int d = 1;
+                for (; d <= EDT_WIN; d++) {
+                    const unsigned dd = (unsigned)(d * d);
+                    if (dd >= best) break;
+                    if (x - d < 0 && x + d >= W) break;  // nothing left on either side
+                    const unsigned ga = tile[tr - d][c], gb = tile[tr + d][c];  // rows outside the grid were staged as NONE
+                    if (ga != EDT_NONE) best = min(best, dd + ga * ga);
+                    if (gb != EDT_NONE) best = min(best, dd + gb * gb);
+                }
+                if (d > EDT_WIN && (unsigned)(d * d) < best && !(x - d < 0 && x + d >= W)) open = true;
+                __stcs(out + (size_t)x * H + y0 + c, best > 0x7FFFFFFFu ? 0x7FFFFFFF : (int32_t)best);
+            }
+        }
+        __syncthreads();
     }
     if (open) *flag = 1;
 }
@@ -253,20 +259,55 @@ __global__ void __launch_bounds__(128) k_edt_cols_exact(const uint16_t *__restri
 // masks of the pairs with d^2 + r^2 == D settles 32 cells per operation: the level at which a cell's bit first turns
 // on IS its exact squared distance.  Up to EDT_R (cells farther than that from every obstacle are rare on the maps
 // this path is for: they go to a fix-up list; if that list overflows the grid is redone by the windowed path above).
-//   k_edt_pack: occupancy bytes -> bit words along y (268 MB -> 33 MB at 16384^2)
-//   k_edt_bits: one CTA per 64 x 256-cell tile; shared memory holds B_0..B_R for the tile's rows + R halo rows
-//               (built from three-word windows with funnel shifts), the per-cell level index, and the output is
-//               written with 16-byte streaming stores.  Traffic: bits in, int32 out -- the algorithmic 5 B/cell.
-//   k_edt_fix:  brute-force search on the bit grid for the listed cells.
-#define EDT_R 12 /* 10 left 0.18 % of the cells of a 2 %-filled grid to the fix-up kernel (22 % of the time); 12 leaves 0.011 % */
-#define EDT_BT_ROWS 64
-#define EDT_BT_WORDS 8
+//   k_edt_pack:   occupancy bytes -> bit words along y, stored column-major (268 MB -> 33 MB at 16384^2)
+//   k_edt_strips: one WARP per strip of 32 columns (one bit word) x a segment of rows, sliding down the rows 64 at a time
+//                 (two adjacent rows per lane); the masks B_0..B_R of the 64 + 2 R rows around them live in the warp's
+//                 own shared memory.  Traffic: bits in, int32 out -- the algorithmic 5 B/cell.
+//   k_edt_fix:    brute-force search on the bit grid for the listed cells.
+// History of the bound (16384^2, 2 % fill; profiles/r02i_edt_*): rounds 1-2 ran one CTA per 64 x 256-cell tile (stage raw
+// words, barrier, build the masks incl. 2 R halo rows, barrier, walk; a thread = one row x one word, 128 bytes of output
+// each): 0.52 ms, integer pipe saturated (math-pipe throttle the top stall).  Halving the instruction count (items
+// below) moved the bound to the two block barriers (7.0 stalls per issue), removing the barriers (warp strips) to the
+// LSU data pipe -- 86 % busy, three quarters of it the output stores: a store in which every lane writes 16 bytes of its
+// own row is 32 wavefronts, not 4 -- and coalescing those to the raw-word loads (every lane its own row again).  Now:
+//   * no block barrier, no per-tile prologue: a warp is a self-contained pipeline (__syncwarp only); the raw words of
+//     the next 64 rows are loaded before the current 64 rows are walked; halo rows are built once per segment, not
+//     once per tile; going to the next step the last 2 R rows of masks move to the front of the buffer (one lane per
+//     row) and 64 new rows are built behind them, so the walk keeps its immediate shared-memory offsets;
+//   * a lane owns two ADJACENT rows: row x + 1 at row offset d reads the word row x reads at offset d + 1 -- the same
+//     address in the unrolled code, loaded once (246 instead of 466 loads for both rows over the whole walk); rows at
+//     even and odd buffer positions are stored in separate halves so that the lanes' stride-2 rows hit 32 different banks;
+//   * coalesced global traffic on both sides: the bit grid is column-major (a lane's two rows are one 8-byte load, a
+//     warp's 64 rows one 256-byte run), the output is staged through shared memory as bytes and written so that eight
+//     lanes cover one row's 128 bytes (edt_flush_rows);
+//   * masks: a 64-bit window (16 bits of the left word | the word | 16 bits of the right word) is dilated by one cell
+//     per r (6 logic ops) and the centre word extracted with one funnel shift -- exact while r <= 16;
+//   * walk: `cum |= OR of the level's pairs` is the whole per-level work; the squared distance is recorded bit-sliced
+//     (plane k = cells whose D has bit k set), but per RUN of consecutive levels whose D has bit k set instead of per
+//     level: plane k |= cum(after the run) & ~cum(before it); `all 64 cells settled` is tested every third level;
+//   * planes -> bytes: the 8 planes are 4 x (8 x 8) bit matrices side by side (one per byte); three rounds of delta swaps
+//     between plane registers transpose all four at once (60 ops), two 4 x 4 byte transposes (16 permutes) put four
+//     consecutive cells into one word, one byte permute per cell widens them after the staging.  (Round 1: 8 x 8 x 5
+//     spread / multiply / mask operations + 3 per cell to substitute INT32_MAX in unsettled cells = 450 ops; unsettled
+//     cells are overwritten by the fix-up anyway, so whatever the planes hold for them is stored.)
+#ifndef EDT_R
+#define EDT_R 14 /* cells farther than this from every obstacle go to the fix-up kernel: 0.18 % of a 2 %-filled grid at R = 10 (146 us at 16384^2), 0.014 % at 12 (40 us), 0.0004 % at 14 */
+#endif
+#define EDT_STEP 64                       /* rows a warp settles per step: two adjacent rows per lane */
+#define EDT_NB (EDT_STEP + 2 * EDT_R)     /* rows of masks a warp keeps: the step's rows + R on either side */
+#define EDT_HALF (EDT_NB / 2)
+#ifndef EDT_WS_WARPS
+#define EDT_WS_WARPS 8  /* warps per CTA (no block barrier: the CTA is only a container) */
+#endif
+#define EDT_STAGE_WORDS (33 * 8)
 #define EDT_MAX_PAIRS 256
 #define EDT_MAX_LEVELS 128
-#define EDT_BITS_SMEM (4 * (EDT_R + 1) * (EDT_BT_ROWS + 2 * EDT_R) * EDT_BT_WORDS + 4 * (EDT_BT_ROWS + 2 * EDT_R) * (EDT_BT_WORDS + 2))
+#define EDT_WS_SMEM (EDT_WS_WARPS * ((EDT_R + 1) * EDT_NB + 2 * EDT_STAGE_WORDS) * 4)
+static_assert(EDT_R <= 16, "the 64-bit dilation window is exact for the centre word while r <= 16");
+static_assert(EDT_R % 2 == 0 && 2 * EDT_R <= 32, "lane l owns buffer rows R + 2 l (even) and R + 2 l + 1; the 2 R kept rows are copied by one lane each");
 // distinct D = d^2 + r^2 (0 <= d, r <= EDT_R) in increasing order, limited to D <= EDT_R^2 (beyond that a pair with a
-// larger d or r, which the tile does not hold, could win); built at compile time so that the level walk is straight-line
-// code with immediate shared-memory offsets
+// larger d or r, which the buffer does not hold, could win); built at compile time so that the level walk is
+// straight-line code with immediate shared-memory offsets
 struct EdtLevels {
     int nlevels, npairs;
     int D[EDT_MAX_LEVELS];
@@ -292,131 +333,230 @@ __host__ __device__ constexpr EdtLevels edt_make_levels()
     return h;
 }
 static_assert(edt_make_levels().nlevels <= EDT_MAX_LEVELS && edt_make_levels().npairs <= EDT_MAX_PAIRS, "EDT level table sizes");
+static_assert(EDT_R * EDT_R < 256, "eight bit planes");
 
-// OR of the masks of pairs [P, PEND): base points at T[0][tile row][word]
-template <int P, int PEND>
+// The buffer of one r: rows at even positions first, then the rows at odd positions (lane l's rows are positions
+// R + 2 l and R + 2 l + 1, so a warp reads 32 consecutive words whatever the row offset: no bank conflicts).
+// Word offset of mask r of the row `e` positions below the lane's first row, relative to T + lane:
+__host__ __device__ constexpr int edt_off(int r, int e) { return r * EDT_NB + ((EDT_R + e) & 1) * EDT_HALF + ((EDT_R + e) >> 1); }
+
+// OR of the masks of pairs [P, PEND) for the lane's row ROW (0 / 1).  Row 1 at offset d reads the word row 0 reads at
+// offset d + 1 -- the same immediate address, which the compiler loads once.
+template <int P, int PEND, int ROW>
 __device__ __forceinline__ unsigned edt_pairs(const unsigned *__restrict__ base)
 {
     if constexpr (P >= PEND) return 0u;
     else {
         constexpr EdtLevels tab = edt_make_levels();
-        constexpr int ROWS = EDT_BT_ROWS + 2 * EDT_R;
         constexpr int d = tab.pd[P], r = tab.pr[P];
-        constexpr int offA = (r * ROWS - d) * EDT_BT_WORDS, offB = (r * ROWS + d) * EDT_BT_WORDS;
-        if constexpr (d == 0) return base[offA] | edt_pairs<P + 1, PEND>(base);
-        else return base[offA] | base[offB] | edt_pairs<P + 1, PEND>(base);
+        if constexpr (d == 0) return base[edt_off(r, ROW)] | edt_pairs<P + 1, PEND, ROW>(base);
+        else return base[edt_off(r, ROW - d)] | base[edt_off(r, ROW + d)] | edt_pairs<P + 1, PEND, ROW>(base);
     }
 }
-// level LV settles the cells in `nw`; their squared distance D (a compile-time constant) is recorded bit-sliced:
-// plane k collects the cells whose D has bit k set -- no per-cell work, no divergence
+// Level LV: cum = cells within squared distance D[LV] of an obstacle.  A cell's squared distance is the D of the level
+// that turned its bit on; plane k collects the cells whose D has bit k set, one update per run of consecutive levels
+// with that bit set (sv[k] = cum before the run; in the unrolled code it is just the name of an older register).
 template <int LV>
-__device__ __forceinline__ void edt_levels(const unsigned *__restrict__ base, unsigned &done, unsigned (&pl)[8])
+__device__ __forceinline__ void edt_walk(const unsigned *__restrict__ base, unsigned &cumA, unsigned &cumB, unsigned (&plA)[8], unsigned (&plB)[8],
+                                         unsigned (&svA)[8], unsigned (&svB)[8])
 {
     constexpr EdtLevels tab = edt_make_levels();
     if constexpr (LV < tab.nlevels) {
-        const unsigned nw = edt_pairs<tab.start[LV], tab.start[LV + 1]>(base) & ~done;
-        done |= nw;
         constexpr int D = tab.D[LV];
-        static_assert(D < 256, "eight bit planes");
+        constexpr int Dprev = LV > 0 ? tab.D[LV - 1] : 0;
+        constexpr int Dnext = LV + 1 < tab.nlevels ? tab.D[LV + 1] : 0;
 #pragma unroll
         for (int k = 0; k < 8; k++)
-            if ((D >> k) & 1) pl[k] |= nw;
-        if (done != 0xFFFFFFFFu) edt_levels<LV + 1>(base, done, pl);
-    }
-}
-
-__global__ void __launch_bounds__(256) k_edt_pack(const uint8_t *__restrict__ occ, unsigned *__restrict__ bits, size_t nwords)
-{
-    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (size_t)gridDim.x * blockDim.x) {
-        const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(occ) + 2 * w), b = __ldcs(reinterpret_cast<const uint4 *>(occ) + 2 * w + 1);
-        const unsigned v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        unsigned m = 0;
+            if (((D >> k) & 1) && !((Dprev >> k) & 1)) { svA[k] = cumA; svB[k] = cumB; }
+        cumA |= edt_pairs<tab.start[LV], tab.start[LV + 1], 0>(base);
+        cumB |= edt_pairs<tab.start[LV], tab.start[LV + 1], 1>(base);
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const unsigned nz = __vcmpne4(v[i], 0u) & 0x01010101u;
-            m |= (((nz * 0x01020408u) >> 24) & 0xFu) << (4 * i);
+        for (int k = 0; k < 8; k++)
+            if (((D >> k) & 1) && !((Dnext >> k) & 1)) { plA[k] |= cumA & ~svA[k]; plB[k] |= cumB & ~svB[k]; }
+        if constexpr (LV % 3 == 2 && LV + 1 < tab.nlevels) {
+            if ((cumA & cumB) == 0xFFFFFFFFu) {  // every cell of both words is settled: close the runs that are still open and stop
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (((D >> k) & 1) && ((Dnext >> k) & 1)) { plA[k] |= cumA & ~svA[k]; plB[k] |= cumB & ~svB[k]; }
+                return;
+            }
         }
-        bits[w] = m;
+        edt_walk<LV + 1>(base, cumA, cumB, plA, plB, svA, svB);
     }
 }
 
-__global__ void __launch_bounds__(EDT_BT_ROWS * EDT_BT_WORDS) k_edt_bits(const unsigned *__restrict__ bits, int32_t *__restrict__ out, int W, int HW,
-                                                                         unsigned *__restrict__ fix_list, unsigned *__restrict__ fix_count, unsigned fix_cap,
-                                                                         int *__restrict__ flag)
+// occupancy bytes -> bit words, stored COLUMN-major: word w of row x at bitsT[w * Wp + x] (Wp = W rounded up to even, the
+// pad row is zero).  A strip (one word column) is then contiguous along x: the two rows a lane of k_edt_strips owns
+// are one 8-byte load and a warp's 64 rows one 256-byte run (row-major, every lane fetched its own 32-byte sector three
+// times per step: as many data-pipe wavefronts as the whole walk).  One CTA per 32 rows x 32 words, transposed through
+// shared memory so that both the byte reads and the word writes are coalesced.
+__global__ void __launch_bounds__(256) k_edt_pack(const uint8_t *__restrict__ occ, unsigned *__restrict__ bitsT, int W, int HW, int Wp)
 {
-    (void)flag;
-    constexpr int ROWS = EDT_BT_ROWS + 2 * EDT_R, TW = EDT_BT_WORDS;
-    extern __shared__ __align__(16) unsigned char edt_smem[];
-    unsigned(*T)[ROWS][TW] = reinterpret_cast<unsigned(*)[ROWS][TW]>(edt_smem);                                   // [EDT_R + 1]
-    unsigned(*raw)[TW + 2] = reinterpret_cast<unsigned(*)[TW + 2]>(edt_smem + sizeof(unsigned) * (EDT_R + 1) * ROWS * TW);
-    const int x0 = blockIdx.y * EDT_BT_ROWS, w0 = blockIdx.x * TW;
-    const int tid = threadIdx.x;
-    // raw occupancy words of the tile + halo (zero outside the grid)
-    for (int i = tid; i < ROWS * (TW + 2); i += blockDim.x) {
-        const int rr = i / (TW + 2), ww = i - rr * (TW + 2);
-        const int x = x0 - EDT_R + rr, w = w0 - 1 + ww;
-        raw[rr][ww] = (x >= 0 && x < W && w >= 0 && w < HW) ? __ldg(bits + (size_t)x * HW + w) : 0u;
+    __shared__ unsigned tile[32][33];
+    const int x0 = blockIdx.y * 32, w0 = blockIdx.x * 32;
+    const int wi = threadIdx.x & 31, r0 = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int x = x0 + r0 + 8 * j, w = w0 + wi;
+        unsigned m = 0;
+        if (x < W && w < HW) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(occ + ((size_t)x * HW + w) * 32);
+            const uint4 a = __ldcs(src), b = __ldcs(src + 1);
+            const unsigned v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const unsigned nz = __vcmpne4(v[i], 0u) & 0x01010101u;
+                m |= (((nz * 0x01020408u) >> 24) & 0xFu) << (4 * i);
+            }
+        }
+        tile[r0 + 8 * j][wi] = m;
     }
     __syncthreads();
-    // B_r for r = 0..EDT_R from a three-word window (exact for the centre word while r <= 32)
-    for (int i = tid; i < ROWS * TW; i += blockDim.x) {
-        const int rr = i / TW, ww = i - rr * TW;
-        unsigned L = raw[rr][ww], C = raw[rr][ww + 1], R = raw[rr][ww + 2];
-        T[0][rr][ww] = C;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int w = w0 + r0 + 8 * j, x = x0 + wi;
+        if (w < HW && x < Wp) bitsT[(size_t)w * Wp + x] = tile[wi][r0 + 8 * j];
+    }
+}
+
+// a <-> b: the bits of `a` selected by (m << s) change places with the bits of `b` selected by m
+#define EDT_DSWAP(a, b, s, m) { const unsigned t__ = (((a) >> (s)) ^ (b)) & (m); (b) ^= t__; (a) ^= t__ << (s); }
+
+// 8 bit planes of one word -> the 32 squared distances as bytes, parked in the warp's staging buffer (row-major, 8 words
+// per row, every group of four rows shifted by one word: conflict-free for the row-wise writes here and for the
+// column-wise reads of edt_flush_rows)
+__device__ __forceinline__ void edt_stage_row(unsigned (&q)[8], unsigned *__restrict__ st /* stage + 33 (lane >> 2) + 8 (lane & 3) */)
+{
+    // transpose the four 8 x 8 bit matrices (rows: planes, columns: the bits of one byte): afterwards byte j of q[i] is the
+    // squared distance of cell 8 j + i
+#pragma unroll
+    for (int k = 0; k < 4; k++) EDT_DSWAP(q[k], q[k + 4], 4, 0x0F0F0F0Fu)
+    EDT_DSWAP(q[0], q[2], 2, 0x33333333u) EDT_DSWAP(q[1], q[3], 2, 0x33333333u)
+    EDT_DSWAP(q[4], q[6], 2, 0x33333333u) EDT_DSWAP(q[5], q[7], 2, 0x33333333u)
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) EDT_DSWAP(q[k], q[k + 1], 1, 0x55555555u)
+    // 4 x 4 byte transposes: word c = cells 4 c .. 4 c + 3 = byte (c >> 1) of q[4 (c & 1) + 0..3]
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const unsigned t0 = __byte_perm(q[4 * h], q[4 * h + 1], 0x5140u), t1 = __byte_perm(q[4 * h], q[4 * h + 1], 0x7362u);
+        const unsigned t2 = __byte_perm(q[4 * h + 2], q[4 * h + 3], 0x5140u), t3 = __byte_perm(q[4 * h + 2], q[4 * h + 3], 0x7362u);
+        st[h] = __byte_perm(t0, t2, 0x5410u);
+        st[2 + h] = __byte_perm(t0, t2, 0x7632u);
+        st[4 + h] = __byte_perm(t1, t3, 0x5410u);
+        st[6 + h] = __byte_perm(t1, t3, 0x7632u);
+    }
+}
+// The staged rows go out coalesced: in store i the eight lanes 8 k .. 8 k + 7 write the 128 bytes of staged row 4 i + k
+// (grid row x0 + 2 (4 i + k): a lane's two rows are adjacent, so a staging buffer holds every other row).  A store in
+// which every lane writes its own row costs 32 data-pipe wavefronts instead of 4 -- that, not DRAM, bounded the
+// transform (ncu: LSU data pipe 86 % busy, 3/4 of it these stores).
+__device__ __forceinline__ void edt_flush_rows(const unsigned *__restrict__ stage, int32_t *__restrict__ out, int x0, int xe, int HW, int w, int lane)
+{
+    const int k = lane >> 3, c = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const unsigned v = stage[lane + 33 * i];
+        const int x = x0 + 2 * (4 * i + k);
+        if (x < xe) {
+            int4 o;
+            o.x = (int)__byte_perm(v, 0u, 0x4440u); o.y = (int)__byte_perm(v, 0u, 0x4441u);
+            o.z = (int)__byte_perm(v, 0u, 0x4442u); o.w = (int)__byte_perm(v, 0u, 0x4443u);
+            __stcs(reinterpret_cast<int4 *>(out + ((size_t)x * HW + w) * 32) + c, o);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(EDT_WS_WARPS * 32) k_edt_strips(const unsigned *__restrict__ bitsT, int32_t *__restrict__ out, int W, int HW, int Wp, int seg_rows,
+                                                                  unsigned *__restrict__ fix_list, unsigned *__restrict__ fix_count, unsigned fix_cap)
+{
+    extern __shared__ __align__(16) unsigned edt_buf[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = blockIdx.x * EDT_WS_WARPS + warp;  // the strip: bit word w of every row = columns 32 w .. 32 w + 31
+    if (w >= HW) return;                             // (whole warps leave; there is no block barrier below)
+    unsigned *__restrict__ T = edt_buf + warp * ((EDT_R + 1) * EDT_NB + 2 * EDT_STAGE_WORDS);  // T[r][even rows | odd rows]
+    unsigned *__restrict__ stage = T + (EDT_R + 1) * EDT_NB;  // two staging buffers: the lanes' first rows, the lanes' second rows
+    unsigned *__restrict__ st_mine = stage + 33 * (lane >> 2) + 8 * (lane & 3);
+    const int xs = blockIdx.y * seg_rows, xe = min(xs + seg_rows, W);
+    const bool hasL = w > 0, hasR = w + 1 < HW;
+    unsigned raw[2][3];
+    auto load_raw = [&](int x) {  // the three words around the strip of rows x (even) and x + 1 (zero outside the grid)
+#pragma unroll
+        for (int i = 0; i < 3; i++) { raw[0][i] = 0; raw[1][i] = 0; }
+        if (x >= 0 && x < W) {
+            const uint2 *__restrict__ p = reinterpret_cast<const uint2 *>(bitsT + (size_t)w * Wp + x);
+            const uint2 c = __ldg(p);
+            raw[0][1] = c.x; raw[1][1] = c.y;
+            if (hasL) { const uint2 l = __ldg(p - (Wp >> 1)); raw[0][0] = l.x; raw[1][0] = l.y; }
+            if (hasR) { const uint2 r = __ldg(p + (Wp >> 1)); raw[0][2] = r.x; raw[1][2] = r.y; }
+        }
+    };
+    auto build = [&](unsigned *__restrict__ t, const unsigned (&v)[3]) {  // B_r for r = 0..EDT_R of one row, t = its slot in the r = 0 buffer
+        unsigned lo = __funnelshift_r(v[0], v[1], 16), hi = __funnelshift_r(v[1], v[2], 16);
+        t[0] = v[1];
 #pragma unroll
         for (int r = 1; r <= EDT_R; r++) {
-            const unsigned nl = L | (L << 1) | __funnelshift_r(L, C, 1);
-            const unsigned nc = C | __funnelshift_l(L, C, 1) | __funnelshift_r(C, R, 1);
-            const unsigned nr = R | __funnelshift_l(C, R, 1) | (R >> 1);
-            L = nl; C = nc; R = nr;
-            T[r][rr][ww] = C;
+            const unsigned nlo = lo | (lo << 1) | __funnelshift_r(lo, hi, 1);
+            const unsigned nhi = hi | __funnelshift_l(lo, hi, 1) | (hi >> 1);
+            lo = nlo; hi = nhi;
+            t[r * EDT_NB] = __funnelshift_r(lo, hi, 16);
         }
+    };
+    // Buffer position p holds row a - R + p of the current step (rows a .. a + 63 are settled, lane l: positions R + 2 l
+    // and R + 2 l + 1).  Going to the next step the last 2 R rows move to the front (one lane per row), 64 new rows are
+    // built behind them.  Prologue: the 2 R rows in front of the segment, built where the first step's move expects them.
+    if (lane < EDT_R) {
+        load_raw(xs - EDT_R + 2 * lane);
+        build(T + EDT_STEP / 2 + lane, raw[0]); build(T + EDT_HALF + EDT_STEP / 2 + lane, raw[1]);
     }
-    __syncthreads();
-    // level walk + write-out: thread = (row, word) = 32 cells = 128 contiguous output bytes
-    {
-        const int row = tid / TW, ww = tid - row * TW, tr = row + EDT_R;
-        const int x = x0 + row, w = w0 + ww;
-        unsigned um = 0;
-        if (x < W && w < HW) {
-            unsigned done = 0;
-            unsigned pl[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-            edt_levels<0>(&T[0][tr][ww], done, pl);
-            int4 *dst = reinterpret_cast<int4 *>(out + ((size_t)x * HW + w) * 32);
+    load_raw(xs + EDT_R + 2 * lane);
+    unsigned *__restrict__ mv = T + (lane & 1) * EDT_HALF + (lane >> 1);  // lane j < 2 R moves position 64 + j to position j
+    for (int a = xs; a < xe; a += EDT_STEP) {
+        __syncwarp();
+        if (lane < 2 * EDT_R) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                unsigned acc = 0;  // four cells, one byte each
-#pragma unroll
-                for (int k = 0; k < 8; k++) acc |= ((((pl[k] >> (4 * j)) & 0xFu) * 0x00204081u) & 0x01010101u) << k;
-                const unsigned dn = done >> (4 * j);
-                int4 v;
-                v.x = (dn & 1u) ? (int)(acc & 0xFFu) : 0x7FFFFFFF;
-                v.y = (dn & 2u) ? (int)((acc >> 8) & 0xFFu) : 0x7FFFFFFF;
-                v.z = (dn & 4u) ? (int)((acc >> 16) & 0xFFu) : 0x7FFFFFFF;
-                v.w = (dn & 8u) ? (int)(acc >> 24) : 0x7FFFFFFF;
-                __stcs(dst + j, v);
-            }
-            um = ~done;  // farther than EDT_R from every obstacle: fix-up list
+            for (int r = 0; r <= EDT_R; r++) mv[r * EDT_NB] = mv[r * EDT_NB + EDT_STEP / 2];
         }
-        // The unresolved cells go straight to the global list, one reservation per warp: no block barrier after the walk (its
-        // length differs from word to word -- the barrier that used to collect a per-tile list was the top stall of this
-        // kernel, r01: 8.2 per issue), warps retire as they finish.  A list longer than fix_cap makes k_edt_fix raise the
-        // flag and the windowed path redoes the grid.
-        const unsigned lane = (unsigned)tid & 31u;
-        const unsigned mine = (unsigned)__popc(um);
-        unsigned incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (unsigned)o) incl += t; }
-        const unsigned total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        __syncwarp();
+        build(T + EDT_R + lane, raw[0]); build(T + EDT_HALF + EDT_R + lane, raw[1]);  // positions 2 R + 2 l, 2 R + 2 l + 1 = rows a + R + 2 l (+ 1)
+        if (a + EDT_STEP < xe) load_raw(a + EDT_STEP + EDT_R + 2 * lane);
+        __syncwarp();
+        const int x = a + 2 * lane;
+        unsigned umA = 0, umB = 0;
+        if (x < xe) {
+            unsigned cumA = 0, cumB = 0;
+            unsigned qA[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, qB[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            unsigned svA[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, svB[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            edt_walk<0>(T + lane, cumA, cumB, qA, qB, svA, svB);
+            umA = ~cumA;  // farther than EDT_R from every obstacle: fix-up list
+            edt_stage_row(qA, st_mine);
+            if (x + 1 < xe) umB = ~cumB;
+            edt_stage_row(qB, st_mine + EDT_STAGE_WORDS);
+        }
+        __syncwarp();
+        edt_flush_rows(stage, out, a, xe, HW, w, lane);
+        edt_flush_rows(stage + EDT_STAGE_WORDS, out, a + 1, xe, HW, w, lane);
+        // The unresolved cells go to the global list, one reservation per warp.  A list longer than fix_cap makes
+        // k_edt_fix raise the flag and the windowed path redoes the grid.
+        const unsigned mine = (unsigned)(__popc(umA) + __popc(umB));
+        const unsigned total = __reduce_add_sync(0xFFFFFFFFu, mine);
         if (total) {
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(fix_count, total);
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            size_t pos = (size_t)base + (incl - mine);
-            while (um) {
-                const int b = __ffs(um) - 1;
-                um &= um - 1;
+            unsigned incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+            unsigned rbase = 0;
+            if (lane == 0) rbase = atomicAdd(fix_count, total);
+            rbase = __shfl_sync(0xFFFFFFFFu, rbase, 0);
+            size_t pos = (size_t)rbase + (incl - mine);
+            while (umA) {
+                const int b = __ffs(umA) - 1;
+                umA &= umA - 1;
                 if (pos < fix_cap) { fix_list[2 * pos] = (unsigned)x; fix_list[2 * pos + 1] = (unsigned)(w * 32 + b); }
+                pos++;
+            }
+            while (umB) {
+                const int b = __ffs(umB) - 1;
+                umB &= umB - 1;
+                if (pos < fix_cap) { fix_list[2 * pos] = (unsigned)(x + 1); fix_list[2 * pos + 1] = (unsigned)(w * 32 + b); }
                 pos++;
             }
         }
@@ -424,24 +564,48 @@ __global__ void __launch_bounds__(EDT_BT_ROWS * EDT_BT_WORDS) k_edt_bits(const u
 }
 
 // nearest set bit to column y in one row of the bit grid, looking no farther than `lim` cells; returns the distance or -1
-__device__ int edt_row_nearest(const unsigned *__restrict__ rowbits, int HW, int y, int lim)
+// (rowbits[w * stride] is word w of the row: the bit grid is stored column-major, k_edt_pack)
+__device__ int edt_row_nearest(const unsigned *__restrict__ rowbits, size_t stride, int HW, int y, int lim)
 {
     const int w = y >> 5, b = y & 31;
     int best = -1;
     {
-        const unsigned m = rowbits[w];
+        const unsigned m = rowbits[w * stride];
         const unsigned below = m & (0xFFFFFFFFu >> (31 - b)), above = m >> b;
         if (below) best = b - (31 - __clz(below));
         if (above) { const int d = __ffs(above) - 1; if (best < 0 || d < best) best = d; }
     }
     for (int k = 1; (k - 1) * 32 < lim && (best < 0 || (k - 1) * 32 < best); k++) {
-        if (w - k >= 0) { const unsigned m = rowbits[w - k]; if (m) { const int d = y - ((w - k) * 32 + 31 - __clz(m)); if (best < 0 || d < best) best = d; } }
-        if (w + k < HW) { const unsigned m = rowbits[w + k]; if (m) { const int d = (w + k) * 32 + __ffs(m) - 1 - y; if (best < 0 || d < best) best = d; } }
+        if (w - k >= 0) { const unsigned m = rowbits[(w - k) * stride]; if (m) { const int d = y - ((w - k) * 32 + 31 - __clz(m)); if (best < 0 || d < best) best = d; } }
+        if (w + k < HW) { const unsigned m = rowbits[(w + k) * stride]; if (m) { const int d = (w + k) * 32 + __ffs(m) - 1 - y; if (best < 0 || d < best) best = d; } }
     }
     return (best >= 0 && best <= lim) ? best : -1;
 }
 
-__global__ void __launch_bounds__(128) k_edt_fix(const unsigned *__restrict__ bits, int32_t *__restrict__ out, int W, int HW,
+// exact squared distance of cell (x, y) by brute force on the bit grid, the 32 lanes of a warp sharing the row offsets:
+// lane l looks at the rows x +- d for d = l, l + 32, ...; the warp's best so far bounds every lane's search after each round
+__device__ __forceinline__ long long edt_cell_warp(const unsigned *__restrict__ bits, int W, int HW, int Wp, int x, int y, unsigned lane)
+{
+    const int H = HW * 32;
+    long long best = (long long)1 << 40;
+    for (int d0 = 0; (long long)d0 * d0 < best && (x - d0 >= 0 || x + d0 < W); d0 += 32) {
+        const int d = d0 + (int)lane;
+        long long mine = (long long)1 << 40;
+        if ((long long)d * d < best) {
+            const long long room = best - (long long)d * d;
+            int lim = H;
+            if (room < (long long)H * H) { lim = (int)sqrtf((float)room) + 1; if (lim > H) lim = H; }
+            if (x - d >= 0) { const int g = edt_row_nearest(bits + (x - d), (size_t)Wp, HW, y, lim); if (g >= 0) mine = min(mine, (long long)d * d + (long long)g * g); }
+            if (d > 0 && x + d < W) { const int g = edt_row_nearest(bits + (x + d), (size_t)Wp, HW, y, lim); if (g >= 0) mine = min(mine, (long long)d * d + (long long)g * g); }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mine = min(mine, __shfl_xor_sync(0xFFFFFFFFu, mine, o));
+        best = min(best, mine);
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(128) k_edt_fix(const unsigned *__restrict__ bits, int32_t *__restrict__ out, int W, int HW, int Wp,
                                                  const unsigned *__restrict__ fix_list, const unsigned *__restrict__ fix_count, unsigned fix_cap,
                                                  int *__restrict__ flag)
 {
@@ -458,33 +622,18 @@ __global__ void __launch_bounds__(128) k_edt_fix(const unsigned *__restrict__ bi
                 const long long room = best - (long long)d * d;
                 int lim = H;
                 if (room < (long long)H * H) { lim = (int)sqrtf((float)room) + 1; if (lim > H) lim = H; }
-                if (x - d >= 0) { const int g = edt_row_nearest(bits + (size_t)(x - d) * HW, HW, y, lim); if (g >= 0) best = min(best, (long long)d * d + (long long)g * g); }
-                if (d > 0 && x + d < W) { const int g = edt_row_nearest(bits + (size_t)(x + d) * HW, HW, y, lim); if (g >= 0) best = min(best, (long long)d * d + (long long)g * g); }
+                if (x - d >= 0) { const int g = edt_row_nearest(bits + (x - d), (size_t)Wp, HW, y, lim); if (g >= 0) best = min(best, (long long)d * d + (long long)g * g); }
+                if (d > 0 && x + d < W) { const int g = edt_row_nearest(bits + (x + d), (size_t)Wp, HW, y, lim); if (g >= 0) best = min(best, (long long)d * d + (long long)g * g); }
             }
             out[(size_t)x * H + y] = best > 0x7FFFFFFFLL ? 0x7FFFFFFF : (int32_t)best;
         }
         return;
     }
-    // short list (small grids): one warp per cell, lane l looks at the rows x +- d for d = l, l + 32, ...; the warp's
-    // best so far bounds every lane's search after each round (a listed cell is > EDT_R from everything, so the brute
-    // force walks tens of rows: one thread doing that alone was the longest kernel of the whole transform at 1024^2)
+    // short list (small grids): one warp per cell (a listed cell is > EDT_R from everything, so the brute force walks tens
+    // of rows: one thread doing that alone was the longest kernel of the whole transform at 1024^2)
     for (unsigned i = warp; i < n; i += nwarps) {
         const int x = (int)fix_list[2 * (size_t)i], y = (int)fix_list[2 * (size_t)i + 1];
-        long long best = (long long)1 << 40;
-        for (int d0 = 0; (long long)d0 * d0 < best && (x - d0 >= 0 || x + d0 < W); d0 += 32) {
-            const int d = d0 + (int)lane;
-            long long mine = (long long)1 << 40;
-            if ((long long)d * d < best) {
-                const long long room = best - (long long)d * d;
-                int lim = H;
-                if (room < (long long)H * H) { lim = (int)sqrtf((float)room) + 1; if (lim > H) lim = H; }
-                if (x - d >= 0) { const int g = edt_row_nearest(bits + (size_t)(x - d) * HW, HW, y, lim); if (g >= 0) mine = min(mine, (long long)d * d + (long long)g * g); }
-                if (d > 0 && x + d < W) { const int g = edt_row_nearest(bits + (size_t)(x + d) * HW, HW, y, lim); if (g >= 0) mine = min(mine, (long long)d * d + (long long)g * g); }
-            }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) mine = min(mine, __shfl_xor_sync(0xFFFFFFFFu, mine, o));
-            best = min(best, mine);
-        }
+        const long long best = edt_cell_warp(bits, W, HW, Wp, x, y, lane);
         if (lane == 0) out[(size_t)x * H + y] = best > 0x7FFFFFFFLL ? 0x7FFFFFFF : (int32_t)best;
     }
 }
@@ -493,7 +642,7 @@ static int edt_upload_levels(fx_context *ctx)
 {
     static bool done[64] = {false};
     if (ctx->device >= 0 && ctx->device < 64 && done[ctx->device]) return FX_OK;
-    FX_CUDA(ctx, cudaFuncSetAttribute(k_edt_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, EDT_BITS_SMEM));
+    FX_CUDA(ctx, cudaFuncSetAttribute(k_edt_strips, cudaFuncAttributeMaxDynamicSharedMemorySize, EDT_WS_SMEM));
     if (ctx->device >= 0 && ctx->device < 64) done[ctx->device] = true;
     return FX_OK;
 }
@@ -512,6 +661,12 @@ static int edt_reserve(fx_context *ctx, size_t cells)
     return FX_OK;
 }
 static int edt_rows_launch(fx_context *ctx, const uint8_t *occ, uint16_t *g, int W, int H, cudaStream_t st);
+static int edt_cols_grid(fx_context *ctx, int W, int H)
+{
+    const long long tiles = (long long)((H + EDT_TYC - 1) / EDT_TYC) * ((W + EDT_TX - 1) / EDT_TX);
+    const long long cap = (long long)ctx->sm_count * 16;
+    return (int)(tiles < cap ? tiles : cap);
+}
 static int edt_cols_launch(fx_context *ctx, const uint16_t *g, int32_t *dist2, int W, int H, cudaStream_t st);
 
 extern "C" int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W, int H, void *stream)
@@ -534,19 +689,28 @@ extern "C" int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W
         int rc = edt_upload_levels(ctx);
         if (rc) return rc;
         const int HW = H / 32;
-        const size_t nw = (size_t)W * HW;
+        const int Wp = (W + 1) & ~1;  // column stride of the bit grid (even: a lane's two rows are one aligned 8-byte load)
         unsigned *bitsb = reinterpret_cast<unsigned *>(ctx->edt_s);        // scratch reuse: cells*2 bytes >= cells/8
         unsigned *fix_list = reinterpret_cast<unsigned *>(ctx->edt_t);     // cells*2 bytes -> cells/4 entries of 8 bytes
         unsigned *fix_count = reinterpret_cast<unsigned *>(ctx->edt_flag) + 1;
         size_t cap = cells / 4; if (cap > (1u << 22)) cap = 1u << 22;
         FX_CUDA(ctx, cudaMemsetAsync(fix_count, 0, sizeof(unsigned), st));
-        int pb = (int)((nw + 255) / 256); if (pb > ctx->sm_count * 16) pb = ctx->sm_count * 16;
-        k_edt_pack<<<pb, 256, 0, st>>>(occ, bitsb, nw);
+        k_edt_pack<<<dim3((HW + 31) / 32, (Wp + 31) / 32), 256, 0, st>>>(occ, bitsb, W, HW, Wp);
         FX_LAUNCH_CHECK(ctx);
-        dim3 gt((HW + EDT_BT_WORDS - 1) / EDT_BT_WORDS, (W + EDT_BT_ROWS - 1) / EDT_BT_ROWS);
-        k_edt_bits<<<gt, EDT_BT_ROWS * EDT_BT_WORDS, EDT_BITS_SMEM, st>>>(bitsb, dist2, W, HW, fix_list, fix_count, (unsigned)cap, ctx->edt_flag);
+        // segments of rows per strip: about four CTAs per resident slot (strips differ in work: the walk stops when a word
+        // is settled), each segment a multiple of the 64-row step and at least four steps (a segment starts with 2 R extra rows)
+        const int gx = (HW + EDT_WS_WARPS - 1) / EDT_WS_WARPS;
+        int resident = 0;
+        FX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_edt_strips, EDT_WS_WARPS * 32, EDT_WS_SMEM));
+        if (resident < 1) resident = 1;
+        int segs = ctx->sm_count * resident * 4 / gx;
+        if (segs < 1) segs = 1;
+        int seg_rows = ((W + segs - 1) / segs + EDT_STEP - 1) / EDT_STEP * EDT_STEP;
+        if (seg_rows < 4 * EDT_STEP) seg_rows = 4 * EDT_STEP;
+        segs = (W + seg_rows - 1) / seg_rows;
+        k_edt_strips<<<dim3(gx, segs), EDT_WS_WARPS * 32, EDT_WS_SMEM, st>>>(bitsb, dist2, W, HW, Wp, seg_rows, fix_list, fix_count, (unsigned)cap);
         FX_LAUNCH_CHECK(ctx);
-        k_edt_fix<<<ctx->sm_count * 4, 128, 0, st>>>(bitsb, dist2, W, HW, fix_list, fix_count, (unsigned)cap, ctx->edt_flag);
+        k_edt_fix<<<ctx->sm_count * 4, 128, 0, st>>>(bitsb, dist2, W, HW, Wp, fix_list, fix_count, (unsigned)cap, ctx->edt_flag);
         FX_LAUNCH_CHECK(ctx);
         // the windowed path below runs only if the flag was raised
         const int nwords = (H + 31) / 32;
@@ -557,8 +721,7 @@ extern "C" int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W
         if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
         k_edt_rows<<<blocks, warps * 32, smem, st>>>(occ, ctx->edt_g, W, H, ctx->edt_flag);
         FX_LAUNCH_CHECK(ctx);
-        dim3 g2((H + EDT_TYC - 1) / EDT_TYC, (W + EDT_TX - 1) / EDT_TX);
-        k_edt_cols_tile<<<g2, 256, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_flag + 2, ctx->edt_flag);
+        k_edt_cols_tile<<<edt_cols_grid(ctx, W, H), 256, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_flag + 2, ctx->edt_flag);
         FX_LAUNCH_CHECK(ctx);
         k_edt_cols_exact<<<(H + 127) / 128, 128, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_s, ctx->edt_t, ctx->edt_flag + 2);
         FX_LAUNCH_CHECK(ctx);
@@ -591,8 +754,7 @@ static int edt_cols_launch(fx_context *ctx, const uint16_t *g, int32_t *dist2, i
     int b2 = (int)((cells + 255) / 256);
     if (b2 > ctx->sm_count * 16) b2 = ctx->sm_count * 16;
     if (H % 8 == 0 && ((uintptr_t)g & 15u) == 0) {
-        dim3 gt((H + EDT_TYC - 1) / EDT_TYC, (W + EDT_TX - 1) / EDT_TX);
-        k_edt_cols_tile<<<gt, 256, 0, st>>>(g, dist2, W, H, ctx->edt_flag, nullptr);
+        k_edt_cols_tile<<<edt_cols_grid(ctx, W, H), 256, 0, st>>>(g, dist2, W, H, ctx->edt_flag, nullptr);
     } else {
         k_edt_cols_window<<<b2, 256, 0, st>>>(g, dist2, W, H, ctx->edt_flag);
     }

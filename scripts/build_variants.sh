@@ -21,6 +21,8 @@ for v in "$@"; do
     t128b10_cg) b $v -DFX_SEARCH_THREADS=128 -DFX_SEARCH_MINB=10;;
     t256b5_cg) b $v -DFX_SEARCH_THREADS=256 -DFX_SEARCH_MINB=5;;
     clk128) b $v -DFX_PHASE_CLOCKS -DFX_SEARCH_MINB=8;;
+    edt_*) # edt_<R>_<inline>_<rows>_<words>
+      IFS=_ read -r _ r inl rows words <<< "$v"; b $v -DEDT_R=$r -DEDT_INLINE_FIX=${inl}u -DEDT_BT_ROWS=$rows -DEDT_BT_WORDS=$words;;
     *) echo unknown variant $v; exit 1;;
   esac
 done
