@@ -2,6 +2,14 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <atomic>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -57,8 +65,10 @@ extern "C" int fx_create(int device, fx_context **out)
     if (const char *e = getenv("FUXI_B200_CLUSTER")) ctx->cfg_cluster = e[0] != '0';  // tests run the latency form both ways
     if (const char *e = getenv("FUXI_B200_WIDE_BELOW")) ctx->cfg_wide_below = atoi(e);  // tuning experiments only
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
-    e = cudaMalloc(&ctx->counters, 16 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemset(ctx->counters, 0, 16 * sizeof(unsigned long long));
+    // [0..15] per-launch counters (zeroed by every launch), [16..23] the 16 x u32 first-bound table of the latency forms
+    // of the search (persists across launches, search.cu: fx_first_bound)
+    e = cudaMalloc(&ctx->counters, 24 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ctx->counters, 0, 24 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->fstate, 32 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(ctx->fstate, 0, 32 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->edt_flag, 4 * sizeof(int));
@@ -153,39 +163,187 @@ static int grow_pinned(fx_context *ctx, size_t want) { return fx_grow_pinned(ctx
 // (scripts/jps1.py:20-29).  Converting 16 Mi cells with numpy costs 15 ms on the host (r01f), more than the search:
 // the f64 entry point does `== 1.0 -> uint8` straight into the pinned staging buffer with a few host threads,
 // chunk by chunk, each chunk's H2D copy overlapping the conversion of the next.
-static void convert_f64_chunk(const double *src, uint8_t *dst, size_t n, int nthreads)
-{
-    auto work = [=](size_t a, size_t b) {
-        for (size_t i = a; i < b; i++) dst[i] = src[i] == 1.0 ? (uint8_t)1 : (uint8_t)0;
-    };
-    if (nthreads <= 1 || n < (1u << 18)) { work(0, n); return; }
-    std::vector<std::thread> th;
-    const size_t per = (n + nthreads - 1) / nthreads;
-    for (int t = 1; t < nthreads; t++) {
-        const size_t a = (size_t)t * per, b = a + per < n ? a + per : n;
-        if (a < b) th.emplace_back(work, a, b);
+// Host worker pool (process-wide, created on first use): pageable <-> pinned staging copies of tens of MB and the
+// float64 -> uint8 conversion run on a few host threads.  Round 1 spawned std::threads per call: 15 spawns per chunk
+// x 4 chunks cost more than a millisecond of a 7 ms single-query call.
+namespace {
+struct HostPool {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<void(int)> fn;
+    int ntasks = 0;
+    std::atomic<int> next{0}, pending{0};
+    unsigned long long gen = 0;
+    bool stop = false;
+    explicit HostPool(int n)
+    {
+        for (int i = 0; i < n; i++)
+            workers.emplace_back([this]() {
+                unsigned long long seen = 0;
+                for (;;) {
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [&]() { return stop || gen != seen; });
+                        if (stop) return;
+                        seen = gen;
+                    }
+                    drain();
+                }
+            });
     }
-    work(0, per < n ? per : n);
-    for (auto &t : th) t.join();
+    ~HostPool()
+    {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        for (auto &t : workers) t.join();
+    }
+    void drain()
+    {
+        for (;;) {
+            const int i = next.fetch_add(1, std::memory_order_acq_rel);
+            if (i >= ntasks) return;
+            fn(i);
+            pending.fetch_sub(1, std::memory_order_acq_rel);
+        }
+    }
+    // run f(0..n-1) on the pool and the calling thread; `between`, if given, is called by the calling thread after each
+    // of its own tasks (used to issue H2D copies of the parts that are complete while the rest is still being filled)
+    void run(int n, std::function<void(int)> f, const std::function<void()> &between = nullptr)
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            fn = std::move(f); ntasks = n; next.store(0); pending.store(n); gen++;
+        }
+        cv.notify_all();
+        for (;;) {
+            const int i = next.fetch_add(1, std::memory_order_acq_rel);
+            if (i >= ntasks) break;
+            fn(i);
+            pending.fetch_sub(1, std::memory_order_acq_rel);
+            if (between) between();
+        }
+        while (pending.load(std::memory_order_acquire) > 0) {
+            if (between) between();
+            std::this_thread::yield();
+        }
+    }
+};
+HostPool &host_pool()
+{
+    static std::mutex one;       // one job at a time (contexts on several threads share the pool)
+    static HostPool *pool = nullptr;
+    std::lock_guard<std::mutex> lk(one);
+    if (!pool) {
+        unsigned hc = std::thread::hardware_concurrency();
+        int n = (int)(hc == 0 ? 1 : (hc > 16 ? 16 : hc)) - 1;
+        if (const char *e = getenv("FUXI_B200_HOST_THREADS")) n = atoi(e) - 1;  // tuning experiments only
+        pool = new HostPool(n < 0 ? 0 : n);  // never destroyed: worker threads must not be joined from a static destructor
+    }
+    return *pool;
 }
+std::mutex g_pool_job;
+}  // namespace
 
 // pageable <-> pinned staging copies of tens of MB (the grid in, the path buffers out): a few host threads instead of
 // one memcpy (67 MB of path buffers per 8192-query batch took 8 ms single-threaded, 6 % of the end-to-end step)
 static void par_memcpy(void *dst, const void *src, size_t bytes)
 {
-    unsigned hc = std::thread::hardware_concurrency();
-    const int nthreads = (int)(hc == 0 ? 1 : (hc > 8 ? 8 : hc));
-    if (nthreads <= 1 || bytes < ((size_t)4 << 20)) { memcpy(dst, src, bytes); return; }
-    std::vector<std::thread> th;
-    const size_t per = ((bytes + nthreads - 1) / nthreads + 4095) & ~(size_t)4095;
-    for (int t = 1; t < nthreads; t++) {
-        const size_t a = (size_t)t * per;
-        if (a >= bytes) break;
-        const size_t nb = a + per < bytes ? per : bytes - a;
-        th.emplace_back([=]() { memcpy((char *)dst + a, (const char *)src + a, nb); });
+    if (bytes < ((size_t)4 << 20)) { memcpy(dst, src, bytes); return; }
+    const size_t per = (size_t)1 << 20;
+    const int n = (int)((bytes + per - 1) / per);
+    std::lock_guard<std::mutex> job(g_pool_job);
+    host_pool().run(n, [=](int i) {
+        const size_t a = (size_t)i * per, nb = a + per < bytes ? per : bytes - a;
+        memcpy((char *)dst + a, (const char *)src + a, nb);
+    });
+}
+
+// Filling the pinned staging buffer with NON-TEMPORAL stores: written with ordinary stores, the 16 MB of a 4096^2 grid
+// sit dirty in the caches of the worker threads' cores, and the DMA engine's reads have to snoop them out one line at a
+// time -- the H2D copy then runs at 7 GB/s instead of 29 (r02j trace: 2.3 ms instead of 0.6 for the same bytes).
+static inline void nt_copy_u8(uint8_t *dst, const uint8_t *src, size_t n)
+{
+#if defined(__x86_64__)
+    size_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 15u)) { dst[i] = src[i]; i++; }
+    for (; i + 16 <= n; i += 16) _mm_stream_si128((__m128i *)(dst + i), _mm_loadu_si128((const __m128i *)(src + i)));
+    for (; i < n; i++) dst[i] = src[i];
+    _mm_sfence();
+#else
+    memcpy(dst, src, n);
+#endif
+}
+static inline void nt_eq1_f64(uint8_t *dst, const double *src, size_t n)  // dst[i] = src[i] == 1.0 (scripts/jps1.py:20-29)
+{
+#if defined(__x86_64__)
+    size_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 15u)) { dst[i] = src[i] == 1.0 ? (uint8_t)1 : (uint8_t)0; i++; }
+    const __m128d one = _mm_set1_pd(1.0);
+    for (; i + 16 <= n; i += 16) {
+        __m128i w[4];
+        for (int k = 0; k < 4; k++) {  // 4 doubles -> 4 x 32-bit masks
+            const __m128 lo = _mm_castpd_ps(_mm_cmpeq_pd(_mm_loadu_pd(src + i + 4 * k), one));
+            const __m128 hi = _mm_castpd_ps(_mm_cmpeq_pd(_mm_loadu_pd(src + i + 4 * k + 2), one));
+            w[k] = _mm_castps_si128(_mm_shuffle_ps(lo, hi, _MM_SHUFFLE(2, 0, 2, 0)));
+        }
+        const __m128i b = _mm_packs_epi16(_mm_packs_epi32(w[0], w[1]), _mm_packs_epi32(w[2], w[3]));  // 0 / -1 per byte
+        _mm_stream_si128((__m128i *)(dst + i), _mm_and_si128(b, _mm_set1_epi8(1)));
     }
-    memcpy(dst, src, per < bytes ? per : bytes);
-    for (auto &t : th) t.join();
+    for (; i < n; i++) dst[i] = src[i] == 1.0 ? (uint8_t)1 : (uint8_t)0;
+    _mm_sfence();
+#else
+    for (size_t i = 0; i < n; i++) dst[i] = src[i] == 1.0 ? (uint8_t)1 : (uint8_t)0;
+#endif
+}
+
+// The grid into the pinned staging buffer and on to the device: `fill(a, b)` produces cells [a, b) of the staging buffer
+// (a copy of the caller's uint8 grid, or `== 1.0` of its float64 matrix); the grid is cut into tasks, the tasks into four
+// upload parts, and the calling thread issues a part's H2D copy as soon as its tasks are done, so the copies overlap the
+// filling of the rest.
+static int staged_upload(fx_context *ctx, uint8_t *d_dst, uint8_t *pin_grid, size_t cells, const std::function<void(size_t, size_t)> &fill, cudaStream_t st)
+{
+    if (cells < ((size_t)1 << 20)) {
+        fill(0, cells);
+        FX_CUDA(ctx, cudaMemcpyAsync(d_dst, pin_grid, cells, cudaMemcpyHostToDevice, st));
+        return FX_OK;
+    }
+    constexpr int PARTS = 4, TPP = 16;  // tasks per part
+    const size_t per = ((cells + PARTS * TPP - 1) / (PARTS * TPP) + 63) & ~(size_t)63;
+    const int ntasks = (int)((cells + per - 1) / per);
+    std::atomic<int> done[PARTS];
+    for (auto &d : done) d.store(0);
+    int issued = 0;
+    cudaError_t err = cudaSuccess;
+    auto part_tasks = [&](int p) { const int lo = p * TPP, hi = lo + TPP < ntasks ? lo + TPP : ntasks; return hi > lo ? hi - lo : 0; };
+    auto issue = [&]() {
+        while (issued < PARTS && done[issued].load(std::memory_order_acquire) >= part_tasks(issued)) {
+            const size_t a = (size_t)issued * TPP * per;
+            if (a < cells && err == cudaSuccess) {
+                const size_t nb = a + TPP * per < cells ? TPP * per : cells - a;
+                err = cudaMemcpyAsync(d_dst + a, pin_grid + a, nb, cudaMemcpyHostToDevice, st);
+            }
+            issued++;
+        }
+    };
+    {
+        std::lock_guard<std::mutex> job(g_pool_job);
+        host_pool().run(ntasks, [&](int i) {
+            const size_t a = (size_t)i * per, b = a + per < cells ? a + per : cells;
+            fill(a, b);
+            done[i / TPP].fetch_add(1, std::memory_order_acq_rel);
+        }, issue);
+    }
+    issue();
+    FX_CUDA(ctx, err);
+    return FX_OK;
+}
+
+// h_src (pageable) -> start of the pinned staging buffer (which must hold `bytes`) -> d_dst, as above
+int fx_staged_copy_in(fx_context *ctx, uint8_t *d_dst, const uint8_t *h_src, size_t bytes, cudaStream_t st)
+{
+    uint8_t *pp = (uint8_t *)ctx->h_pin;
+    return staged_upload(ctx, d_dst, pp, bytes, [=](size_t a, size_t b) { nt_copy_u8(pp + a, h_src + a, b - a); }, st);
 }
 
 // csr != NULL: paths are returned packed (offsets[Q+1] + xy[total][2]) instead of in padded rows
@@ -258,6 +416,13 @@ static int plan_host_impl(fx_context *ctx, const uint8_t *h_grid, const double *
            off_p = off_o + ((size_t)Q + 1) * 8;
     if ((rc = grow_pinned(ctx, off_p + path_bytes))) return rc;
     char *pin = (char *)ctx->h_pin;
+    // FUXI_B200_TRACE=1: wall-clock of the host stages of this call on stderr (tuning aid)
+    static const bool trace = getenv("FUXI_B200_TRACE") && getenv("FUXI_B200_TRACE")[0] == '1';
+    auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = trace ? now() : 0.0;
+    double t_up = 0.0, t_enq = 0.0, t_sync = 0.0;
+    cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (trace) { for (auto &e : tev) cudaEventCreate(&e); cudaEventRecord(tev[0], st); }
     memcpy(pin + off_s, h_starts_xy, qb);
     memcpy(pin + off_g, h_goals_xy, qb);
     {
@@ -266,7 +431,7 @@ static int plan_host_impl(fx_context *ctx, const uint8_t *h_grid, const double *
         // queries from it once and writes its few result bytes straight back: one launch, one synchronisation.
         const char *e = getenv("FUXI_B200_SMALL");
         if (cells <= FX_SMALL_CELLS && Q <= 64 && !(e && e[0] == '0')) {
-            if (h_matrix) convert_f64_chunk(h_matrix, (uint8_t *)pin + off_grid, cells, 1);
+            if (h_matrix) { uint8_t *pg = (uint8_t *)pin + off_grid; for (size_t i = 0; i < cells; i++) pg[i] = h_matrix[i] == 1.0 ? (uint8_t)1 : (uint8_t)0; }
             else memcpy(pin + off_grid, h_grid, cells);
             rc = fx_search_small(ctx, (const uint8_t *)pin + off_grid, W, H, (const int32_t *)(pin + off_s), (const int32_t *)(pin + off_g), Q,
                                  metric, (int32_t *)(pin + off_ci), (double *)(pin + off_cf), want_path ? (int32_t *)(pin + off_p) : nullptr,
@@ -296,25 +461,23 @@ static int plan_host_impl(fx_context *ctx, const uint8_t *h_grid, const double *
             return FX_OK;
         }
     }
-    if (h_matrix) {
-        unsigned hc = std::thread::hardware_concurrency();
-        const int nthreads = (int)(hc == 0 ? 1 : (hc > 16 ? 16 : hc));
-        const size_t chunk = cells > (1u << 22) ? (cells + 3) / 4 : cells;
-        for (size_t a = 0; a < cells; a += chunk) {
-            const size_t nb = a + chunk < cells ? chunk : cells - a;
-            convert_f64_chunk(h_matrix + a, (uint8_t *)pin + off_grid + a, nb, nthreads);
-            FX_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid + a, pin + off_grid + a, nb, cudaMemcpyHostToDevice, st));
-        }
-    } else {
-        par_memcpy(pin + off_grid, h_grid, cells);
-        FX_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid, pin + off_grid, cells, cudaMemcpyHostToDevice, st));
+    {
+        uint8_t *pg = (uint8_t *)pin + off_grid;
+        static const bool nt = !(getenv("FUXI_B200_NT") && getenv("FUXI_B200_NT")[0] == '0');  // tuning experiments only
+        if (h_matrix && nt) rc = staged_upload(ctx, ctx->d_grid, pg, cells, [=](size_t a, size_t b) { nt_eq1_f64(pg + a, h_matrix + a, b - a); }, st);
+        else if (h_matrix) rc = staged_upload(ctx, ctx->d_grid, pg, cells, [=](size_t a, size_t b) { for (size_t i = a; i < b; i++) pg[i] = h_matrix[i] == 1.0 ? (uint8_t)1 : (uint8_t)0; }, st);
+        else if (nt) rc = staged_upload(ctx, ctx->d_grid, pg, cells, [=](size_t a, size_t b) { nt_copy_u8(pg + a, h_grid + a, b - a); }, st);
+        else rc = staged_upload(ctx, ctx->d_grid, pg, cells, [=](size_t a, size_t b) { memcpy(pg + a, h_grid + a, b - a); }, st);
+        if (rc) return rc;
     }
+    if (trace) { t_up = now(); cudaEventRecord(tev[1], st); }
     FX_CUDA(ctx, cudaMemcpyAsync(ctx->d_q, pin + off_s, 2 * qb, cudaMemcpyHostToDevice, st));
     int32_t *d_s = ctx->d_q, *d_g = ctx->d_q + (size_t)Q * 2;
     int32_t *d_ci = ctx->d_out_i, *d_pl = ctx->d_out_i + Q;
     rc = fx_search_batch(ctx, ctx->d_grid, W, H, d_s, d_g, Q, metric, d_ci, ctx->d_out_f, want_path ? ctx->d_path : nullptr,
                          d_pl, want_path ? max_path : 0, (void *)st);
     if (rc) return rc;
+    if (trace) cudaEventRecord(tev[2], st);
     if (want_path) {
         rc = fx_paths_compact(ctx, ctx->d_path, d_pl, Q, max_path, ctx->d_coff, ctx->d_cpath, (int64_t)Q * max_path, (void *)st);
         if (rc) return rc;
@@ -322,7 +485,18 @@ static int plan_host_impl(fx_context *ctx, const uint8_t *h_grid, const double *
     }
     FX_CUDA(ctx, cudaMemcpyAsync(pin + off_ci, d_ci, (size_t)Q * 8, cudaMemcpyDeviceToHost, st));  // cost_i + path_len
     FX_CUDA(ctx, cudaMemcpyAsync(pin + off_cf, ctx->d_out_f, (size_t)Q * 8, cudaMemcpyDeviceToHost, st));
+    if (trace) { t_enq = now(); cudaEventRecord(tev[3], st); }
     FX_CUDA(ctx, cudaStreamSynchronize(st));
+    if (trace) {
+        t_sync = now();
+        float kms = 0.f;
+        if (ctx->ev_search_valid) cudaEventElapsedTime(&kms, ctx->ev_search[0], ctx->ev_search[1]);
+        float d01 = 0.f, d12 = 0.f, d23 = 0.f;
+        cudaEventElapsedTime(&d01, tev[0], tev[1]); cudaEventElapsedTime(&d12, tev[1], tev[2]); cudaEventElapsedTime(&d23, tev[2], tev[3]);
+        for (auto &e : tev) cudaEventDestroy(e);
+        fprintf(stderr, "fx_plan_host trace: host: fill+upload issue %.0f us, enqueue %.0f us, wait %.0f us | device: upload %.0f us, fx_search_batch %.0f us (search kernel %.0f us), paths+D2H %.0f us\n",
+                t_up - t_begin, t_enq - t_up, t_sync - t_enq, 1e3 * d01, 1e3 * d12, 1e3 * kms, 1e3 * d23);
+    }
     memcpy(h_cost_i, pin + off_ci, (size_t)Q * 4);
     if (h_path_len) memcpy(h_path_len, pin + off_pl, (size_t)Q * 4);
     if (h_cost_f) memcpy(h_cost_f, pin + off_cf, (size_t)Q * 8);
@@ -350,16 +524,11 @@ static int plan_host_impl(fx_context *ctx, const uint8_t *h_grid, const double *
                     if (n > 0) memcpy(h_path_xy + (size_t)q * max_path * 2, pin + off_p + (size_t)offs[q] * 8, (size_t)n * 8);
                 }
             };
-            unsigned hc = std::thread::hardware_concurrency();
-            const int nthreads = total < (1 << 18) ? 1 : (int)(hc == 0 ? 1 : (hc > 8 ? 8 : hc));
-            if (nthreads <= 1) rows(0, Q);
+            if (total < (1 << 18)) rows(0, Q);
             else {
-                std::vector<std::thread> th;
-                const int per = (Q + nthreads - 1) / nthreads;
-                for (int t = 1; t < nthreads; t++)
-                    if (t * per < Q) th.emplace_back(rows, t * per, (t + 1) * per < Q ? (t + 1) * per : Q);
-                rows(0, per < Q ? per : Q);
-                for (auto &t : th) t.join();
+                const int per = 64, n = (Q + per - 1) / per;
+                std::lock_guard<std::mutex> job(g_pool_job);
+                host_pool().run(n, [=](int i) { rows(i * per, (i + 1) * per < Q ? (i + 1) * per : Q); });
             }
         }
     }
@@ -381,7 +550,14 @@ extern "C" int fx_map_host(fx_context *ctx, const float *h_pts, int64_t n, int s
     if ((rc = grow(ctx, &ctx->d_grid, &ctx->d_grid_cap, cells))) return rc;
     if ((rc = grow(ctx, &ctx->d_grid2, &ctx->d_grid2_cap, cells))) return rc;
     if ((rc = grow(ctx, &ctx->d_pts, &ctx->d_pts_cap, pbytes + 16))) return rc;
-    FX_CUDA(ctx, cudaMemcpyAsync(ctx->d_pts, h_pts, pbytes, cudaMemcpyHostToDevice, st));
+    // the cloud goes through the pinned staging buffer (non-temporal host copy on the worker pool, H2D of the finished
+    // parts overlapping the rest): a cudaMemcpyAsync from the caller's pageable array ran at a third of the PCIe rate
+    if ((rc = grow_pinned(ctx, pbytes > cells ? pbytes : cells))) return rc;
+    {
+        uint8_t *pp = (uint8_t *)ctx->h_pin;
+        const uint8_t *src = (const uint8_t *)h_pts;
+        if (pbytes && (rc = staged_upload(ctx, (uint8_t *)ctx->d_pts, pp, pbytes, [=](size_t a, size_t b) { nt_copy_u8(pp + a, src + a, b - a); }, st))) return rc;
+    }
     rc = fx_project(ctx, ctx->d_pts, n, stride_floats, h_affine3x4, zmin, zmax, ox, oy, reso, W, H, ctx->d_grid, 1, (void *)st);
     if (rc) return rc;
     const uint8_t *result = ctx->d_grid;
@@ -390,7 +566,8 @@ extern "C" int fx_map_host(fx_context *ctx, const float *h_pts, int64_t n, int s
         if (rc) return rc;
         result = ctx->d_grid2;
     }
-    FX_CUDA(ctx, cudaMemcpyAsync(h_grid_out, result, cells, cudaMemcpyDeviceToHost, st));
+    FX_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, result, cells, cudaMemcpyDeviceToHost, st));  // (stream order: after the H2D copies out of the same buffer)
     FX_CUDA(ctx, cudaStreamSynchronize(st));
+    par_memcpy(h_grid_out, ctx->h_pin, cells);
     return FX_OK;
 }

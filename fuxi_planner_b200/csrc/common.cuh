@@ -209,6 +209,8 @@ __device__ __forceinline__ int fx_cidx(int x, int y, int H, int TY)
 
 int fx_grow_bytes(fx_context *ctx, void **p, size_t *cap, size_t want_bytes);
 int fx_grow_pinned(fx_context *ctx, size_t want);
+// pageable host bytes -> start of the pinned staging buffer (non-temporal stores on the host worker pool) -> device (api.cu)
+int fx_staged_copy_in(fx_context *ctx, uint8_t *d_dst, const uint8_t *h_src, size_t bytes, cudaStream_t st);
 int fx_search_reserve(fx_context *ctx, int which, int W, int H, int max_path, cudaStream_t st);
 void fx_search_release(fx_context *ctx, int which);
 // band.cu: LPT query order + per-query upper bounds from the band pass (one warp per query)

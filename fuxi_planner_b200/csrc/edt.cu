@@ -697,16 +697,18 @@ extern "C" int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W
         FX_CUDA(ctx, cudaMemsetAsync(fix_count, 0, sizeof(unsigned), st));
         k_edt_pack<<<dim3((HW + 31) / 32, (Wp + 31) / 32), 256, 0, st>>>(occ, bitsb, W, HW, Wp);
         FX_LAUNCH_CHECK(ctx);
-        // segments of rows per strip: about four CTAs per resident slot (strips differ in work: the walk stops when a word
-        // is settled), each segment a multiple of the 64-row step and at least four steps (a segment starts with 2 R extra rows)
+        // segments of rows per strip (multiples of the 64-row step; a segment starts with 2 R extra rows of masks): about
+        // four CTAs per resident slot on large grids (strips differ in work: the walk stops when a word is settled), one
+        // wave of shorter segments when that would leave a segment less than four steps
         const int gx = (HW + EDT_WS_WARPS - 1) / EDT_WS_WARPS;
         int resident = 0;
         FX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_edt_strips, EDT_WS_WARPS * 32, EDT_WS_SMEM));
         if (resident < 1) resident = 1;
-        int segs = ctx->sm_count * resident * 4 / gx;
+        const int slots = ctx->sm_count * resident;
+        int segs = slots * 4 / gx;
+        if (segs < 1 || W / segs < 4 * EDT_STEP) segs = slots / gx;
         if (segs < 1) segs = 1;
         int seg_rows = ((W + segs - 1) / segs + EDT_STEP - 1) / EDT_STEP * EDT_STEP;
-        if (seg_rows < 4 * EDT_STEP) seg_rows = 4 * EDT_STEP;
         segs = (W + seg_rows - 1) / seg_rows;
         k_edt_strips<<<dim3(gx, segs), EDT_WS_WARPS * 32, EDT_WS_SMEM, st>>>(bitsb, dist2, W, HW, Wp, seg_rows, fix_list, fix_count, (unsigned)cap);
         FX_LAUNCH_CHECK(ctx);

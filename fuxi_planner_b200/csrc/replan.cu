@@ -52,8 +52,7 @@ extern "C" int fx_replan_host(fx_context *ctx, const void *h_map, int width, int
     const size_t off_rp = (msg_bytes + 255) / 256 * 256, off_p = off_rp + 256, off_w = off_p + path_ints * sizeof(int32_t);
     if ((rc = fx_grow_pinned(ctx, off_w + world_bytes))) return rc;
     char *pin = (char *)ctx->h_pin;
-    memcpy(pin, h_map, msg_bytes);
-    FX_CUDA(ctx, cudaMemcpyAsync(ctx->d_msg, pin, msg_bytes, cudaMemcpyHostToDevice, st));
+    if ((rc = fx_staged_copy_in(ctx, (uint8_t *)ctx->d_msg, (const uint8_t *)h_map, msg_bytes, st))) return rc;
     int32_t *d_bbox = ctx->d_rp, *d_goal = ctx->d_rp + 4, *d_start = ctx->d_rp + 8, *d_len = ctx->d_rp + 10, *d_cost = ctx->d_rp + 11,
             *d_plen = ctx->d_rp + 12;
     double *d_costf = (double *)(ctx->d_rp + 32);

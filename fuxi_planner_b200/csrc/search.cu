@@ -73,6 +73,38 @@ __device__ __forceinline__ unsigned fx_atoms_add(unsigned *p, unsigned v)
     return old;
 }
 
+// First prune bound of the latency forms.  How far the optimum lies above the octile lower bound h0 depends, on a given
+// map, mostly on the MIX of the query's moves: with t = min(diagonal, straight) / max(diagonal, straight) steps of the
+// octile path, queries near t = 0 (nearly pure straight or pure diagonal) have no free choice of lanes and pay for every
+// obstacle (5.4 % over h0 on the 20 %-filled headline grid), balanced ones hardly anything (0.05 %).  A fixed guess is
+// too small for the first group (a second pass: 39 % of the headline queries) or needlessly wide for the second.  So
+// the context keeps, per t-bin, a decaying maximum of the ratios (U* - h0) / h0 it has seen (16 x u32 in units of 2^-20,
+// 0 on a fresh context) and guesses from it.  Only a guess: a pass is accepted iff its result is <= the bound it pruned
+// with (run_pass), so the table changes how many passes a query takes, never its answer.
+#define FX_CALIB_FLOOR 1024u /* 2^-10: what a fresh table guesses (+ 4 WD) */
+__device__ __forceinline__ int fx_calib_bin(int adx, int ady)
+{
+    const int mn = min(adx, ady), st = max(adx, ady) - mn;  // diagonal / straight steps of the octile path
+    const int lo = min(mn, st), hi = max(max(mn, st), 1);
+    return min(15, (int)(16.f * sqrtf((float)lo / (float)hi)));
+}
+__device__ __forceinline__ uint64_t fx_first_bound(const uint32_t *calib, int bin, uint32_t h0, uint32_t wd)
+{
+    if (!calib) return (uint64_t)h0 + h0 / 128 + 4ull * wd;  // FUXI_B200_CALIB=0: the fixed guess of the first version
+    uint32_t r = __ldcg(calib + bin);
+    if (bin < 15) r = max(r, __ldcg(calib + bin + 1) >> 1);  // a sparsely visited bin borrows from its neighbour
+    r = r + (r >> 3) + FX_CALIB_FLOOR;                                 // 1/8 margin over the recent maximum
+    return (uint64_t)h0 + (((uint64_t)h0 * r) >> 20) + 4ull * wd;
+}
+__device__ __forceinline__ void fx_calib_update(uint32_t *calib, int bin, uint32_t h0, uint32_t best, uint32_t ws)
+{
+    if (!calib || h0 < 64u * ws || best < h0) return;  // short queries say little about the ratio
+    const uint64_t r64 = (((uint64_t)(best - h0)) << 20) / h0;
+    const uint32_t r = r64 > 0x3FFFFFFFull ? 0x3FFFFFFFu : (uint32_t)r64;
+    const uint32_t old = __ldcg(calib + bin);
+    __stcg(calib + bin, max(r, old - (old >> 5)));  // racy among concurrent queries on purpose: any of the values will do
+}
+
 struct SearchParams {
     const uint8_t *grid;
     const uint8_t *moves;
@@ -94,6 +126,7 @@ struct SearchParams {
     int band0;
     const uint32_t *order;   // LPT query order (band.cu) or NULL
     const uint32_t *ubound;  // per-query upper bound from the band pass or NULL
+    uint32_t *calib;         // latency forms: first-bound table (fx_first_bound)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -630,7 +663,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
         bool hit = false, unreachable = false;
         bool bidir = false;
         if constexpr (LAT) {
-            uint64_t U_try = (uint64_t)h0 + h0 / 128 + 4 * WD;
+            const int cbin = fx_calib_bin(abs(sx - gx), abs(sy - gy));
+            uint64_t U_try = fx_first_bound(P.calib, cbin, h0, WD);
             for (int attempt = 0; attempt < 6; attempt++) {
                 const bool last = attempt == 5 || U_try >= 0x7FFFFFFFull;
                 const uint32_t U0 = last ? 0x7FFFFFFFu : (uint32_t)U_try;
@@ -639,7 +673,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_search_batch(const SearchPara
                 bidir = true;
                 overflow = (S.flags & FLAG_OVERFLOW) != 0;
                 if (overflow) break;
-                if (r != FX_INF && r <= U0) { best = r; break; }           // the bound held: exact
+                if (r != FX_INF && r <= U0) { best = r; if (tid == 0) fx_calib_update(P.calib, cbin, h0, r, WS); break; }  // the bound held: exact
                 if ((S.flags & FLAG_UNREACH) || last || (r == FX_INF && !S.pruned)) { unreachable = true; break; }
                 U_try = r != FX_INF ? (uint64_t)r : (uint64_t)h0 + (U_try - h0) * 4;  // a real path's cost / a wider guess
                 __syncthreads();
@@ -1154,7 +1188,8 @@ __global__ void __launch_bounds__(FX_CL_THREADS, 1) k_search_cluster(const Searc
         const uint32_t h0 = octile(abs(sx - gx), abs(sy - gy), WS, WD - WS);
         uint32_t best = FX_INF;
         bool overflow = false;
-        uint64_t U_try = (uint64_t)h0 + h0 / 128 + 4 * WD;
+        const int cbin = fx_calib_bin(abs(sx - gx), abs(sy - gy));
+        uint64_t U_try = fx_first_bound(P.calib, cbin, h0, WD);
         for (int attempt = 0; attempt < 6; attempt++) {
             const bool last = attempt == 5 || U_try >= 0x7FFFFFFFull;
             const uint32_t U0 = last ? 0x7FFFFFFFu : (uint32_t)U_try;
@@ -1163,7 +1198,7 @@ __global__ void __launch_bounds__(FX_CL_THREADS, 1) k_search_cluster(const Searc
             const unsigned fl = L.flags, pruned = L.pruned;  // identical in every CTA (derived from the replicated words)
             overflow = (fl & FLAG_OVERFLOW) != 0;
             if (overflow) break;
-            if (r != FX_INF && r <= U0) { best = r; break; }
+            if (r != FX_INF && r <= U0) { best = r; if (ctid == 0) fx_calib_update(P.calib, cbin, h0, r, WS); break; }
             if ((fl & FLAG_UNREACH) || last || (r == FX_INF && !pruned)) break;
             U_try = r != FX_INF ? (uint64_t)r : (uint64_t)h0 + (U_try - h0) * 4;
             reset_slot_cluster(L, peers, field, dirty, P.dirty_n, P.cells, H);
@@ -1306,6 +1341,10 @@ extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int 
     P.fields = X.fields; P.dirty = X.dirty; P.queues = reinterpret_cast<uint2 *>(X.queues); P.tmp_path = X.tmp_path;
     P.cells = X.cells; P.dirty_n = X.dirty_n; P.qcap = X.qcap; P.path_cap = X.path_cap;
     P.counters = ctx->counters;
+    {
+        const char *e = getenv("FUXI_B200_CALIB");  // tuning experiments only
+        P.calib = (e && e[0] == '0') ? nullptr : reinterpret_cast<uint32_t *>(ctx->counters + 16);
+    }
     // half-width (cells along the minor axis) of the band-limited passes of the search kernel; one more than the band kernel's
     // 15 + rounding of its fixed-point centre line, so that a path the band kernel found lies inside it
     P.band0 = ctx->cfg_band0 > 0 ? ctx->cfg_band0 : 17;
