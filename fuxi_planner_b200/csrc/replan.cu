@@ -15,6 +15,32 @@ extern "C" int fx_relocate_goal(fx_context *, const uint8_t *, int, int, int32_t
 extern "C" int fx_path_post(fx_context *, const uint8_t *, int, int, const int32_t *, const int32_t *, int, int, int, const double *,
                             const double *, int32_t *, int32_t *, double *, void *);
 
+// Small planning grids (the reference's own maps): the message is read straight out of the mapped pinned staging buffer
+// and EVERY cell of the planning grid is written in one pass -- window cells decoded (scripts/global_planner_st.py:15-25:
+// 100 -> 1, -1 -> 0) or copied, the padding zeroed -- instead of H2D copy + memset + tiled decode / paste.
+__global__ void __launch_bounds__(256) k_assemble_small(const uint8_t *__restrict__ src, int layout_msg, int sW, int sH, int wx0, int wy0, int ww, int wh,
+                                                        uint8_t *__restrict__ dst, int W, int H, int px, int py)
+{
+    const int total = W * H;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int x = i / H, y = i - x * H;
+        const int wx = x - px, wy = y - py;
+        uint8_t v = 0;
+        if (wx >= 0 && wx < ww && wy >= 0 && wy < wh) {
+            const int mx = wx0 + wx, my = wy0 + wy;
+            if (mx >= 0 && mx < sW && my >= 0 && my < sH) {
+                if (layout_msg) {
+                    const int8_t m = (int8_t)src[(size_t)my * sW + mx];
+                    v = m == 100 ? (uint8_t)1 : m == -1 ? (uint8_t)0 : (uint8_t)m;
+                } else {
+                    v = src[(size_t)mx * sH + my];
+                }
+            }
+        }
+        dst[i] = v;
+    }
+}
+
 // `((xy - origin) / reso).astype(int)`: double arithmetic, truncation toward zero
 static inline long long cell_of(double v, double o, double reso) { return (long long)((v - o) / reso); }
 
@@ -52,10 +78,16 @@ extern "C" int fx_replan_host(fx_context *ctx, const void *h_map, int width, int
     const size_t off_rp = (msg_bytes + 255) / 256 * 256, off_p = off_rp + 256, off_w = off_p + path_ints * sizeof(int32_t);
     if ((rc = fx_grow_pinned(ctx, off_w + world_bytes))) return rc;
     char *pin = (char *)ctx->h_pin;
-    if ((rc = fx_staged_copy_in(ctx, (uint8_t *)ctx->d_msg, (const uint8_t *)h_map, msg_bytes, st))) return rc;
-    int32_t *d_bbox = ctx->d_rp, *d_goal = ctx->d_rp + 4, *d_start = ctx->d_rp + 8, *d_len = ctx->d_rp + 10, *d_cost = ctx->d_rp + 11,
-            *d_plen = ctx->d_rp + 12;
-    double *d_costf = (double *)(ctx->d_rp + 32);
+    // Small messages stay in the pinned staging buffer, which the device reads in place (unified addressing), and the
+    // parameter block / path / world points are written by the kernels straight into it: no copy-engine transfers at all
+    // on the critical path of a replan (each one is a few microseconds of engine hand-over).
+    const bool mapped = msg_bytes <= ((size_t)256 << 10) && !(getenv("FUXI_B200_REPLAN_MAPPED") && getenv("FUXI_B200_REPLAN_MAPPED")[0] == '0');
+    const void *d_msg_in = ctx->d_msg;
+    if (mapped) { memcpy(pin, h_map, msg_bytes); d_msg_in = pin; }
+    else if ((rc = fx_staged_copy_in(ctx, (uint8_t *)ctx->d_msg, (const uint8_t *)h_map, msg_bytes, st))) return rc;
+    int32_t *d_rp = mapped ? (int32_t *)(pin + off_rp) : ctx->d_rp;
+    int32_t *d_bbox = ctx->d_rp /* reduced with atomics: always device memory */, *d_goal = d_rp + 4, *d_start = d_rp + 8, *d_len = d_rp + 10, *d_cost = d_rp + 11, *d_plen = d_rp + 12;
+    double *d_costf = (double *)(d_rp + 32);
 
     // the map as the reference sees it: array [x][y] of extent (map_c, map_r) at world origin map_o; in the message
     // layout x is the fast axis (index y*width + x), in the array layout y is (index x*height + y), W = width, H = height
@@ -66,7 +98,7 @@ extern "C" int fx_replan_host(fx_context *ctx, const void *h_map, int width, int
     if (in->crop) {
         // remove_zero_rowscols, ccst:36-63: window [min(min x, start x) : max x) x [min(min y, start y) : max y) --
         // exclusive upper ends, i.e. the last occupied row and column are dropped like in the reference
-        if ((rc = fx_grid_bbox(ctx, ctx->d_msg, aW, aH, in->layout == 0, d_bbox, (void *)st))) return rc;
+        if ((rc = fx_grid_bbox(ctx, d_msg_in, aW, aH, in->layout == 0, d_bbox, (void *)st))) return rc;
         int32_t bb[4];
         FX_CUDA(ctx, cudaMemcpyAsync(pin + off_rp, d_bbox, 16, cudaMemcpyDeviceToHost, st));
         FX_CUDA(ctx, cudaStreamSynchronize(st));
@@ -111,12 +143,21 @@ extern "C" int fx_replan_host(fx_context *ctx, const void *h_map, int width, int
     const size_t cells = (size_t)W * H;
     if ((rc = fx_grow_bytes(ctx, (void **)&ctx->d_grid, &ctx->d_grid_cap, cells))) return rc;
     if ((rc = fx_grow_bytes(ctx, (void **)&ctx->d_grid2, &ctx->d_grid2_cap, cells))) return rc;
-    FX_CUDA(ctx, cudaMemsetAsync(ctx->d_grid, 0, cells, st));
-    if (in->layout == 0)
-        rc = fx_grid_decode(ctx, ctx->d_msg, width, height, wx0, wy0, wx1 - wx0, wy1 - wy0, ctx->d_grid, W, H, (int)dx, (int)dy, (void *)st);
-    else
-        rc = fx_grid_paste(ctx, (const uint8_t *)ctx->d_msg, aW, aH, wx0, wy0, wx1 - wx0, wy1 - wy0, ctx->d_grid, W, H, (int)dx, (int)dy,
-                           (void *)st);
+    if (mapped && cells <= ((size_t)1 << 20)) {
+        int blocks = (int)((cells + 255) / 256);
+        if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+        k_assemble_small<<<blocks, 256, 0, st>>>((const uint8_t *)d_msg_in, in->layout == 0, aW, aH, wx0, wy0, wx1 - wx0, wy1 - wy0, ctx->d_grid, W, H,
+                                                 (int)dx, (int)dy);
+        FX_LAUNCH_CHECK(ctx);
+        rc = FX_OK;
+    } else {
+        FX_CUDA(ctx, cudaMemsetAsync(ctx->d_grid, 0, cells, st));
+        if (in->layout == 0)
+            rc = fx_grid_decode(ctx, (const int8_t *)d_msg_in, width, height, wx0, wy0, wx1 - wx0, wy1 - wy0, ctx->d_grid, W, H, (int)dx, (int)dy, (void *)st);
+        else
+            rc = fx_grid_paste(ctx, (const uint8_t *)d_msg_in, aW, aH, wx0, wy0, wx1 - wx0, wy1 - wy0, ctx->d_grid, W, H, (int)dx, (int)dy,
+                               (void *)st);
+    }
     if (rc) return rc;
     // inflation: st = 9-point stencil {-ifa, 0, ifa}^2 (st:256-262), ccst = dense square (ccst:442-448)
     if ((rc = fx_inflate(ctx, ctx->d_grid, ctx->d_grid2, W, H, ifa, ccst ? 1 : ifa, (void *)st))) return rc;
@@ -126,24 +167,25 @@ extern "C" int fx_replan_host(fx_context *ctx, const void *h_map, int width, int
     memset(h_blk, 0, 256);
     h_blk[4] = (int)gx; h_blk[5] = (int)gy; h_blk[8] = (int)sx; h_blk[9] = (int)sy;
     h_blk[10] = FX_COST_UNREACHABLE; h_blk[11] = FX_COST_UNREACHABLE; h_blk[12] = FX_COST_UNREACHABLE;
-    FX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rp, h_blk, 256, cudaMemcpyHostToDevice, st));
+    if (!mapped) FX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rp, h_blk, 256, cudaMemcpyHostToDevice, st));
     if (gx < 0 || gx >= W || gy < 0 || gy >= H)
         return fx_set_err(ctx, FX_ERR_ARG, "fx_replan_host: goal cell (%lld, %lld) outside the %d x %d grid", gx, gy, W, H);
     if ((rc = fx_relocate_goal(ctx, ctx->d_grid2, W, H, d_goal, ifa, ccst, (void *)st))) return rc;
     // st:280 / ccst:466 `if map_start[0] > map_c or map_start[1] > map_r: wp = global_goal` (no search)
     const bool skip = sx > mc || sy > mr;
-    int32_t *d_raw = ctx->d_path, *d_post = ctx->d_path + path_ints;
+    int32_t *d_raw = ctx->d_path, *d_post = mapped ? (int32_t *)(pin + off_p) : ctx->d_path + path_ints;
+    double *d_world = mapped ? (double *)(pin + off_w) : (double *)ctx->d_pts;
     double world5[5] = {in->reso, nox, noy, 1.0, ccst ? 0.0 : 1.0};  // st:291 `+ [1,1]`, ccst:487 `+ [1,0]`
     double drop4[4] = {in->drop_px, in->drop_py, in->drop_pz, in->drop_radius};
     if (!skip) {
         if ((rc = fx_search_batch(ctx, ctx->d_grid2, W, H, d_start, d_goal, 1, in->hchoice, d_cost, d_costf, d_raw, d_len, max_path, (void *)st)))
             return rc;
         if ((rc = fx_path_post(ctx, ctx->d_grid2, W, H, d_raw, d_len, 1, max_path, in->shortcut, in->drop_radius > 0.0 ? drop4 : nullptr,
-                               world5, d_post, d_plen, (double *)ctx->d_pts, (void *)st)))
+                               world5, d_post, d_plen, d_world, (void *)st)))
             return rc;
     }
-    FX_CUDA(ctx, cudaMemcpyAsync(h_blk, ctx->d_rp, 256, cudaMemcpyDeviceToHost, st));
-    if (!skip) {
+    if (!mapped) FX_CUDA(ctx, cudaMemcpyAsync(h_blk, ctx->d_rp, 256, cudaMemcpyDeviceToHost, st));
+    if (!skip && !mapped) {
         FX_CUDA(ctx, cudaMemcpyAsync(pin + off_p, d_post, path_ints * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         FX_CUDA(ctx, cudaMemcpyAsync(pin + off_w, ctx->d_pts, world_bytes, cudaMemcpyDeviceToHost, st));
     }
