@@ -414,7 +414,9 @@ __device__ uint32_t run_pass(const SearchParams &P, CtaState &S, const uint8_t *
             const bool diag2 = (g - kbase) + WD >= 2u * WS;
             if (succ) {
                 // queue space: one shared-memory atomic per lane and class (the unit serialises same-address lanes in
-                // ~1-2 cycles each; cheaper than a warp scan + broadcast, and no warp-collective in the loop body)
+                // ~1-2 cycles each).  Measured against a per-warp reservation (packed prefix scan over five shuffles, one
+                // three-address atomic by lanes 0..2, two shuffles to hand the bases back): the scan costs more issue slots
+                // than the serialised atomics cost LSU wavefronts, k_search_batch 92.4 -> 96.0 ms (r02j), so this stays.
                 const unsigned ns = (unsigned)__popc(succ & 0x0Fu), nd = (unsigned)__popc(succ & 0xF0u);
                 if (ns) posS = fx_atoms_add(&S.tailS[(k + 1) & 3], ns);
                 if (nd) posD = fx_atoms_add(&S.tailD[(k + (diag2 ? 2 : 1)) & 3], nd);
