@@ -65,6 +65,8 @@ extern "C" int fx_create(int device, fx_context **out)
     if (const char *e = getenv("FUXI_B200_CLUSTER")) ctx->cfg_cluster = e[0] != '0';  // tests run the latency form both ways
     if (const char *e = getenv("FUXI_B200_WIDE_BELOW")) ctx->cfg_wide_below = atoi(e);  // tuning experiments only
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
+    ctx->cfg_graphs = 1;
+    if (const char *e = getenv("FUXI_B200_GRAPHS")) ctx->cfg_graphs = e[0] != '0';
     // [0..15] per-launch counters (zeroed by every launch), [16..23] the 16 x u32 first-bound table of the latency forms
     // of the search (persists across launches, search.cu: fx_first_bound)
     e = cudaMalloc(&ctx->counters, 24 * sizeof(unsigned long long));
@@ -102,12 +104,55 @@ extern "C" int fx_destroy(fx_context *ctx)
     for (size_t i = 0; i < sizeof(dev) / sizeof(dev[0]); i++)
         if (dev[i]) cudaFree(dev[i]);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    for (auto &g : ctx->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->ev_search[0]) cudaEventDestroy(ctx->ev_search[0]);
     if (ctx->ev_search[1]) cudaEventDestroy(ctx->ev_search[1]);
     if (ctx->ev_band[0]) cudaEventDestroy(ctx->ev_band[0]);
     if (ctx->ev_band[1]) cudaEventDestroy(ctx->ev_band[1]);
     free(ctx);
+    return FX_OK;
+}
+
+int fx_graph_run(fx_context *ctx, int slot, const void *key, size_t keylen, cudaStream_t st, const std::function<int(cudaStream_t)> &enqueue)
+{
+    fx_context::GraphSlot &g = ctx->graphs[slot];
+    if (!ctx->cfg_graphs || keylen > sizeof(g.key)) return enqueue(st);
+    const bool same = g.keylen == keylen && memcmp(g.key, key, keylen) == 0;
+    if (same && g.exec) {
+        ctx->launches++;
+        FX_CUDA(ctx, cudaGraphLaunch(g.exec, st));
+        return FX_OK;
+    }
+    if (!same) {
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        memcpy(g.key, key, keylen);
+        g.keylen = keylen;
+        g.sightings = 1;
+        return enqueue(st);
+    }
+    if (++g.sightings < 2) return enqueue(st);
+    // the capture must not be disturbed by (and must not disturb) work the caller has in flight on `st`
+    if (!ctx->cap_stream) FX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
+    if (cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); g.keylen = 0; return enqueue(st); }
+    const int64_t launches0 = ctx->launches;
+    const int rc = enqueue(ctx->cap_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(ctx->cap_stream, &graph);
+    ctx->launches = launches0;  // nothing ran yet
+    if (rc != FX_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        g.keylen = 0;  // do not try again with this key until it has been seen twice more
+        return enqueue(st);
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { cudaGetLastError(); g.exec = nullptr; g.keylen = 0; return enqueue(st); }
+    ctx->launches++;
+    FX_CUDA(ctx, cudaGraphLaunch(g.exec, st));
     return FX_OK;
 }
 

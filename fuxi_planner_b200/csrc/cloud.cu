@@ -462,39 +462,49 @@ extern "C" int fx_cloud_filter(fx_context *ctx, const float *pts, int64_t n, con
     a.inv[0] = 1.0f / p->leaf_x, a.inv[1] = 1.0f / p->leaf_y, a.inv[2] = 1.0f / p->leaf_z;  // Array4f::Ones() / leaf_size
     const float r2 = (float)(p->radius * p->radius);  // pcl::KdTreeFLANN::radiusSearch: static_cast<float>(radius * radius)
     const int gp = grid_for(ctx, n, 256, 8), gw = ctx->sm_count * 8;
-    k_cl_reset<<<1, 32, 0, st>>>(s);
-    FX_LAUNCH_CHECK(ctx);
-    k_cl_bbox<<<grid_for(ctx, n, 1024, 4), 256, 0, st>>>(a, s);
-    FX_LAUNCH_CHECK(ctx);
-    k_cl_setup<<<1, 32, 0, st>>>(s, a.inv[0], a.inv[1], a.inv[2], ctx->cl_cap_bits);
-    FX_LAUNCH_CHECK(ctx);
-    k_cl_zero_bits<<<gw, 256, 0, st>>>(ctx->cl_bits, &s->total_bits);
-    FX_LAUNCH_CHECK(ctx);
-    k_cl_mark<<<gp, 256, 0, st>>>(a, s, ctx->cl_bits);
-    FX_LAUNCH_CHECK(ctx);
-    k_scan_groups<<<ctx->sm_count * 2, 1024, 0, st>>>(ctx->cl_bits, &s->total_bits, ctx->cl_gpref, ctx->cl_chunk);
-    FX_LAUNCH_CHECK(ctx);
-    k_scan_chunks<<<1, 1024, 0, st>>>(ctx->cl_chunk, &s->total_bits, &s->n_vox);
-    FX_LAUNCH_CHECK(ctx);
-    k_scan_emit<0><<<gw, 256, 0, st>>>(ctx->cl_bits, &s->total_bits, ctx->cl_gpref, ctx->cl_chunk, ctx->cl_vidx, nullptr, nullptr, 0);
-    FX_LAUNCH_CHECK(ctx);
-    k_cl_zero_acc<<<gw, 256, 0, st>>>(ctx->cl_acc, &s->n_vox);
-    FX_LAUNCH_CHECK(ctx);
-    k_cl_accum<<<gp, 256, 0, st>>>(a, s, ctx->cl_bits, ctx->cl_gpref, ctx->cl_acc);
-    FX_LAUNCH_CHECK(ctx);
-    k_cl_centroid<<<gw, 256, 0, st>>>(ctx->cl_acc, &s->n_vox, ctx->cl_vox);
-    FX_LAUNCH_CHECK(ctx);
-    k_cl_ror<<<gw, 256, 0, st>>>(ctx->cl_vox, ctx->cl_vidx, ctx->cl_bits, ctx->cl_gpref, s, wx, wy, wz, r2, p->min_neighbors, ctx->cl_keep);
-    FX_LAUNCH_CHECK(ctx);
-    k_scan_groups<<<ctx->sm_count * 2, 1024, 0, st>>>(ctx->cl_keep, &s->n_vox, ctx->cl_gpref2, ctx->cl_chunk2);
-    FX_LAUNCH_CHECK(ctx);
-    k_scan_chunks<<<1, 1024, 0, st>>>(ctx->cl_chunk2, &s->n_vox, &s->n_keep);
-    FX_LAUNCH_CHECK(ctx);
-    k_cl_compact<<<gw, 256, 0, st>>>(ctx->cl_keep, &s->n_vox, ctx->cl_gpref2, ctx->cl_chunk2, ctx->cl_vox, (float4 *)out, cap);
-    FX_LAUNCH_CHECK(ctx);
-    k_cl_counts<<<1, 32, 0, st>>>(s, (long long *)d_counts);
-    FX_LAUNCH_CHECK(ctx);
-    return FX_OK;
+    auto enqueue = [&](cudaStream_t st) -> int {
+        k_cl_reset<<<1, 32, 0, st>>>(s);
+        FX_LAUNCH_CHECK(ctx);
+        k_cl_bbox<<<grid_for(ctx, n, 1024, 4), 256, 0, st>>>(a, s);
+        FX_LAUNCH_CHECK(ctx);
+        k_cl_setup<<<1, 32, 0, st>>>(s, a.inv[0], a.inv[1], a.inv[2], ctx->cl_cap_bits);
+        FX_LAUNCH_CHECK(ctx);
+        k_cl_zero_bits<<<gw, 256, 0, st>>>(ctx->cl_bits, &s->total_bits);
+        FX_LAUNCH_CHECK(ctx);
+        k_cl_mark<<<gp, 256, 0, st>>>(a, s, ctx->cl_bits);
+        FX_LAUNCH_CHECK(ctx);
+        k_scan_groups<<<ctx->sm_count * 2, 1024, 0, st>>>(ctx->cl_bits, &s->total_bits, ctx->cl_gpref, ctx->cl_chunk);
+        FX_LAUNCH_CHECK(ctx);
+        k_scan_chunks<<<1, 1024, 0, st>>>(ctx->cl_chunk, &s->total_bits, &s->n_vox);
+        FX_LAUNCH_CHECK(ctx);
+        k_scan_emit<0><<<gw, 256, 0, st>>>(ctx->cl_bits, &s->total_bits, ctx->cl_gpref, ctx->cl_chunk, ctx->cl_vidx, nullptr, nullptr, 0);
+        FX_LAUNCH_CHECK(ctx);
+        k_cl_zero_acc<<<gw, 256, 0, st>>>(ctx->cl_acc, &s->n_vox);
+        FX_LAUNCH_CHECK(ctx);
+        k_cl_accum<<<gp, 256, 0, st>>>(a, s, ctx->cl_bits, ctx->cl_gpref, ctx->cl_acc);
+        FX_LAUNCH_CHECK(ctx);
+        k_cl_centroid<<<gw, 256, 0, st>>>(ctx->cl_acc, &s->n_vox, ctx->cl_vox);
+        FX_LAUNCH_CHECK(ctx);
+        k_cl_ror<<<gw, 256, 0, st>>>(ctx->cl_vox, ctx->cl_vidx, ctx->cl_bits, ctx->cl_gpref, s, wx, wy, wz, r2, p->min_neighbors, ctx->cl_keep);
+        FX_LAUNCH_CHECK(ctx);
+        k_scan_groups<<<ctx->sm_count * 2, 1024, 0, st>>>(ctx->cl_keep, &s->n_vox, ctx->cl_gpref2, ctx->cl_chunk2);
+        FX_LAUNCH_CHECK(ctx);
+        k_scan_chunks<<<1, 1024, 0, st>>>(ctx->cl_chunk2, &s->n_vox, &s->n_keep);
+        FX_LAUNCH_CHECK(ctx);
+        k_cl_compact<<<gw, 256, 0, st>>>(ctx->cl_keep, &s->n_vox, ctx->cl_gpref2, ctx->cl_chunk2, ctx->cl_vox, (float4 *)out, cap);
+        FX_LAUNCH_CHECK(ctx);
+        k_cl_counts<<<1, 32, 0, st>>>(s, (long long *)d_counts);
+        FX_LAUNCH_CHECK(ctx);
+        return FX_OK;
+    };
+    // everything the 16 launches depend on: arguments, derived constants, scratch pointers
+    struct { const float *pts; int64_t n; fx_cloud_params p; float *out; int64_t cap; int64_t *counts; unsigned long long cap_bits;
+             void *b[11]; } key;
+    memset(&key, 0, sizeof(key));
+    key.pts = pts; key.n = n; key.p = *p; key.out = out; key.cap = cap; key.counts = d_counts; key.cap_bits = ctx->cl_cap_bits;
+    void *bufs[11] = {ctx->cl_bits, ctx->cl_gpref, ctx->cl_chunk, ctx->cl_vidx, ctx->cl_keep, ctx->cl_gpref2, ctx->cl_chunk2, ctx->cl_acc, ctx->cl_vox, ctx->cl_state, nullptr};
+    memcpy(key.b, bufs, sizeof(bufs));
+    return fx_graph_run(ctx, FX_GRAPH_CLOUD, &key, sizeof(key), st, enqueue);
 }
 
 extern "C" int fx_cloud_filter_host(fx_context *ctx, const float *h_pts, int64_t n, const fx_cloud_params *p, float *h_out, int64_t cap,
@@ -630,23 +640,27 @@ extern "C" int fx_distance_filter(fx_context *ctx, const double *pts, int64_t n,
     int rc = fx_grow_bytes(ctx, (void **)&ctx->df_rec, &ctx->df_rec_bytes, (size_t)np2 * sizeof(DfRec));
     if (rc) return rc;
     DfRec *rec = (DfRec *)ctx->df_rec;
-    FX_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(int), st));
-    k_df_keys<<<grid_for(ctx, np2, 256, 8), 256, 0, st>>>(pts, n, np2, dis, rec, d_count);
-    FX_LAUNCH_CHECK(ctx);
-    const int nblk = (int)(np2 / DF_LOCAL);
-    k_df_local<true><<<nblk, DF_LOCAL / 2, 0, st>>>(rec, pts, 0);
-    FX_LAUNCH_CHECK(ctx);
-    for (unsigned long long k = 2ull * DF_LOCAL; k <= (unsigned long long)np2; k <<= 1) {
-        for (unsigned long long j = k >> 1; j >= DF_LOCAL; j >>= 1) {
-            k_df_global<<<grid_for(ctx, np2 / 2, 256, 8), 256, 0, st>>>(rec, pts, np2, k, j);
+    auto enqueue = [&](cudaStream_t st) -> int {
+        FX_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(int), st));
+        k_df_keys<<<grid_for(ctx, np2, 256, 8), 256, 0, st>>>(pts, n, np2, dis, rec, d_count);
+        FX_LAUNCH_CHECK(ctx);
+        const int nblk = (int)(np2 / DF_LOCAL);
+        k_df_local<true><<<nblk, DF_LOCAL / 2, 0, st>>>(rec, pts, 0);
+        FX_LAUNCH_CHECK(ctx);
+        for (unsigned long long k = 2ull * DF_LOCAL; k <= (unsigned long long)np2; k <<= 1) {
+            for (unsigned long long j = k >> 1; j >= DF_LOCAL; j >>= 1) {
+                k_df_global<<<grid_for(ctx, np2 / 2, 256, 8), 256, 0, st>>>(rec, pts, np2, k, j);
+                FX_LAUNCH_CHECK(ctx);
+            }
+            k_df_local<false><<<nblk, DF_LOCAL / 2, 0, st>>>(rec, pts, (unsigned)k);
             FX_LAUNCH_CHECK(ctx);
         }
-        k_df_local<false><<<nblk, DF_LOCAL / 2, 0, st>>>(rec, pts, (unsigned)k);
+        k_df_emit<<<grid_for(ctx, n > 0 ? n : 1, 256, 8), 256, 0, st>>>(rec, pts, d_count, out);
         FX_LAUNCH_CHECK(ctx);
-    }
-    k_df_emit<<<grid_for(ctx, n > 0 ? n : 1, 256, 8), 256, 0, st>>>(rec, pts, d_count, out);
-    FX_LAUNCH_CHECK(ctx);
-    return FX_OK;
+        return FX_OK;
+    };
+    struct { const void *pts, *out, *cnt, *rec; int64_t n; double dis; } key = {pts, out, d_count, rec, n, dis};
+    return fx_graph_run(ctx, FX_GRAPH_DFILTER, &key, sizeof(key), st, enqueue);
 }
 
 extern "C" int fx_distance_filter_host(fx_context *ctx, const double *h_pts, int64_t n, double dis, double *h_out, int64_t *h_count)

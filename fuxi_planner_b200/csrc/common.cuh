@@ -99,7 +99,17 @@ struct fx_context {
     cudaEvent_t ev_band[2];    // around the last k_band_bound launch (fx_search_timings)
     int ev_search_valid;
     int small_attr_set, cfg_small_off, lat_attr_set;
+    // CUDA-graph cache of the multi-launch device entry points (fx_graph_run)
+    struct GraphSlot {
+        unsigned char key[192];
+        size_t keylen;
+        int sightings;          // consecutive calls with this key
+        cudaGraphExec_t exec;   // instantiated on the second sighting
+    } graphs[4];
+    cudaStream_t cap_stream;    // capture happens here (the caller's stream may be the legacy default stream)
+    int cfg_graphs;             // FUXI_B200_GRAPHS=0: plain launches
 };
+enum { FX_GRAPH_CLOUD = 0, FX_GRAPH_EDT = 1, FX_GRAPH_DFILTER = 2, FX_GRAPH_TFILTER = 3 };
 
 int fx_set_err(fx_context *ctx, int code, const char *fmt, ...);
 #define FX_CUDA(ctx, call)                                                                        \
@@ -209,6 +219,13 @@ __device__ __forceinline__ int fx_cidx(int x, int y, int H, int TY)
 
 int fx_grow_bytes(fx_context *ctx, void **p, size_t *cap, size_t want_bytes);
 int fx_grow_pinned(fx_context *ctx, size_t want);
+#include <functional>
+// Launch-bound sizes (one camera frame through the 16 kernels of the cloud filter, a 1024^2 distance transform): the
+// launch sequence of an entry point is a function of its arguments and of the scratch pointers it uses -- `key`.  The
+// first call with a key runs `enqueue(stream)` as plain launches (and sizes the scratch), the second captures the same
+// sequence into a CUDA graph on a private stream, later calls replay it: one launch instead of 8-16, no gaps between the
+// kernels.  Device-side decisions (flags, counts) stay inside the kernels, so the replay is exact.  (api.cu)
+int fx_graph_run(fx_context *ctx, int slot, const void *key, size_t keylen, cudaStream_t st, const std::function<int(cudaStream_t)> &enqueue);
 // pageable host bytes -> start of the pinned staging buffer (non-temporal stores on the host worker pool) -> device (api.cu)
 int fx_staged_copy_in(fx_context *ctx, uint8_t *d_dst, const uint8_t *h_src, size_t bytes, cudaStream_t st);
 int fx_search_reserve(fx_context *ctx, int which, int W, int H, int max_path, cudaStream_t st);

@@ -682,7 +682,6 @@ extern "C" int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W
     const size_t cells = (size_t)W * H;
     int rc0 = edt_reserve(ctx, cells);
     if (rc0) return rc0;
-    FX_CUDA(ctx, cudaMemsetAsync(ctx->edt_flag, 0, 4 * sizeof(int), st));
     if (H % 32 == 0 && ((uintptr_t)occ & 15u) == 0 && ((uintptr_t)dist2 & 15u) == 0) {
         // dense-map fast path; falls through to the windowed path (conditionally, on the device flag) if too many
         // cells are farther than EDT_R from every obstacle
@@ -694,9 +693,6 @@ extern "C" int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W
         unsigned *fix_list = reinterpret_cast<unsigned *>(ctx->edt_t);     // cells*2 bytes -> cells/4 entries of 8 bytes
         unsigned *fix_count = reinterpret_cast<unsigned *>(ctx->edt_flag) + 1;
         size_t cap = cells / 4; if (cap > (1u << 22)) cap = 1u << 22;
-        FX_CUDA(ctx, cudaMemsetAsync(fix_count, 0, sizeof(unsigned), st));
-        k_edt_pack<<<dim3((HW + 31) / 32, (Wp + 31) / 32), 256, 0, st>>>(occ, bitsb, W, HW, Wp);
-        FX_LAUNCH_CHECK(ctx);
         // segments of rows per strip (multiples of the 64-row step; a segment starts with 2 R extra rows of masks): about
         // four CTAs per resident slot on large grids (strips differ in work: the walk stops when a word is settled), one
         // wave of shorter segments when that would leave a segment less than four steps
@@ -708,27 +704,35 @@ extern "C" int fx_edt(fx_context *ctx, const uint8_t *occ, int32_t *dist2, int W
         int segs = slots * 4 / gx;
         if (segs < 1 || W / segs < 4 * EDT_STEP) segs = slots / gx;
         if (segs < 1) segs = 1;
-        int seg_rows = ((W + segs - 1) / segs + EDT_STEP - 1) / EDT_STEP * EDT_STEP;
+        const int seg_rows = ((W + segs - 1) / segs + EDT_STEP - 1) / EDT_STEP * EDT_STEP;
         segs = (W + seg_rows - 1) / seg_rows;
-        k_edt_strips<<<dim3(gx, segs), EDT_WS_WARPS * 32, EDT_WS_SMEM, st>>>(bitsb, dist2, W, HW, Wp, seg_rows, fix_list, fix_count, (unsigned)cap);
-        FX_LAUNCH_CHECK(ctx);
-        k_edt_fix<<<ctx->sm_count * 4, 128, 0, st>>>(bitsb, dist2, W, HW, Wp, fix_list, fix_count, (unsigned)cap, ctx->edt_flag);
-        FX_LAUNCH_CHECK(ctx);
-        // the windowed path below runs only if the flag was raised
-        const int nwords = (H + 31) / 32;
-        int warps = 8;
-        size_t smem = (size_t)warps * 3 * nwords * 4;
-        while (smem > 48 * 1024 && warps > 1) { warps >>= 1; smem = (size_t)warps * 3 * nwords * 4; }
-        int blocks = (W + warps - 1) / warps;
-        if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-        k_edt_rows<<<blocks, warps * 32, smem, st>>>(occ, ctx->edt_g, W, H, ctx->edt_flag);
-        FX_LAUNCH_CHECK(ctx);
-        k_edt_cols_tile<<<edt_cols_grid(ctx, W, H), 256, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_flag + 2, ctx->edt_flag);
-        FX_LAUNCH_CHECK(ctx);
-        k_edt_cols_exact<<<(H + 127) / 128, 128, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_s, ctx->edt_t, ctx->edt_flag + 2);
-        FX_LAUNCH_CHECK(ctx);
-        return FX_OK;
+        auto enqueue = [&](cudaStream_t st) -> int {
+            FX_CUDA(ctx, cudaMemsetAsync(ctx->edt_flag, 0, 4 * sizeof(int), st));  // [0] fallback flag, [1] fix_count, [2] window-left-open flag
+            k_edt_pack<<<dim3((HW + 31) / 32, (Wp + 31) / 32), 256, 0, st>>>(occ, bitsb, W, HW, Wp);
+            FX_LAUNCH_CHECK(ctx);
+            k_edt_strips<<<dim3(gx, segs), EDT_WS_WARPS * 32, EDT_WS_SMEM, st>>>(bitsb, dist2, W, HW, Wp, seg_rows, fix_list, fix_count, (unsigned)cap);
+            FX_LAUNCH_CHECK(ctx);
+            k_edt_fix<<<ctx->sm_count * 4, 128, 0, st>>>(bitsb, dist2, W, HW, Wp, fix_list, fix_count, (unsigned)cap, ctx->edt_flag);
+            FX_LAUNCH_CHECK(ctx);
+            // the windowed path below runs only if the flag was raised
+            const int nwords = (H + 31) / 32;
+            int warps = 8;
+            size_t smem = (size_t)warps * 3 * nwords * 4;
+            while (smem > 48 * 1024 && warps > 1) { warps >>= 1; smem = (size_t)warps * 3 * nwords * 4; }
+            int blocks = (W + warps - 1) / warps;
+            if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+            k_edt_rows<<<blocks, warps * 32, smem, st>>>(occ, ctx->edt_g, W, H, ctx->edt_flag);
+            FX_LAUNCH_CHECK(ctx);
+            k_edt_cols_tile<<<edt_cols_grid(ctx, W, H), 256, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_flag + 2, ctx->edt_flag);
+            FX_LAUNCH_CHECK(ctx);
+            k_edt_cols_exact<<<(H + 127) / 128, 128, 0, st>>>(ctx->edt_g, dist2, W, H, ctx->edt_s, ctx->edt_t, ctx->edt_flag + 2);
+            FX_LAUNCH_CHECK(ctx);
+            return FX_OK;
+        };
+        struct { const void *occ, *out, *g, *s, *t, *flag; int W, H; } key = {occ, dist2, ctx->edt_g, ctx->edt_s, ctx->edt_t, ctx->edt_flag, W, H};
+        return fx_graph_run(ctx, FX_GRAPH_EDT, &key, sizeof(key), st, enqueue);
     }
+    FX_CUDA(ctx, cudaMemsetAsync(ctx->edt_flag, 0, 4 * sizeof(int), st));
     int rc = edt_rows_launch(ctx, occ, ctx->edt_g, W, H, st);
     if (rc) return rc;
     return edt_cols_launch(ctx, ctx->edt_g, dist2, W, H, st);
