@@ -82,18 +82,25 @@ def _cloud_params(stride, rgb_offset, pass_lim, leaf, radius, min_neighbors):
                        float(leaf[2]), int(min_neighbors), float(radius))
 
 
-def cloud_filter(points, rgb_offset=-1, pass_lim=(0.0, 4.0), leaf=(0.17, 0.17, 0.2), radius=0.35, min_neighbors=13, ctx=None):
+def cloud_filter(points, rgb_offset=-1, pass_lim=(0.0, 4.0), leaf=(0.17, 0.17, 0.2), radius=0.35, min_neighbors=13, ctx=None,
+                 out=None, counts=None):
     """PCL chain of src/chen_filter_rgb.cpp:52-71 on a float32 CUDA tensor [n, stride] (x, y, z first; rgb_offset = column
     of PCL's packed rgb word or -1).  Returns (out float32 [n, 4] = x, y, z, rgb word; counts int64 CUDA tensor [4] =
-    {after PassThrough, voxels, kept, status}); rows [0, counts[2]) of out are valid.  Enqueues only (no host sync)."""
+    {after PassThrough, voxels, kept, status}); rows [0, counts[2]) of out are valid.  Enqueues only (no host sync).
+    `out` / `counts`: reuse these tensors (a node that filters every frame into the same buffers replays one CUDA graph)."""
     if not (isinstance(points, torch.Tensor) and points.is_cuda and points.dtype == torch.float32 and points.dim() == 2
             and points.shape[1] >= 3):
         raise FuxiError("points must be a float32 CUDA tensor [n, stride >= 3]")
     points = points.contiguous()
     ctx = api._ctx(ctx, points)
     n, stride = points.shape
-    out = torch.empty((max(n, 1), 4), dtype=torch.float32, device=points.device)
-    counts = torch.empty(4, dtype=torch.int64, device=points.device)
+    if out is None:
+        out = torch.empty((max(n, 1), 4), dtype=torch.float32, device=points.device)
+    if counts is None:
+        counts = torch.empty(4, dtype=torch.int64, device=points.device)
+    if not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.dim() == 2 and out.shape[1] == 4
+            and counts.is_cuda and counts.dtype == torch.int64 and counts.numel() >= 4 and counts.is_contiguous()):
+        raise FuxiError("out must be a contiguous float32 CUDA tensor [cap, 4], counts an int64 CUDA tensor [4]")
     prm = _cloud_params(stride, rgb_offset, pass_lim, leaf, radius, min_neighbors)
     ctx.check(ctx.lib.fx_cloud_filter(ctx.handle, api._ptr(points), n, C.byref(prm), api._ptr(out), out.shape[0],
                                       api._ptr(counts), api._stream()), "fx_cloud_filter")
@@ -117,7 +124,7 @@ def cloud_filter_host(points, rgb_offset=-1, pass_lim=(0.0, 4.0), leaf=(0.17, 0.
     return out[:counts[2]].copy(), counts
 
 
-def distance_filter(points, dis, ctx=None):
+def distance_filter(points, dis, ctx=None, out=None, count=None):
     """convert_plc.distance_filter (plc_point2_st.py:139-148) on a float64 CUDA tensor [n, 3]: returns (out float64
     [n, 3], count int32 CUDA tensor [1]); rows [0, count) are the points with |p| < dis ordered by (|p|, z, y, x)."""
     if not (isinstance(points, torch.Tensor) and points.is_cuda and points.dtype == torch.float64 and points.dim() == 2
@@ -125,8 +132,13 @@ def distance_filter(points, dis, ctx=None):
         raise FuxiError("points must be a float64 CUDA tensor [n, 3]")
     points = points.contiguous()
     ctx = api._ctx(ctx, points)
-    out = torch.empty_like(points)
-    count = torch.empty(1, dtype=torch.int32, device=points.device)
+    if out is None:
+        out = torch.empty_like(points)
+    if count is None:
+        count = torch.empty(1, dtype=torch.int32, device=points.device)
+    if not (out.is_cuda and out.dtype == torch.float64 and out.is_contiguous() and out.shape == points.shape
+            and count.is_cuda and count.dtype == torch.int32 and count.numel() >= 1):
+        raise FuxiError("out must be a contiguous float64 CUDA tensor [n, 3], count an int32 CUDA tensor [1]")
     ctx.check(ctx.lib.fx_distance_filter(ctx.handle, api._ptr(points), points.shape[0], float(dis), api._ptr(out),
                                          api._ptr(count), api._stream()), "fx_distance_filter")
     return out, count

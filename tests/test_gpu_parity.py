@@ -134,6 +134,21 @@ def test_edt_exact(fx, dev, oracle, shape, fill):
     assert np.array_equal(got, want)
 
 
+def test_edt_graph_replay_follows_the_data(fx, dev, oracle):
+    """fx_edt replays a captured CUDA graph from its third call with the same buffers on: the device-side decisions (fix-up
+    list, fallback to the windowed path on the overflow flag) must still follow the data of each call."""
+    import torch
+    rng = np.random.default_rng(5)
+    shape = (640, 1024)
+    occ = torch.empty(shape, dtype=torch.uint8, device=dev)
+    d2 = torch.empty(shape, dtype=torch.int32, device=dev)
+    for it, fill in enumerate((0.02, 0.02, 0.02, 0.0002, 0.3, 0.0, 0.004)):  # dense / sparse (list overflows) / empty / fix-up list
+        m = (rng.random(shape) < fill).astype(np.uint8)
+        occ.copy_(torch.from_numpy(m))
+        fx.edt(occ, out=d2)
+        assert np.array_equal(d2.cpu().numpy(), oracle.edt(m)), (it, fill)
+
+
 def test_edt_single_obstacle_and_clusters(fx, dev, oracle):
     m = np.zeros((128, 128), dtype=np.uint8)
     m[5, 120] = 1
@@ -508,6 +523,23 @@ def test_plan_host_float64_matrix_and_wide_ctas(fx, oracle):
     S[:6], G[:6] = s, g
     c = fx.plan_host(occ, S, G, metric=1, max_path=0)
     assert np.array_equal(c[0][:6], a[0])
+
+
+def test_plan_host_odd_sizes_through_the_staged_upload(fx, oracle):
+    """Grids above 2^20 cells reach the device through the worker pool's non-temporal fill of the pinned staging buffer,
+    cut into 64 tasks / four upload parts (csrc/api.cu staged_upload): odd extents leave ragged last tasks and unaligned
+    rows, for the uint8 copy and for the float64 `== 1.0` conversion alike."""
+    rng = np.random.default_rng(123)
+    for W, H in ((1031, 1057), (1500, 701)):
+        occ = (rng.random((W, H)) < 0.2).astype(np.uint8)
+        s, g = random_queries(occ, 5, rng)
+        want, status, _ = oracle.jps_batch(occ, s, g, 1)
+        mat = occ.astype(np.float64)
+        mat[(occ == 0) & (rng.random((W, H)) < 0.03)] = 1.0000000000000002   # not == 1.0: free
+        for grid in (occ, mat, np.asfortranarray(occ)):
+            r = fx.plan_host(grid, s, g, metric=1, max_path=0)
+            for q in range(5):
+                assert (r[0][q] == int(want[q])) if status[q] == 1 else (r[0][q] == -1), (W, H, grid.dtype, q)
 
 
 def test_search_extreme_shapes_and_empty_batches(fx, dev, oracle):
