@@ -570,12 +570,17 @@ __device__ int edt_row_nearest(const unsigned *__restrict__ rowbits, size_t stri
     const int w = y >> 5, b = y & 31;
     int best = -1;
     {
+        // the word of the cell and its two neighbours in one go (three independent loads: everything within 32 cells on
+        // either side, which is where the answer nearly always is -- a listed cell is just over EDT_R from an obstacle)
         const unsigned m = rowbits[w * stride];
+        const unsigned ml = w > 0 ? rowbits[(w - 1) * stride] : 0u, mr = w + 1 < HW ? rowbits[(w + 1) * stride] : 0u;
         const unsigned below = m & (0xFFFFFFFFu >> (31 - b)), above = m >> b;
         if (below) best = b - (31 - __clz(below));
         if (above) { const int d = __ffs(above) - 1; if (best < 0 || d < best) best = d; }
+        if (ml) { const int d = y - ((w - 1) * 32 + 31 - __clz(ml)); if (best < 0 || d < best) best = d; }
+        if (mr) { const int d = (w + 1) * 32 + __ffs(mr) - 1 - y; if (best < 0 || d < best) best = d; }
     }
-    for (int k = 1; (k - 1) * 32 < lim && (best < 0 || (k - 1) * 32 < best); k++) {
+    for (int k = 2; (k - 1) * 32 < lim && (best < 0 || (k - 1) * 32 < best); k++) {
         if (w - k >= 0) { const unsigned m = rowbits[(w - k) * stride]; if (m) { const int d = y - ((w - k) * 32 + 31 - __clz(m)); if (best < 0 || d < best) best = d; } }
         if (w + k < HW) { const unsigned m = rowbits[(w + k) * stride]; if (m) { const int d = (w + k) * 32 + __ffs(m) - 1 - y; if (best < 0 || d < best) best = d; } }
     }
