@@ -106,6 +106,7 @@ struct fx_context {
         int sightings;          // consecutive calls with this key
         cudaGraphExec_t exec;   // instantiated on the second sighting
     } graphs[4];
+    int calib_W, calib_H, calib_metric;  // what the first-bound table of the latency forms was learnt on (search.cu)
     cudaStream_t cap_stream;    // capture happens here (the caller's stream may be the legacy default stream)
     int cfg_graphs;             // FUXI_B200_GRAPHS=0: plain launches
 };

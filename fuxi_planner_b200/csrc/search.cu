@@ -93,6 +93,7 @@ __device__ __forceinline__ uint64_t fx_first_bound(const uint32_t *calib, int bi
     if (!calib) return (uint64_t)h0 + h0 / 128 + 4ull * wd;  // FUXI_B200_CALIB=0: the fixed guess of the first version
     uint32_t r = __ldcg(calib + bin);
     if (bin < 15) r = max(r, __ldcg(calib + bin + 1) >> 1);  // a sparsely visited bin borrows from its neighbour
+    r = min(r, 1u << 19);                                              // never guess beyond 1.5 h0: a maze-like map is served by the widening
     r = r + (r >> 3) + FX_CALIB_FLOOR;                                 // 1/8 margin over the recent maximum
     return (uint64_t)h0 + (((uint64_t)h0 * r) >> 20) + 4ull * wd;
 }
@@ -1284,7 +1285,10 @@ int fx_search_reserve(fx_context *ctx, int which, int W, int H, int max_path, cu
     const int nfields = which == 1 ? 2 : 1;
     const size_t cells_al = (cells + 511) / 512 * 512;
     size_t dirty_n = (nfields * cells_al) >> FX_DIRTY_SHIFT;  // a multiple of 16
-    int qcap = 8 * (W + H) + 1024;
+    // entries per bucket queue.  The latency forms get eight times the room: there are few slots, and the cluster form cuts
+    // a bucket half into one segment per CTA (1 / 16 of qcap), which a wide first bound on a small grid can fill from a
+    // single CTA (r02j fuzz: a 121 x 42 grid, effectively unpruned, overflowed 145-entry segments)
+    int qcap = which == 1 ? 64 * (W + H) + 8192 : 8 * (W + H) + 1024;
     size_t per_slot = nfields * cells_al * 4 + dirty_n + (size_t)qcap * 32 + (size_t)path_cap * 16;
     size_t free_b = 0, total_b = 0;
     FX_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
@@ -1346,6 +1350,11 @@ extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int 
     {
         const char *e = getenv("FUXI_B200_CALIB");  // tuning experiments only
         P.calib = (e && e[0] == '0') ? nullptr : reinterpret_cast<uint32_t *>(ctx->counters + 16);
+        // the table describes a map: another grid shape or metric starts it afresh
+        if (P.calib && (ctx->calib_W != W || ctx->calib_H != H || ctx->calib_metric != metric)) {
+            FX_CUDA(ctx, cudaMemsetAsync(P.calib, 0, 16 * sizeof(uint32_t), st));
+            ctx->calib_W = W; ctx->calib_H = H; ctx->calib_metric = metric;
+        }
     }
     // half-width (cells along the minor axis) of the band-limited passes of the search kernel; one more than the band kernel's
     // 15 + rounding of its fixed-point centre line, so that a path the band kernel found lies inside it

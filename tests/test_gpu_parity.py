@@ -542,6 +542,34 @@ def test_plan_host_odd_sizes_through_the_staged_upload(fx, oracle):
                 assert (r[0][q] == int(want[q])) if status[q] == 1 else (r[0][q] == -1), (W, H, grid.dtype, q)
 
 
+def test_latency_forms_after_a_maze_of_the_same_shape(fx, dev, oracle, monkeypatch):
+    """The latency forms size their first pass from a per-context table of how far above the octile bound earlier optima
+    lay (search.cu fx_first_bound).  A serpentine maze teaches it ratios of 10 and more; the next map of the same shape is
+    an open one.  The guess is capped (1.5 h0) and the cluster form's per-CTA queue segments must hold the wide levels of
+    a barely pruned search on a small grid (r02j fuzz: FX_COST_OVERFLOW on a 121 x 42 grid).  Answers never depend on
+    the table."""
+    monkeypatch.setenv("FUXI_B200_SMALL", "0")
+    rng = np.random.default_rng(2024)
+    W, H = 121, 42
+    maze = np.zeros((W, H), dtype=np.uint8)
+    for x in range(3, W, 6):
+        maze[x, :] = 1
+        maze[x, (H - 2) if (x // 6) % 2 else 1] = 0
+    ms = np.array([[0, 0], [1, 20], [0, 41], [2, 5]], dtype=np.int32)
+    mg = np.array([[120, 41], [119, 3], [120, 0], [118, 30]], dtype=np.int32)
+    open_map = (rng.random((W, H)) < 0.05).astype(np.uint8)
+    s, g = random_queries(open_map, 12, rng)
+    s[0], g[0] = (68, 12), (112, 17)
+    open_map[68, 12] = 0; open_map[112, 17] = 0
+    for metric in (1, 2):
+        for rep in range(3):                                   # the table decays slowly: the open map sees the maze's values
+            r = fx.plan_batch(_t(maze, dev), _t(ms, dev), _t(mg, dev), metric=metric, max_path=4096)
+            assert np.array_equal(r.cost_i.cpu().numpy().astype(np.int64), oracle.sssp_batch(maze, ms, mg, metric))
+        for Q in (1, 3, 12):                                   # cluster form (<= 18 queries)
+            r = fx.plan_batch(_t(open_map, dev), _t(s[:Q], dev), _t(g[:Q], dev), metric=metric, max_path=4096)
+            assert np.array_equal(r.cost_i.cpu().numpy().astype(np.int64), oracle.sssp_batch(open_map, s[:Q], g[:Q], metric)), (metric, Q)
+
+
 def test_search_extreme_shapes_and_empty_batches(fx, dev, oracle):
     """The largest extent the packed (x << 16 | y) queue entries allow (32767), one-cell-wide corridors, an empty batch,
     max_path = 0, and the refusal above the limit."""
