@@ -1278,6 +1278,16 @@ int fx_search_reserve(fx_context *ctx, int which, int W, int H, int max_path, cu
     size_t cells = fx_scratch_cells(W, H);
     int path_cap = max_path > 0 ? max_path : 1;
     if (S.fields && S.sW == W && S.sH == H && S.path_cap >= path_cap) return FX_OK;
+    if (S.fields && S.sW == W && S.sH == H) {
+        // only the path staging is too small (a path with more turning points than any before): grow that alone -- the
+        // cost fields of the latency forms are 20 GB at 4096^2, freeing and refilling them cost a 25 ms outlier per retry
+        FX_CUDA(ctx, cudaStreamSynchronize(st));
+        if (S.tmp_path) cudaFree(S.tmp_path);
+        S.tmp_path = nullptr;
+        FX_CUDA(ctx, cudaMalloc(&S.tmp_path, (size_t)S.slots * path_cap * 16));
+        S.path_cap = path_cap;
+        return FX_OK;
+    }
     fx_search_release(ctx, which);
 
     // cells padded to a multiple of 512: field rows stay 16-byte aligned for the uint4 reset and a second field's dirty

@@ -26,7 +26,7 @@ import numpy as np
 from . import api
 from ._lib import FX_COST_OVERFLOW, FX_COST_START_OOB, FuxiError
 
-_MAX_PATH = 1024
+_MAX_PATH = 4096    # turning points kept per call before a retry (a path across a 4096^2 grid at 20 % fill has 300-1100)
 POINTS = "turning"      # or "jump": the reference's jump-point list (fx_jump_points_host)
 
 
@@ -72,9 +72,12 @@ def _plan_one(occ, start, goal, hchoice):
         n = int(f.path_len[0])
         if n <= _MAX_PATH:
             return int(f.cost_i[0]), float(f.cost_f[0]), n, (f.path_xy[0, :n].tolist() if n > 0 else [])
+        first = n                      # longer than the cached buffer: one more search with room for exactly that many
+    else:
+        first = _MAX_PATH
     if occ.dtype != np.float64:        # float64 (what the planners pass) is compared `== 1` inside the library
         occ = (occ == 1).astype(np.uint8)
-    max_path = _MAX_PATH
+    max_path = first
     while True:
         cost_i, cost_f, path_xy, path_len = api.plan_host(occ, [start], [goal], metric=hchoice, max_path=max_path)
         n = int(path_len[0])
