@@ -115,6 +115,9 @@ int fx_edt_cols(fx_context *ctx, const uint16_t *g, int32_t *dist2, int W, int H
  * are searched by one CTA per query entirely in shared memory, one launch per batch; larger maps by the batched
  * wavefront kernel, with 512-thread CTAs when the batch is smaller than the machine (latency) and 128-thread CTAs,
  * eight per SM, otherwise (throughput).  W, H <= 32767.
+ * The latency forms size their first pass from a table the context keeps (how far above the octile bound the optimum
+ * lay on earlier queries of the same grid shape, by direction mix): it changes how many passes a query takes, never
+ * its answer.
  */
 int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int H,
                     const int32_t *starts_xy, const int32_t *goals_xy, int Q, int metric,
@@ -319,6 +322,8 @@ typedef struct fx_cloud_params {
     double radius;
 } fx_cloud_params;
 int fx_cloud_reserve(fx_context *ctx, int64_t max_voxel_space);   /* default 2^28 */
+/* fx_cloud_filter (16 launches), fx_edt (8) and fx_distance_filter are replayed as one CUDA graph from the third call with
+ * identical arguments (same pointers, sizes, parameters) on; the graph is launched into `stream` like the kernels would be. */
 int fx_cloud_filter(fx_context *ctx, const float *pts, int64_t n, const fx_cloud_params *h_params, float *out, int64_t cap,
                     int64_t *d_counts, void *stream);
 int fx_cloud_filter_host(fx_context *ctx, const float *h_pts, int64_t n, const fx_cloud_params *h_params, float *h_out,
