@@ -346,11 +346,13 @@ static inline void nt_eq1_f64(uint8_t *dst, const double *src, size_t n)  // dst
 // (a copy of the caller's uint8 grid, or `== 1.0` of its float64 matrix); the grid is cut into tasks, the tasks into four
 // upload parts, and the calling thread issues a part's H2D copy as soon as its tasks are done, so the copies overlap the
 // filling of the rest.
-static int staged_upload(fx_context *ctx, uint8_t *d_dst, uint8_t *pin_grid, size_t cells, const std::function<void(size_t, size_t)> &fill, cudaStream_t st)
+static int staged_upload(fx_context *ctx, uint8_t *d_dst, uint8_t *pin_grid, size_t cells, const std::function<void(size_t, size_t)> &fill, cudaStream_t st,
+                         const std::function<cudaError_t(size_t)> &after_part = nullptr /* called with the bytes uploaded so far */)
 {
     if (cells < ((size_t)1 << 20)) {
         fill(0, cells);
         FX_CUDA(ctx, cudaMemcpyAsync(d_dst, pin_grid, cells, cudaMemcpyHostToDevice, st));
+        if (after_part) FX_CUDA(ctx, after_part(cells));
         return FX_OK;
     }
     constexpr int PARTS = 4, TPP = 16;  // tasks per part
@@ -367,6 +369,7 @@ static int staged_upload(fx_context *ctx, uint8_t *d_dst, uint8_t *pin_grid, siz
             if (a < cells && err == cudaSuccess) {
                 const size_t nb = a + TPP * per < cells ? TPP * per : cells - a;
                 err = cudaMemcpyAsync(d_dst + a, pin_grid + a, nb, cudaMemcpyHostToDevice, st);
+                if (err == cudaSuccess && after_part) err = after_part(a + nb);
             }
             issued++;
         }
@@ -509,11 +512,22 @@ static int plan_host_impl(fx_context *ctx, const uint8_t *h_grid, const double *
     {
         uint8_t *pg = (uint8_t *)pin + off_grid;
         static const bool nt = !(getenv("FUXI_B200_NT") && getenv("FUXI_B200_NT")[0] == '0');  // tuning experiments only
-        if (h_matrix && nt) rc = staged_upload(ctx, ctx->d_grid, pg, cells, [=](size_t a, size_t b) { nt_eq1_f64(pg + a, h_matrix + a, b - a); }, st);
-        else if (h_matrix) rc = staged_upload(ctx, ctx->d_grid, pg, cells, [=](size_t a, size_t b) { for (size_t i = a; i < b; i++) pg[i] = h_matrix[i] == 1.0 ? (uint8_t)1 : (uint8_t)0; }, st);
-        else if (nt) rc = staged_upload(ctx, ctx->d_grid, pg, cells, [=](size_t a, size_t b) { nt_copy_u8(pg + a, h_grid + a, b - a); }, st);
-        else rc = staged_upload(ctx, ctx->d_grid, pg, cells, [=](size_t a, size_t b) { memcpy(pg + a, h_grid + a, b - a); }, st);
+        // the legal-move mask of the rows that have arrived is built behind each part of the upload (rows x need rows
+        // x - 1 .. x + 1), so that only the last part's share of that kernel is left on the critical path
+        int rows_done = 0, mrc = FX_OK;
+        auto after_part = [&](size_t bytes_up) -> cudaError_t {
+            const int avail = (int)(bytes_up / (size_t)H);                 // complete rows on the device
+            const int upto = bytes_up >= cells ? W : (avail > 0 ? avail - 1 : 0);
+            if (upto > rows_done && mrc == FX_OK) { mrc = fx_build_moves_rows(ctx, ctx->d_grid, W, H, true, rows_done, upto, st); rows_done = upto; }
+            return cudaSuccess;
+        };
+        if (h_matrix && nt) rc = staged_upload(ctx, ctx->d_grid, pg, cells, [=](size_t a, size_t b) { nt_eq1_f64(pg + a, h_matrix + a, b - a); }, st, after_part);
+        else if (h_matrix) rc = staged_upload(ctx, ctx->d_grid, pg, cells, [=](size_t a, size_t b) { for (size_t i = a; i < b; i++) pg[i] = h_matrix[i] == 1.0 ? (uint8_t)1 : (uint8_t)0; }, st, after_part);
+        else if (nt) rc = staged_upload(ctx, ctx->d_grid, pg, cells, [=](size_t a, size_t b) { nt_copy_u8(pg + a, h_grid + a, b - a); }, st, after_part);
+        else rc = staged_upload(ctx, ctx->d_grid, pg, cells, [=](size_t a, size_t b) { memcpy(pg + a, h_grid + a, b - a); }, st, after_part);
         if (rc) return rc;
+        if (mrc) return mrc;
+        ctx->moves_prebuilt_for = ctx->d_grid;
     }
     if (trace) { t_up = now(); cudaEventRecord(tev[1], st); }
     FX_CUDA(ctx, cudaMemcpyAsync(ctx->d_q, pin + off_s, 2 * qb, cudaMemcpyHostToDevice, st));
@@ -521,6 +535,7 @@ static int plan_host_impl(fx_context *ctx, const uint8_t *h_grid, const double *
     int32_t *d_ci = ctx->d_out_i, *d_pl = ctx->d_out_i + Q;
     rc = fx_search_batch(ctx, ctx->d_grid, W, H, d_s, d_g, Q, metric, d_ci, ctx->d_out_f, want_path ? ctx->d_path : nullptr,
                          d_pl, want_path ? max_path : 0, (void *)st);
+    ctx->moves_prebuilt_for = nullptr;  // (a batch that took the shared-memory kernel did not consume it)
     if (rc) return rc;
     if (trace) cudaEventRecord(tev[2], st);
     if (want_path) {

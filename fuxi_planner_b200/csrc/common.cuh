@@ -106,6 +106,7 @@ struct fx_context {
         int sightings;          // consecutive calls with this key
         cudaGraphExec_t exec;   // instantiated on the second sighting
     } graphs[4];
+    const uint8_t *moves_prebuilt_for;  // fx_plan_host -> fx_search_batch: the legal-move mask of this grid is already enqueued
     int calib_W, calib_H, calib_metric;  // what the first-bound table of the latency forms was learnt on (search.cu)
     cudaStream_t cap_stream;    // capture happens here (the caller's stream may be the legacy default stream)
     int cfg_graphs;             // FUXI_B200_GRAPHS=0: plain launches
@@ -238,3 +239,4 @@ int fx_band_bounds(fx_context *ctx, const uint8_t *grid, int W, int H, const int
 int fx_search_small(fx_context *ctx, const uint8_t *grid, int W, int H, const int32_t *starts_xy, const int32_t *goals_xy, int Q,
                     int metric, int32_t *cost_i, double *cost_f, int32_t *path_xy, int32_t *path_len, int max_path, cudaStream_t st);
 int fx_build_moves(fx_context *ctx, const uint8_t *grid, int W, int H, bool tiled, cudaStream_t st);
+int fx_build_moves_rows(fx_context *ctx, const uint8_t *grid, int W, int H, bool tiled, int x0, int x1, cudaStream_t st);

@@ -135,11 +135,12 @@ struct SearchParams {
 // ------------------------------------------------------------------------------------------------
 template <bool TILED>
 __global__ void __launch_bounds__(256) k_build_moves(const uint8_t *__restrict__ grid, int W, int H,
-                                                     uint8_t *__restrict__ moves)
+                                                     uint8_t *__restrict__ moves, int x0, int x1)
 {
     const int TY = fx_tiles_y(H);
-    size_t total = (size_t)W * H;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t total = (size_t)(x1 - x0) * H;  // rows [x0, x1) (their masks read rows x0 - 1 .. x1 of the grid)
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = j + (size_t)x0 * H;
         int x = (int)(i / H), y = (int)(i - (size_t)x * H);
         // 3x3 neighbourhood: 1 = obstacle (== 1) or outside the array
         unsigned nb = 0;  // bit (dx+1)*3 + (dy+1)
@@ -165,7 +166,8 @@ __global__ void __launch_bounds__(256) k_build_moves(const uint8_t *__restrict__
     }
 }
 
-int fx_build_moves(fx_context *ctx, const uint8_t *grid, int W, int H, bool tiled, cudaStream_t st)
+// rows [x0, x1) of the mask (the host upload builds it part by part behind the H2D copies: fx_plan_host)
+int fx_build_moves_rows(fx_context *ctx, const uint8_t *grid, int W, int H, bool tiled, int x0, int x1, cudaStream_t st)
 {
     size_t total = (size_t)W * H;
     const size_t need = fx_scratch_cells(W, H) > total ? fx_scratch_cells(W, H) : total;
@@ -175,13 +177,20 @@ int fx_build_moves(fx_context *ctx, const uint8_t *grid, int W, int H, bool tile
         FX_CUDA(ctx, cudaMalloc(&ctx->moves, need));
         ctx->moves_cap = need;
     }
-    int blocks = (int)((total + 255) / 256);
+    if (x1 <= x0) return FX_OK;
+    const size_t part = (size_t)(x1 - x0) * H;
+    int blocks = (int)((part + 255) / 256);
     int maxb = ctx->sm_count * 16;
     if (blocks > maxb) blocks = maxb;
-    if (tiled && FX_TILED) k_build_moves<true><<<blocks, 256, 0, st>>>(grid, W, H, ctx->moves);
-    else k_build_moves<false><<<blocks, 256, 0, st>>>(grid, W, H, ctx->moves);
+    if (tiled && FX_TILED) k_build_moves<true><<<blocks, 256, 0, st>>>(grid, W, H, ctx->moves, x0, x1);
+    else k_build_moves<false><<<blocks, 256, 0, st>>>(grid, W, H, ctx->moves, x0, x1);
     FX_LAUNCH_CHECK(ctx);
     return FX_OK;
+}
+
+int fx_build_moves(fx_context *ctx, const uint8_t *grid, int W, int H, bool tiled, cudaStream_t st)
+{
+    return fx_build_moves_rows(ctx, grid, W, H, tiled, 0, W, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1345,8 +1354,11 @@ extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int 
     const int which = Q <= wide ? 1 : 0;
     int rc = fx_search_reserve(ctx, which, W, H, path_xy ? max_path : 1, st);
     if (rc) return rc;
-    rc = fx_build_moves(ctx, grid, W, H, true, st);
-    if (rc) return rc;
+    if (ctx->moves_prebuilt_for == grid) ctx->moves_prebuilt_for = nullptr;  // fx_plan_host built the mask behind its upload
+    else {
+        rc = fx_build_moves(ctx, grid, W, H, true, st);
+        if (rc) return rc;
+    }
     FX_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, 16 * sizeof(unsigned long long), st));
     const fx_context::SearchScratch &X = ctx->scr[which];
     SearchParams P;
