@@ -362,7 +362,7 @@ def latency_probe(fx, m4096, s, g, hchoice):
     m1 = z["-16.40-4.80_out.png"].astype(np.float64)
     free = np.argwhere(m1 == 0)
     rng = np.random.default_rng(0)
-    pairs = [(tuple(free[rng.integers(len(free))]), tuple(free[rng.integers(len(free))])) for _ in range(300)]
+    pairs = [(tuple(free[rng.integers(len(free))]), tuple(free[rng.integers(len(free))])) for _ in range(1050)]   # 1000 reps after 50 warm-ups
     sink = io.StringIO()
 
     def run(mat, pairs, warm):
@@ -378,8 +378,8 @@ def latency_probe(fx, m4096, s, g, hchoice):
         return {"p50_ms": float(np.percentile(ts, 50)), "p90_ms": float(np.percentile(ts, 90)),
                 "p99_ms": float(np.percentile(ts, 99)), "n": len(ts)}
 
-    res["cfg1_map_148x52"] = run(m1, pairs, 20)
-    # the same 280 queries through the C restatement of jps1.py on ONE host core of this box (the reference's own
+    res["cfg1_map_148x52"] = run(m1, pairs, 50)
+    # the same 1000 queries through the C restatement of jps1.py on ONE host core of this box (the reference's own
     # Python is ~2 orders of magnitude slower: BASELINE.md §2 measured p50 10.5 ms on another machine)
     try:
         import oracle
@@ -388,27 +388,42 @@ def latency_probe(fx, m4096, s, g, hchoice):
         for i, (a, b) in enumerate(pairs):
             t0 = time.perf_counter()
             oracle.capi.jps(occ1, a, b, hchoice, max_path=4096)
-            if i >= 20:
+            if i >= 50:
                 ts.append(time.perf_counter() - t0)
         ts = np.array(ts) * 1e3
         res["cfg1_map_148x52"]["cpu_port_p50_ms"] = float(np.percentile(ts, 50))
         res["cfg1_map_148x52"]["cpu_port_p99_ms"] = float(np.percentile(ts, 99))
-        res["cfg1_map_148x52"]["cpu_port"] = "oracle/fuxi_oracle.c fxo_jps, 1 core, same box, same 280 queries"
+        res["cfg1_map_148x52"]["cpu_port"] = "oracle/fuxi_oracle.c fxo_jps, 1 core, same box, same 1000 queries"
     except Exception as exc:
         res["cfg1_map_148x52"]["cpu_port_error"] = repr(exc)
     m4 = m4096.astype(np.float64)
-    pairs4 = [(tuple(int(v) for v in s[i]), tuple(int(v) for v in g[i])) for i in range(220)]
-    res["grid_%dx%d" % m4096.shape] = run(m4, pairs4, 20)
+    pairs4 = [(tuple(int(v) for v in s[i]), tuple(int(v) for v in g[i])) for i in range(450)]
+    res["grid_%dx%d" % m4096.shape] = run(m4, pairs4, 50)
     # the same through the uint8 host entry point (no float64 -> uint8 conversion of 16 Mi cells on the host)
     tsu = []
     for i, (a, b) in enumerate(pairs4):
         t0 = time.perf_counter()
         fx.plan_host(m4096, np.array([a], dtype=np.int32), np.array([b], dtype=np.int32), metric=hchoice, max_path=2048)
-        if i >= 20:
+        if i >= 50:
             tsu.append(time.perf_counter() - t0)
     tsu = np.array(tsu) * 1e3
     res["grid_%dx%d_uint8_host" % m4096.shape] = {"p50_ms": float(np.percentile(tsu, 50)), "p90_ms": float(np.percentile(tsu, 90)),
                                                   "p99_ms": float(np.percentile(tsu, 99)), "n": len(tsu)}
+    # where such a call spends its time: medians over 60 traced calls, host wall clock and CUDA events
+    try:
+        names = ("host_fill_and_upload_issue", "host_enqueue", "host_wait", "device_grid_upload", "device_search_incl_move_mask", "device_paths_and_d2h")
+        for label, mat in (("uint8", m4096), ("float64", m4)):
+            os.environ["FUXI_B200_TRACE"] = "2"
+            rows = []
+            for (a, b) in pairs4[20:80]:
+                fx.plan_host(mat, np.array([a], dtype=np.int32), np.array([b], dtype=np.int32), metric=hchoice, max_path=2048)
+                rows.append(fx.plan_host_stages())
+            os.environ.pop("FUXI_B200_TRACE", None)
+            med = np.median(np.array(rows), axis=0)
+            res["grid_%dx%d_%s_host_stages_us_median" % (m4096.shape + (label,))] = {k: float(v) for k, v in zip(names, med)}
+    except Exception as exc:
+        os.environ.pop("FUXI_B200_TRACE", None)
+        res["host_stages_error"] = repr(exc)
     # the whole planner iteration in one call (decode + pad/shift + inflate + goal relocation + search + shortcutting +
     # world coordinates, fx_replan_host): OccupancyGrid message of the cfg1 map in, world path out
     from fuxi_planner_b200 import planner

@@ -7,7 +7,7 @@ Everything compute runs in hand-written CUDA behind the C ABI in include/fuxi_b2
 from ._lib import (Context, FuxiError, default_context, load, SO_PATH,  # noqa: F401
                    FX_EUCLID_WS, FX_EUCLID_WD)
 from .api import (PlanResult, edt, field, field_relax, field_status, inflate, map_host, plan_batch, plan_host,  # noqa: F401
-                  project, search_stats, search_kernel_ms, search_timings, grid_decode, grid_encode, grid_paste, grid_bbox, relocate_goal, path_post,
+                  project, search_stats, search_kernel_ms, search_timings, plan_host_stages, grid_decode, grid_encode, grid_paste, grid_bbox, relocate_goal, path_post,
                   replan_host, grid_to_image, image_to_grid, paths_compact, plan_host_csr, paths_jump_points, jump_points_host)
 from . import jps1  # noqa: F401
 from . import tiled  # noqa: F401

@@ -17,7 +17,7 @@ FX_EUCLID_WD = 3363
 # every symbol include/fuxi_b200.h declares (tests/test_boundary.py checks the .so exports all of them)
 SYMBOLS = ["fx_create", "fx_destroy", "fx_last_error", "fx_version", "fx_launch_count", "fx_set_search_tuning", "fx_set_search_form", "fx_canon_successors",
            "fx_project", "fx_inflate", "fx_edt", "fx_edt_rows", "fx_edt_cols", "fx_search_batch", "fx_field", "fx_field_relax", "fx_field_status",
-           "fx_search_stats", "fx_search_kernel_ms", "fx_search_timings", "fx_plan_host", "fx_plan_host_f64", "fx_plan_host_csr", "fx_last_d2h_bytes",
+           "fx_search_stats", "fx_search_kernel_ms", "fx_search_timings", "fx_plan_host_stages", "fx_plan_host", "fx_plan_host_f64", "fx_plan_host_csr", "fx_last_d2h_bytes",
            "fx_paths_compact", "fx_paths_jump_points", "fx_jump_points_host", "fx_map_host", "fx_halo_merge",
            "fx_grid_decode", "fx_grid_encode", "fx_grid_paste", "fx_grid_bbox", "fx_relocate_goal", "fx_path_post",
            "fx_replan_host", "fx_replan_grid_host", "fx_grid_to_image", "fx_image_to_grid",
@@ -89,6 +89,7 @@ def load():
     lib.fx_search_stats.argtypes = [vp, C.POINTER(i64)]
     lib.fx_search_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.fx_search_timings.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.fx_plan_host_stages.argtypes = [vp, C.POINTER(C.c_double)]
     lib.fx_plan_host.argtypes = [vp, vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp, i32]
     lib.fx_plan_host_f64.argtypes = [vp, vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, vp, i32]
     lib.fx_plan_host_csr.argtypes = [vp, vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, i32, vp, vp, i64, C.POINTER(i64)]

@@ -147,6 +147,15 @@ def search_timings(ctx=None):
     return float(ms[0]), float(ms[1])
 
 
+def plan_host_stages(ctx=None):
+    """Stage times (us) of the last traced plan_host call (FUXI_B200_TRACE=1|2 in the environment before the library is
+    first used): host fill + upload issue, host enqueue, host wait, device upload, device search, device paths + D2H."""
+    ctx = _ctx(ctx)
+    us = (C.c_double * 6)()
+    ctx.check(ctx.lib.fx_plan_host_stages(ctx.handle, us), "fx_plan_host_stages")
+    return tuple(float(v) for v in us)
+
+
 def field(grid, source, metric=1, out=None, ctx=None, check=True):
     """Cost-from-source field, int32 [W][H], -1 = unreachable (fx_field)."""
     grid = _u8_grid(grid)

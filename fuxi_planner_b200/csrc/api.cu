@@ -394,6 +394,14 @@ int fx_staged_copy_in(fx_context *ctx, uint8_t *d_dst, const uint8_t *h_src, siz
     return staged_upload(ctx, d_dst, pp, bytes, [=](size_t a, size_t b) { nt_copy_u8(pp + a, h_src + a, b - a); }, st);
 }
 
+extern "C" int fx_plan_host_stages(fx_context *ctx, double *h_us6)
+{
+    if (!ctx || !h_us6) return FX_ERR_ARG;
+    if (!ctx->last_stage_valid) return fx_set_err(ctx, FX_ERR_ARG, "fx_plan_host_stages: the last fx_plan_host call was not traced (FUXI_B200_TRACE=1|2) or took the shared-memory path");
+    memcpy(h_us6, ctx->last_stage_us, 6 * sizeof(double));
+    return FX_OK;
+}
+
 // csr != NULL: paths are returned packed (offsets[Q+1] + xy[total][2]) instead of in padded rows
 struct CsrOut { int64_t *h_offsets; int32_t *h_xy; int64_t cap; int64_t *h_total; };
 static int plan_host_impl(fx_context *ctx, const uint8_t *h_grid, const double *h_matrix, int W, int H, const int32_t *h_starts_xy,
@@ -465,7 +473,10 @@ static int plan_host_impl(fx_context *ctx, const uint8_t *h_grid, const double *
     if ((rc = grow_pinned(ctx, off_p + path_bytes))) return rc;
     char *pin = (char *)ctx->h_pin;
     // FUXI_B200_TRACE=1: wall-clock of the host stages of this call on stderr (tuning aid)
-    static const bool trace = getenv("FUXI_B200_TRACE") && getenv("FUXI_B200_TRACE")[0] == '1';
+    const char *trace_env = getenv("FUXI_B200_TRACE");  // read per call: 1 = print, 2 = record only (fx_plan_host_stages)
+    const int trace_level = trace_env ? atoi(trace_env) : 0;
+    const bool trace = trace_level > 0;
+    ctx->last_stage_valid = 0;
     auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = trace ? now() : 0.0;
     double t_up = 0.0, t_enq = 0.0, t_sync = 0.0;
@@ -554,7 +565,10 @@ static int plan_host_impl(fx_context *ctx, const uint8_t *h_grid, const double *
         float d01 = 0.f, d12 = 0.f, d23 = 0.f;
         cudaEventElapsedTime(&d01, tev[0], tev[1]); cudaEventElapsedTime(&d12, tev[1], tev[2]); cudaEventElapsedTime(&d23, tev[2], tev[3]);
         for (auto &e : tev) cudaEventDestroy(e);
-        fprintf(stderr, "fx_plan_host trace: host: fill+upload issue %.0f us, enqueue %.0f us, wait %.0f us | device: upload %.0f us, fx_search_batch %.0f us (search kernel %.0f us), paths+D2H %.0f us\n",
+        const double st6[6] = {t_up - t_begin, t_enq - t_up, t_sync - t_enq, 1e3 * d01, 1e3 * d12, 1e3 * d23};
+        memcpy(ctx->last_stage_us, st6, sizeof(st6));
+        ctx->last_stage_valid = 1;
+        if (trace_level == 1) fprintf(stderr, "fx_plan_host trace: host: fill+upload issue %.0f us, enqueue %.0f us, wait %.0f us | device: upload %.0f us, fx_search_batch %.0f us (search kernel %.0f us), paths+D2H %.0f us\n",
                 t_up - t_begin, t_enq - t_up, t_sync - t_enq, 1e3 * d01, 1e3 * d12, 1e3 * kms, 1e3 * d23);
     }
     memcpy(h_cost_i, pin + off_ci, (size_t)Q * 4);

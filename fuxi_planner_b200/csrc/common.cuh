@@ -106,6 +106,8 @@ struct fx_context {
         int sightings;          // consecutive calls with this key
         cudaGraphExec_t exec;   // instantiated on the second sighting
     } graphs[4];
+    double last_stage_us[6];            // fx_plan_host_stages (valid when last_stage_valid)
+    int last_stage_valid;
     const uint8_t *moves_prebuilt_for;  // fx_plan_host -> fx_search_batch: the legal-move mask of this grid is already enqueued
     int calib_W, calib_H, calib_metric;  // what the first-bound table of the latency forms was learnt on (search.cu)
     cudaStream_t cap_stream;    // capture happens here (the caller's stream may be the legacy default stream)

@@ -186,6 +186,12 @@ int fx_search_stats(fx_context *ctx, int64_t *h_stats4);
 int fx_search_kernel_ms(fx_context *ctx, float *h_ms);
 /* the same for both kernels of the batched search: h_ms2 = {k_band_bound (upper bounds), k_search_batch} */
 int fx_search_timings(fx_context *ctx, float *h_ms2);
+/* Where a host-buffer planning call spends its time (break-down of the single-replan latency): with the
+ * environment variable FUXI_B200_TRACE set to 1 (also prints a line per call on stderr) or 2 (silent), fx_plan_host*
+ * records, in microseconds, h_us6[0] host: filling the pinned staging buffer and issuing the uploads, [1] host: enqueueing
+ * search and copies, [2] host: waiting for the device, [3] device (CUDA events): grid upload, [4] device: fx_search_batch
+ * (legal-move mask + kernels), [5] device: path compaction + D2H.  FX_ERR_ARG if the last call was not traced. */
+int fx_plan_host_stages(fx_context *ctx, double *h_us6);
 
 /* ---- host-buffer convenience = what the Python drop-in `jps1.method` calls ---------------------
  * Same as fx_search_batch but all buffers are HOST memory; copies in, runs, copies out and

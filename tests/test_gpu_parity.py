@@ -542,6 +542,24 @@ def test_plan_host_odd_sizes_through_the_staged_upload(fx, oracle):
                 assert (r[0][q] == int(want[q])) if status[q] == 1 else (r[0][q] == -1), (W, H, grid.dtype, q)
 
 
+def test_plan_host_stage_trace(fx, oracle, monkeypatch):
+    """FUXI_B200_TRACE=2 records where a host-buffer call spends its time (fx_plan_host_stages: the latency break-down
+    SURVEY 8d asks for); an untraced call, or one that took the shared-memory kernel, has none."""
+    rng = np.random.default_rng(8)
+    occ = (rng.random((1100, 1000)) < 0.2).astype(np.uint8)
+    s, g = random_queries(occ, 2, rng)
+    monkeypatch.setenv("FUXI_B200_TRACE", "2")
+    r = fx.plan_host(occ, s, g, metric=1, max_path=0)
+    st = fx.plan_host_stages()
+    assert len(st) == 6 and all(v >= 0.0 for v in st) and st[3] > 0.0 and st[4] > 0.0
+    want, status, _ = oracle.jps_batch(occ, s, g, 1)
+    assert all((r[0][q] == int(want[q])) if status[q] == 1 else (r[0][q] == -1) for q in range(2))
+    monkeypatch.delenv("FUXI_B200_TRACE")
+    fx.plan_host(occ, s, g, metric=1, max_path=0)
+    with pytest.raises(fx.FuxiError):
+        fx.plan_host_stages()
+
+
 def test_latency_forms_after_a_maze_of_the_same_shape(fx, dev, oracle, monkeypatch):
     """The latency forms size their first pass from a per-context table of how far above the octile bound earlier optima
     lay (search.cu fx_first_bound).  A serpentine maze teaches it ratios of 10 and more; the next map of the same shape is
