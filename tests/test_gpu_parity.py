@@ -125,7 +125,9 @@ def test_inflate_matches_reference_formulation_on_padded_map(fx, dev, oracle, ma
                                         # H % 32 == 0: the bit-parallel path (dense: all resolved in-tile; 0.5-2 %: fix-up
                                         # list; sparse tiles: falls back to the windowed path on the device flag)
                                         ((1024, 1024), 0.02), ((256, 64), 0.05), ((1100, 2048), 0.005), ((96, 32), 0.3),
-                                        ((130, 96), 1.0), ((2048, 4096), 0.02), ((777, 1056), 0.0004)])
+                                        ((130, 96), 1.0), ((2048, 4096), 0.02), ((777, 1056), 0.0004),
+                                        # warp strips: fewer rows than one 64-row step, one word column, ragged last step
+                                        ((1, 32), 0.5), ((2, 64), 0.1), ((63, 32), 0.03), ((65, 64), 0.03), ((129, 288), 0.01)])
 def test_edt_exact(fx, dev, oracle, shape, fill):
     rng = np.random.default_rng(int(fill * 1e6) + shape[0])
     m = (rng.random(shape) < fill).astype(np.uint8)
