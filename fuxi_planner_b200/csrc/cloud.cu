@@ -18,6 +18,7 @@ struct CloudState {
     unsigned total_bits;  // voxel index space actually used (0 when nothing passes or on overflow)
     unsigned n_pass, n_vox, n_keep;
     long long status;  // 0 ok; > 0: voxel index space needed (exceeds capacity); -1: coordinates outside int range
+    unsigned ticket[2];  // "last CTA of the launch" counters of the two prefix-count kernels (zeroed by k_cl_reset)
 };
 
 struct CloudArgs {
@@ -49,6 +50,7 @@ __global__ void k_cl_reset(CloudState *s)
         for (int k = 0; k < 3; k++) s->bb[k] = 0xFFFFFFFFu, s->bb[3 + k] = 0u, s->min_b[k] = 0, s->div[k] = 0;
         s->total_bits = s->n_pass = s->n_vox = s->n_keep = 0;
         s->status = 0;
+        s->ticket[0] = s->ticket[1] = 0;
     }
 }
 
@@ -92,27 +94,32 @@ __global__ void __launch_bounds__(256) k_cl_bbox(CloudArgs a, CloudState *s)
 }
 
 // VoxelGrid<PointT>::applyFilter: min_b = floor(min_p * inverse_leaf), div_b = max_b - min_b + 1
-__global__ void k_cl_setup(CloudState *s, float ix, float iy, float iz, unsigned long long cap_bits)
+// Evaluated by thread 0 of EVERY CTA of k_cl_zero_bits (same inputs, same result; CTA 0 also stores it): the separate
+// one-thread launch that used to do this was 2.6 us of a 90 us frame.  Returns the voxel index space in use.
+__device__ unsigned cl_setup(CloudState *s, float ix, float iy, float iz, unsigned long long cap_bits, bool store)
 {
-    if (threadIdx.x != 0 || s->n_pass == 0) return;
+    if (s->n_pass == 0) return 0u;
     const float inv[3] = {ix, iy, iz};
     unsigned long long total = 1;
+    int mb[3] = {0, 0, 0}, dv[3] = {0, 0, 0};
+    long long status = 0;
     for (int k = 0; k < 3; k++) {
         float lo = floorf(__fmul_rn(ord2f(s->bb[k]), inv[k])), hi = floorf(__fmul_rn(ord2f(s->bb[3 + k]), inv[k]));
-        if (!(fabsf(lo) < 1.0e9f) || !(fabsf(hi) < 1.0e9f)) {
-            s->status = -1;
-            return;
-        }
-        s->min_b[k] = (int)lo;
-        s->div[k] = (int)hi - (int)lo + 1;
-        total *= (unsigned long long)s->div[k];
+        if (!(fabsf(lo) < 1.0e9f) || !(fabsf(hi) < 1.0e9f)) { status = -1; break; }
+        mb[k] = (int)lo;
+        dv[k] = (int)hi - (int)lo + 1;
+        total *= (unsigned long long)dv[k];
         if (total > (1ull << 40)) break;
     }
-    if (total > cap_bits) {
-        s->status = (long long)total;
-        return;
+    if (status == 0 && total > cap_bits) status = (long long)total;
+    const unsigned used = status == 0 ? (unsigned)total : 0u;
+    if (store) {
+        if (status != -1)
+            for (int k = 0; k < 3; k++) s->min_b[k] = mb[k], s->div[k] = dv[k];
+        s->status = status;
+        s->total_bits = used;
     }
-    s->total_bits = (unsigned)total;
+    return used;
 }
 
 __device__ __forceinline__ unsigned cl_voxel(const CloudState *s, const CloudArgs &a, float x, float y, float z)
@@ -125,9 +132,12 @@ __device__ __forceinline__ unsigned cl_voxel(const CloudState *s, const CloudArg
 }
 
 // zero the words a scan will read: whole 256-bit groups
-__global__ void k_cl_zero_bits(unsigned *bits, const unsigned *nbits)
+__global__ void k_cl_zero_bits(unsigned *bits, CloudState *s, float ix, float iy, float iz, unsigned long long cap_bits)
 {
-    const size_t words = ((size_t)*nbits + 255) / 256 * 8;
+    __shared__ unsigned s_bits;
+    if (threadIdx.x == 0) s_bits = cl_setup(s, ix, iy, iz, cap_bits, blockIdx.x == 0);
+    __syncthreads();
+    const size_t words = ((size_t)s_bits + 255) / 256 * 8;
     for (size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; w < words; w += (size_t)gridDim.x * blockDim.x) bits[w] = 0;
 }
 
@@ -203,9 +213,13 @@ __device__ __forceinline__ unsigned block_excl_scan_1024(unsigned v, unsigned *s
     return r;
 }
 
-__global__ void __launch_bounds__(1024) k_scan_groups(const unsigned *bits, const unsigned *nbits, unsigned *gpref, unsigned *chunk)
+// per 256-bit group the set bits before it inside its 1024-group chunk, per chunk its total; the CTA that finishes last
+// turns the chunk totals into exclusive prefixes and publishes the grand total (was a second, one-CTA launch)
+__global__ void __launch_bounds__(1024) k_scan_groups(const unsigned *bits, const unsigned *nbits, unsigned *gpref, unsigned *chunk,
+                                                      unsigned *out_total, unsigned *ticket)
 {
     __shared__ unsigned s_w[33];
+    __shared__ bool s_last;
     const size_t groups = ((size_t)*nbits + 255) / 256, chunks = (groups + 1023) / 1024;
     for (size_t c = blockIdx.x; c < chunks; c += gridDim.x) {
         const size_t g = c * 1024 + threadIdx.x;
@@ -214,23 +228,25 @@ __global__ void __launch_bounds__(1024) k_scan_groups(const unsigned *bits, cons
         if (g < groups) gpref[g] = ex;
         if (threadIdx.x == 0) chunk[c] = total;
     }
-}
-
-__global__ void __launch_bounds__(1024) k_scan_chunks(unsigned *chunk, const unsigned *nbits, unsigned *out_total)
-{
-    __shared__ unsigned s_w[33];
-    const size_t groups = ((size_t)*nbits + 255) / 256, chunks = (groups + 1023) / 1024;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
     const size_t per = (chunks + 1023) / 1024;  // consecutive chunks per thread
     const size_t b = threadIdx.x * per, e = min(b + per, chunks);
     unsigned sum = 0;
-    for (size_t c = b; c < e; c++) sum += chunk[c];
+    for (size_t c = b; c < e; c++) sum += __ldcg(chunk + c);
     unsigned total, run = block_excl_scan_1024(sum, s_w, total);
     for (size_t c = b; c < e; c++) {
-        unsigned t = chunk[c];
+        unsigned t = __ldcg(chunk + c);
         chunk[c] = run;
         run += t;
     }
-    if (threadIdx.x == 0) *out_total = total;
+    if (threadIdx.x == 0) { *out_total = total; *ticket = 0; }
 }
 
 // MODE 0: vidx[rank] = bit index.  MODE 1: out[rank] = src[bit index] (rank < cap).  One thread per bitmap word (eight
@@ -238,8 +254,13 @@ __global__ void __launch_bounds__(1024) k_scan_chunks(unsigned *chunk, const uns
 // a group also finalises gpref[g].  (One thread per group walked up to 256 bits one after the other: 75 us per frame.)
 template <int MODE>
 __global__ void __launch_bounds__(256) k_scan_emit(const unsigned *bits, const unsigned *nbits, unsigned *gpref, const unsigned *chunk,
-                                                   unsigned *vidx, const float4 *src, float4 *out, long long cap)
+                                                   unsigned *vidx, const float4 *src, float4 *out, long long cap,
+                                                   unsigned long long *zero_acc, const unsigned *n_vox)
 {
+    if (zero_acc) {  // the voxel accumulators of the next kernel (was a launch of its own)
+        const size_t na = (size_t)*n_vox * 5;
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < na; i += (size_t)gridDim.x * blockDim.x) zero_acc[i] = 0;
+    }
     const size_t groups = ((size_t)*nbits + 255) / 256, nwords = groups * 8;
     const size_t wpad = (nwords + 31) & ~(size_t)31;  // whole warps: the shuffles below need every lane
     for (size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; w < wpad; w += (size_t)gridDim.x * blockDim.x) {
@@ -287,12 +308,6 @@ __device__ __forceinline__ unsigned cl_rank(const unsigned *bits, const unsigned
 
 // accumulators per voxel rank: 5 x u64 = {sum x, sum y, sum z (2^-24 m fixed point), r << 32 | g, b << 32 | count}
 #define CL_FIX 16777216.0
-__global__ void k_cl_zero_acc(unsigned long long *acc, const unsigned *n_vox)
-{
-    const size_t n = (size_t)*n_vox * 5;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc[i] = 0;
-}
-
 __global__ void __launch_bounds__(256) k_cl_accum(CloudArgs a, const CloudState *s, const unsigned *bits, const unsigned *gpref,
                                                   unsigned long long *acc)
 {
@@ -386,8 +401,10 @@ __global__ void __launch_bounds__(256) k_cl_ror(const float4 *vox, const unsigne
 // order-preserving compaction of the kept centroids: one thread per centroid, its output slot is the (not yet
 // finalised) group prefix of the keep bitmap + the set bits below it inside the group
 __global__ void __launch_bounds__(256) k_cl_compact(const unsigned *keep, const unsigned *n_vox, const unsigned *gpref2, const unsigned *chunk2,
-                                                    const float4 *vox, float4 *out, long long cap)
+                                                    const float4 *vox, float4 *out, long long cap, const CloudState *s, long long *counts)
 {
+    // every count is final before this kernel starts (was a one-thread launch of its own)
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[0] = s->n_pass, counts[1] = s->n_vox, counts[2] = s->n_keep, counts[3] = s->status;
     const unsigned n = *n_vox;
     for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
         if (!((keep[r >> 5] >> (r & 31)) & 1u)) continue;
@@ -396,13 +413,6 @@ __global__ void __launch_bounds__(256) k_cl_compact(const unsigned *keep, const 
         for (unsigned w = g * 8; w < (r >> 5); w++) d += __popc(keep[w]);
         d += __popc(keep[r >> 5] & ((1u << (r & 31)) - 1u));
         if ((long long)d < cap) out[d] = vox[r];
-    }
-}
-
-__global__ void k_cl_counts(const CloudState *s, long long *counts)
-{
-    if (threadIdx.x == 0) {
-        counts[0] = s->n_pass, counts[1] = s->n_vox, counts[2] = s->n_keep, counts[3] = s->status;
     }
 }
 
@@ -467,19 +477,13 @@ extern "C" int fx_cloud_filter(fx_context *ctx, const float *pts, int64_t n, con
         FX_LAUNCH_CHECK(ctx);
         k_cl_bbox<<<grid_for(ctx, n, 1024, 4), 256, 0, st>>>(a, s);
         FX_LAUNCH_CHECK(ctx);
-        k_cl_setup<<<1, 32, 0, st>>>(s, a.inv[0], a.inv[1], a.inv[2], ctx->cl_cap_bits);
-        FX_LAUNCH_CHECK(ctx);
-        k_cl_zero_bits<<<gw, 256, 0, st>>>(ctx->cl_bits, &s->total_bits);
+        k_cl_zero_bits<<<gw, 256, 0, st>>>(ctx->cl_bits, s, a.inv[0], a.inv[1], a.inv[2], ctx->cl_cap_bits);
         FX_LAUNCH_CHECK(ctx);
         k_cl_mark<<<gp, 256, 0, st>>>(a, s, ctx->cl_bits);
         FX_LAUNCH_CHECK(ctx);
-        k_scan_groups<<<ctx->sm_count * 2, 1024, 0, st>>>(ctx->cl_bits, &s->total_bits, ctx->cl_gpref, ctx->cl_chunk);
+        k_scan_groups<<<ctx->sm_count * 2, 1024, 0, st>>>(ctx->cl_bits, &s->total_bits, ctx->cl_gpref, ctx->cl_chunk, &s->n_vox, &s->ticket[0]);
         FX_LAUNCH_CHECK(ctx);
-        k_scan_chunks<<<1, 1024, 0, st>>>(ctx->cl_chunk, &s->total_bits, &s->n_vox);
-        FX_LAUNCH_CHECK(ctx);
-        k_scan_emit<0><<<gw, 256, 0, st>>>(ctx->cl_bits, &s->total_bits, ctx->cl_gpref, ctx->cl_chunk, ctx->cl_vidx, nullptr, nullptr, 0);
-        FX_LAUNCH_CHECK(ctx);
-        k_cl_zero_acc<<<gw, 256, 0, st>>>(ctx->cl_acc, &s->n_vox);
+        k_scan_emit<0><<<gw, 256, 0, st>>>(ctx->cl_bits, &s->total_bits, ctx->cl_gpref, ctx->cl_chunk, ctx->cl_vidx, nullptr, nullptr, 0, ctx->cl_acc, &s->n_vox);
         FX_LAUNCH_CHECK(ctx);
         k_cl_accum<<<gp, 256, 0, st>>>(a, s, ctx->cl_bits, ctx->cl_gpref, ctx->cl_acc);
         FX_LAUNCH_CHECK(ctx);
@@ -487,17 +491,13 @@ extern "C" int fx_cloud_filter(fx_context *ctx, const float *pts, int64_t n, con
         FX_LAUNCH_CHECK(ctx);
         k_cl_ror<<<gw, 256, 0, st>>>(ctx->cl_vox, ctx->cl_vidx, ctx->cl_bits, ctx->cl_gpref, s, wx, wy, wz, r2, p->min_neighbors, ctx->cl_keep);
         FX_LAUNCH_CHECK(ctx);
-        k_scan_groups<<<ctx->sm_count * 2, 1024, 0, st>>>(ctx->cl_keep, &s->n_vox, ctx->cl_gpref2, ctx->cl_chunk2);
+        k_scan_groups<<<ctx->sm_count * 2, 1024, 0, st>>>(ctx->cl_keep, &s->n_vox, ctx->cl_gpref2, ctx->cl_chunk2, &s->n_keep, &s->ticket[1]);
         FX_LAUNCH_CHECK(ctx);
-        k_scan_chunks<<<1, 1024, 0, st>>>(ctx->cl_chunk2, &s->n_vox, &s->n_keep);
-        FX_LAUNCH_CHECK(ctx);
-        k_cl_compact<<<gw, 256, 0, st>>>(ctx->cl_keep, &s->n_vox, ctx->cl_gpref2, ctx->cl_chunk2, ctx->cl_vox, (float4 *)out, cap);
-        FX_LAUNCH_CHECK(ctx);
-        k_cl_counts<<<1, 32, 0, st>>>(s, (long long *)d_counts);
+        k_cl_compact<<<gw, 256, 0, st>>>(ctx->cl_keep, &s->n_vox, ctx->cl_gpref2, ctx->cl_chunk2, ctx->cl_vox, (float4 *)out, cap, s, (long long *)d_counts);
         FX_LAUNCH_CHECK(ctx);
         return FX_OK;
     };
-    // everything the 16 launches depend on: arguments, derived constants, scratch pointers
+    // everything the 11 launches depend on: arguments, derived constants, scratch pointers
     struct { const float *pts; int64_t n; fx_cloud_params p; float *out; int64_t cap; int64_t *counts; unsigned long long cap_bits;
              void *b[11]; } key;
     memset(&key, 0, sizeof(key));
