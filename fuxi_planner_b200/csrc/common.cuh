@@ -224,7 +224,7 @@ __device__ __forceinline__ int fx_cidx(int x, int y, int H, int TY)
 int fx_grow_bytes(fx_context *ctx, void **p, size_t *cap, size_t want_bytes);
 int fx_grow_pinned(fx_context *ctx, size_t want);
 #include <functional>
-// Launch-bound sizes (one camera frame through the 16 kernels of the cloud filter, a 1024^2 distance transform): the
+// Launch-bound sizes (one camera frame through the 11 kernels of the cloud filter, a 1024^2 distance transform): the
 // launch sequence of an entry point is a function of its arguments and of the scratch pointers it uses -- `key`.  The
 // first call with a key runs `enqueue(stream)` as plain launches (and sizes the scratch), the second captures the same
 // sequence into a CUDA graph on a private stream, later calls replay it: one launch instead of 8-16, no gaps between the

@@ -328,7 +328,7 @@ typedef struct fx_cloud_params {
     double radius;
 } fx_cloud_params;
 int fx_cloud_reserve(fx_context *ctx, int64_t max_voxel_space);   /* default 2^28 */
-/* fx_cloud_filter (16 launches), fx_edt (8) and fx_distance_filter are replayed as one CUDA graph from the third call with
+/* fx_cloud_filter (11 launches), fx_edt (8) and fx_distance_filter are replayed as one CUDA graph from the third call with
  * identical arguments (same pointers, sizes, parameters) on; the graph is launched into `stream` like the kernels would be. */
 int fx_cloud_filter(fx_context *ctx, const float *pts, int64_t n, const fx_cloud_params *h_params, float *out, int64_t cap,
                     int64_t *d_counts, void *stream);
