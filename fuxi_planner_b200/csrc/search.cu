@@ -93,6 +93,7 @@ __device__ __forceinline__ uint64_t fx_first_bound(const uint32_t *calib, int bi
     if (!calib) return (uint64_t)h0 + h0 / 128 + 4ull * wd;  // FUXI_B200_CALIB=0: the fixed guess of the first version
     uint32_t r = __ldcg(calib + bin);
     if (bin < 15) r = max(r, __ldcg(calib + bin + 1) >> 1);  // a sparsely visited bin borrows from its neighbour
+    if (r == 0u) r = 7168u;                                  // nothing learnt yet: the fixed guess (1/128 with the margin below)
     r = min(r, 1u << 19);                                              // never guess beyond 1.5 h0: a maze-like map is served by the widening
     r = r + (r >> 3) + FX_CALIB_FLOOR;                                 // 1/8 margin over the recent maximum
     return (uint64_t)h0 + (((uint64_t)h0 * r) >> 20) + 4ull * wd;
@@ -1372,11 +1373,14 @@ extern "C" int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int 
     {
         const char *e = getenv("FUXI_B200_CALIB");  // tuning experiments only
         P.calib = (e && e[0] == '0') ? nullptr : reinterpret_cast<uint32_t *>(ctx->counters + 16);
-        // the table describes a map: another grid shape or metric starts it afresh
-        if (P.calib && (ctx->calib_W != W || ctx->calib_H != H || ctx->calib_metric != metric)) {
+        // The table describes the maps this context plans on.  It survives a change of the grid's shape (a planner's grid
+        // grows and shifts from replan to replan while its obstacle statistics stay: the decaying maximum follows them,
+        // and a stale value only makes a first pass wider or a second one necessary); another metric starts it afresh.
+        if (P.calib && ctx->calib_metric != metric) {
             FX_CUDA(ctx, cudaMemsetAsync(P.calib, 0, 16 * sizeof(uint32_t), st));
-            ctx->calib_W = W; ctx->calib_H = H; ctx->calib_metric = metric;
+            ctx->calib_metric = metric;
         }
+        ctx->calib_W = W; ctx->calib_H = H;
     }
     // half-width (cells along the minor axis) of the band-limited passes of the search kernel; one more than the band kernel's
     // 15 + rounding of its fixed-point centre line, so that a path the band kernel found lies inside it

@@ -116,7 +116,7 @@ int fx_edt_cols(fx_context *ctx, const uint16_t *g, int32_t *dist2, int W, int H
  * wavefront kernel, with 512-thread CTAs when the batch is smaller than the machine (latency) and 128-thread CTAs,
  * eight per SM, otherwise (throughput).  W, H <= 32767.
  * The latency forms size their first pass from a table the context keeps (how far above the octile bound the optimum
- * lay on earlier queries of the same grid shape, by direction mix): it changes how many passes a query takes, never
+ * lay on earlier queries with the same metric, by direction mix): it changes how many passes a query takes, never
  * its answer.
  */
 int fx_search_batch(fx_context *ctx, const uint8_t *grid, int W, int H,
